@@ -1,0 +1,226 @@
+// oracle/match.cc — TEST INFRASTRUCTURE (see oracle.h).
+// CPU restatement of Frame::isInFrustum (mono branch, src/Frame.cc:456-519) with Pinhole::project
+// (src/CameraModels/Pinhole.cpp:45-52), the trackId joins of include/MOVMatcher.h:35-137 and the bucket grid
+// (src/Frame.cc:356-388, 602-680).
+//
+// Float evaluation order. Eigen is not in this container; the fixed-size 3-vector reductions are restated in
+// the order Eigen 3.4's unrolled reduction produces, c0 + (c1 + c2) (redux_novec_unroller splits at Length/2),
+// without FMA contraction. That order is recalled, not re-read: "parity unpinned" for the last bit of the
+// projections. The camera centre mOw comes from Sophus' quaternion inverse in the
+// reference (Frame.cc:429-431); here it is -R^T t evaluated in double and rounded to float.
+#include "oracle.h"
+
+#include <cmath>
+#include <map>
+#include <vector>
+
+namespace {
+
+inline float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+
+// KannalaBrandt8 is absent from the reference tree; ORB-SLAM3 lineage formula
+// (App. A.6), evaluated in double and rounded to float so that host and device libm agree.
+inline void project_fisheye_f(const movfe_camera *cam, const float Pc[3], float uv[2]) {
+    const double x = Pc[0], y = Pc[1], z = Pc[2];
+    const double r = std::sqrt(x * x + y * y);
+    const double theta = std::atan2(r, z);
+    const double t2 = theta * theta;
+    const double thetad = theta * (1.0 + t2 * ((double)cam->k[0] + t2 * ((double)cam->k[1] + t2 * ((double)cam->k[2] + t2 * (double)cam->k[3]))));
+    const double s = r > 1e-12 ? thetad / r : 1.0;
+    uv[0] = (float)((double)cam->fx * s * x + (double)cam->cx);
+    uv[1] = (float)((double)cam->fy * s * y + (double)cam->cy);
+}
+
+}  // namespace
+
+extern "C" void orc_frustum(const movfe_pose *Tcw, const movfe_camera *cam, int width, int height,
+                            float viewingCosLimit, const movfe_map_point *pts, int n, movfe_projection *out) {
+    float mRcw[9], mtcw[3], mOw[3];
+    for (int i = 0; i < 9; i++) mRcw[i] = (float)Tcw->R[i];
+    for (int i = 0; i < 3; i++) mtcw[i] = (float)Tcw->t[i];
+    for (int i = 0; i < 3; i++)
+        mOw[i] = (float)(-(Tcw->R[0 * 3 + i] * Tcw->t[0] + Tcw->R[1 * 3 + i] * Tcw->t[1] + Tcw->R[2 * 3 + i] * Tcw->t[2]));
+    const float mnMinX = 0.0f, mnMaxX = (float)width, mnMinY = 0.0f, mnMaxY = (float)height;  // Frame.cc:739-745
+
+    for (int k = 0; k < n; k++) {
+        const movfe_map_point &mp = pts[k];
+        movfe_projection &o = out[k];
+        o.in_view = 0;  // :460-462
+        o.u = -1;
+        o.v = -1;
+        o.depth = 0;
+        o.view_cos = 0;
+        // Tracking::SearchLocalPoints (:1136-1139) never calls isInFrustum for these
+        if (mp.flags & (MOVFE_MP_BAD | MOVFE_MP_SKIP | MOVFE_MP_NULL)) continue;
+
+        const float *P = mp.pos;  // :465
+        float Pc[3];              // :468  Pc = mRcw * P + mtcw
+        for (int i = 0; i < 3; i++) Pc[i] = dot3(&mRcw[3 * i], P) + mtcw[i];
+        const float Pc_dist = std::sqrt(dot3(Pc, Pc));  // :469
+
+        const float PcZ = Pc[2];  // :472-475
+        if (PcZ < 0.0f) continue;
+
+        float uv[2];  // :477
+        if (cam->model == MOVFE_CAM_FISHEYE) {
+            project_fisheye_f(cam, Pc, uv);
+        } else {  // Pinhole.cpp:48-49: fx * x / z + cx
+            uv[0] = cam->fx * Pc[0] / Pc[2] + cam->cx;
+            uv[1] = cam->fy * Pc[1] / Pc[2] + cam->cy;
+        }
+
+        if (uv[0] < mnMinX || uv[0] > mnMaxX) continue;  // :479-482
+        if (uv[1] < mnMinY || uv[1] > mnMaxY) continue;
+
+        o.u = uv[0];  // :484-485
+        o.v = uv[1];
+
+        const float maxDistance = 1.2f * mp.max_dist;  // :488-489, MapPoint.cc:443-453
+        const float minDistance = 0.8f * mp.min_dist;
+        const float PO[3] = {P[0] - mOw[0], P[1] - mOw[1], P[2] - mOw[2]};  // :490
+        const float dist = std::sqrt(dot3(PO, PO));
+
+        if (dist < minDistance || dist > maxDistance) continue;  // :493
+
+        const float viewCos = dot3(PO, mp.normal) / dist;  // :497-499
+
+        if (viewCos < viewingCosLimit) continue;  // :501
+
+        o.in_view = 1;  // :508-516
+        o.depth = Pc_dist;
+        o.view_cos = viewCos;
+    }
+}
+
+// F.mvVFMap: std::map<int,int>::insert never overwrites, so the first index of a track id wins
+// (MOVExtractor.cc:330).
+static std::map<int, int> build_vfmap(const movfe_track *tracks, int n) {
+    std::map<int, int> m;
+    for (int i = 0; i < n; i++) m.insert({tracks[i].track_id, i});
+    return m;
+}
+
+// MOVMatcher.h:35-68
+extern "C" int orc_search_by_video_feature(const movfe_track *tracks, int n_tracks, const movfe_map_point *pts,
+                                           const movfe_projection *proj, int n_pts, int bFarPoints,
+                                           float thFarPoints, int32_t *match) {
+    std::map<int, int> vfmap = build_vfmap(tracks, n_tracks);
+    int nmatches = 0;
+    for (int iMP = 0; iMP < n_pts; iMP++) {
+        if (bFarPoints && proj[iMP].depth > thFarPoints) continue;  // :43-44
+        if (pts[iMP].flags & MOVFE_MP_BAD) continue;                // :46-47
+        if (proj[iMP].in_view) {                                    // :49
+            auto it = vfmap.find(pts[iMP].track_id);
+            if (it != vfmap.end()) {  // :51-55
+                match[it->second] = iMP;
+                nmatches++;
+            }
+        }
+    }
+    return nmatches;
+}
+
+// MOVMatcher.h:70-103
+extern "C" int orc_search_by_keyframe(const movfe_track *tracks, int n_tracks, const movfe_map_point *kf_pts,
+                                      int n_pts, int32_t *match) {
+    std::map<int, int> vfmap = build_vfmap(tracks, n_tracks);
+    for (int i = 0; i < n_tracks; i++) match[i] = -1;  // :73
+    int nmatches = 0;
+    for (int i = 0; i < n_pts; i++) {
+        if (kf_pts[i].flags & MOVFE_MP_NULL) continue;  // :81
+        if (kf_pts[i].flags & MOVFE_MP_BAD) continue;   // :83-84
+        auto it = vfmap.find(kf_pts[i].track_id);
+        if (it != vfmap.end()) {  // :86-90
+            match[it->second] = i;
+            nmatches++;
+        }
+    }
+    return nmatches;
+}
+
+// MOVMatcher.h:105-137
+extern "C" int orc_search_for_initialization(const movfe_track *f1, int n1, const movfe_track *f2, int n2,
+                                             float *vbPrevMatched, int32_t *vnMatches12) {
+    std::map<int, int> vfmap1 = build_vfmap(f1, n1);
+    int nmatches = 0;
+    for (int i = 0; i < n1; i++) vnMatches12[i] = -1;  // :108
+    for (int i1 = 0; i1 < n2; i1++) {                  // :111-119 (iterates F2 despite the name)
+        auto it = vfmap1.find(f2[i1].track_id);
+        if (it != vfmap1.end()) {
+            vnMatches12[it->second] = i1;
+            nmatches++;
+        }
+    }
+    for (int i1 = 0; i1 < n1; i1++)  // :132-134
+        if (vnMatches12[i1] >= 0) {
+            vbPrevMatched[2 * i1] = f2[vnMatches12[i1]].pt_x;
+            vbPrevMatched[2 * i1 + 1] = f2[vnMatches12[i1]].pt_y;
+        }
+    return nmatches;
+}
+
+// ---- bucket grid ---------------------------------------------------------------------------------------------
+#define FRAME_GRID_ROWS 48  // Frame.h:40-41
+#define FRAME_GRID_COLS 64
+
+// Frame.cc:670-680
+static bool PosInGrid(float x, float y, float mnMinX, float mnMinY, float wInv, float hInv, int &posX, int &posY) {
+    posX = (int)std::round((x - mnMinX) * wInv);
+    posY = (int)std::round((y - mnMinY) * hInv);
+    if (posX < 0 || posX >= FRAME_GRID_COLS || posY < 0 || posY >= FRAME_GRID_ROWS) return false;
+    return true;
+}
+
+// Frame.cc:356-388 (mono: Nleft == -1, mvKeysUn == mvKeys when k1 == 0, Frame.cc:684-688)
+extern "C" void orc_assign_features_to_grid(const movfe_track *tracks, int n, int width, int height,
+                                            int32_t *cell_start, int32_t *cell_items) {
+    const float mnMinX = 0.0f, mnMaxX = (float)width, mnMinY = 0.0f, mnMaxY = (float)height;
+    const float wInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(mnMaxX - mnMinX);  // :147-148
+    const float hInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(mnMaxY - mnMinY);
+    std::vector<std::vector<int>> mGrid(FRAME_GRID_COLS * FRAME_GRID_ROWS);
+    for (int i = 0; i < n; i++) {
+        int gx, gy;
+        if (PosInGrid(tracks[i].pt_x, tracks[i].pt_y, mnMinX, mnMinY, wInv, hInv, gx, gy))
+            mGrid[gx * FRAME_GRID_ROWS + gy].push_back(i);
+    }
+    int k = 0;
+    for (int c = 0; c < FRAME_GRID_COLS * FRAME_GRID_ROWS; c++) {
+        cell_start[c] = k;
+        for (int v : mGrid[c]) cell_items[k++] = v;
+    }
+    cell_start[FRAME_GRID_COLS * FRAME_GRID_ROWS] = k;
+}
+
+// Frame.cc:602-668 (minLevel = 0, maxLevel = -1: no level checks; all keypoints are octave 0)
+extern "C" int orc_get_features_in_area(const movfe_track *tracks, int n, int width, int height,
+                                        const int32_t *cell_start, const int32_t *cell_items, float x, float y,
+                                        float r, int32_t *out) {
+    (void)n;
+    const float mnMinX = 0.0f, mnMaxX = (float)width, mnMinY = 0.0f, mnMaxY = (float)height;
+    const float wInv = static_cast<float>(FRAME_GRID_COLS) / static_cast<float>(mnMaxX - mnMinX);
+    const float hInv = static_cast<float>(FRAME_GRID_ROWS) / static_cast<float>(mnMaxY - mnMinY);
+    int cnt = 0;
+    float factorX = r, factorY = r;
+
+    const int nMinCellX = std::max(0, (int)std::floor((x - mnMinX - factorX) * wInv));
+    if (nMinCellX >= FRAME_GRID_COLS) return 0;
+    const int nMaxCellX = std::min((int)FRAME_GRID_COLS - 1, (int)std::ceil((x - mnMinX + factorX) * wInv));
+    if (nMaxCellX < 0) return 0;
+    const int nMinCellY = std::max(0, (int)std::floor((y - mnMinY - factorY) * hInv));
+    if (nMinCellY >= FRAME_GRID_ROWS) return 0;
+    const int nMaxCellY = std::min((int)FRAME_GRID_ROWS - 1, (int)std::ceil((y - mnMinY + factorY) * hInv));
+    if (nMaxCellY < 0) return 0;
+
+    for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+        for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+            const int c = ix * FRAME_GRID_ROWS + iy;
+            for (int j = cell_start[c]; j < cell_start[c + 1]; j++) {
+                const movfe_track &kp = tracks[cell_items[j]];
+                const float distx = kp.pt_x - x;
+                const float disty = kp.pt_y - y;
+                if (std::fabs(distx) < factorX && std::fabs(disty) < factorY) out[cnt++] = cell_items[j];
+            }
+        }
+    }
+    return cnt;
+}

@@ -1,0 +1,238 @@
+"""Pins the CPU oracle against the hand-derived known-answer vectors of SURVEY.md Appendix B.
+
+The reference ships no tests or golden vectors; these KATs were derived by hand / by a literal
+transcription of VideoDecoder.cc:211-350 and EXPRESS.h:79-192 during the survey.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from movfe import types as T
+
+
+def rec(dst, src, w=16, h=16, ref=0, source=-1):
+    r = np.zeros((), T.MV_RECORD)
+    r["source"], r["w"], r["h"], r["ref"] = source, w, h, ref
+    r["dst_x"], r["dst_y"], r["src_x"], r["src_y"] = dst[0], dst[1], src[0], src[1]
+    r["motion_x"], r["motion_y"], r["motion_scale"] = 4 * (src[0] - dst[0]), 4 * (src[1] - dst[1]), 4
+    return r
+
+
+def clip_of(orc, W, H, frames, max_ref=10):
+    """frames: list of record lists (None = frame without MV side data)."""
+    recs, off, flags = [], [0], []
+    for i, fr in enumerate(frames):
+        fl = T.FRAME_P if i > 0 else 0
+        if fr is not None:
+            fl |= T.FRAME_MV
+            recs += fr
+        off.append(len(recs))
+        flags.append(fl)
+    arr = np.array(recs, T.MV_RECORD) if recs else np.zeros(0, T.MV_RECORD)
+    return orc.Clip(W, H, arr, off, flags, max_ref)
+
+
+def test_kat1_raster_ref0(orc):
+    c = clip_of(orc, 64, 48, [[], [rec((24, 24), (20, 22))]])
+    assert c.n_kps(1) == 1 and tuple(c.kps(1)[0]) == (16, 16, 16, 16)
+    h = c.hops(1)
+    assert len(h) == 1 and (h[0]["mv_x"], h[0]["mv_y"], h[0]["d_indx"]) == (4.0, 2.0, 0)
+    g = c.grid(1)
+    exp = np.full((48, 64, 4), -1, np.int32)
+    exp[14:31, 12:29, 0] = 0
+    assert np.array_equal(g, exp) and (g[..., 0] == 0).sum() == 289
+    assert c.coverage(1) == np.float32(256) / (64 * 48)
+    assert abs(c.coverage(1) - 0.0833333) < 1e-6
+
+
+def test_kat2_chain_ref1(orc):
+    c = clip_of(orc, 64, 48, [[], [], [], [rec((24, 24), (20, 22), ref=1)]])
+    N = 3
+    assert c.n_kps(N) == 0 and c.n_kps(N - 2) == 1 and tuple(c.kps(N - 2)[0]) == (12, 14, 16, 16)
+    for f, rows, cols in ((N - 1, (14, 30), (12, 28)), (N, (15, 31), (14, 30))):
+        h = c.hops(f)
+        assert len(h) == 1 and (h[0]["mv_x"], h[0]["mv_y"], h[0]["d_indx"]) == (2.0, 1.0, -1)
+        exp = np.full((48, 64, 4), -1, np.int32)
+        exp[rows[0]:rows[1] + 1, cols[0]:cols[1] + 1, 0] = 0
+        assert np.array_equal(c.grid(f), exp)
+    assert c.coverage(N) == np.float32(256) / (64 * 48) and c.coverage(N - 1) == 0.0
+    assert c.n_hops(N - 2) == 0
+
+
+def test_kat3_slots(orc):
+    c = clip_of(orc, 64, 48, [[], [rec((24, 24), (24, 24)) for _ in range(5)]])
+    assert tuple(c.grid(1)[24, 24]) == (0, 1, 2, 4)
+    assert c.n_kps(1) == 5 and [int(h["d_indx"]) for h in c.hops(1)] == [0, 1, 2, 3, 4]
+
+
+def test_kat5_skip_rule(orc):
+    c = clip_of(orc, 64, 48, [[], [rec((56, 24), (50, 24))]])
+    assert c.n_kps(1) == 0 and c.n_hops(1) == 0 and c.coverage(1) == 0.0
+    assert (c.grid(1) == -1).all()
+
+
+def test_kat10_fractional_chain_ref2(orc):
+    c = clip_of(orc, 64, 48, [[], [], [], [], [rec((28, 20), (21, 16), w=8, h=8, ref=2)]])
+    N = 4
+    assert tuple(c.kps(N - 3)[0]) == (17, 12, 8, 8)
+    mvx, mvy = np.float32(7) / np.float32(3), np.float32(4) / np.float32(3)
+    assert mvx == np.float32(2.33333325) and mvy == np.float32(1.33333337)
+    for f, r0, c0 in ((N - 2, 12, 17), (N - 1, 13, 19), (N, 14, 21)):
+        h = c.hops(f)
+        assert len(h) == 1 and h[0]["mv_x"] == mvx and h[0]["mv_y"] == mvy and h[0]["d_indx"] == -1
+        exp = np.full((48, 64, 4), -1, np.int32)
+        exp[r0:r0 + 9, c0:c0 + 9, 0] = 0
+        assert np.array_equal(c.grid(f), exp), f
+
+
+def test_window_drop_before_clip_start(orc):
+    # ref=1 record in the first P frame of a clip: its kps target (frame -1) and j=2 hop (frame 0 is OK)
+    c = clip_of(orc, 64, 48, [[], [rec((24, 24), (20, 22), ref=1)]])
+    assert c.n_kps(0) == 0 and c.n_kps(1) == 0          # kps target N-1-ref = -1 dropped
+    assert c.n_hops(0) == 1 and c.n_hops(1) == 1
+    c2 = clip_of(orc, 64, 48, [[rec((24, 24), (20, 22), ref=1)]])
+    assert c2.n_hops(0) == 1 and c2.coverage(0) > 0     # j=2 hop dropped, j=1 kept
+
+
+def test_bad_ref_rejected(orc):
+    c = clip_of(orc, 64, 48, [[], [rec((24, 24), (20, 22), ref=4)]], max_ref=3)
+    assert c.bad_ref() == 1 and c.n_hops(1) == 0 and c.n_kps(1) == 0
+
+
+def test_mv_disabled_frame_receives_hops(orc):
+    # stereo right view: no own records, still receives hops from the next frame (VideoDecoder.cc:200,322)
+    c = clip_of(orc, 64, 48, [[], None, [rec((24, 24), (20, 22), ref=1)]])
+    assert c.n_hops(1) == 1 and c.n_hops(2) == 1 and c.n_kps(0) == 1
+
+
+def _img(fn, n=32):
+    y, x = np.mgrid[0:n, 0:n]
+    return fn(x, y).astype(np.uint8)
+
+
+def test_kat11_express_vertical_edge(orc):
+    im = _img(lambda x, y: np.where(x < 12, 0, 200))
+    assert orc.express_center(im, 8, 8, 16, 16) == 200
+    d = orc.express_descriptor(im, 8, 8, 16, 16, 25)
+    assert [int(v) for v in d] == [0x00070007] * 8 and sum(bin(int(v)).count("1") for v in d) == 48
+    assert orc.express_test(im, 8, 8, 16, 16, 25)
+
+
+def test_kat12_express_horizontal_edge(orc):
+    im = _img(lambda x, y: np.where(y < 12, 0, 200))
+    d = orc.express_descriptor(im, 8, 8, 16, 16, 25)
+    assert [int(v) for v in d] == [0xFFFFFFFF, 0xFFFFFFFF, 0, 0, 0, 0, 0, 0]
+    assert orc.express_test(im, 8, 8, 16, 16, 25)
+
+
+def test_kat13_express_diagonal_and_corner(orc):
+    im = _img(lambda x, y: np.where(x + y < 26, 0, 200))
+    d = orc.express_descriptor(im, 8, 8, 16, 16, 25)
+    assert [int(v) for v in d] == [0x00FF01FF, 0x003F007F, 0x000F001F, 0x00030007, 0x1, 0, 0, 0]
+    assert orc.express_test(im, 8, 8, 16, 16, 25)
+    im = _img(lambda x, y: np.where((x < 13) & (y < 13), 0, 200))
+    d = orc.express_descriptor(im, 8, 8, 16, 16, 25)
+    assert [int(v) for v in d] == [0x000F000F, 0x000F000F, 0xF, 0, 0, 0, 0, 0]
+    assert not orc.express_test(im, 8, 8, 16, 16, 25)
+
+
+def test_kat14_express_uint8_wrap(orc):
+    im = _img(lambda x, y: np.where((x + y) % 7 == 0, 60, 10))
+    assert orc.express_center(im, 8, 8, 16, 16) == 10
+    d = orc.express_descriptor(im, 8, 8, 16, 16, 25)
+    assert sum(bin(int(v)).count("1") for v in d) == 256
+    assert not orc.express_test(im, 8, 8, 16, 16, 25)
+    flat = np.full((32, 32), 128, np.uint8)
+    assert sum(int(v) for v in orc.express_descriptor(flat, 8, 8, 16, 16, 25)) == 0
+    assert not orc.express_test(flat, 8, 8, 16, 16, 25)
+    assert orc.express_distance(d, np.zeros(8, np.uint32)) == 256
+
+
+def test_express_diagonal_closed_form_matches_reference_tables():
+    """oracle/express.cc uses a closed form for EXPRESS.h:20-38; compare with the header when it is present."""
+    path = "/root/reference/include/EXPRESS.h"
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present (GPU box)")
+    src = open(path).read()
+
+    def table(name):
+        m = re.search(r"%s\[[^=]*=\s*\{(.*?)\};" % re.escape(name), src, re.S)
+        body = m.group(1)
+        rows = re.findall(r"\{([^{}]*)\}", body)
+        if rows:
+            return [[int(v) for v in r.split(",")] for r in rows]
+        return [int(v) for v in body.split(",")]
+
+    for name, rows, cols in (("_8X8", 8, 8), ("_16X8", 16, 8), ("_8X16", 8, 16), ("_16X16", 16, 16)):
+        L, S, R = table(name + "_L"), table(name + "_S"), table(name + "_R")
+        n = rows + cols - 1
+        assert len(L) == n
+        for d in range(n):
+            assert L[d] == min(d + 1, rows, cols, n - d)
+            assert S[d] == max(rows - 1 - d, 0)
+            r1 = max(0, d - (rows - 1))
+            assert R[1][d] == r1 and R[0][d] == cols - 1 - r1
+
+
+def test_kat4_propagation_flat(orc):
+    c = clip_of(orc, 64, 48, [[], [rec((24, 24), (20, 22))]])
+    prev = np.zeros(1, T.TRACK)
+    prev[0]["pt_x"], prev[0]["pt_y"] = 20, 22
+    prev[0]["mb"] = (12, 14, 16, 16)
+    prev[0]["age"], prev[0]["track_id"] = 5, 77
+    flat = np.full((48, 64), 128, np.uint8)
+    out, _, cid, nb = orc.extract_frame(64, 48, T.FRAME_P | T.FRAME_MV, flat, c.grid(1), c.hops(1), c.kps(1),
+                                        c.coverage(1), prev, 77)
+    assert len(out) == 1 and nb == 0 and cid == 77
+    t = out[0]
+    assert (t["pt_x"], t["pt_y"]) == (24, 24) and tuple(t["mb"]) == (16, 16, 16, 16)
+    assert t["age"] == 6 and t["track_id"] == 77 and t["q_indx"] == 0 and t["flags"] == 0
+
+
+def test_kat6_pinhole_and_jacobian(orc):
+    cam = T.camera(320, 320, 320, 240)
+    Xc = np.array([0.5, -0.25, 2.0])
+    assert np.allclose(orc.project(cam, Xc), [400, 200], atol=0, rtol=0)
+    assert np.array_equal(orc.project_jac(cam, Xc), [[160, 0, -40], [0, 160, 20]])
+    assert np.array_equal(orc.pose_jacobian(cam, Xc), [[-10, -340, -40, -160, 0, 40], [325, 10, -80, 0, -160, -20]])
+
+
+def test_kat7_huber(orc):
+    delta = np.sqrt(5.991)
+    w = orc.huber_weight(25.0, delta)
+    assert abs(w - 0.489530) < 1e-6 and orc.huber_weight(5.0, delta) == 1.0
+    rho = 2 * 5 * delta - delta * delta
+    assert abs(rho - 18.4855) < 1e-4
+
+
+def test_kat8_joins(orc):
+    tr = np.zeros(4, T.TRACK)
+    tr["track_id"] = [7, 3, 7, 9]
+    mp = np.zeros(3, T.MAP_POINT)
+    mp["track_id"] = [9, 7, 7]
+    proj = np.zeros(3, T.PROJECTION)
+    proj["in_view"] = 1
+    n, m = orc.search_by_video_feature(tr, mp, proj, np.full(4, -1, np.int32))
+    assert n == 3 and list(m) == [2, -1, -1, 0]
+    n, m = orc.search_by_keyframe(tr, mp)
+    assert n == 3 and list(m) == [2, -1, -1, 0]
+    mp["flags"][2] = T.MP_BAD
+    n, m = orc.search_by_keyframe(tr, mp)
+    assert n == 2 and list(m) == [1, -1, -1, 0]
+    f2 = np.zeros(3, T.TRACK)
+    f2["track_id"] = [9, 5, 7]
+    f2["pt_x"], f2["pt_y"] = [1, 2, 3], [4, 5, 6]
+    n, m12, pm = orc.search_for_initialization(tr, f2, np.full((4, 2), -9, np.float32))
+    assert n == 2 and list(m12) == [2, -1, -1, 0]
+    assert pm.tolist() == [[3, 6], [-9, -9], [-9, -9], [1, 4]]
+
+
+def test_se3_exp_small_and_large(orc):
+    R, t = orc.se3_exp(np.zeros(6))
+    assert np.array_equal(R, np.eye(3)) and np.array_equal(t, np.zeros(3))
+    R, t = orc.se3_exp([0, 0, np.pi / 2, 1, 0, 0])
+    assert np.allclose(R, [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-15)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-15)
+    assert np.allclose(t, [2 / np.pi, 2 / np.pi, 0], atol=1e-15)
