@@ -1,0 +1,139 @@
+/*
+ * movfe.h — C-ABI of the B200 tracking front-end (libmovfe.so).
+ *
+ * The reference (MoV-SLAM) has no plugin/FFI layer: its boundary is the C++ signatures of VideoDecoder,
+ * MOVExtractor, MOVMatcher and Optimizer::PoseOptimization. This header is what those classes
+ * bind to in the drop-in shims under mov-slam_b200/shim/ (see INTEGRATION.md). Each entry point cites the
+ * reference interface it replaces. Plain pointers and sizes only; no CUDA, torch or C++ types.
+ *
+ * Conventions
+ *  - Every call returns MOVFE_OK (0) or a negative MOVFE_E_* code; movfe_last_error() gives the text.
+ *  - A context owns one GPU, one CUDA stream and all device buffers. It is not thread-safe; use one context
+ *    per host thread / GPU (streams shard across GPUs with no collective).
+ *  - Work is batched over the context's n_streams independent video streams. All batched arrays are
+ *    stream-major: element (stream s, frame f) of a call with n frames lives at index s*n + f.
+ *  - Calls enqueue work on the context's stream and return; movfe_synchronize() or any download waits.
+ *  - There is no CPU fallback: without a CUDA device movfe_create fails with MOVFE_E_CUDA.
+ */
+#ifndef MOVFE_H
+#define MOVFE_H
+
+#include "movfe_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOVFE_OK            0
+#define MOVFE_E_INVALID    -1   /* bad argument */
+#define MOVFE_E_CUDA       -2   /* CUDA runtime error (no device, launch failure, out of memory) */
+#define MOVFE_E_CAPACITY   -3   /* input exceeds a capacity fixed at movfe_create */
+#define MOVFE_E_STATE      -4   /* call order violated (e.g. raster of frames that were never pushed) */
+
+typedef struct movfe_ctx movfe_ctx;
+
+typedef struct movfe_config {
+    int32_t device;                 /* CUDA device ordinal */
+    int32_t n_streams;              /* independent video streams batched on this GPU */
+    int32_t width, height;          /* frame size, identical for all streams of a context */
+    int32_t max_records_per_frame;  /* capacity of one frame's side data (4 per macroblock for H.264) */
+    int32_t max_ref;                /* largest accepted reference index K; look-ahead is K+1 frames.
+                                       The reference's 12-deep decoder queue bounds K at 10 (VideoDecoder.cc:163) */
+    int32_t window_frames;          /* F: frames per stream rasterised / tracked per call */
+    int32_t max_tracks;             /* capacity of a frame's track table (VideoFeature list) */
+    int32_t max_map_points;         /* capacity of a stream's local map-point table */
+    int32_t express_threshold;      /* MOVExtractor::mThreshold (Settings.cc:376-382) */
+    double  coverage_threshold;     /* MOVExtractor::mCoverageThreshold */
+    int32_t has_grey;               /* 1: grey planes are pushed (descriptor gating on); 0: MV-only mode ==
+                                       the reference's behaviour on a flat image */
+    int32_t reserved;
+} movfe_config;
+
+/* -- lifetime -------------------------------------------------------------------------------------------- */
+int         movfe_create(const movfe_config *cfg, movfe_ctx **out);
+void        movfe_destroy(movfe_ctx *ctx);
+const char *movfe_last_error(const movfe_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
+int         movfe_synchronize(movfe_ctx *ctx);
+void       *movfe_cuda_stream(movfe_ctx *ctx);        /* the cudaStream_t work is enqueued on */
+const char *movfe_version(void);
+
+/* -- ingest: replaces av_frame_get_side_data -> the loop head of VideoDecoder::NextImage
+ *    (src/VideoDecoder.cc:198-211). Appends n_frames frames to every stream; frames get consecutive absolute
+ *    indices starting at movfe_frames_pushed(). recs: all records, packed, stream-major then frame order;
+ *    rec_off: n_streams*n_frames+1 offsets into recs; frame_flags: MOVFE_FRAME_*; grey: n_streams*n_frames
+ *    planes of width*height bytes or NULL. The *_device variant takes device pointers (inputs already in HBM). */
+int     movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_record *recs, const int64_t *rec_off,
+                          const uint8_t *frame_flags, const uint8_t *grey);
+int     movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs,
+                                 const int64_t *d_rec_off, int64_t n_records, const uint8_t *d_frame_flags,
+                                 const uint8_t *d_grey);
+int64_t movfe_frames_pushed(const movfe_ctx *ctx);
+
+/* -- raster: replaces the MV loop of VideoDecoder::NextImage (src/VideoDecoder.cc:211-350).
+ *    Produces, for frames [first_frame, first_frame+n_out) of every stream, the hop list (VideoImage::mvs),
+ *    the candidate-keypoint list (kps), the per-pixel slot grid (mvi) and coverageArea, bit-identical to the
+ *    reference given the same records. Records of up to max_ref+1 later frames that were already pushed are
+ *    used as look-ahead (they back-fill hops/kps into earlier frames, VideoDecoder.cc:245-248,315-323);
+ *    hops aimed at frames before first_frame are not re-emitted (they belong to the previous window). */
+int movfe_raster(movfe_ctx *ctx, int64_t first_frame, int n_out);
+
+/* Results of the last movfe_raster call (download = device->host copy + synchronise). */
+int movfe_raster_counts(movfe_ctx *ctx, int stream, int64_t frame, int32_t *n_hops, int32_t *n_kps,
+                        double *coverage_area);
+int movfe_download_grid(movfe_ctx *ctx, int stream, int64_t frame, int32_t *out /* height*width*4 */);
+int movfe_download_hops(movfe_ctx *ctx, int stream, int64_t frame, movfe_hop *out, int capacity);
+int movfe_download_kps(movfe_ctx *ctx, int stream, int64_t frame, movfe_rect *out, int capacity);
+int64_t movfe_rejected_records(movfe_ctx *ctx);   /* records dropped for ref > max_ref or capacity, since create */
+
+/* -- propagation: replaces MOVExtractor::operator() (include/MOVExtractor.h:36-37, src/MOVExtractor.cc:63-455)
+ *    for frames [first_frame, first_frame+n_frames) of every stream, in frame order, on the raster results of
+ *    the last movfe_raster call. Track tables persist per stream across calls (prev frame = Frame::mpPrevFrame).
+ *    LK-carried features (cv::calcOpticalFlowPyrLK, :91,:196,:347) are host work and are dropped here. */
+int movfe_set_tracks(movfe_ctx *ctx, int stream, const movfe_track *tracks, int n, int32_t current_id);
+int movfe_extract(movfe_ctx *ctx, int64_t first_frame, int n_frames);
+int movfe_track_count(movfe_ctx *ctx, int stream, int64_t frame, int32_t *n_tracks, int32_t *current_id);
+int movfe_download_tracks(movfe_ctx *ctx, int stream, int64_t frame, movfe_track *out, int capacity);
+
+/* -- matching: replaces Frame::isInFrustum (src/Frame.cc:456-519) + MOVMatcher::SearchByVideoFeature
+ *    (include/MOVMatcher.h:35-68, 70-103) and -- pose: replaces Optimizer::PoseOptimization
+ *    (include/Optimizer.h:55, src/Optimizer.cc:397-459), batched over streams and run per frame in the order
+ *    Tracking.cc drives them (TrackReferenceKeyFrame :796-811, TrackLocalMap :890-905). */
+int movfe_set_camera(movfe_ctx *ctx, const movfe_camera *cam, const movfe_pose_params *pp, float viewing_cos_limit);
+int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_point *pts, int n, int n_keyframe_points);
+int movfe_set_pose(movfe_ctx *ctx, int stream, const movfe_pose *pose);
+int movfe_track_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames);
+int movfe_download_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames, movfe_pose *poses /* S*n */,
+                         int32_t *n_inliers /* S*n, may be NULL */);
+int movfe_download_matches(movfe_ctx *ctx, int stream, int64_t frame, int32_t *match, uint8_t *outlier, int capacity);
+
+/* -- instrumentation (bench.py): CUDA events around every stage on the context's stream, kernel-launch counts --- */
+#define MOVFE_STAGE_INGEST   0   /* ingest_kernel (+ meta, grey copies) */
+#define MOVFE_STAGE_HOPS     1   /* count / bases / emit / bbox */
+#define MOVFE_STAGE_GRID     2   /* grid_kernel: the per-pixel slot grid (dominant HBM writer) */
+#define MOVFE_STAGE_EXTRACT  3   /* propagation kernels */
+#define MOVFE_STAGE_POSE     4   /* join / frustum / pose kernels */
+#define MOVFE_N_STAGES       5
+int movfe_profile_enable(movfe_ctx *ctx, int on);
+/* Waits for the stream, then adds up the event-timed milliseconds and kernel launches per stage since the last
+ * reset. ms / launches have MOVFE_N_STAGES entries (either may be NULL). */
+int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset);
+
+/* -- single-shot operators (batch of independent problems; used by the drop-in shims and the parity tests) --- */
+/* Frame::isInFrustum for n_problems point sets. pts/out are packed; off has n_problems+1 entries. */
+int movfe_frustum(movfe_ctx *ctx, int n_problems, const movfe_pose *poses, const movfe_map_point *pts,
+                  const int32_t *off, movfe_projection *out);
+/* Track-id join (MOVMatcher.h:35-137): for problem p, match[t] = index of the LAST probe (in order) whose key
+ * equals track t's id through the first-wins id->index map; probes with valid[i]==0 are skipped.
+ * match entries not hit keep their input value. n_matches[p] counts hits. */
+int movfe_join(movfe_ctx *ctx, int n_problems, const int32_t *track_ids, const int32_t *track_off,
+               const int32_t *probe_ids, const uint8_t *probe_valid, const int32_t *probe_off, int32_t *match,
+               int32_t *n_matches);
+/* Optimizer::PoseOptimization for n_problems correspondence sets (pts xyz float, obs uv float, packed). */
+int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_camera *cam, const movfe_pose_params *pp,
+                        const float *pts, const float *obs, const int32_t *off, movfe_pose *poses /* in/out */,
+                        uint8_t *outlier, int32_t *n_inliers, int32_t *stats /* 4 per problem, may be NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVFE_H */

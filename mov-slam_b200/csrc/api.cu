@@ -1,0 +1,358 @@
+// api.cu — the C-ABI of include/movfe.h: context lifetime, ingest, raster and downloads.
+// There is no CPU fallback anywhere in this library: without a CUDA device movfe_create fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+static std::string g_create_error;
+
+extern "C" const char *movfe_version(void) { return "movfe 0.1 (sm_100a)"; }
+
+extern "C" const char *movfe_last_error(const movfe_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+template <typename T>
+static cudaError_t dalloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    return cudaMalloc((void **)p, n * sizeof(T));
+}
+
+extern "C" void movfe_destroy(movfe_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    void *bufs[] = {ctx->d_stage, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected, ctx->d_cls_cnt,
+                    ctx->d_area, ctx->d_hop_base, ctx->d_kps_base, ctx->d_nhops, ctx->d_nkps, ctx->d_cov, ctx->d_hops,
+                    ctx->d_hop_rect, ctx->d_kps, ctx->d_chunk_bbox, ctx->d_grid, ctx->d_tracks, ctx->d_ntracks,
+                    ctx->d_cur_id, ctx->d_ext_scratch, ctx->d_map, ctx->d_nmap, ctx->d_nkf, ctx->d_pose_cur,
+                    ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier, ctx->d_pose_scratch, ctx->d_op};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto e : ctx->prof_free) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
+    if (!cfg || !out) {
+        g_create_error = "movfe_create: null argument";
+        return MOVFE_E_INVALID;
+    }
+    *out = nullptr;
+    movfe_ctx *ctx = new (std::nothrow) movfe_ctx;
+    if (!ctx) {
+        g_create_error = "movfe_create: out of host memory";
+        return MOVFE_E_INVALID;
+    }
+    ctx->cfg = *cfg;
+    auto fail = [&](int code) {
+        g_create_error = ctx->err;
+        movfe_destroy(ctx);
+        return code;
+    };
+    const movfe_config &c = ctx->cfg;
+    if (c.n_streams < 1 || c.width < 16 || c.height < 16 || c.width > 16384 || c.height > 16384 ||
+        c.max_records_per_frame < 1 || c.max_ref < 0 || c.max_ref > MOVFE_MAX_K || c.window_frames < 1 ||
+        c.max_tracks < 1 || c.max_tracks > 65536 || c.max_map_points < 0) {
+        ctx->err = "movfe_create: configuration out of range";
+        return fail(MOVFE_E_INVALID);
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        ctx->err = std::string("movfe_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path";
+        return fail(MOVFE_E_CUDA);
+    }
+#define CK(x)                                                                     \
+    do {                                                                          \
+        cudaError_t _e = (x);                                                     \
+        if (_e != cudaSuccess) {                                                  \
+            ctx->err = std::string(#x) + ": " + cudaGetErrorString(_e);           \
+            return fail(MOVFE_E_CUDA);                                            \
+        }                                                                         \
+    } while (0)
+    CK(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c.device));
+    ctx->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
+    ctx->K = c.max_ref;
+    ctx->LA = ctx->K + 1;
+    ctx->NIN = c.window_frames + ctx->LA;
+    ctx->RING = ctx->NIN;
+    ctx->NB = (c.height + 7) / 8;
+    ctx->NT = (c.width + 31) / 32;
+    ctx->max_hops = c.max_records_per_frame * (ctx->K + 1);
+    ctx->max_kps = c.max_records_per_frame * (ctx->K + 1);
+    ctx->max_chunks = (ctx->max_hops + 31) / 32;
+    if (ctx->max_hops >= (1 << 24)) {
+        ctx->err = "movfe_create: max_records_per_frame*(max_ref+1) must stay below 2^24";
+        return fail(MOVFE_E_INVALID);
+    }
+    const size_t S = c.n_streams, F = c.window_frames, NIN = ctx->NIN, RING = ctx->RING;
+    const size_t plane = (size_t)c.width * c.height;
+    CK(dalloc(&ctx->d_rec, S * RING * c.max_records_per_frame));
+    CK(dalloc(&ctx->d_rec_cnt, S * RING));
+    CK(dalloc(&ctx->d_fflags, S * RING));
+    if (c.has_grey) CK(dalloc(&ctx->d_grey, S * RING * plane));
+    CK(dalloc(&ctx->d_rejected, 1));
+    CK(cudaMemset(ctx->d_rejected, 0, sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->d_rec_cnt, 0, S * RING * sizeof(int32_t)));
+    CK(cudaMemset(ctx->d_fflags, 0, S * RING));
+    CK(dalloc(&ctx->d_cls_cnt, S * NIN * MOVFE_NCLS(MOVFE_MAX_K)));
+    CK(dalloc(&ctx->d_area, S * NIN));
+    CK(dalloc(&ctx->d_hop_base, S * NIN * (ctx->K + 2)));
+    CK(dalloc(&ctx->d_kps_base, S * NIN * (ctx->K + 2)));
+    CK(dalloc(&ctx->d_nhops, S * NIN));
+    CK(dalloc(&ctx->d_nkps, S * NIN));
+    CK(dalloc(&ctx->d_cov, S * NIN));
+    CK(dalloc(&ctx->d_hops, S * F * ctx->max_hops));
+    CK(dalloc(&ctx->d_hop_rect, S * F * ctx->max_hops));
+    CK(dalloc(&ctx->d_kps, S * F * ctx->max_kps));
+    CK(dalloc(&ctx->d_chunk_bbox, S * F * ctx->max_chunks));
+    CK(dalloc(&ctx->d_grid, S * F * plane));
+    // track tables
+    CK(dalloc(&ctx->d_tracks, S * (F + 1) * c.max_tracks));
+    CK(dalloc(&ctx->d_ntracks, S * (F + 1)));
+    CK(dalloc(&ctx->d_cur_id, S * (F + 1)));
+    CK(cudaMemset(ctx->d_ntracks, 0, S * (F + 1) * sizeof(int32_t)));
+    CK(cudaMemset(ctx->d_cur_id, 0, S * (F + 1) * sizeof(int32_t)));
+    ctx->ext_scratch_bytes = movfe_extract_scratch_bytes(ctx);
+    CK(cudaMalloc(&ctx->d_ext_scratch, std::max<size_t>(ctx->ext_scratch_bytes, 16)));
+    // map / pose
+    CK(dalloc(&ctx->d_map, S * (size_t)std::max(c.max_map_points, 1)));
+    CK(dalloc(&ctx->d_nmap, S));
+    CK(dalloc(&ctx->d_nkf, S));
+    CK(cudaMemset(ctx->d_nmap, 0, S * sizeof(int32_t)));
+    CK(cudaMemset(ctx->d_nkf, 0, S * sizeof(int32_t)));
+    CK(dalloc(&ctx->d_pose_cur, S));
+    CK(dalloc(&ctx->d_poses, S * F));
+    CK(dalloc(&ctx->d_ninl, S * F));
+    CK(dalloc(&ctx->d_match, S * F * c.max_tracks));
+    CK(dalloc(&ctx->d_outlier, S * F * c.max_tracks));
+    {
+        std::vector<movfe_pose> id(S);
+        for (auto &p : id) {
+            memset(&p, 0, sizeof p);
+            p.R[0] = p.R[4] = p.R[8] = 1.0;
+        }
+        CK(cudaMemcpy(ctx->d_pose_cur, id.data(), S * sizeof(movfe_pose), cudaMemcpyHostToDevice));
+    }
+    ctx->pose_scratch_bytes = movfe_pose_scratch_bytes(ctx);
+    CK(cudaMalloc(&ctx->d_pose_scratch, std::max<size_t>(ctx->pose_scratch_bytes, 16)));
+    memset(&ctx->cam, 0, sizeof ctx->cam);
+    ctx->cam.fx = ctx->cam.fy = 1.f;
+    memset(&ctx->pp, 0, sizeof ctx->pp);
+    ctx->pp.iteration_count = 50;
+    ctx->pp.reprojection_error = 5.0;
+    ctx->pp.reprojection_error_lost = 8.0;
+    ctx->pp.confidence = 0.95;
+    ctx->pp.algorithm = 38;
+    CK(cudaStreamSynchronize(ctx->stream));
+#undef CK
+    *out = ctx;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_synchronize(movfe_ctx *ctx) {
+    if (!ctx) return MOVFE_E_INVALID;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" void *movfe_cuda_stream(movfe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+extern "C" int64_t movfe_frames_pushed(const movfe_ctx *ctx) { return ctx ? ctx->pushed : -1; }
+
+static int ensure_stage(movfe_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->stage_bytes) return MOVFE_OK;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    ctx->d_stage = nullptr;
+    ctx->stage_bytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_stage, want));
+    ctx->stage_bytes = want;
+    return MOVFE_OK;
+}
+
+static int ensure_op(movfe_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->op_bytes) return MOVFE_OK;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_op) cudaFree(ctx->d_op);
+    ctx->d_op = nullptr;
+    ctx->op_bytes = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_op, want));
+    ctx->op_bytes = want;
+    return MOVFE_OK;
+}
+int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes) { return ensure_op(ctx, bytes); }
+
+static int check_push(movfe_ctx *ctx, int n_frames) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (n_frames < 1 || n_frames > ctx->RING)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "push of %d frames exceeds the ring depth %d (window_frames + max_ref + 1)", n_frames, ctx->RING);
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs,
+                                        const int64_t *d_rec_off, int64_t n_records, const uint8_t *d_frame_flags,
+                                        const uint8_t *d_grey) {
+    int rc = check_push(ctx, n_frames);
+    if (rc) return rc;
+    if (!d_rec_off || !d_frame_flags || (n_records > 0 && !d_recs)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: null pointer");
+    if (((uintptr_t)d_recs & 15) != 0) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: device record array must be 16-byte aligned");
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    rc = movfe_ingest_launch(ctx, n_frames, d_recs, d_rec_off, n_records, d_frame_flags, d_grey);
+    if (rc) return rc;
+    ctx->pushed += n_frames;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_record *recs, const int64_t *rec_off,
+                                 const uint8_t *frame_flags, const uint8_t *grey) {
+    int rc = check_push(ctx, n_frames);
+    if (rc) return rc;
+    if (!rec_off || !frame_flags) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: null pointer");
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t n_seg = (size_t)ctx->cfg.n_streams * n_frames;
+    const int64_t n_records = rec_off[n_seg];
+    if (n_records < 0 || (n_records > 0 && !recs)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: bad record offsets");
+    // staging layout: [records, padded to 16 B][offsets][flags]
+    const size_t rec_bytes = ((size_t)n_records * sizeof(movfe_mv_record) + 15) & ~(size_t)15;
+    const size_t off_bytes = ((n_seg + 1) * sizeof(int64_t) + 15) & ~(size_t)15;
+    const size_t total = rec_bytes + off_bytes + n_seg + 16;
+    rc = ensure_stage(ctx, total);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_stage;
+    if (n_records > 0)
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(base, recs, (size_t)n_records * sizeof(movfe_mv_record), cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes, rec_off, (n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes + off_bytes, frame_flags, n_seg, cudaMemcpyHostToDevice, ctx->stream));
+    rc = movfe_ingest_launch(ctx, n_frames, (const movfe_mv_record *)base, (const int64_t *)(base + rec_bytes), n_records,
+                             base + rec_bytes + off_bytes, grey);
+    if (rc) return rc;
+    ctx->pushed += n_frames;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_raster(movfe_ctx *ctx, int64_t first_frame, int n_out) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (n_out < 1 || n_out > ctx->cfg.window_frames)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "raster: n_out=%d outside [1, window_frames=%d]", n_out, ctx->cfg.window_frames);
+    if (first_frame < 0 || first_frame + n_out > ctx->pushed)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "raster: frames [%lld,%lld) were not pushed (pushed=%lld)", (long long)first_frame,
+                   (long long)(first_frame + n_out), (long long)ctx->pushed);
+    if (ctx->pushed - first_frame > ctx->RING)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "raster: frame %lld has left the ring (pushed=%lld, ring=%d)", (long long)first_frame,
+                   (long long)ctx->pushed, ctx->RING);
+    const int n_in = (int)std::min<int64_t>(ctx->pushed - first_frame, (int64_t)n_out + ctx->LA);
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int rc = movfe_raster_launch(ctx, first_frame, n_out, n_in);
+    if (rc) return rc;
+    ctx->win_first = first_frame;
+    ctx->win_nout = n_out;
+    ctx->win_nin = n_in;
+    return MOVFE_OK;
+}
+
+static int win_index(movfe_ctx *ctx, int stream, int64_t frame, int *fi) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (stream < 0 || stream >= ctx->cfg.n_streams) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "stream %d out of range", stream);
+    if (ctx->win_first < 0 || frame < ctx->win_first || frame >= ctx->win_first + ctx->win_nout)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "frame %lld is not in the last raster window", (long long)frame);
+    *fi = (int)(frame - ctx->win_first);
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_raster_counts(movfe_ctx *ctx, int stream, int64_t frame, int32_t *n_hops, int32_t *n_kps,
+                                   double *coverage_area) {
+    int fi;
+    int rc = win_index(ctx, stream, frame, &fi);
+    if (rc) return rc;
+    const size_t sg = (size_t)stream * ctx->win_nin + fi;
+    if (n_hops) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_hops, ctx->d_nhops + sg, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_kps) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_kps, ctx->d_nkps + sg, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (coverage_area) MOVFE_CUDA(ctx, cudaMemcpyAsync(coverage_area, ctx->d_cov + sg, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_download_grid(movfe_ctx *ctx, int stream, int64_t frame, int32_t *out) {
+    int fi;
+    int rc = win_index(ctx, stream, frame, &fi);
+    if (rc) return rc;
+    const size_t plane = (size_t)ctx->cfg.width * ctx->cfg.height;
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_grid + ((size_t)stream * ctx->win_nout + fi) * plane, plane * sizeof(int4),
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_download_hops(movfe_ctx *ctx, int stream, int64_t frame, movfe_hop *out, int capacity) {
+    int fi, n = 0;
+    int rc = win_index(ctx, stream, frame, &fi);
+    if (rc) return rc;
+    rc = movfe_raster_counts(ctx, stream, frame, &n, nullptr, nullptr);
+    if (rc) return rc;
+    if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_hops: %d hops, capacity %d", n, capacity);
+    if (n > 0) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_hops + ((size_t)stream * ctx->win_nout + fi) * ctx->max_hops,
+                                        (size_t)n * sizeof(movfe_hop), cudaMemcpyDeviceToHost, ctx->stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return n;
+}
+
+extern "C" int movfe_download_kps(movfe_ctx *ctx, int stream, int64_t frame, movfe_rect *out, int capacity) {
+    int fi, n = 0;
+    int rc = win_index(ctx, stream, frame, &fi);
+    if (rc) return rc;
+    rc = movfe_raster_counts(ctx, stream, frame, nullptr, &n, nullptr);
+    if (rc) return rc;
+    if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_kps: %d kps, capacity %d", n, capacity);
+    if (n > 0) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_kps + ((size_t)stream * ctx->win_nout + fi) * ctx->max_kps,
+                                        (size_t)n * sizeof(movfe_rect), cudaMemcpyDeviceToHost, ctx->stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return n;
+}
+
+extern "C" int64_t movfe_rejected_records(movfe_ctx *ctx) {
+    if (!ctx) return -1;
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, ctx->d_rejected, sizeof v, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+
+extern "C" int movfe_profile_enable(movfe_ctx *ctx, int on) {
+    if (!ctx) return MOVFE_E_INVALID;
+    ctx->prof_on = on != 0;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset) {
+    if (!ctx) return MOVFE_E_INVALID;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto &sp : ctx->prof_spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ctx->prof_ms[sp.stage] += t;
+        ctx->prof_free.push_back(sp.a);
+        ctx->prof_free.push_back(sp.b);
+    }
+    ctx->prof_spans.clear();
+    for (int i = 0; i < MOVFE_N_STAGES; i++) {
+        if (ms) ms[i] = ctx->prof_ms[i];
+        if (launches) launches[i] = ctx->prof_launches[i];
+        if (reset) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
+    }
+    return MOVFE_OK;
+}

@@ -1,0 +1,170 @@
+// common.cuh — context layout and helpers shared by the front-end's translation units.
+// Device code targets sm_100a only (B200): 148 SMs, 126 MB L2, HBM3e. Nothing here is a dense contraction, so
+// there is no tensor-core path; the kernels are HBM / LSU / integer-ALU work.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/movfe.h"
+
+#define MOVFE_WARP 32
+
+// Compact device-side record: the 7 fields of the 40-byte AVMotionVector that the hot path reads
+// (VideoDecoder.cc:211-228), repacked to one aligned 128-bit word by the ingest kernel.
+struct __align__(16) Rec16 {
+    int16_t sx, sy, dx, dy;
+    uint8_t w, h;
+    int8_t  src_sign;  // sign of AVMotionVector::source (-1, 0, +1)
+    uint8_t pad;
+    int32_t ref;
+};
+static_assert(sizeof(Rec16) == 16, "Rec16 must be one 128-bit word");
+
+// Inclusive pixel rectangle a hop covers in its target frame's slot grid (VideoDecoder.cc:295-306,330-333).
+// Empty rectangles are {0, 32767, -1, -32768} so that no overlap test ever accepts them.
+struct __align__(8) HopRect {
+    int16_t x0, y0, x1, y1;
+};
+
+// Per-frame class counts produced by the count pass (index into cls_cnt[frame][...]):
+//   [0..K]        valid P-branch records with ref >= k          -> hop segment k of frame (f-k)
+//   [K+1]         valid records that push their block into this frame's kps (not "chained")
+//   [K+2..2K+1]   valid chained records with ref == r (r=1..K)  -> kps segment r of frame (f-1-r)
+#define MOVFE_MAX_K 10
+#define MOVFE_NCLS(K) (2 * (K) + 2)
+
+struct movfe_ctx {
+    movfe_config cfg;
+    int K = 0, LA = 0, RING = 0, NIN = 0;  // max_ref, look-ahead frames, ring depth, max input frames per window
+    int NB = 0, NT = 0;                    // 8-row bands per frame, 32-px tiles per band
+    int max_hops = 0, max_kps = 0, max_chunks = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    int64_t pushed = 0;            // frames pushed per stream so far
+    int64_t win_first = -1;        // last raster window
+    int     win_nout = 0, win_nin = 0;
+    int64_t ext_first = -1;        // last extract window
+    int     ext_n = 0;
+    int64_t pose_first = -1;
+    int     pose_n = 0;
+
+    // staging for host pushes (grown on demand)
+    void   *d_stage = nullptr;
+    size_t  stage_bytes = 0;
+
+    // record / image ring, slot = absolute frame % RING
+    Rec16   *d_rec = nullptr;      // [S][RING][max_records]
+    int32_t *d_rec_cnt = nullptr;  // [S][RING]
+    uint8_t *d_fflags = nullptr;   // [S][RING]
+    uint8_t *d_grey = nullptr;     // [S][RING][H*W]   (has_grey)
+    unsigned long long *d_rejected = nullptr;
+
+    // raster window (window-local frame index fi = frame - win_first)
+    int32_t *d_cls_cnt = nullptr;   // [S][NIN][NCLS]
+    int64_t *d_area = nullptr;      // [S][NIN]
+    int32_t *d_hop_base = nullptr;  // [S][NIN][K+2]
+    int32_t *d_kps_base = nullptr;  // [S][NIN][K+2]
+    int32_t *d_nhops = nullptr;     // [S][NIN]
+    int32_t *d_nkps = nullptr;      // [S][NIN]
+    double  *d_cov = nullptr;       // [S][NIN]
+    movfe_hop  *d_hops = nullptr;   // [S][F][max_hops]
+    HopRect    *d_hop_rect = nullptr;
+    movfe_rect *d_kps = nullptr;    // [S][F][max_kps]
+    int32_t *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  (ymin | ymax<<16)
+    int4    *d_grid = nullptr;      // [S][F][H*W]
+
+    // track tables: [S][F+1][max_tracks]; slot 0 of a window holds the previous window's last table
+    movfe_track *d_tracks = nullptr;
+    int32_t *d_ntracks = nullptr;   // [S][F+1]
+    int32_t *d_cur_id = nullptr;    // [S][F+1]  mCurrentId after each frame
+    void    *d_ext_scratch = nullptr;
+    size_t   ext_scratch_bytes = 0;
+
+    // map / pose
+    movfe_camera cam;
+    movfe_pose_params pp;
+    float view_cos = 0.5f;
+    movfe_map_point *d_map = nullptr;  // [S][max_map_points]
+    int32_t *d_nmap = nullptr, *d_nkf = nullptr;  // [S]
+    movfe_pose *d_pose_cur = nullptr;  // [S]
+    movfe_pose *d_poses = nullptr;     // [S][F]
+    int32_t *d_ninl = nullptr;         // [S][F]
+    int32_t *d_match = nullptr;        // [S][F][max_tracks]
+    uint8_t *d_outlier = nullptr;      // [S][F][max_tracks]
+    void    *d_pose_scratch = nullptr;
+    size_t   pose_scratch_bytes = 0;
+
+    // instrumentation
+    bool prof_on = false;
+    struct ProfSpan { int stage; cudaEvent_t a, b; };
+    std::vector<ProfSpan> prof_spans;
+    std::vector<cudaEvent_t> prof_free;
+    double  prof_ms[MOVFE_N_STAGES] = {0};
+    int64_t prof_launches[MOVFE_N_STAGES] = {0};
+
+    // scratch for the single-shot operators (grown on demand)
+    void   *d_op = nullptr;
+    size_t  op_bytes = 0;
+};
+
+#define MOVFE_FAIL(ctx, code, ...)                         \
+    do {                                                   \
+        char _b[512];                                      \
+        snprintf(_b, sizeof _b, __VA_ARGS__);              \
+        (ctx)->err = _b;                                   \
+        return (code);                                     \
+    } while (0)
+
+#define MOVFE_CUDA(ctx, expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) MOVFE_FAIL(ctx, MOVFE_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// 128-bit streaming store: the slot grid is written once and not re-read by the writer.
+__device__ __forceinline__ void st_cs_v4(int4 *p, int4 v) {
+    asm volatile("st.global.cs.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// RAII span: records an event pair around a stage when profiling is on, and always counts kernel launches.
+struct ProfScope {
+    movfe_ctx *ctx;
+    int stage;
+    cudaEvent_t a = nullptr, b = nullptr;
+    static cudaEvent_t get(movfe_ctx *c) {
+        cudaEvent_t e;
+        if (!c->prof_free.empty()) { e = c->prof_free.back(); c->prof_free.pop_back(); return e; }
+        cudaEventCreate(&e);
+        return e;
+    }
+    ProfScope(movfe_ctx *c, int st) : ctx(c), stage(st) {
+        if (ctx->prof_on) { a = get(ctx); b = get(ctx); cudaEventRecord(a, ctx->stream); }
+    }
+    void launches(int n) { ctx->prof_launches[stage] += n; }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, ctx->stream); ctx->prof_spans.push_back({stage, a, b}); }
+    }
+};
+
+// raster.cu
+int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in);
+int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs, const int64_t *d_rec_off,
+                        int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey);
+// extract.cu
+int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
+size_t movfe_extract_scratch_bytes(const movfe_ctx *ctx);
+// match.cu / pose.cu
+int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
+size_t movfe_pose_scratch_bytes(const movfe_ctx *ctx);

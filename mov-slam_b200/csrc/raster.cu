@@ -1,0 +1,696 @@
+// raster.cu — motion-vector side data -> hop lists, candidate-keypoint lists, per-pixel slot grid.
+// Replaces the MV loop of VideoDecoder::NextImage (src/VideoDecoder.cc:211-350), batched over
+// (stream x frame-window). Compiled with -fmad=false: the float expressions below must round exactly like the
+// reference's non-contracted binary32 arithmetic ("float bit-exactness").
+//
+// Kernels:
+//   ingest_kernel   40-byte AVMotionVector records -> 16-byte Rec16 in the per-stream frame ring.
+//                   Coalesced 128-bit loads of the packed records, staged through shared memory.
+//   count_kernel    per frame: how many records fall in each order class (hop segment k, own kps, chained kps r).
+//   bases_kernel    per target frame: start of every segment of its hop / kps list (exclusive sums over the
+//                   look-ahead frames) -> every output index is known without atomics.
+//   emit_kernel     per record: hop j = ref+1..1 written at its final index in frame f-(j-1)'s list, kps rectangle
+//                   written at its final index; order = the reference's push_back order (ballot ranks).
+//   bbox_kernel     y-extent of every 32-hop chunk (lets the grid kernel skip chunks without reading them).
+//   grid_kernel     one CTA owns an 8-row band of one frame's grid: ordered compaction of the hops touching
+//                   the band into shared memory, then one warp per 32x8 tile: column masks by a 32x32 bit
+//                   transpose, row masks by ballots, slots 0..2 = three lowest set bits, slot 3 = highest of the
+//                   rest. Every pixel is written exactly once with one 128-bit streaming store (no atomics,
+//                   no read-modify-write, the -1 fill is implicit).
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ ingest -----
+constexpr int INGEST_WARPS = 8;
+constexpr int INGEST_REC_PER_WARP = 64;  // 64 records = 2560 B = 160 x 16 B: five coalesced 128-bit loads per lane
+
+__global__ void __launch_bounds__(INGEST_WARPS * 32)
+ingest_kernel(const uint4 *__restrict__ recs16, int64_t n_records, const int64_t *__restrict__ rec_off, int n_seg,
+              int n_frames, int64_t first_abs, int RING, int maxM, Rec16 *__restrict__ d_rec,
+              unsigned long long *__restrict__ rejected) {
+    __shared__ uint4 stage[INGEST_WARPS][INGEST_REC_PER_WARP * 40 / 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * INGEST_WARPS + warp) * INGEST_REC_PER_WARP;  // first record of this warp
+    if (w0 >= n_records) return;
+    const int64_t total16 = (n_records * 40 + 15) / 16;  // staging buffers are padded to a 16-byte multiple
+    const int64_t base16 = w0 * 40 / 16;                 // 2560*k/16: exact
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+        const int q = i * 32 + lane;
+        if (base16 + q < total16) stage[warp][q] = __ldg(&recs16[base16 + q]);
+    }
+    __syncwarp();
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage[warp]);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int li = j * 32 + lane;
+        const int64_t i = w0 + li;
+        if (i >= n_records) continue;
+        const uint32_t *r = sw + li * 10;  // 40-byte record = 10 words (layout: include/movfe_types.h)
+        Rec16 o;
+        const int32_t source = (int32_t)r[0];
+        o.w = (uint8_t)(r[1] & 0xff);
+        o.h = (uint8_t)((r[1] >> 8) & 0xff);
+        o.sx = (int16_t)(r[1] >> 16);
+        o.sy = (int16_t)(r[2] & 0xffff);
+        o.dx = (int16_t)(r[2] >> 16);
+        o.dy = (int16_t)(r[3] & 0xffff);
+        o.src_sign = source < 0 ? -1 : (source > 0 ? 1 : 0);
+        o.pad = 0;
+        o.ref = (int32_t)r[9];
+        // segment (stream, frame) of record i: last seg with rec_off[seg] <= i
+        int lo = 0, hi = n_seg;  // invariant rec_off[lo] <= i < rec_off[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(&rec_off[mid]) <= i) lo = mid; else hi = mid;
+        }
+        const int s = lo / n_frames, f = lo - s * n_frames;
+        const int64_t pos = i - __ldg(&rec_off[lo]);
+        if (pos < maxM) {
+            const int slot = (int)((first_abs + f) % RING);
+            d_rec[((size_t)s * RING + slot) * maxM + pos] = o;
+        } else {
+            atomicAdd(rejected, 1ull);  // error counter only; never on the data path
+        }
+    }
+}
+
+__global__ void ingest_meta_kernel(const int64_t *__restrict__ rec_off, const uint8_t *__restrict__ flags, int n_seg,
+                                   int n_frames, int64_t first_abs, int RING, int maxM, int32_t *__restrict__ rec_cnt,
+                                   uint8_t *__restrict__ fflags) {
+    const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg >= n_seg) return;
+    const int s = seg / n_frames, f = seg - s * n_frames;
+    const int slot = (int)((first_abs + f) % RING);
+    const int64_t n = rec_off[seg + 1] - rec_off[seg];
+    rec_cnt[s * RING + slot] = (int32_t)(n < maxM ? n : maxM);
+    fflags[s * RING + slot] = flags[seg];
+}
+
+// ------------------------------------------------------------------------------------------ record classes ---
+struct RecInfo {
+    bool valid;    // passes the skip rule (VideoDecoder.cc:236-241) and ref <= K
+    bool pbranch;  // source <= 0: hops + coverage (VideoDecoder.cc:287)
+    bool chained;  // ref > 0 && source < 0: block goes to frame N-1-ref's kps (VideoDecoder.cc:245)
+    bool bad;      // ref > K
+    int  nh;       // number of hops = ref+1 for the P branch
+    float mv_x, mv_y, half_w, half_h;
+    int  kx, ky;   // top-left of dMB
+};
+
+__device__ __forceinline__ RecInfo classify(const Rec16 &r, int W, int H, int K) {
+    RecInfo c;
+    c.bad = r.ref > K;
+    const float mb_w = (float)r.w, mb_h = (float)r.h;          // :215-216
+    c.half_w = mb_w / 2;                                        // :217-218
+    c.half_h = mb_h / 2;
+    const float dxs = (float)((int)r.dx - (int)r.sx);           // :220-221
+    const float dys = (float)((int)r.dy - (int)r.sy);
+    const float den = (float)(r.ref + 1);
+    c.mv_x = __fdiv_rn(dxs, den);                               // :223-224
+    c.mv_y = __fdiv_rn(dys, den);
+    c.chained = r.ref > 0 && r.src_sign < 0;
+    const float dst_x = c.chained ? (float)r.sx : (float)r.dx;  // :227-228
+    const float dst_y = c.chained ? (float)r.sy : (float)r.dy;
+    float d_x_top = __fsub_rn(dst_x, c.half_w);                 // :230-235
+    if (d_x_top < 0) d_x_top = 0;
+    float d_y_top = __fsub_rn(dst_y, c.half_h);
+    if (d_y_top < 0) d_y_top = 0;
+    const float d_x_bottom = __fadd_rn(dst_x, c.half_w);        // :236-241
+    const float d_y_bottom = __fadd_rn(dst_y, c.half_h);
+    c.valid = !c.bad && !(d_x_bottom >= (float)W) && !(d_y_bottom >= (float)H);
+    c.kx = (int)d_x_top;                                        // :244 cv::Rect(float...) truncates
+    c.ky = (int)d_y_top;
+    c.pbranch = r.src_sign <= 0;
+    c.nh = c.pbranch ? (r.ref + 1 > 0 ? r.ref + 1 : 0) : 0;
+    return c;
+}
+
+// Source rectangle of hop j (VideoDecoder.cc:289-306 + loop bounds :330-333), inclusive, or the empty encoding.
+__device__ __forceinline__ HopRect hop_rect(const Rec16 &r, const RecInfo &c, int j, int W, int H) {
+    const float fj = (float)j;
+    const float src_x = __fadd_rn((float)r.dx, __fmul_rn(__fmul_rn(c.mv_x, fj), -1.0f));  // :291-292
+    const float src_y = __fadd_rn((float)r.dy, __fmul_rn(__fmul_rn(c.mv_y, fj), -1.0f));
+    float s_x_top = __fsub_rn(src_x, c.half_w);
+    if (s_x_top < 0) s_x_top = 0;
+    float s_y_top = __fsub_rn(src_y, c.half_h);
+    if (s_y_top < 0) s_y_top = 0;
+    float s_x_bottom = __fadd_rn(src_x, c.half_w);
+    if (s_x_bottom >= (float)W) s_x_bottom = (float)(W - 1);
+    float s_y_bottom = __fadd_rn(src_y, c.half_h);
+    if (s_y_bottom >= (float)H) s_y_bottom = (float)(H - 1);
+    HopRect o = {0, 32767, -1, -32768};
+    // for (int h = s_y_top; h <= s_y_bottom; h++): first value (int)s_y_top, runs while (float)h <= bound.
+    // NaN / inf displacements (ref = -1) never reach here because nh == 0.
+    if (!(s_x_top <= 40000.0f) || !(s_y_top <= 40000.0f)) return o;  // far outside: loop is empty, avoid int overflow
+    const int x0 = (int)s_x_top, y0 = (int)s_y_top;
+    if (!((float)x0 <= s_x_bottom) || !((float)y0 <= s_y_bottom)) return o;
+    o.x0 = (int16_t)x0;
+    o.y0 = (int16_t)y0;
+    o.x1 = (int16_t)(int)s_x_bottom;  // bound >= x0 >= 0: truncation == floor
+    o.y1 = (int16_t)(int)s_y_bottom;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------- count -----
+constexpr int CNT_THREADS = 512;
+constexpr int CNT_WARPS = CNT_THREADS / 32;
+constexpr int MAXCLS = MOVFE_NCLS(MOVFE_MAX_K);
+
+struct WinParams {
+    int S, n_in, n_out, K, RING, maxM, W, H;
+    int64_t first;
+    int max_hops, max_kps, max_chunks;
+};
+
+__global__ void __launch_bounds__(CNT_THREADS)
+count_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
+             const uint8_t *__restrict__ fflags, int32_t *__restrict__ cls_cnt, int64_t *__restrict__ area,
+             unsigned long long *__restrict__ rejected) {
+    __shared__ int32_t part[CNT_WARPS][MAXCLS + 2];
+    const int sf = blockIdx.x;  // s*n_in + fi
+    const int s = sf / p.n_in, fi = sf - s * p.n_in;
+    const int slot = (int)((p.first + fi) % p.RING);
+    const int ncls = MOVFE_NCLS(p.K);
+    const bool mv_on = fflags[s * p.RING + slot] & MOVFE_FRAME_MV;
+    const int M = mv_on ? rec_cnt[s * p.RING + slot] : 0;
+    const Rec16 *recs = d_rec + ((size_t)s * p.RING + slot) * p.maxM;
+
+    int cnt[MAXCLS];
+#pragma unroll
+    for (int c = 0; c < MAXCLS; c++) cnt[c] = 0;
+    int ar = 0, bad = 0;
+    for (int i = threadIdx.x; i < M; i += CNT_THREADS) {
+        const Rec16 r = recs[i];
+        const RecInfo c = classify(r, p.W, p.H, p.K);
+        bad += c.bad;
+        if (!c.valid) continue;
+#pragma unroll
+        for (int k = 0; k <= MOVFE_MAX_K; k++)
+            if (k <= p.K && c.nh > k) cnt[k]++;
+        if (!c.chained) cnt[p.K + 1]++;
+#pragma unroll
+        for (int rr = 1; rr <= MOVFE_MAX_K; rr++)
+            if (rr <= p.K && c.chained && r.ref == rr) cnt[p.K + 1 + rr]++;
+        if (c.pbranch) ar += (int)r.w * (int)r.h;  // :347 coverage += dMB.area()
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < MAXCLS; c++) {
+        int v = cnt[c];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) part[warp][c] = v;
+    }
+    for (int o = 16; o; o >>= 1) {
+        ar += __shfl_xor_sync(0xffffffffu, ar, o);
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane == 0) {
+        part[warp][MAXCLS] = ar;
+        part[warp][MAXCLS + 1] = bad;
+    }
+    __syncthreads();
+    if (threadIdx.x < MAXCLS + 2) {
+        long long v = 0;
+        for (int w = 0; w < CNT_WARPS; w++) v += part[w][threadIdx.x];
+        if (threadIdx.x < ncls) cls_cnt[(size_t)sf * MAXCLS + threadIdx.x] = (int32_t)v;
+        if (threadIdx.x == MAXCLS) area[sf] = v;
+        // a look-ahead frame is counted again when it becomes an output frame: charge rejects once
+        if (threadIdx.x == MAXCLS + 1 && v && fi < p.n_out) atomicAdd(rejected, (unsigned long long)v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- bases -----
+__global__ void bases_kernel(WinParams p, const int32_t *__restrict__ cls_cnt, const int64_t *__restrict__ area,
+                             int32_t *__restrict__ hop_base, int32_t *__restrict__ kps_base,
+                             int32_t *__restrict__ nhops, int32_t *__restrict__ nkps, double *__restrict__ cov) {
+    const int sg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sg >= p.S * p.n_in) return;
+    const int s = sg / p.n_in, g = sg - s * p.n_in;
+    const int K = p.K;
+    int hb = 0;
+    for (int k = 0; k <= K; k++) {  // hop segment k of frame g = frame g+k's records with ref >= k (j = k+1)
+        hop_base[(size_t)sg * (K + 2) + k] = hb;
+        if (g + k < p.n_in) hb += cls_cnt[((size_t)s * p.n_in + g + k) * MAXCLS + k];
+    }
+    hop_base[(size_t)sg * (K + 2) + K + 1] = hb;
+    nhops[sg] = hb < p.max_hops ? hb : p.max_hops;
+    int kb = 0;
+    kps_base[(size_t)sg * (K + 2) + 0] = 0;
+    kb = cls_cnt[(size_t)sg * MAXCLS + K + 1];  // own
+    for (int r = 1; r <= K; r++) {              // kps segment r = frame g+1+r's chained records with ref == r
+        kps_base[(size_t)sg * (K + 2) + r] = kb;
+        if (g + 1 + r < p.n_in) kb += cls_cnt[((size_t)s * p.n_in + g + 1 + r) * MAXCLS + K + 1 + r];
+    }
+    kps_base[(size_t)sg * (K + 2) + K + 1] = kb;
+    nkps[sg] = kb < p.max_kps ? kb : p.max_kps;
+    // :204,:347,:350 — float accumulation of integer areas is exact below 2^24, then / (double)(W*H)
+    cov[sg] = (double)(float)area[sg] / (double)(p.W * p.H);
+}
+
+// -------------------------------------------------------------------------------------------------- emit -----
+__global__ void __launch_bounds__(CNT_THREADS)
+emit_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
+            const uint8_t *__restrict__ fflags, const int32_t *__restrict__ hop_base,
+            const int32_t *__restrict__ kps_base, movfe_hop *__restrict__ hops, HopRect *__restrict__ hop_rects,
+            movfe_rect *__restrict__ kps) {
+    __shared__ int32_t wtot[MAXCLS][CNT_WARPS];  // per-chunk: exclusive prefix over warps (after the scan step)
+    __shared__ int32_t cbase[MAXCLS];            // records of each class seen in earlier chunks
+    const int sf = blockIdx.x;
+    const int s = sf / p.n_in, fi = sf - s * p.n_in;
+    const int slot = (int)((p.first + fi) % p.RING);
+    const int K = p.K, ncls = MOVFE_NCLS(K);
+    const bool mv_on = fflags[s * p.RING + slot] & MOVFE_FRAME_MV;
+    const int M = mv_on ? rec_cnt[s * p.RING + slot] : 0;
+    const Rec16 *recs = d_rec + ((size_t)s * p.RING + slot) * p.maxM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    if (threadIdx.x < MAXCLS) cbase[threadIdx.x] = 0;
+    __syncthreads();
+
+    for (int base = 0; base < M; base += CNT_THREADS) {
+        const int i = base + threadIdx.x;
+        Rec16 r = {};
+        RecInfo c = {};
+        if (i < M) {
+            r = recs[i];
+            c = classify(r, p.W, p.H, K);
+        }
+        int rank_hop[MOVFE_MAX_K + 1];
+#pragma unroll
+        for (int k = 0; k <= MOVFE_MAX_K; k++) {
+            rank_hop[k] = 0;
+            if (k <= K) {
+                const unsigned b = __ballot_sync(0xffffffffu, c.valid && c.nh > k);
+                rank_hop[k] = __popc(b & lt);
+                if (lane == 0) wtot[k][warp] = __popc(b);
+            }
+        }
+        int rank_kps;
+        {
+            const unsigned b = __ballot_sync(0xffffffffu, c.valid && !c.chained);
+            rank_kps = __popc(b & lt);
+            if (lane == 0) wtot[K + 1][warp] = __popc(b);
+        }
+#pragma unroll
+        for (int rr = 1; rr <= MOVFE_MAX_K; rr++) {
+            if (rr <= K) {
+                const bool mine = c.valid && c.chained && r.ref == rr;
+                const unsigned b = __ballot_sync(0xffffffffu, mine);
+                if (mine) rank_kps = __popc(b & lt);
+                if (lane == 0) wtot[K + 1 + rr][warp] = __popc(b);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < ncls) {  // exclusive scan over warps, offset by the chunks before
+            int run = cbase[threadIdx.x];
+            for (int w = 0; w < CNT_WARPS; w++) {
+                const int t = wtot[threadIdx.x][w];
+                wtot[threadIdx.x][w] = run;
+                run += t;
+            }
+            cbase[threadIdx.x] = run;
+        }
+        __syncthreads();
+        if (c.valid) {
+            // candidate-keypoint rectangle dMB (:243-253)
+            const movfe_rect dMB = {(int16_t)c.kx, (int16_t)c.ky, (int16_t)r.w, (int16_t)r.h};
+            int d_indx = -1;
+            if (!c.chained) {
+                d_indx = wtot[K + 1][warp] + rank_kps;  // == smv->kps.size()-1 after the push
+                if (fi < p.n_out && d_indx < p.max_kps)
+                    kps[((size_t)s * p.n_out + fi) * p.max_kps + d_indx] = dMB;
+            } else {
+                const int g = fi - 1 - r.ref;  // vqueue[(size-1)-ref]
+                if (g >= 0 && g < p.n_out) {
+                    const int idx = kps_base[((size_t)s * p.n_in + g) * (K + 2) + r.ref] + wtot[K + 1 + r.ref][warp] + rank_kps;
+                    if (idx < p.max_kps) kps[((size_t)s * p.n_out + g) * p.max_kps + idx] = dMB;
+                }
+            }
+            // hops j = ref+1 .. 1 (:289-346): hop j lands in frame fi-(j-1), segment k = j-1
+#pragma unroll
+            for (int k = 0; k <= MOVFE_MAX_K; k++) {
+                if (k <= K && k < c.nh) {
+                    const int g = fi - k;
+                    if (g >= 0 && g < p.n_out) {
+                        const int idx = hop_base[((size_t)s * p.n_in + g) * (K + 2) + k] + wtot[k][warp] + rank_hop[k];
+                        if (idx < p.max_hops) {
+                            const size_t o = ((size_t)s * p.n_out + g) * p.max_hops + idx;
+                            movfe_hop hv;
+                            hv.mv_x = c.mv_x;
+                            hv.mv_y = c.mv_y;
+                            hv.d_indx = d_indx;
+                            hv._pad = 0;
+                            hops[o] = hv;
+                            hop_rects[o] = hop_rect(r, c, k + 1, p.W, p.H);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------- bbox -----
+__global__ void bbox_kernel(WinParams p, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
+                            int32_t *__restrict__ chunk_bbox) {
+    const int sg = blockIdx.y;  // s*n_out + g
+    const int s = sg / p.n_out, g = sg - s * p.n_out;
+    const int n = nhops[s * p.n_in + g];
+    const int nchunks = (n + 31) >> 5;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nchunks) return;
+    const int h = warp * 32 + lane;
+    int ymin = 32767, ymax = -32768;
+    if (h < n) {
+        const HopRect r = hop_rects[(size_t)sg * p.max_hops + h];
+        ymin = r.y0;
+        ymax = r.y1;
+    }
+    for (int o = 16; o; o >>= 1) {
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+    }
+    if (lane == 0) chunk_bbox[(size_t)sg * p.max_chunks + warp] = (ymin & 0xffff) | (ymax << 16);
+}
+
+// -------------------------------------------------------------------------------------------------- grid -----
+constexpr int GRID_MAX_WARPS = 16;
+constexpr int GRID_LIST_CAP = 4096;   // band-list entries staged in shared memory (32 KB)
+constexpr int GRID_CHUNK_CAP = 2048;  // surviving chunk ids per band (4 KB as uint16 pairs -> stored as int)
+
+// 32x32 bit-matrix transpose across a warp: lane r ends with bit c == (lane c's input bit r).
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
+}
+
+// Running slot state of the 8 pixels (one column, 8 rows) a lane owns.
+struct TileState {
+    int s0[8], s1[8], s2[8], s3[8];
+    unsigned cnt;  // 2 bits per row: number of slots 0..2 filled
+};
+
+// Fold up to 32 candidates (lane l holds candidate l: hop index `idx`, column mask `cm`, row mask `rm`; inactive
+// lanes pass cm = 0) into the tile state. Candidates arrive in ascending hop index, so bit order == list order.
+template <bool FIRST>
+__device__ __forceinline__ void apply_chunk(TileState &st, unsigned cm, unsigned rm, int idx, int lane) {
+    const unsigned col = transpose32(cm, lane);  // bit l: candidate l covers my column
+#pragma unroll
+    for (int y = 0; y < 8; y++) {
+        const unsigned rowm = __ballot_sync(0xffffffffu, (rm >> y) & 1u);
+        const unsigned m0 = col & rowm;
+        const unsigned m1 = m0 & (m0 - 1);
+        const unsigned m2 = m1 & (m1 - 1);
+        const unsigned m3 = m2 & (m2 - 1);
+        const int v0 = __shfl_sync(0xffffffffu, idx, __ffs(m0) - 1);
+        const int v1 = __shfl_sync(0xffffffffu, idx, __ffs(m1) - 1);
+        const int v2 = __shfl_sync(0xffffffffu, idx, __ffs(m2) - 1);
+        if (FIRST) {
+            st.s0[y] = m0 ? v0 : -1;
+            st.s1[y] = m1 ? v1 : -1;
+            st.s2[y] = m2 ? v2 : -1;
+            const int vl = __shfl_sync(0xffffffffu, idx, 31 - __clz(m3));
+            st.s3[y] = m3 ? vl : -1;
+            const unsigned c = min(3, __popc(m0));
+            st.cnt |= c << (2 * y);
+        } else {
+            const unsigned c = (st.cnt >> (2 * y)) & 3u;
+            const unsigned rem = c == 0 ? m3 : c == 1 ? m2 : c == 2 ? m1 : m0;
+            const int vl = __shfl_sync(0xffffffffu, idx, 31 - __clz(rem));
+            if (c == 0) {
+                if (m0) st.s0[y] = v0;
+                if (m1) st.s1[y] = v1;
+                if (m2) st.s2[y] = v2;
+            } else if (c == 1) {
+                if (m0) st.s1[y] = v0;
+                if (m1) st.s2[y] = v1;
+            } else if (c == 2) {
+                if (m0) st.s2[y] = v0;
+            }
+            if (rem) st.s3[y] = vl;
+            const unsigned nc = min(3u, c + (unsigned)__popc(m0));
+            st.cnt = (st.cnt & ~(3u << (2 * y))) | (nc << (2 * y));
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned col_mask(int x0, int x1, int tx) {
+    const int lo = max(x0 - tx, 0), hi = min(x1 - tx, 31);
+    return ((2u << (hi - lo)) - 1u) << lo;  // hi-lo in [0,31]; 2u<<31 wraps to 0 -> all ones
+}
+
+__global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 1)
+grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
+            const int32_t *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *list_x = smem;                         // [CAP] x0 | x1<<16
+    uint32_t *list_i = smem + GRID_LIST_CAP;         // [CAP] hop index | rowmask<<24
+    int32_t  *clist = (int32_t *)(smem + 2 * GRID_LIST_CAP);  // [CHUNK_CAP] surviving chunk ids
+    __shared__ int32_t wcnt[GRID_MAX_WARPS];
+    __shared__ uint32_t cand[GRID_MAX_WARPS][2][64];  // per-warp candidate queue (x word, i word)
+
+    const int nwarps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    const int band = blockIdx.x % NB;
+    const int sg = blockIdx.x / NB;  // s*n_out + g
+    const int s = sg / p.n_out, g = sg - s * p.n_out;
+    const int ylo = band * 8, yhi = min(ylo + 7, p.H - 1);
+    const int n_h = nhops[s * p.n_in + g];
+    const HopRect *rects = hop_rects + (size_t)sg * p.max_hops;
+    const int32_t *bbox = chunk_bbox + (size_t)sg * p.max_chunks;
+    const int nchunks = (n_h + 31) >> 5;
+
+    // ---- phase 1a: ordered list of the 32-hop chunks whose y-extent touches the band --------------------------
+    int n_cl = 0;  // identical in every thread
+    for (int base = 0; base < nchunks; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        bool pred = false;
+        if (c < nchunks) {
+            const int bb = __ldg(&bbox[c]);
+            const int ymin = (int16_t)(bb & 0xffff), ymax = bb >> 16;
+            pred = ymax >= ylo && ymin <= yhi;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, pred);
+        if (lane == 0) wcnt[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < nwarps; w++) {
+            const int t = wcnt[w];
+            before += w < warp ? t : 0;
+            tot += t;
+        }
+        const int pos = n_cl + before + __popc(b & lt);
+        if (pred && pos < GRID_CHUNK_CAP) clist[pos] = c;
+        n_cl += tot;
+        __syncthreads();
+    }
+    const bool chunk_overflow = n_cl > GRID_CHUNK_CAP;
+
+    // ---- phase 1b: ordered list of the hops touching the band, staged in shared memory -----------------------
+    int n_list = 0;
+    if (!chunk_overflow) {
+        for (int base = 0; base < n_cl; base += nwarps) {
+            const int ci = base + warp;
+            bool pred = false;
+            HopRect r = {0, 32767, -1, -32768};
+            int h = 0;
+            if (ci < n_cl) {
+                h = clist[ci] * 32 + lane;
+                if (h < n_h) {
+                    r = rects[h];
+                    pred = r.y1 >= ylo && r.y0 <= yhi;
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, pred);
+            if (lane == 0) wcnt[warp] = __popc(b);
+            __syncthreads();
+            int before = 0, tot = 0;
+            for (int w = 0; w < nwarps; w++) {
+                const int t = wcnt[w];
+                before += w < warp ? t : 0;
+                tot += t;
+            }
+            const int pos = n_list + before + __popc(b & lt);
+            if (pred && pos < GRID_LIST_CAP) {
+                const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
+                const unsigned rowmask = ((2u << (r1 - r0)) - 1u) << r0;
+                list_x[pos] = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
+                list_i[pos] = (uint32_t)h | (rowmask << 24);
+            }
+            n_list += tot;
+            __syncthreads();
+        }
+    }
+    const bool direct = chunk_overflow || n_list > GRID_LIST_CAP;  // pathological input: scan global memory per tile
+
+    // ---- phase 2: one warp per 32x8 tile ----------------------------------------------------------------------
+    uint32_t *qx = cand[warp][0], *qi = cand[warp][1];
+    for (int tile = warp; tile < NT; tile += nwarps) {
+        const int tx = tile * 32;
+        TileState st;
+        st.cnt = 0;
+        bool first = true;
+        int nq = 0;  // queued candidates (uniform across the warp)
+        const int n_src = direct ? n_h : n_list;
+        for (int base = 0; base < n_src; base += 32) {
+            const int e = base + lane;
+            bool pred = false;
+            uint32_t wx = 0, wi = 0;
+            if (e < n_src) {
+                if (!direct) {
+                    wx = list_x[e];
+                    wi = list_i[e];
+                    const int x0 = (int)(wx & 0xffff), x1 = (int)(wx >> 16);
+                    pred = x1 >= tx && x0 <= tx + 31;
+                } else {
+                    const HopRect r = rects[e];
+                    pred = r.y1 >= ylo && r.y0 <= yhi && r.x1 >= tx && r.x0 <= tx + 31;
+                    if (pred) {
+                        const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
+                        wx = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
+                        wi = (uint32_t)e | ((((2u << (r1 - r0)) - 1u) << r0) << 24);
+                    }
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, pred);
+            if (b == 0) continue;
+            if (pred) {
+                const int pos = nq + __popc(b & lt);
+                qx[pos] = wx;
+                qi[pos] = wi;
+            }
+            nq += __popc(b);
+            __syncwarp();
+            if (nq >= 32) {
+                const uint32_t cx = qx[lane], ci = qi[lane];
+                const unsigned cm = col_mask((int)(cx & 0xffff), (int)(cx >> 16), tx);
+                if (first) apply_chunk<true>(st, cm, ci >> 24, (int)(ci & 0xffffffu), lane);
+                else apply_chunk<false>(st, cm, ci >> 24, (int)(ci & 0xffffffu), lane);
+                first = false;
+                __syncwarp();
+                if (lane < nq - 32) {  // move the remainder to the front of the queue
+                    const uint32_t a = qx[32 + lane], c2 = qi[32 + lane];  // reads 32..62, writes 0..30: disjoint
+                    qx[lane] = a;
+                    qi[lane] = c2;
+                }
+                nq -= 32;
+                __syncwarp();
+            }
+        }
+        if (nq > 0 || first) {
+            uint32_t cx = 0, ci = 0;
+            unsigned cm = 0;
+            if (lane < nq) {
+                cx = qx[lane];
+                ci = qi[lane];
+                cm = col_mask((int)(cx & 0xffff), (int)(cx >> 16), tx);
+            }
+            const unsigned rm = lane < nq ? (ci >> 24) : 0u;
+            if (first) apply_chunk<true>(st, cm, rm, (int)(ci & 0xffffffu), lane);
+            else apply_chunk<false>(st, cm, rm, (int)(ci & 0xffffffu), lane);
+        }
+        __syncwarp();
+        const int x = tx + lane;
+        if (x < p.W) {
+            int4 *row = grid + ((size_t)sg * p.H + ylo) * p.W + x;
+#pragma unroll
+            for (int y = 0; y < 8; y++)
+                if (ylo + y < p.H) st_cs_v4(row + (size_t)y * p.W, make_int4(st.s0[y], st.s1[y], st.s2[y], st.s3[y]));
+        }
+    }
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------- launchers -----
+int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs, const int64_t *d_rec_off,
+                        int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey) {
+    const movfe_config &c = ctx->cfg;
+    const int n_seg = c.n_streams * n_frames;
+    ProfScope prof(ctx, MOVFE_STAGE_INGEST);
+    prof.launches(n_records > 0 ? 2 : 1);
+    if (n_records > 0) {
+        const int64_t warps = (n_records + INGEST_REC_PER_WARP - 1) / INGEST_REC_PER_WARP;
+        const int blocks = (int)((warps + INGEST_WARPS - 1) / INGEST_WARPS);
+        ingest_kernel<<<blocks, INGEST_WARPS * 32, 0, ctx->stream>>>(
+            reinterpret_cast<const uint4 *>(d_recs), n_records, d_rec_off, n_seg, n_frames, ctx->pushed, ctx->RING,
+            c.max_records_per_frame, ctx->d_rec, ctx->d_rejected);
+    }
+    ingest_meta_kernel<<<(n_seg + 255) / 256, 256, 0, ctx->stream>>>(d_rec_off, d_flags, n_seg, n_frames, ctx->pushed,
+                                                                     ctx->RING, c.max_records_per_frame,
+                                                                     ctx->d_rec_cnt, ctx->d_fflags);
+    if (c.has_grey && d_grey) {
+        const size_t plane = (size_t)c.width * c.height;
+        for (int s = 0; s < c.n_streams; s++) {
+            int f = 0;
+            while (f < n_frames) {  // contiguous run of ring slots
+                const int slot = (int)((ctx->pushed + f) % ctx->RING);
+                const int run = std::min(n_frames - f, ctx->RING - slot);
+                MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_grey + ((size_t)s * ctx->RING + slot) * plane,
+                                                d_grey + ((size_t)s * n_frames + f) * plane, plane * run,
+                                                cudaMemcpyDefault, ctx->stream));
+                f += run;
+            }
+        }
+    }
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    return MOVFE_OK;
+}
+
+int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in) {
+    const movfe_config &c = ctx->cfg;
+    WinParams p;
+    p.S = c.n_streams;
+    p.n_in = n_in;
+    p.n_out = n_out;
+    p.K = ctx->K;
+    p.RING = ctx->RING;
+    p.maxM = c.max_records_per_frame;
+    p.W = c.width;
+    p.H = c.height;
+    p.first = first_frame;
+    p.max_hops = ctx->max_hops;
+    p.max_kps = ctx->max_kps;
+    p.max_chunks = ctx->max_chunks;
+    const int SF = p.S * n_in;
+    {
+    ProfScope prof(ctx, MOVFE_STAGE_HOPS);
+    prof.launches(4);
+    count_kernel<<<SF, CNT_THREADS, 0, ctx->stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_cls_cnt,
+                                                      ctx->d_area, ctx->d_rejected);
+    bases_kernel<<<(SF + 127) / 128, 128, 0, ctx->stream>>>(p, ctx->d_cls_cnt, ctx->d_area, ctx->d_hop_base,
+                                                            ctx->d_kps_base, ctx->d_nhops, ctx->d_nkps, ctx->d_cov);
+    emit_kernel<<<SF, CNT_THREADS, 0, ctx->stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_hop_base,
+                                                     ctx->d_kps_base, ctx->d_hops, ctx->d_hop_rect, ctx->d_kps);
+    {
+        dim3 g((ctx->max_chunks * 32 + 255) / 256, p.S * n_out);
+        bbox_kernel<<<g, 256, 0, ctx->stream>>>(p, ctx->d_hop_rect, ctx->d_nhops, ctx->d_chunk_bbox);
+    }
+    }
+    {
+        ProfScope prof(ctx, MOVFE_STAGE_GRID);
+        prof.launches(1);
+        // warps per CTA: the largest divisor of NT that is <= 16 keeps every warp equally loaded
+        int nw = 8;
+        for (int w = GRID_MAX_WARPS; w >= 4; w--)
+            if (ctx->NT % w == 0) { nw = w; break; }
+        const size_t smem = (2 * GRID_LIST_CAP + GRID_CHUNK_CAP) * sizeof(uint32_t);
+        MOVFE_CUDA(ctx, cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int blocks = p.S * n_out * ctx->NB;
+        grid_kernel<<<blocks, nw * 32, smem, ctx->stream>>>(p, ctx->NB, ctx->NT, ctx->d_hop_rect, ctx->d_nhops,
+                                                           ctx->d_chunk_bbox, ctx->d_grid);
+    }
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    return MOVFE_OK;
+}

@@ -1,0 +1,269 @@
+"""ctypes binding of libmovfe.so (the C-ABI in include/movfe.h).
+
+Thin convenience layer for the tests and bench.py: numpy in, numpy out, every call goes through the C-ABI.
+It never falls back to a CPU path: if the library or a CUDA device is missing, it raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import types as T
+
+_PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # mov-slam_b200/
+SO_PATH = os.path.join(_PKG, "lib", "libmovfe.so")
+_LIB = None
+
+
+class MovfeError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_streams", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("max_records_per_frame", C.c_int32), ("max_ref", C.c_int32), ("window_frames", C.c_int32),
+                ("max_tracks", C.c_int32), ("max_map_points", C.c_int32), ("express_threshold", C.c_int32),
+                ("coverage_threshold", C.c_double), ("has_grey", C.c_int32), ("reserved", C.c_int32)]
+
+
+def load():
+    """Loads libmovfe.so; raises if it has not been built (python __graft_entry__.py build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(SO_PATH):
+        raise MovfeError("libmovfe.so not built: run `make -C mov-slam_b200` (there is no CPU fallback)")
+    L = C.CDLL(SO_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    L.movfe_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.movfe_destroy.argtypes = [vp]
+    L.movfe_last_error.restype = C.c_char_p
+    L.movfe_last_error.argtypes = [vp]
+    L.movfe_version.restype = C.c_char_p
+    L.movfe_synchronize.argtypes = [vp]
+    L.movfe_cuda_stream.restype = vp
+    L.movfe_cuda_stream.argtypes = [vp]
+    L.movfe_push_frames.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.movfe_push_frames_device.argtypes = [vp, i32, vp, vp, i64, vp, vp]
+    L.movfe_frames_pushed.restype = i64
+    L.movfe_frames_pushed.argtypes = [vp]
+    L.movfe_raster.argtypes = [vp, i64, i32]
+    L.movfe_raster_counts.argtypes = [vp, i32, i64, vp, vp, vp]
+    L.movfe_download_grid.argtypes = [vp, i32, i64, vp]
+    L.movfe_download_hops.argtypes = [vp, i32, i64, vp, i32]
+    L.movfe_download_kps.argtypes = [vp, i32, i64, vp, i32]
+    L.movfe_rejected_records.restype = i64
+    L.movfe_rejected_records.argtypes = [vp]
+    L.movfe_set_tracks.argtypes = [vp, i32, vp, i32, i32]
+    L.movfe_extract.argtypes = [vp, i64, i32]
+    L.movfe_track_count.argtypes = [vp, i32, i64, vp, vp]
+    L.movfe_download_tracks.argtypes = [vp, i32, i64, vp, i32]
+    L.movfe_set_camera.argtypes = [vp, vp, vp, C.c_float]
+    L.movfe_set_map_points.argtypes = [vp, i32, vp, i32, i32]
+    L.movfe_set_pose.argtypes = [vp, i32, vp]
+    L.movfe_track_poses.argtypes = [vp, i64, i32]
+    L.movfe_download_poses.argtypes = [vp, i64, i32, vp, vp]
+    L.movfe_download_matches.argtypes = [vp, i32, i64, vp, vp, i32]
+    L.movfe_frustum.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.movfe_join.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.movfe_pose_optimize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.movfe_profile_enable.argtypes = [vp, i32]
+    L.movfe_profile_read.argtypes = [vp, vp, vp, i32]
+    _LIB = L
+    return L
+
+
+EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchronize", "movfe_cuda_stream",
+           "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_frames_pushed", "movfe_raster",
+           "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
+           "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_track_count",
+           "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_pose",
+           "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
+           "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read"]
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))        # raw device pointer
+
+
+class Context:
+    def __init__(self, n_streams, width, height, max_records_per_frame=4800, max_ref=3, window_frames=16,
+                 max_tracks=4096, max_map_points=4096, express_threshold=25, coverage_threshold=0.20, has_grey=True,
+                 device=0):
+        self.L = load()
+        self.cfg = Config(device, n_streams, width, height, max_records_per_frame, max_ref, window_frames, max_tracks,
+                          max_map_points, express_threshold, coverage_threshold, int(bool(has_grey)), 0)
+        h = C.c_void_p()
+        rc = self.L.movfe_create(C.byref(self.cfg), C.byref(h))
+        if rc != 0:
+            raise MovfeError("movfe_create failed (%d): %s" % (rc, self.L.movfe_last_error(None).decode()))
+        self.h = h
+        self.S, self.W, self.H = n_streams, width, height
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.movfe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise MovfeError("movfe error %d: %s" % (rc, self.L.movfe_last_error(self.h).decode()))
+        return rc
+
+    def synchronize(self):
+        self._ck(self.L.movfe_synchronize(self.h))
+
+    @property
+    def stream_ptr(self):
+        return self.L.movfe_cuda_stream(self.h)
+
+    STAGES = ("ingest", "hops", "grid", "extract", "pose")
+
+    def profile_enable(self, on=True):
+        self._ck(self.L.movfe_profile_enable(self.h, int(on)))
+
+    def profile_read(self, reset=True):
+        """-> ({stage: ms}, {stage: kernel launches}) since the last reset (synchronises the stream)."""
+        ms = np.zeros(len(self.STAGES), np.float64)
+        ln = np.zeros(len(self.STAGES), np.int64)
+        self._ck(self.L.movfe_profile_read(self.h, _p(ms), _p(ln), int(reset)))
+        return dict(zip(self.STAGES, ms.tolist())), dict(zip(self.STAGES, ln.tolist()))
+
+    # -- ingest ----------------------------------------------------------------------------------------------
+    def push_frames(self, n_frames, recs, rec_off, frame_flags, grey=None):
+        recs = np.ascontiguousarray(recs, T.MV_RECORD)
+        rec_off = np.ascontiguousarray(rec_off, np.int64)
+        frame_flags = np.ascontiguousarray(frame_flags, np.uint8)
+        assert len(rec_off) == self.S * n_frames + 1 and len(frame_flags) == self.S * n_frames
+        if grey is not None:
+            grey = np.ascontiguousarray(grey, np.uint8)
+            assert grey.size == self.S * n_frames * self.W * self.H
+        self._ck(self.L.movfe_push_frames(self.h, n_frames, _p(recs), _p(rec_off), _p(frame_flags), _p(grey)))
+
+    def push_frames_device(self, n_frames, d_recs, d_rec_off, n_records, d_flags, d_grey=None):
+        self._ck(self.L.movfe_push_frames_device(self.h, n_frames, _p(d_recs), _p(d_rec_off), n_records, _p(d_flags),
+                                                 _p(d_grey)))
+
+    def frames_pushed(self):
+        return self.L.movfe_frames_pushed(self.h)
+
+    # -- raster ----------------------------------------------------------------------------------------------
+    def raster(self, first_frame, n_out):
+        self._ck(self.L.movfe_raster(self.h, first_frame, n_out))
+
+    def raster_counts(self, stream, frame):
+        nh, nk, cov = C.c_int32(), C.c_int32(), C.c_double()
+        self._ck(self.L.movfe_raster_counts(self.h, stream, frame, C.byref(nh), C.byref(nk), C.byref(cov)))
+        return nh.value, nk.value, cov.value
+
+    def grid(self, stream, frame):
+        out = np.empty((self.H, self.W, 4), np.int32)
+        self._ck(self.L.movfe_download_grid(self.h, stream, frame, _p(out)))
+        return out
+
+    def hops(self, stream, frame):
+        nh, _, _ = self.raster_counts(stream, frame)
+        out = np.zeros(max(nh, 1), T.HOP)
+        n = self._ck(self.L.movfe_download_hops(self.h, stream, frame, _p(out), len(out)))
+        return out[:n]
+
+    def kps(self, stream, frame):
+        _, nk, _ = self.raster_counts(stream, frame)
+        out = np.zeros(max(nk, 1), T.RECT)
+        n = self._ck(self.L.movfe_download_kps(self.h, stream, frame, _p(out), len(out)))
+        return out[:n]
+
+    def rejected_records(self):
+        return self.L.movfe_rejected_records(self.h)
+
+    # -- propagation -------------------------------------------------------------------------------------------
+    def set_tracks(self, stream, tracks, current_id):
+        tracks = np.ascontiguousarray(tracks, T.TRACK)
+        self._ck(self.L.movfe_set_tracks(self.h, stream, _p(tracks), len(tracks), current_id))
+
+    def extract(self, first_frame, n_frames):
+        self._ck(self.L.movfe_extract(self.h, first_frame, n_frames))
+
+    def track_count(self, stream, frame):
+        n, cid = C.c_int32(), C.c_int32()
+        self._ck(self.L.movfe_track_count(self.h, stream, frame, C.byref(n), C.byref(cid)))
+        return n.value, cid.value
+
+    def tracks(self, stream, frame):
+        n, _ = self.track_count(stream, frame)
+        out = np.zeros(max(n, 1), T.TRACK)
+        n = self._ck(self.L.movfe_download_tracks(self.h, stream, frame, _p(out), len(out)))
+        return out[:n]
+
+    # -- match / pose --------------------------------------------------------------------------------------------
+    def set_camera(self, cam, pose_params, viewing_cos_limit=0.5):
+        cam = np.ascontiguousarray(cam, T.CAMERA)
+        pp = np.ascontiguousarray(pose_params, T.POSE_PARAMS)
+        self._ck(self.L.movfe_set_camera(self.h, _p(cam), _p(pp), viewing_cos_limit))
+
+    def set_map_points(self, stream, pts, n_keyframe_points):
+        pts = np.ascontiguousarray(pts, T.MAP_POINT)
+        self._ck(self.L.movfe_set_map_points(self.h, stream, _p(pts), len(pts), n_keyframe_points))
+
+    def set_pose(self, stream, pose):
+        pose = np.ascontiguousarray(pose, T.POSE)
+        self._ck(self.L.movfe_set_pose(self.h, stream, _p(pose)))
+
+    def track_poses(self, first_frame, n_frames):
+        self._ck(self.L.movfe_track_poses(self.h, first_frame, n_frames))
+
+    def poses(self, first_frame, n_frames):
+        poses = np.zeros((self.S, n_frames), T.POSE)
+        ninl = np.zeros((self.S, n_frames), np.int32)
+        self._ck(self.L.movfe_download_poses(self.h, first_frame, n_frames, _p(poses), _p(ninl)))
+        return poses, ninl
+
+    def matches(self, stream, frame):
+        cap = self.cfg.max_tracks
+        m = np.zeros(cap, np.int32)
+        o = np.zeros(cap, np.uint8)
+        n = self._ck(self.L.movfe_download_matches(self.h, stream, frame, _p(m), _p(o), cap))
+        return m[:n], o[:n]
+
+    # -- single-shot operators -------------------------------------------------------------------------------------
+    def frustum(self, poses, pts, off):
+        poses = np.ascontiguousarray(poses, T.POSE)
+        pts = np.ascontiguousarray(pts, T.MAP_POINT)
+        off = np.ascontiguousarray(off, np.int32)
+        out = np.zeros(len(pts), T.PROJECTION)
+        self._ck(self.L.movfe_frustum(self.h, len(off) - 1, _p(poses), _p(pts), _p(off), _p(out)))
+        return out
+
+    def join(self, track_ids, track_off, probe_ids, probe_valid, probe_off, match_init):
+        track_ids = np.ascontiguousarray(track_ids, np.int32)
+        track_off = np.ascontiguousarray(track_off, np.int32)
+        probe_ids = np.ascontiguousarray(probe_ids, np.int32)
+        probe_valid = np.ascontiguousarray(probe_valid, np.uint8)
+        probe_off = np.ascontiguousarray(probe_off, np.int32)
+        match = np.array(match_init, np.int32, copy=True)
+        n = np.zeros(len(track_off) - 1, np.int32)
+        self._ck(self.L.movfe_join(self.h, len(track_off) - 1, _p(track_ids), _p(track_off), _p(probe_ids),
+                                   _p(probe_valid), _p(probe_off), _p(match), _p(n)))
+        return match, n
+
+    def pose_optimize(self, cam, pp, pts, obs, off, poses):
+        cam = np.ascontiguousarray(cam, T.CAMERA)
+        pp = np.ascontiguousarray(pp, T.POSE_PARAMS)
+        pts = np.ascontiguousarray(pts, np.float32)
+        obs = np.ascontiguousarray(obs, np.float32)
+        off = np.ascontiguousarray(off, np.int32)
+        poses = np.array(poses, T.POSE, copy=True)
+        n = len(off) - 1
+        outl = np.zeros(max(int(off[-1]), 1), np.uint8)
+        ninl = np.zeros(n, np.int32)
+        stats = np.zeros((n, 4), np.int32)
+        self._ck(self.L.movfe_pose_optimize(self.h, n, _p(cam), _p(pp), _p(pts), _p(obs), _p(off), _p(poses), _p(outl),
+                                            _p(ninl), _p(stats)))
+        return poses, outl[:int(off[-1])], ninl, stats

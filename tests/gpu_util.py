@@ -1,0 +1,67 @@
+"""Helpers shared by the GPU parity tests: run the CUDA path through the C-ABI over a whole clip, window by
+window, exactly as a streaming caller would."""
+import numpy as np
+
+from movfe import lib, types as T
+
+
+def pack_streams(per_stream, n_frames, f0, f1):
+    """per_stream: list of (recs, rec_off, flags) covering n_frames. -> packed arrays for frames [f0,f1)."""
+    recs, off, flags = [], [0], []
+    for r, o, fl in per_stream:
+        for f in range(f0, f1):
+            seg = r[o[f]:o[f + 1]]
+            recs.append(seg)
+            off.append(off[-1] + len(seg))
+            flags.append(fl[f])
+    recs = np.concatenate(recs) if recs else np.zeros(0, T.MV_RECORD)
+    return recs, np.array(off, np.int64), np.array(flags, np.uint8)
+
+
+def run_raster_clip(per_stream, W, H, n_frames, window, max_ref, max_records=4800, grey=None, collect=True, ctx=None,
+                    **ctx_kw):
+    """Pushes and rasterises the clip window by window. Returns {(s,f): dict(grid,hops,kps,cov)} and the ctx."""
+    S = len(per_stream)
+    own = ctx is None
+    if own:
+        ctx = lib.Context(S, W, H, max_records_per_frame=max_records, max_ref=max_ref, window_frames=window,
+                          has_grey=grey is not None, **ctx_kw)
+    LA = max_ref + 1
+    out = {}
+    pushed = 0
+    first = 0
+    while first < n_frames:
+        n_out = min(window, n_frames - first)
+        want = min(n_frames, first + n_out + LA)
+        if want > pushed:
+            r, o, fl = pack_streams(per_stream, n_frames, pushed, want)
+            g = None
+            if grey is not None:
+                g = np.stack([grey[s][pushed:want] for s in range(S)])
+            ctx.push_frames(want - pushed, r, o, fl, g)
+            pushed = want
+        ctx.raster(first, n_out)
+        if collect:
+            for s in range(S):
+                for f in range(first, first + n_out):
+                    nh, nk, cov = ctx.raster_counts(s, f)
+                    out[(s, f)] = dict(grid=ctx.grid(s, f), hops=ctx.hops(s, f), kps=ctx.kps(s, f), cov=cov)
+        yield_point = (first, n_out)
+        first += n_out
+    return out, ctx
+
+
+def assert_raster_equal(orc_clip, got, s, f):
+    g = got[(s, f)]
+    eh, ek = orc_clip.hops(f), orc_clip.kps(f)
+    assert len(g["hops"]) == len(eh), (s, f, len(g["hops"]), len(eh))
+    assert len(g["kps"]) == len(ek), (s, f, len(g["kps"]), len(ek))
+    assert g["hops"].tobytes() == eh.tobytes(), (s, f, "hops differ")
+    assert g["kps"].tobytes() == ek.tobytes(), (s, f, "kps differ")
+    assert g["cov"] == orc_clip.coverage(f), (s, f, g["cov"], orc_clip.coverage(f))
+    eg = orc_clip.grid(f)
+    if not np.array_equal(g["grid"], eg):
+        bad = np.argwhere((g["grid"] != eg).any(-1))
+        y, x = bad[0]
+        raise AssertionError("grid differs at stream %d frame %d: %d px, first (y=%d,x=%d) got %s want %s" %
+                             (s, f, len(bad), y, x, g["grid"][y, x], eg[y, x]))
