@@ -125,6 +125,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(cudaMemset(ctx->d_cur_id, 0, S * (F + 1) * sizeof(int32_t)));
     ctx->ext_scratch_bytes = movfe_extract_scratch_bytes(ctx);
     CK(cudaMalloc(&ctx->d_ext_scratch, std::max<size_t>(ctx->ext_scratch_bytes, 16)));
+    if (int rc = movfe_extract_init(ctx)) return fail(rc);
     // map / pose
     CK(dalloc(&ctx->d_map, S * (size_t)std::max(c.max_map_points, 1)));
     CK(dalloc(&ctx->d_nmap, S));

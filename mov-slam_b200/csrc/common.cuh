@@ -165,6 +165,7 @@ int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_r
 // extract.cu
 int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 size_t movfe_extract_scratch_bytes(const movfe_ctx *ctx);
+int movfe_extract_init(movfe_ctx *ctx);
 // match.cu / pose.cu
 int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 size_t movfe_pose_scratch_bytes(const movfe_ctx *ctx);

@@ -35,34 +35,36 @@ def texture(seed=0x5EED0000):
 
 class Spec:
     def __init__(self, width=640, height=480, n_frames=20, refs=4, seed=0x5EED0001, fx=320.0, fy=320.0, cx=None,
-                 cy=None, stereo=False, dense4x4=False, baseline=0.25, phase=0.0):
+                 cy=None, stereo=False, dense4x4=False, baseline=0.25, phase=0.0, start_p=False):
         self.W, self.H, self.n_frames, self.refs, self.seed = width, height, n_frames, refs, seed
         self.fx, self.fy = fx, fy
         self.cx = width / 2 if cx is None else cx
         self.cy = height / 2 if cy is None else cy
         self.stereo, self.dense4x4, self.baseline, self.phase = stereo, dense4x4, baseline, phase
+        self.start_p = start_p      # mid-stream clip: frame 0 is a P frame whose records reference frames before the clip
 
     def camera(self):
         return T.camera(self.fx, self.fy, self.cx, self.cy)
 
 
+def pose_at(spec, f):
+    """(R_cw, t_cw) of frame f (any integer), double. Stereo: frame 2k = left view at time k, 2k+1 = right view."""
+    k, right = (f // 2, f % 2 == 1) if spec.stereo else (f, False)
+    a = 0.12 * k + spec.phase
+    x = 0.25 * np.sin(a)                 # <= 0.03 m / frame
+    y = 0.05 * np.sin(0.7 * a + 1.0)
+    yaw = np.deg2rad(1.2) * np.sin(0.15 * k + 0.5 * spec.phase)   # <= 0.2 deg / frame
+    c, s = np.cos(yaw), np.sin(yaw)
+    Rwc = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+    Ow = np.array([x, y, 0.0])
+    if right:
+        Ow = Ow + Rwc @ np.array([spec.baseline, 0, 0])
+    Rcw = Rwc.T
+    return Rcw, -Rcw @ Ow
+
+
 def trajectory(spec):
-    """Per-frame (R_cw, t_cw), double. Stereo: frame 2k = left view at time k, 2k+1 = right view (x shifted)."""
-    out = []
-    for f in range(spec.n_frames):
-        k, right = (f // 2, f % 2 == 1) if spec.stereo else (f, False)
-        a = 0.12 * k + spec.phase
-        x = 0.25 * np.sin(a)                 # <= 0.03 m / frame
-        y = 0.05 * np.sin(0.7 * a + 1.0)
-        yaw = np.deg2rad(1.2) * np.sin(0.15 * k + 0.5 * spec.phase)   # <= 0.2 deg / frame
-        c, s = np.cos(yaw), np.sin(yaw)
-        Rwc = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
-        Ow = np.array([x, y, 0.0])
-        if right:
-            Ow = Ow + Rwc @ np.array([spec.baseline, 0, 0])
-        Rcw = Rwc.T
-        out.append((Rcw, -Rcw @ Ow))
-    return out
+    return [pose_at(spec, f) for f in range(spec.n_frames)]
 
 
 def _backproject(spec, pose, u, v):
@@ -88,10 +90,8 @@ def make_records(spec):
     all_recs, off, flags = [], [0], []
     for f in range(spec.n_frames):
         is_right = spec.stereo and f % 2 == 1
-        fl = (T.FRAME_P if f > 0 else 0)
-        if f == 0 or is_right:
-            if f > 0 and not is_right:
-                fl |= T.FRAME_MV
+        fl = (T.FRAME_P if (f > 0 or spec.start_p) else 0)
+        if (f == 0 and not spec.start_p) or is_right:
             flags.append(fl)
             off.append(off[-1])
             continue
@@ -104,10 +104,7 @@ def make_records(spec):
         else:
             mbw, mbh = spec.W // 16, spec.H // 16
             part = rng.choice(5, size=(mbh, mbw), p=[0.5, 0.125, 0.125, 0.2, 0.05])
-            cxl, cyl, wl, hl = [], [], [], []
             # records are emitted in macroblock raster order, sub-blocks in ffmpeg's order
-            my, mx = np.mgrid[0:mbh, 0:mbw]
-            order = np.argsort((my * mbw + mx).ravel(), kind="stable")
             sub = {0: [(8, 8, 16, 16)], 1: [(8, 4, 16, 8), (8, 12, 16, 8)], 2: [(4, 8, 8, 16), (12, 8, 8, 16)],
                    3: [(4, 4, 8, 8), (12, 4, 8, 8), (4, 12, 8, 8), (12, 12, 8, 8)], 4: []}
             counts = np.array([1, 2, 2, 4, 0])[part.ravel()]
@@ -124,16 +121,15 @@ def make_records(spec):
                     cys[k] = 16 * (idx // mbw) + oy
                     ws[k], hs[k] = w, h
         n = len(cxs)
-        max_ref = min(spec.refs - 1, f - 1)
-        if spec.stereo:                       # left frames: ref 0 = right view before, ref 1 = previous left
-            max_ref = min(spec.refs - 1, f - 1)
+        # stereo left frames: ref 0 = the right view just before, ref 1 = the previous left view
+        max_ref = spec.refs - 1 if spec.start_p else min(spec.refs - 1, f - 1)
         refs = rng.integers(0, max_ref + 1, n) if max_ref > 0 else np.zeros(n, np.int64)
         Xw = _backproject(spec, traj[f], cxs.astype(np.float64), cys.astype(np.float64))
         sx, sy = np.zeros(n), np.zeros(n)
         for r in range(max_ref + 1):
             m = refs == r
             if m.any():
-                sx[m], sy[m] = _project(spec, traj[f - 1 - r], Xw[m])
+                sx[m], sy[m] = _project(spec, pose_at(spec, f - 1 - r), Xw[m])
         mot_x = np.clip(np.rint(4 * (sx - cxs)), -256, 256).astype(np.int64)
         mot_y = np.clip(np.rint(4 * (sy - cys)), -256, 256).astype(np.int64)
         recs = np.zeros(n, T.MV_RECORD)

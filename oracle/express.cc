@@ -77,7 +77,8 @@ extern "C" void orc_express_descriptor(const uint8_t *img, int stride, int x0, i
             p++;  // increment BEFORE the read: the tested pixel is (y, x+1)
             if ((low_bounds > *p) || (high_bounds < *p)) {
                 const int bit = (y * rows) + x;  // desc.set((y * img.rows) + x, true)
-                desc[bit >> 5] |= 1u << (bit & 31);
+                // bitset<256>::set throws beyond 255 (blocks larger than 16x16 never reach here in the reference)
+                if (bit < 256) desc[bit >> 5] |= 1u << (bit & 31);
             }
         }
     }

@@ -53,16 +53,10 @@ extern "C" int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_reco
 
     for (int f = 0; f < NF; f++) {
         const uint8_t *img = grey ? grey + (size_t)f * W * H : flat.data();
-        int n;
-        if (f == 0 && n_prev > 0) {
-            // seeded state (MV-only configs): the seed table IS frame 0's table; extraction starts at frame 1
-            n = n_prev;
-            std::memcpy(cur.data(), prev.data(), sizeof(movfe_track) * (size_t)n);
-        } else {
-            n = orc_extract_frame(W, H, frame_flags[f], img, orc_clip_grid(clip, f), orc_clip_hops(clip, f),
-                                  orc_clip_kps(clip, f), orc_clip_n_kps(clip, f), orc_clip_coverage(clip, f),
-                                  prev.data(), n_prev, nullptr, nullptr, &ep, &current_id, cur.data(), nullptr);
-        }
+        // seed_tracks (if any) are the table of the frame before the clip (Frame::mpPrevFrame of frame 0)
+        const int n = orc_extract_frame(W, H, frame_flags[f], img, orc_clip_grid(clip, f), orc_clip_hops(clip, f),
+                                        orc_clip_kps(clip, f), orc_clip_n_kps(clip, f), orc_clip_coverage(clip, f),
+                                        prev.data(), n_prev, nullptr, nullptr, &ep, &current_id, cur.data(), nullptr);
         int n_inl = 0;
         if (n_map > 0 && n > 0) {
             auto gather = [&]() {

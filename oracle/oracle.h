@@ -136,7 +136,7 @@ typedef struct orc_frontend_out {
 
 /* Runs raster -> extract -> [join(kf) -> pose -> frustum -> join(local) -> pose] per frame, as Tracking.cc
  * drives them (Tracking.cc:796-811, 890-905, 1109-1158). grey: n_frames*H*W or NULL (flat 128 image).
- * seed_tracks/n_seed: optional initial track table (MV-only configs seed tracks as input state). */
+ * seed_tracks/n_seed: optional table of the frame before the clip (MV-only configs seed tracks as input state). */
 int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_record *recs, const int64_t *rec_off,
                      const uint8_t *frame_flags, const uint8_t *grey, const movfe_track *seed_tracks, int n_seed,
                      const movfe_map_point *map_pts, int n_map, const movfe_pose *pose0,

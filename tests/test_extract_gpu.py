@@ -1,0 +1,63 @@
+"""GPU parity: track propagation + EXPRESS (through the C-ABI) against the CPU oracle — bit-exact track tables."""
+import numpy as np
+import pytest
+
+from movfe import synth, types as T
+
+from gpu_util import assert_tracks_equal, oracle_tracks, run_frontend_clip
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(orc, specs, window, max_ref, with_grey=True, seeds=None, max_tracks=4096, **kw):
+    streams = [synth.make_records(sp) for sp in specs]
+    grey = [synth.make_grey(sp) for sp in specs] if with_grey else None
+    W, H, NF = specs[0].W, specs[0].H, specs[0].n_frames
+    got, _, ctx = run_frontend_clip(streams, W, H, NF, window, max_ref, grey=grey, seeds=seeds, max_tracks=max_tracks, **kw)
+    total = 0
+    for s, sp in enumerate(specs):
+        want = oracle_tracks(orc, streams[s], W, H, max_ref, grey=None if grey is None else grey[s],
+                             seeds=None if seeds is None else seeds[s], max_tracks=max_tracks, **kw)
+        for f in range(NF):
+            assert_tracks_equal(got[(s, f)], want[f], (s, f))
+            total += len(want[f])
+    ctx.close()
+    return total
+
+
+def test_textured_scene_ref4(orc):
+    specs = [synth.Spec(640, 480, n_frames=12, refs=4, seed=0x5EED0010 + s, phase=0.4 * s) for s in range(2)]
+    assert _run(orc, specs, window=5, max_ref=3) > 20000
+
+
+def test_textured_euroc_shape(orc):
+    specs = [synth.Spec(752, 480, n_frames=7, refs=2, seed=0x5EED0011, fx=458.654, fy=457.296, cx=367.215, cy=248.375)]
+    assert _run(orc, specs, window=3, max_ref=1) > 3000
+
+
+def test_backfill_and_low_threshold(orc):
+    # a high coverage threshold forces the coverage back-fill pass on every P frame
+    specs = [synth.Spec(320, 240, n_frames=6, refs=2, seed=0x5EED0012)]
+    assert _run(orc, specs, window=6, max_ref=1, coverage_threshold=2.0, threshold=10) > 500
+
+
+def test_mv_only_seeded(orc):
+    specs = [synth.Spec(640, 480, n_frames=9, refs=4, seed=0x5EED0013 + s, start_p=True) for s in range(2)]
+    seeds = [synth.seed_tracks_lattice(sp) for sp in specs]
+    assert _run(orc, specs, window=4, max_ref=3, with_grey=False, seeds=seeds) > 5000
+
+
+def test_table_truncation(orc):
+    specs = [synth.Spec(640, 480, n_frames=5, refs=2, seed=0x5EED0014)]
+    _run(orc, specs, window=5, max_ref=1, max_tracks=700)
+
+
+def test_dense4x4_mv_only(orc):
+    specs = [synth.Spec(480, 272, n_frames=4, refs=1, seed=0x5EED0015, dense4x4=True, start_p=True)]
+    seeds = [synth.seed_tracks_lattice(sp) for sp in specs]
+    streams = [synth.make_records(sp) for sp in specs]
+    got, _, ctx = run_frontend_clip(streams, 480, 272, 4, 2, 0, seeds=seeds, max_records=(480 // 4) * (272 // 4))
+    want = oracle_tracks(orc, streams[0], 480, 272, 0, seeds=seeds[0])
+    for f in range(4):
+        assert_tracks_equal(got[(0, f)], want[f], (0, f))
+    ctx.close()
