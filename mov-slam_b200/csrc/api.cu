@@ -147,6 +147,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     }
     ctx->pose_scratch_bytes = movfe_pose_scratch_bytes(ctx);
     CK(cudaMalloc(&ctx->d_pose_scratch, std::max<size_t>(ctx->pose_scratch_bytes, 16)));
+    CK(cudaMemset(ctx->d_pose_scratch, 0, std::max<size_t>(ctx->pose_scratch_bytes, 16)));
     memset(&ctx->cam, 0, sizeof ctx->cam);
     ctx->cam.fx = ctx->cam.fy = 1.f;
     memset(&ctx->pp, 0, sizeof ctx->pp);

@@ -1,14 +1,846 @@
-// pose.cu — placeholder until the match/pose kernels land.
+// pose.cu — frustum projection, track-id joins and the pose-only Gauss-Newton / Huber solver.
+// Replaces Frame::isInFrustum (src/Frame.cc:456-519) + Pinhole::project (src/CameraModels/Pinhole.cpp:45-52),
+// MOVMatcher::SearchByVideoFeature x2 / SearchForInitialization (include/MOVMatcher.h:35-137) and
+// Optimizer::PoseOptimization (include/Optimizer.h:55) with the residual / Jacobian of
+// EdgeSE3ProjectXYZOnlyPose (include/OptimizableTypes.h:41-46, src/OptimizableTypes.cpp:54-69).
+// Compiled with -fmad=false: the frustum's binary32 arithmetic must round like the reference's.
+//
+// Streams are independent, and inside a stream the chain  join(KF) -> pose -> frustum -> join(local) -> pose
+// (Tracking.cc:796-811, 890-905, 1109-1158) is sequential over frames, so the batched driver is ONE persistent
+// kernel with one CTA per stream that walks the window's frames: no grid-wide sync, no collective, no launch per
+// step. The 27 normal-equation sums (21 JtJ + 6 Jtr) are reduced with a fixed warp-shuffle tree + a fixed
+// shared-memory order, so results are run-to-run identical; no atomics touch floating-point data.
+#include <algorithm>
+#include <cstdio>
+
 #include "common.cuh"
-size_t movfe_pose_scratch_bytes(const movfe_ctx *) { return 0; }
-int movfe_track_poses_launch(movfe_ctx *ctx, int64_t, int) { MOVFE_FAIL(ctx, MOVFE_E_STATE, "pose: not built yet"); }
-#define NYI(ctx) do { if (!(ctx)) return MOVFE_E_INVALID; MOVFE_FAIL(ctx, MOVFE_E_STATE, "not built yet"); } while (0)
-extern "C" int movfe_set_camera(movfe_ctx *ctx, const movfe_camera *, const movfe_pose_params *, float) { NYI(ctx); }
-extern "C" int movfe_set_map_points(movfe_ctx *ctx, int, const movfe_map_point *, int, int) { NYI(ctx); }
-extern "C" int movfe_set_pose(movfe_ctx *ctx, int, const movfe_pose *) { NYI(ctx); }
-extern "C" int movfe_track_poses(movfe_ctx *ctx, int64_t, int) { NYI(ctx); }
-extern "C" int movfe_download_poses(movfe_ctx *ctx, int64_t, int, movfe_pose *, int32_t *) { NYI(ctx); }
-extern "C" int movfe_download_matches(movfe_ctx *ctx, int, int64_t, int32_t *, uint8_t *, int) { NYI(ctx); }
-extern "C" int movfe_frustum(movfe_ctx *ctx, int, const movfe_pose *, const movfe_map_point *, const int32_t *, movfe_projection *) { NYI(ctx); }
-extern "C" int movfe_join(movfe_ctx *ctx, int, const int32_t *, const int32_t *, const int32_t *, const uint8_t *, const int32_t *, int32_t *, int32_t *) { NYI(ctx); }
-extern "C" int movfe_pose_optimize(movfe_ctx *ctx, int, const movfe_camera *, const movfe_pose_params *, const float *, const float *, const int32_t *, movfe_pose *, uint8_t *, int32_t *, int32_t *) { NYI(ctx); }
+
+namespace {
+
+constexpr int TP_THREADS = 512;
+constexpr int TP_WARPS = TP_THREADS / 32;
+constexpr int HASH_EMPTY = (int)0x80000000;
+
+// ------------------------------------------------------------------------------------------------ camera -----
+struct CamD {
+    int model;
+    double fx, fy, cx, cy, k0, k1, k2, k3;
+};
+
+__device__ __forceinline__ CamD widen(const movfe_camera &c) {
+    CamD r;
+    r.model = c.model;
+    r.fx = c.fx;
+    r.fy = c.fy;
+    r.cx = c.cx;
+    r.cy = c.cy;
+    r.k0 = c.k[0];
+    r.k1 = c.k[1];
+    r.k2 = c.k[2];
+    r.k3 = c.k[3];
+    return r;
+}
+
+// Pinhole.cpp:37-43 / KannalaBrandt8 (ORB-SLAM3 lineage), double
+__device__ __forceinline__ void project_d(const CamD &c, double x, double y, double z, double &u, double &v) {
+    if (c.model == MOVFE_CAM_FISHEYE) {
+        const double r = sqrt(x * x + y * y);
+        const double theta = atan2(r, z);
+        const double t2 = theta * theta;
+        const double thetad = theta * (1.0 + t2 * (c.k0 + t2 * (c.k1 + t2 * (c.k2 + t2 * c.k3))));
+        const double s = r > 1e-12 ? thetad / r : 1.0;
+        u = c.fx * s * x + c.cx;
+        v = c.fy * s * y + c.cy;
+    } else {
+        u = c.fx * x / z + c.cx;
+        v = c.fy * y / z + c.cy;
+    }
+}
+
+// Pinhole.cpp:77-88 / KB8 Jacobian, 2x3 row-major
+__device__ __forceinline__ void project_jac_d(const CamD &c, double x, double y, double z, double J[6]) {
+    if (c.model == MOVFE_CAM_FISHEYE) {
+        const double r2 = x * x + y * y;
+        const double r = sqrt(r2);
+        if (r >= 1e-8) {
+            const double theta = atan2(r, z);
+            const double t2 = theta * theta;
+            const double f = theta * (1.0 + t2 * (c.k0 + t2 * (c.k1 + t2 * (c.k2 + t2 * c.k3))));
+            const double fd = 1.0 + t2 * (3 * c.k0 + t2 * (5 * c.k1 + t2 * (7 * c.k2 + t2 * 9 * c.k3)));
+            const double D = r2 + z * z;
+            const double r3 = r2 * r;
+            J[0] = c.fx * (fd * z * x * x / (r2 * D) + f * y * y / r3);
+            J[1] = c.fx * (fd * z * x * y / (r2 * D) - f * x * y / r3);
+            J[2] = -c.fx * fd * x / D;
+            J[3] = c.fy * (fd * z * x * y / (r2 * D) - f * x * y / r3);
+            J[4] = c.fy * (fd * z * y * y / (r2 * D) + f * x * x / r3);
+            J[5] = -c.fy * fd * y / D;
+            return;
+        }
+    }
+    J[0] = c.fx / z;
+    J[1] = 0;
+    J[2] = -c.fx * x / (z * z);
+    J[3] = 0;
+    J[4] = c.fy / z;
+    J[5] = -c.fy * y / (z * z);
+}
+
+// ------------------------------------------------------------------------------------------------ frustum ----
+__device__ __forceinline__ float dot3f(const float a[3], const float b[3]) {
+    // Eigen 3.4's unrolled 3-vector reduction: c0 + (c1 + c2) (see oracle/match.cc)
+    return __fadd_rn(__fmul_rn(a[0], b[0]), __fadd_rn(__fmul_rn(a[1], b[1]), __fmul_rn(a[2], b[2])));
+}
+
+struct FrustumPose {
+    float R[9], t[3], Ow[3];
+};
+
+__device__ __forceinline__ FrustumPose frustum_pose(const movfe_pose &T) {
+    FrustumPose f;
+    for (int i = 0; i < 9; i++) f.R[i] = (float)T.R[i];
+    for (int i = 0; i < 3; i++) f.t[i] = (float)T.t[i];
+    for (int i = 0; i < 3; i++)
+        f.Ow[i] = (float)(-(T.R[0 * 3 + i] * T.t[0] + T.R[1 * 3 + i] * T.t[1] + T.R[2 * 3 + i] * T.t[2]));
+    return f;
+}
+
+// Frame::isInFrustum, mono branch (Frame.cc:458-519); `skip` = mnLastFrameSeen == current frame (Tracking.cc:1136)
+__device__ __forceinline__ movfe_projection frustum_point(const FrustumPose &fp, const movfe_camera &cam, int W, int H,
+                                                          float cosLimit, const movfe_map_point &mp, bool skip) {
+    movfe_projection o;
+    o.in_view = 0;
+    o.u = -1.f;
+    o.v = -1.f;
+    o.depth = 0.f;
+    o.view_cos = 0.f;
+    if (skip || (mp.flags & (MOVFE_MP_BAD | MOVFE_MP_SKIP | MOVFE_MP_NULL))) return o;
+    float Pc[3];
+    for (int i = 0; i < 3; i++) Pc[i] = __fadd_rn(dot3f(&fp.R[3 * i], mp.pos), fp.t[i]);  // :468
+    const float Pc_dist = __fsqrt_rn(dot3f(Pc, Pc));                                       // :469
+    if (Pc[2] < 0.0f) return o;                                                            // :474
+    float u, v;
+    if (cam.model == MOVFE_CAM_FISHEYE) {
+        double ud, vd;
+        project_d(widen(cam), (double)Pc[0], (double)Pc[1], (double)Pc[2], ud, vd);
+        u = (float)ud;
+        v = (float)vd;
+    } else {  // Pinhole.cpp:48-49
+        u = __fadd_rn(__fdiv_rn(__fmul_rn(cam.fx, Pc[0]), Pc[2]), cam.cx);
+        v = __fadd_rn(__fdiv_rn(__fmul_rn(cam.fy, Pc[1]), Pc[2]), cam.cy);
+    }
+    if (u < 0.0f || u > (float)W) return o;  // :479-482 (mnMinX = 0, mnMaxX = cols)
+    if (v < 0.0f || v > (float)H) return o;
+    o.u = u;
+    o.v = v;
+    const float maxD = __fmul_rn(1.2f, mp.max_dist), minD = __fmul_rn(0.8f, mp.min_dist);  // MapPoint.cc:443-453
+    const float PO[3] = {__fsub_rn(mp.pos[0], fp.Ow[0]), __fsub_rn(mp.pos[1], fp.Ow[1]), __fsub_rn(mp.pos[2], fp.Ow[2])};
+    const float dist = __fsqrt_rn(dot3f(PO, PO));
+    if (dist < minD || dist > maxD) return o;  // :493
+    const float viewCos = __fdiv_rn(dot3f(PO, mp.normal), dist);  // :499
+    if (viewCos < cosLimit) return o;
+    o.in_view = 1;
+    o.depth = Pc_dist;
+    o.view_cos = viewCos;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------ joins ------
+__device__ __forceinline__ unsigned hash_id(int id) { return (unsigned)id * 2654435761u; }
+
+// F.mvVFMap: first index per track id (std::map::insert never overwrites, MOVExtractor.cc:330).
+// keys/vals: cap entries of shared memory, cap = power of two >= 2n. CTA-cooperative.
+template <typename IdFn>
+__device__ void hash_build(IdFn id_of, int n, int *keys, int *vals, int cap) {
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        keys[i] = HASH_EMPTY;
+        vals[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int id = id_of(t);
+        unsigned h = hash_id(id) & (cap - 1);
+        while (true) {
+            const int prev = atomicCAS(&keys[h], HASH_EMPTY, id);
+            if (prev == HASH_EMPTY || prev == id) {
+                atomicMin(&vals[h], t);  // integer min: first index wins whatever the thread order
+                break;
+            }
+            h = (h + 1) & (cap - 1);
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int hash_find(int id, const int *keys, const int *vals, int cap) {
+    if (id == HASH_EMPTY) return -1;
+    unsigned h = hash_id(id) & (cap - 1);
+    while (true) {
+        const int k = keys[h];
+        if (k == id) return vals[h];
+        if (k == HASH_EMPTY) return -1;
+        h = (h + 1) & (cap - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ solver -----
+__device__ __forceinline__ double shfl_xor_d(double v, int o) {
+    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o), __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+}
+
+// g2o SE3Quat::exp, update = [omega, upsilon]
+__device__ void se3_exp_d(const double dx[6], double R[9], double t[3]) {
+    const double wx = dx[0], wy = dx[1], wz = dx[2];
+    const double theta = sqrt(wx * wx + wy * wy + wz * wz);
+    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double O2[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+    double a, b, c;
+    if (theta < 0.00001) {
+        a = 1.0;
+        b = 0.5;
+        c = 1.0 / 6.0;
+    } else {
+        a = sin(theta) / theta;
+        b = (1 - cos(theta)) / (theta * theta);
+        c = (theta - sin(theta)) / (theta * theta * theta);
+    }
+    double V[9];
+    for (int i = 0; i < 9; i++) {
+        const double I = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+        R[i] = I + a * O[i] + b * O2[i];
+        V[i] = I + b * O[i] + c * O2[i];
+    }
+    for (int i = 0; i < 3; i++) t[i] = V[i * 3] * dx[3] + V[i * 3 + 1] * dx[4] + V[i * 3 + 2] * dx[5];
+}
+
+// 6x6 Cholesky solve; H given as its 21 upper-triangle entries in row order. Same pivot rule as the oracle.
+__device__ bool solve6_d(const double *Hu, const double b[6], double x[6]) {
+    double H[36];
+    int k = 0;
+    for (int a = 0; a < 6; a++)
+        for (int c = a; c < 6; c++) {
+            H[a * 6 + c] = Hu[k];
+            H[c * 6 + a] = Hu[k];
+            k++;
+        }
+    double L[36];
+    for (int i = 0; i < 36; i++) L[i] = 0;
+    double maxd = 0;
+    for (int i = 0; i < 6; i++) maxd = fmax(maxd, fabs(H[i * 6 + i]));
+    if (!(maxd > 0)) return false;
+    const double tiny = 1e-13 * maxd;
+    for (int j = 0; j < 6; j++) {
+        double d = H[j * 6 + j];
+        for (int q = 0; q < j; q++) d -= L[j * 6 + q] * L[j * 6 + q];
+        if (!(d > tiny)) return false;
+        L[j * 6 + j] = sqrt(d);
+        for (int i = j + 1; i < 6; i++) {
+            double s = H[i * 6 + j];
+            for (int q = 0; q < j; q++) s -= L[i * 6 + q] * L[j * 6 + q];
+            L[i * 6 + j] = s / L[j * 6 + j];
+        }
+    }
+    double y[6];
+    for (int i = 0; i < 6; i++) {
+        double s = b[i];
+        for (int q = 0; q < i; q++) s -= L[i * 6 + q] * y[q];
+        y[i] = s / L[i * 6 + i];
+    }
+    for (int i = 5; i >= 0; i--) {
+        double s = y[i];
+        for (int q = i + 1; q < 6; q++) s -= L[q * 6 + i] * x[q];
+        x[i] = s / L[i * 6 + i];
+    }
+    return true;
+}
+
+struct SolverShared {
+    double R[9], t[3];
+    double part[TP_WARPS][28];  // per-warp partial sums: 21 JtJ + 6 Jtr (+1 pad)
+    int    ipart[TP_WARPS];
+    int    flag;                // 0 continue, 1 converged, 2 solver failure
+    int    n_bad;
+    int    stats[4];
+};
+
+// One correspondence: residual, Huber weight, 2x6 Jacobian -> 27 sums.
+__device__ __forceinline__ void accumulate_point(const CamD &cam, const double *R, const double *t, float X0, float X1, float X2,
+                                                 float ou, float ov, bool robust, double delta, double acc[27]) {
+    const double X[3] = {X0, X1, X2};
+    double Xc[3];
+    for (int r = 0; r < 3; r++) Xc[r] = R[r * 3] * X[0] + R[r * 3 + 1] * X[1] + R[r * 3 + 2] * X[2] + t[r];
+    if (!(Xc[2] > 0.0)) return;  // isDepthPositive (OptimizableTypes.h:48-52)
+    double u, v;
+    project_d(cam, Xc[0], Xc[1], Xc[2], u, v);
+    const double e0 = (double)ou - u, e1 = (double)ov - v;  // OptimizableTypes.h:41-46
+    const double chi2 = e0 * e0 + e1 * e1;
+    const double w = (robust && chi2 > delta * delta) ? delta / sqrt(chi2) : 1.0;  // RobustKernelHuber rho'
+    double Jp[6];
+    project_jac_d(cam, Xc[0], Xc[1], Xc[2], Jp);
+    const double x = Xc[0], y = Xc[1], z = Xc[2];
+    // J = -Jp * [ -[Xc]x | I ]  (OptimizableTypes.cpp:63-68)
+    const double D[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
+    double J0[6], J1[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        J0[k] = -(Jp[0] * D[0][k] + Jp[1] * D[1][k] + Jp[2] * D[2][k]);
+        J1[k] = -(Jp[3] * D[0][k] + Jp[4] * D[1][k] + Jp[5] * D[2][k]);
+    }
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+#pragma unroll
+        for (int c = a; c < 6; c++) acc[q++] += w * (J0[a] * J0[c] + J1[a] * J1[c]);
+    }
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc[21 + a] -= w * (J0[a] * e0 + J1[a] * e1);
+}
+
+__device__ __forceinline__ bool classify_point(const CamD &cam, const double *R, const double *t, float X0, float X1, float X2,
+                                               float ou, float ov, double chi2thr) {
+    const double X[3] = {X0, X1, X2};
+    double Xc[3];
+    for (int r = 0; r < 3; r++) Xc[r] = R[r * 3] * X[0] + R[r * 3 + 1] * X[1] + R[r * 3 + 2] * X[2] + t[r];
+    if (!(Xc[2] > 0.0)) return true;
+    double u, v;
+    project_d(cam, Xc[0], Xc[1], Xc[2], u, v);
+    const double e0 = (double)ou - u, e1 = (double)ov - v;
+    return (e0 * e0 + e1 * e1) > chi2thr;
+}
+
+// CTA-cooperative PoseOptimization. `Src` yields correspondence i of n slots: valid(i), X(i), obs(i).
+// outlier[i] is written for every slot: 1 = unmatched or outlier, 0 = inlier (== Frame::mvbOutlier, Optimizer.cc:452-456).
+// pose (global) is read and, unless fewer than 4 valid correspondences exist, overwritten. Returns the inlier count.
+template <typename Src>
+__device__ int pose_solve(const Src &src, int n, const movfe_camera &cam_, const movfe_pose_params &pp, movfe_pose *pose,
+                          uint8_t *outlier, int32_t *stats_out, SolverShared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const CamD cam = widen(cam_);
+    const float repErrorF = pp.is_lost ? (float)pp.reprojection_error_lost : (float)pp.reprojection_error;  // Optimizer.cc:423-427
+    const double delta = repErrorF, chi2thr = delta * delta;
+    const int its = pp.iteration_count / 4 > 1 ? pp.iteration_count / 4 : 1;
+
+    // count valid correspondences, initialise outlier flags
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const bool v = src.valid(i);
+        outlier[i] = v ? 0 : 1;
+        cnt += v;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) sh.ipart[warp] = cnt;
+    if (threadIdx.x < 9) sh.R[threadIdx.x] = pose->R[threadIdx.x];
+    if (threadIdx.x < 3) sh.t[threadIdx.x] = pose->t[threadIdx.x];
+    if (threadIdx.x < 4) sh.stats[threadIdx.x] = 0;
+    __syncthreads();
+    int P = 0;
+    for (int w = 0; w < TP_WARPS; w++) P += sh.ipart[w];
+    __syncthreads();
+    if (P < 4) {  // Optimizer.cc:415-418
+        if (stats_out && threadIdx.x < 4) stats_out[threadIdx.x] = 0;
+        return 0;
+    }
+    int n_bad = 0;
+    for (int round = 0; round < 4; round++) {
+        const bool robust = round < 3;
+        for (int it = 0; it < its; it++) {
+            double acc[27];
+#pragma unroll
+            for (int q = 0; q < 27; q++) acc[q] = 0.0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                if (!src.valid(i) || outlier[i]) continue;
+                float X0, X1, X2, ou, ov;
+                src.get(i, X0, X1, X2, ou, ov);
+                accumulate_point(cam, sh.R, sh.t, X0, X1, X2, ou, ov, robust, delta, acc);
+            }
+#pragma unroll
+            for (int q = 0; q < 27; q++) {
+                double v = acc[q];
+                for (int o = 16; o; o >>= 1) v += shfl_xor_d(v, o);
+                if (lane == 0) sh.part[warp][q] = v;
+            }
+            __syncthreads();
+            if (threadIdx.x < 27) {
+                double v = 0;
+                for (int w = 0; w < TP_WARPS; w++) v += sh.part[w][threadIdx.x];
+                sh.part[0][threadIdx.x] = v;  // only thread q touches column q
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                sh.stats[0]++;
+                sh.stats[2]++;
+                double dx[6];
+                if (!solve6_d(sh.part[0], &sh.part[0][21], dx)) {
+                    sh.flag = 2;
+                    sh.stats[3]++;
+                } else {
+                    double dR[9], dt[3], Rn[9], tn[3];
+                    se3_exp_d(dx, dR, dt);
+                    for (int i = 0; i < 3; i++)
+                        for (int j = 0; j < 3; j++)
+                            Rn[i * 3 + j] = dR[i * 3] * sh.R[j] + dR[i * 3 + 1] * sh.R[3 + j] + dR[i * 3 + 2] * sh.R[6 + j];
+                    for (int r = 0; r < 3; r++) tn[r] = dR[r * 3] * sh.t[0] + dR[r * 3 + 1] * sh.t[1] + dR[r * 3 + 2] * sh.t[2] + dt[r];
+                    for (int i = 0; i < 9; i++) sh.R[i] = Rn[i];
+                    for (int i = 0; i < 3; i++) sh.t[i] = tn[i];
+                    double m = 0;
+                    for (int a = 0; a < 6; a++) m = fmax(m, fabs(dx[a]));
+                    sh.flag = m < 1e-10 ? 1 : 0;
+                }
+            }
+            __syncthreads();
+            const int flag = sh.flag;
+            if (flag) break;
+        }
+        // re-classification of every valid correspondence
+        int bad = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            if (!src.valid(i)) continue;
+            float X0, X1, X2, ou, ov;
+            src.get(i, X0, X1, X2, ou, ov);
+            const bool b = classify_point(cam, sh.R, sh.t, X0, X1, X2, ou, ov, chi2thr);
+            outlier[i] = b ? 1 : 0;
+            bad += b;
+        }
+        for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        __syncthreads();  // everyone is past the flag read / previous ipart use
+        if (lane == 0) sh.ipart[warp] = bad;
+        if (threadIdx.x == 0) {
+            sh.stats[1]++;
+            sh.stats[2]++;
+        }
+        __syncthreads();
+        n_bad = 0;
+        for (int w = 0; w < TP_WARPS; w++) n_bad += sh.ipart[w];
+        if (P - n_bad < 3) break;
+    }
+    __syncthreads();
+    if (threadIdx.x < 9) pose->R[threadIdx.x] = sh.R[threadIdx.x];
+    if (threadIdx.x < 3) pose->t[threadIdx.x] = sh.t[threadIdx.x];
+    if (stats_out && threadIdx.x < 4) stats_out[threadIdx.x] = sh.stats[threadIdx.x];
+    __syncthreads();
+    return P - n_bad;
+}
+
+// correspondence sources
+struct DirectSrc {
+    const float *pts, *obs;
+    __device__ bool valid(int) const { return true; }
+    __device__ void get(int i, float &X0, float &X1, float &X2, float &u, float &v) const {
+        X0 = pts[3 * i];
+        X1 = pts[3 * i + 1];
+        X2 = pts[3 * i + 2];
+        u = obs[2 * i];
+        v = obs[2 * i + 1];
+    }
+};
+
+// Optimizer.cc:404-413: for every keypoint i with a map point: (GetWorldPos(), mvKeys[i].pt)
+struct FrameSrc {
+    const movfe_track *tracks;
+    const int32_t *match;
+    const movfe_map_point *map;
+    __device__ bool valid(int i) const { return match[i] >= 0; }
+    __device__ void get(int i, float &X0, float &X1, float &X2, float &u, float &v) const {
+        const movfe_map_point &mp = map[match[i]];
+        X0 = mp.pos[0];
+        X1 = mp.pos[1];
+        X2 = mp.pos[2];
+        u = tracks[i].pt_x;
+        v = tracks[i].pt_y;
+    }
+};
+
+// ----------------------------------------------------------------------------------- persistent driver ------
+struct TrackPoseParams {
+    int S, W, H, maxT, maxMap, TSLOTS, F, hash_cap;
+    int n_frames;
+    int tslot0;       // track-table slot of the first frame; slots advance modulo TSLOTS
+    int out0;         // output slot (frame - pose window start) of the first frame
+    float view_cos;
+    movfe_camera cam;
+    movfe_pose_params pp;
+};
+
+__global__ void __launch_bounds__(TP_THREADS)
+track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
+                   const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
+                   movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses, int32_t *__restrict__ ninl,
+                   int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out, int32_t *__restrict__ skip_tag) {
+    extern __shared__ int hsm[];  // keys[cap] vals[cap] hit[maxT]
+    __shared__ SolverShared sh;
+    int *keys = hsm, *vals = hsm + p.hash_cap, *hit = hsm + 2 * p.hash_cap;
+    const int s = blockIdx.x;
+    const movfe_map_point *mp = map + (size_t)s * p.maxMap;
+    const int n_map = nmap[s], n_kf = min(nkf[s], n_map);
+    int32_t *tag = skip_tag + (size_t)s * p.maxMap;
+    movfe_pose *pc = pose_cur + s;
+
+    for (int k = 0; k < p.n_frames; k++) {
+        const int ts = (p.tslot0 + k) % p.TSLOTS;
+        const movfe_track *tr = tracks + ((size_t)s * p.TSLOTS + ts) * p.maxT;
+        const int n = ntracks[s * p.TSLOTS + ts];
+        int32_t *match = match_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
+        uint8_t *outl = outlier_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
+        int n_inl = 0;
+        if (n > 0 && n_map > 0) {
+            int cap = 2;
+            while (cap < 2 * n) cap <<= 1;
+            hash_build([&](int t) { return tr[t].track_id; }, n, keys, vals, cap);
+            // --- TrackReferenceKeyFrame: SearchByVideoFeature(KF, F, matches) (MOVMatcher.h:70-103)
+            for (int t = threadIdx.x; t < n; t += blockDim.x) hit[t] = -1;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_kf; i += blockDim.x) {
+                if (mp[i].flags & (MOVFE_MP_NULL | MOVFE_MP_BAD)) continue;
+                const int t = hash_find(mp[i].track_id, keys, vals, cap);
+                if (t >= 0) atomicMax(&hit[t], i);  // last map point in list order wins
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < n; t += blockDim.x) match[t] = hit[t];
+            __syncthreads();
+            FrameSrc src{tr, match, mp};
+            pose_solve(src, n, p.cam, p.pp, pc, outl, nullptr, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
+            // --- TrackLocalMap / SearchLocalPoints (Tracking.cc:1109-1158)
+            const int frame_tag = 1;  // tags are cleared again below, so one value is enough
+            for (int t = threadIdx.x; t < n; t += blockDim.x)
+                if (match[t] >= 0) tag[match[t]] = frame_tag;  // mnLastFrameSeen = current frame
+            __syncthreads();
+            const FrustumPose fp = frustum_pose(*pc);
+            for (int t = threadIdx.x; t < n; t += blockDim.x) hit[t] = -1;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
+                const movfe_projection pr = frustum_point(fp, p.cam, p.W, p.H, p.view_cos, mp[i], tag[i] == frame_tag);
+                if (!pr.in_view || (mp[i].flags & MOVFE_MP_BAD)) continue;  // MOVMatcher.h:43-49 (far-point filter off)
+                const int t = hash_find(mp[i].track_id, keys, vals, cap);
+                if (t >= 0) atomicMax(&hit[t], i);
+            }
+            __syncthreads();
+            for (int t = threadIdx.x; t < n; t += blockDim.x)
+                if (hit[t] >= 0) match[t] = hit[t];
+            __syncthreads();
+            n_inl = pose_solve(src, n, p.cam, p.pp, pc, outl, nullptr, sh);
+            for (int i = threadIdx.x; i < n_map; i += blockDim.x) tag[i] = 0;  // leave the tags clean for the next launch
+            __syncthreads();
+        } else {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                match[t] = -1;
+                outl[t] = 1;
+            }
+        }
+        if (threadIdx.x == 0) {
+            poses[(size_t)s * p.F + p.out0 + k] = *pc;
+            ninl[(size_t)s * p.F + p.out0 + k] = n_inl;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------ single-shot kernels ----
+__global__ void frustum_kernel(const movfe_pose *__restrict__ poses, const movfe_map_point *__restrict__ pts,
+                               const int32_t *__restrict__ off, movfe_camera cam, int W, int H, float cosLimit,
+                               movfe_projection *__restrict__ out) {
+    const int pidx = blockIdx.y;
+    const FrustumPose fp = frustum_pose(poses[pidx]);
+    const int b = off[pidx], e = off[pidx + 1];
+    for (int i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x)
+        out[i] = frustum_point(fp, cam, W, H, cosLimit, pts[i], false);
+}
+
+__global__ void __launch_bounds__(TP_THREADS)
+join_kernel(const int32_t *__restrict__ track_ids, const int32_t *__restrict__ track_off, const int32_t *__restrict__ probe_ids,
+            const uint8_t *__restrict__ probe_valid, const int32_t *__restrict__ probe_off, int32_t *__restrict__ match,
+            int32_t *__restrict__ n_matches, int hash_cap_max) {
+    extern __shared__ int hsm[];
+    __shared__ int red[TP_WARPS];
+    const int pidx = blockIdx.x;
+    const int tb = track_off[pidx], n = track_off[pidx + 1] - tb;
+    const int pb = probe_off[pidx], m = probe_off[pidx + 1] - pb;
+    int cap = 2;
+    while (cap < 2 * n) cap <<= 1;
+    int *keys = hsm, *vals = hsm + hash_cap_max, *hit = hsm + 2 * hash_cap_max;
+    hash_build([&](int t) { return track_ids[tb + t]; }, n, keys, vals, cap);
+    for (int t = threadIdx.x; t < n; t += blockDim.x) hit[t] = -1;
+    __syncthreads();
+    int cnt = 0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        if (!probe_valid[pb + i]) continue;
+        const int t = hash_find(probe_ids[pb + i], keys, vals, cap);
+        if (t >= 0) {
+            atomicMax(&hit[t], i);
+            cnt++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x)
+        if (hit[t] >= 0) match[tb + t] = hit[t];
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < TP_WARPS; w++) tot += red[w];
+        n_matches[pidx] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(TP_THREADS)
+pose_kernel(const float *__restrict__ pts, const float *__restrict__ obs, const int32_t *__restrict__ off, movfe_camera cam,
+            movfe_pose_params pp, movfe_pose *__restrict__ poses, uint8_t *__restrict__ outlier, int32_t *__restrict__ n_inl,
+            int32_t *__restrict__ stats) {
+    __shared__ SolverShared sh;
+    const int pidx = blockIdx.x;
+    const int b = off[pidx], n = off[pidx + 1] - b;
+    DirectSrc src{pts + 3 * (size_t)b, obs + 2 * (size_t)b};
+    const int r = pose_solve(src, n, cam, pp, poses + pidx, outlier + b, stats ? stats + 4 * pidx : nullptr, sh);
+    if (threadIdx.x == 0) n_inl[pidx] = r;
+}
+
+int pow2_at_least(int v) {
+    int c = 2;
+    while (c < v) c <<= 1;
+    return c;
+}
+
+}  // namespace
+
+size_t movfe_pose_scratch_bytes(const movfe_ctx *ctx) {
+    return (size_t)ctx->cfg.n_streams * std::max(ctx->cfg.max_map_points, 1) * sizeof(int32_t);  // skip tags
+}
+
+int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes);
+
+int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
+    const movfe_config &c = ctx->cfg;
+    TrackPoseParams p;
+    p.S = c.n_streams;
+    p.W = c.width;
+    p.H = c.height;
+    p.maxT = c.max_tracks;
+    p.maxMap = std::max(c.max_map_points, 1);
+    p.TSLOTS = c.window_frames + 1;
+    p.F = c.window_frames;
+    p.hash_cap = pow2_at_least(2 * c.max_tracks);
+    p.n_frames = n_frames;
+    p.tslot0 = (int)(first_frame % p.TSLOTS);
+    p.out0 = 0;
+    p.view_cos = ctx->view_cos;
+    p.cam = ctx->cam;
+    p.pp = ctx->pp;
+    const size_t smem = ((size_t)2 * p.hash_cap + c.max_tracks) * sizeof(int);
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(track_poses_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(ctx, MOVFE_STAGE_POSE);
+    prof.launches(1);
+    track_poses_kernel<<<c.n_streams, TP_THREADS, smem, ctx->stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap,
+                                                                       ctx->d_nkf, ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl,
+                                                                       ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    return MOVFE_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- C-ABI --------
+extern "C" int movfe_set_camera(movfe_ctx *ctx, const movfe_camera *cam, const movfe_pose_params *pp, float viewing_cos_limit) {
+    if (!ctx || !cam || !pp) return MOVFE_E_INVALID;
+    if (cam->model != MOVFE_CAM_PINHOLE && cam->model != MOVFE_CAM_FISHEYE) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "unknown camera model %d", cam->model);
+    ctx->cam = *cam;
+    ctx->pp = *pp;
+    ctx->view_cos = viewing_cos_limit;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_point *pts, int n, int n_keyframe_points) {
+    if (!ctx) return MOVFE_E_INVALID;
+    const movfe_config &c = ctx->cfg;
+    if (stream < 0 || stream >= c.n_streams || n < 0 || (n > 0 && !pts) || n_keyframe_points < 0)
+        MOVFE_FAIL(ctx, MOVFE_E_INVALID, "set_map_points: bad argument");
+    if (n > c.max_map_points) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "set_map_points: %d points, capacity %d", n, c.max_map_points);
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    if (n > 0)
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_map + (size_t)stream * std::max(c.max_map_points, 1), pts, (size_t)n * sizeof(movfe_map_point),
+                                        cudaMemcpyHostToDevice, ctx->stream));
+    const int32_t nn = n, nk = std::min(n_keyframe_points, n);
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nmap + stream, &nn, 4, cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkf + stream, &nk, 4, cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_set_pose(movfe_ctx *ctx, int stream, const movfe_pose *pose) {
+    if (!ctx || !pose) return MOVFE_E_INVALID;
+    if (stream < 0 || stream >= ctx->cfg.n_streams) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "stream %d out of range", stream);
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_pose_cur + stream, pose, sizeof(movfe_pose), cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_track_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
+    if (!ctx) return MOVFE_E_INVALID;
+    const int64_t ext_end = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
+    if (n_frames < 1 || n_frames > ctx->cfg.window_frames || ctx->ext_first < 0 || first_frame < ctx->ext_first || first_frame + n_frames > ext_end)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "track_poses: frames [%lld,%lld) are not inside the last extract call", (long long)first_frame,
+                   (long long)(first_frame + n_frames));
+    const int64_t next = ctx->pose_first < 0 ? 0 : ctx->pose_first + ctx->pose_n;
+    if (first_frame != next)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "track_poses: frames must be consumed in order (expected %lld, got %lld)", (long long)next, (long long)first_frame);
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int rc = movfe_track_poses_launch(ctx, first_frame, n_frames);
+    if (rc) return rc;
+    ctx->pose_first = first_frame;
+    ctx->pose_n = n_frames;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_download_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames, movfe_pose *poses, int32_t *n_inliers) {
+    if (!ctx || !poses) return MOVFE_E_INVALID;
+    if (ctx->pose_first < 0 || first_frame < ctx->pose_first || first_frame + n_frames > ctx->pose_first + ctx->pose_n || n_frames < 1)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "download_poses: frames are not inside the last track_poses call");
+    const int S = ctx->cfg.n_streams, F = ctx->cfg.window_frames;
+    const int o = (int)(first_frame - ctx->pose_first);
+    MOVFE_CUDA(ctx, cudaMemcpy2DAsync(poses, (size_t)n_frames * sizeof(movfe_pose), ctx->d_poses + o, (size_t)F * sizeof(movfe_pose),
+                                      (size_t)n_frames * sizeof(movfe_pose), S, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_inliers)
+        MOVFE_CUDA(ctx, cudaMemcpy2DAsync(n_inliers, (size_t)n_frames * 4, ctx->d_ninl + o, (size_t)F * 4, (size_t)n_frames * 4, S,
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_download_matches(movfe_ctx *ctx, int stream, int64_t frame, int32_t *match, uint8_t *outlier, int capacity) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (stream < 0 || stream >= ctx->cfg.n_streams) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "stream %d out of range", stream);
+    if (ctx->pose_first < 0 || frame < ctx->pose_first || frame >= ctx->pose_first + ctx->pose_n)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "download_matches: frame is not inside the last track_poses call");
+    int n = 0;
+    int rc = movfe_track_count(ctx, stream, frame, &n, nullptr);
+    if (rc) return rc;
+    if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_matches: %d tracks, capacity %d", n, capacity);
+    const size_t o = ((size_t)stream * ctx->cfg.window_frames + (frame - ctx->pose_first)) * ctx->cfg.max_tracks;
+    if (n > 0) {
+        if (match) MOVFE_CUDA(ctx, cudaMemcpyAsync(match, ctx->d_match + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (outlier) MOVFE_CUDA(ctx, cudaMemcpyAsync(outlier, ctx->d_outlier + o, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return n;
+}
+
+// single-shot operators: inputs are staged into the context's operator scratch, results copied back
+namespace {
+struct Carver {
+    uint8_t *base;
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t n) {
+        T *p = (T *)(base + off);
+        off += (n * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
+};
+}  // namespace
+
+extern "C" int movfe_frustum(movfe_ctx *ctx, int n_problems, const movfe_pose *poses, const movfe_map_point *pts,
+                             const int32_t *off, movfe_projection *out) {
+    if (!ctx || n_problems < 1 || !poses || !off || !out) return MOVFE_E_INVALID;
+    const int n = off[n_problems];
+    if (n < 0 || (n > 0 && !pts)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "frustum: bad offsets");
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t need = (size_t)n_problems * sizeof(movfe_pose) + (size_t)n * (sizeof(movfe_map_point) + sizeof(movfe_projection)) +
+                        (size_t)(n_problems + 1) * 4 + 4 * 256;
+    int rc = movfe_ensure_op_scratch(ctx, need);
+    if (rc) return rc;
+    Carver cv{(uint8_t *)ctx->d_op};
+    movfe_pose *d_pose = cv.take<movfe_pose>(n_problems);
+    movfe_map_point *d_pts = cv.take<movfe_map_point>(n);
+    int32_t *d_off = cv.take<int32_t>(n_problems + 1);
+    movfe_projection *d_out = cv.take<movfe_projection>(n);
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pose, poses, (size_t)n_problems * sizeof(movfe_pose), cudaMemcpyHostToDevice, ctx->stream));
+    if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pts, pts, (size_t)n * sizeof(movfe_map_point), cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_off, off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    dim3 g(std::max(1, std::min(64, (n / n_problems + 255) / 256)), n_problems);
+    {
+        ProfScope prof(ctx, MOVFE_STAGE_POSE);
+        prof.launches(1);
+        frustum_kernel<<<g, 256, 0, ctx->stream>>>(d_pose, d_pts, d_off, ctx->cam, ctx->cfg.width, ctx->cfg.height, ctx->view_cos, d_out);
+    }
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n * sizeof(movfe_projection), cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_join(movfe_ctx *ctx, int n_problems, const int32_t *track_ids, const int32_t *track_off,
+                          const int32_t *probe_ids, const uint8_t *probe_valid, const int32_t *probe_off, int32_t *match,
+                          int32_t *n_matches) {
+    if (!ctx || n_problems < 1 || !track_off || !probe_off || !match || !n_matches) return MOVFE_E_INVALID;
+    const int nt = track_off[n_problems], np = probe_off[n_problems];
+    int max_n = 0;
+    for (int i = 0; i < n_problems; i++) max_n = std::max(max_n, track_off[i + 1] - track_off[i]);
+    if (max_n > 16384) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "join: %d tracks in one problem (limit 16384)", max_n);
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t need = (size_t)nt * 8 + (size_t)np * 5 + (size_t)(n_problems + 1) * 12 + 8 * 256;
+    int rc = movfe_ensure_op_scratch(ctx, need);
+    if (rc) return rc;
+    Carver cv{(uint8_t *)ctx->d_op};
+    int32_t *d_tid = cv.take<int32_t>(nt), *d_toff = cv.take<int32_t>(n_problems + 1);
+    int32_t *d_pid = cv.take<int32_t>(np), *d_poff = cv.take<int32_t>(n_problems + 1);
+    uint8_t *d_pv = cv.take<uint8_t>(np);
+    int32_t *d_match = cv.take<int32_t>(nt), *d_nm = cv.take<int32_t>(n_problems);
+    if (nt) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_tid, track_ids, (size_t)nt * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_match, match, (size_t)nt * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (np) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pid, probe_ids, (size_t)np * 4, cudaMemcpyHostToDevice, ctx->stream));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pv, probe_valid, (size_t)np, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_toff, track_off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_poff, probe_off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const int cap = pow2_at_least(2 * std::max(max_n, 1));
+    const size_t smem = ((size_t)2 * cap + std::max(max_n, 1)) * sizeof(int);
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        ProfScope prof(ctx, MOVFE_STAGE_POSE);
+        prof.launches(1);
+        join_kernel<<<n_problems, TP_THREADS, smem, ctx->stream>>>(d_tid, d_toff, d_pid, d_pv, d_poff, d_match, d_nm, cap);
+    }
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    if (nt) MOVFE_CUDA(ctx, cudaMemcpyAsync(match, d_match, (size_t)nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(n_matches, d_nm, (size_t)n_problems * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_camera *cam, const movfe_pose_params *pp,
+                                   const float *pts, const float *obs, const int32_t *off, movfe_pose *poses, uint8_t *outlier,
+                                   int32_t *n_inliers, int32_t *stats) {
+    if (!ctx || n_problems < 1 || !cam || !pp || !off || !poses || !outlier || !n_inliers) return MOVFE_E_INVALID;
+    const int n = off[n_problems];
+    if (n < 0 || (n > 0 && (!pts || !obs))) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "pose_optimize: bad offsets");
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t need = (size_t)n * 21 + (size_t)n_problems * (sizeof(movfe_pose) + 24) + 8 * 256;
+    int rc = movfe_ensure_op_scratch(ctx, need);
+    if (rc) return rc;
+    Carver cv{(uint8_t *)ctx->d_op};
+    float *d_pts = cv.take<float>(3 * (size_t)n), *d_obs = cv.take<float>(2 * (size_t)n);
+    int32_t *d_off = cv.take<int32_t>(n_problems + 1);
+    movfe_pose *d_pose = cv.take<movfe_pose>(n_problems);
+    uint8_t *d_out = cv.take<uint8_t>(n);
+    int32_t *d_ninl = cv.take<int32_t>(n_problems), *d_stats = cv.take<int32_t>(4 * (size_t)n_problems);
+    if (n) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pts, pts, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_obs, obs, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_off, off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pose, poses, (size_t)n_problems * sizeof(movfe_pose), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        ProfScope prof(ctx, MOVFE_STAGE_POSE);
+        prof.launches(1);
+        pose_kernel<<<n_problems, TP_THREADS, 0, ctx->stream>>>(d_pts, d_obs, d_off, *cam, *pp, d_pose, d_out, d_ninl, d_stats);
+    }
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(poses, d_pose, (size_t)n_problems * sizeof(movfe_pose), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(outlier, d_out, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(n_inliers, d_ninl, (size_t)n_problems * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (stats) MOVFE_CUDA(ctx, cudaMemcpyAsync(stats, d_stats, (size_t)n_problems * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MOVFE_OK;
+}
