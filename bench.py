@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — front-end frames/s of the B200 tracking front-end (BASELINE.json metric) on config C2:
+640x480 mono, ref=4 MV chaining (max_ref 3), textured plane, 64 streams batched per GPU.
+
+One "step" = one pass of the hot path over one batch: 64 streams x 16 new frames go through
+ingest -> raster (hop lists, kps, per-pixel slot grid) -> track propagation -> [join, pose, frustum, join, pose].
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          product arm (CUDA, through the C-ABI)
+  python bench.py --impl reference ...                          reference arm: the CPU restatement of the reference's
+                                                                front-end on the host cores (the reference itself cannot
+                                                                be built in this image)
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "mov-slam_b200", "python"))
+
+from movfe import synth, types as T  # noqa: E402
+
+W, H = 640, 480
+S_PER_GPU = 64
+F = 16              # frames per stream per step
+MAX_REF = 3         # ref=4 chaining -> reference indices 0..3
+N_BASE = 8          # distinct synthetic clips; stream s replays clip s % N_BASE (every stream is processed separately)
+MAX_RECORDS = 4800
+MAX_TRACKS = 4096
+METRIC = "front_end_frames_per_s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_clips(n_frames, n_base=N_BASE, with_grey=True):
+    clips = []
+    for b in range(n_base):
+        spec = synth.Spec(W, H, n_frames=n_frames, refs=MAX_REF + 1, seed=0x5EED0002 + 977 * b, phase=0.37 * b)
+        recs, off, flags = synth.make_records(spec)
+        grey = synth.make_grey(spec) if with_grey else None
+        clips.append(dict(spec=spec, recs=recs, off=off, flags=flags, grey=grey))
+    return clips
+
+
+def pack_window(clips, S, f0, f1, pinned=None):
+    """Stream-major packed inputs for frames [f0,f1) of S streams (stream s replays clip s % len(clips))."""
+    import torch
+    per = []
+    for c in clips:
+        r0, r1 = c["off"][f0], c["off"][f1]
+        per.append((c["recs"][r0:r1], c["off"][f0:f1 + 1] - r0, c["flags"][f0:f1]))
+    n = f1 - f0
+    tot = sum(len(per[s % len(per)][0]) for s in range(S))
+    recs = torch.empty(max(tot, 1) * 40 + 16, dtype=torch.uint8, pin_memory=pinned is not False)
+    off = torch.empty(S * n + 1, dtype=torch.int64, pin_memory=pinned is not False)
+    flags = torch.empty(S * n, dtype=torch.uint8, pin_memory=pinned is not False)
+    grey = None
+    if clips[0]["grey"] is not None:
+        grey = torch.empty((S, n, H, W), dtype=torch.uint8, pin_memory=pinned is not False)
+    rv = recs.numpy()[:tot * 40].view(T.MV_RECORD)
+    ov, fv = off.numpy(), flags.numpy()
+    pos = 0
+    for s in range(S):
+        r, o, fl = per[s % len(per)]
+        rv[pos:pos + len(r)] = r
+        ov[s * n:(s + 1) * n] = o[:-1] + pos
+        fv[s * n:(s + 1) * n] = fl
+        if grey is not None:
+            grey.numpy()[s] = clips[s % len(clips)]["grey"][f0:f1]
+        pos += len(r)
+    ov[S * n] = pos
+    return dict(recs=recs, off=off, flags=flags, grey=grey, n_records=tot, n=n)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm ------
+def cpu_frontend_sample(clips, n_frames, threads):
+    """Times the oracle's whole front-end (raster -> extract -> joins/frustum -> pose x2) on `threads` host threads,
+    one stream per thread, n_frames frames each. Returns (frames/s, seconds)."""
+    from oracle import pyoracle as orc
+    orc.lib()
+    cam = clips[0]["spec"].camera()
+    pp = T.pose_params()
+    jobs = []
+    for t in range(threads):
+        c = clips[t % len(clips)]
+        sp = c["spec"]
+        off = c["off"][:n_frames + 1]
+        recs = c["recs"][:off[-1]]
+        # map points from the frame-0 seeds (same construction as the GPU arm)
+        clip0 = orc.Clip(W, H, recs[:off[1]], off[:2], c["flags"][:1], MAX_REF)
+        t0, _, _, _ = orc.extract_frame(W, H, c["flags"][0], c["grey"][0], clip0.grid(0), clip0.hops(0), clip0.kps(0),
+                                        clip0.coverage(0), np.zeros(0, T.TRACK), 0, max_tracks=MAX_TRACKS)
+        mp = synth.map_from_tracks(sp, t0, synth.pose_at(sp, 0))
+        jobs.append((recs, off, c["flags"][:n_frames], c["grey"][:n_frames], mp, synth.pose_struct(synth.pose_at(sp, 0))))
+    res = [None] * threads
+
+    def run(i):
+        recs, off, fl, grey, mp, p0 = jobs[i]
+        res[i] = orc.frontend_run(W, H, recs, off, fl, grey, None, mp, p0, cam, pp, max_ref=MAX_REF, max_tracks=MAX_TRACKS,
+                                  n_kf_points=len(mp) // 2)
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    return threads * n_frames / dt, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU front-end (oracle port) on all host cores, same config / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_frames = F + MAX_REF + 1
+    clips = make_clips(n_frames)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        fps, dt = cpu_frontend_sample(clips, n_frames, cores)
+        if i >= args.warmup:
+            vals.append((fps, dt))
+        log("reference step %d: %.1f frames/s (%.2fs)" % (i, fps, dt))
+    fps = float(np.mean([v[0] for v in vals]))
+    sample = "%d streams (one per host thread) x %d frames of the C2 clip per step" % (cores, n_frames)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean([v[1] for v in vals])), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "i32/f32 raster+tracks, f64 pose", "data": "synthetic",
+            "config": config_dict(1, cores), "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(n_gpus, cores=None):
+    return {"workload": "C2: 640x480 mono, x264-style MV records with ref=4 chaining (max_ref 3), textured plane, descriptor gating on",
+            "streams_per_gpu": S_PER_GPU, "frames_per_stream_per_step": F, "n_gpus": n_gpus, "distinct_clips": N_BASE,
+            "l2": "inputs+outputs per step (~5.4 GB) are far larger than the 126 MB L2; no explicit flush",
+            "map_points_per_stream": "one per frame-0 track (~450), half of them as the reference keyframe's list"}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm ------
+def run_product(args):
+    import torch
+    from movfe import lib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    S = S_PER_GPU
+    n_steps = args.warmup + args.steps
+    n_frames = F * (n_steps + 1) + MAX_REF + 1
+    t0 = time.time()
+    clips = make_clips(n_frames)
+    log("[rank %d] generated %d clips x %d frames in %.1fs" % (rank, N_BASE, n_frames, time.time() - t0))
+
+    ctx = lib.Context(S, W, H, max_records_per_frame=MAX_RECORDS, max_ref=MAX_REF, window_frames=F, max_tracks=MAX_TRACKS,
+                      max_map_points=2048, has_grey=True, device=local)
+    cam = clips[0]["spec"].camera()
+    ctx.set_camera(cam, T.pose_params(), 0.5)
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=local)
+
+    # ---- setup (untimed): window 0 seeds the tracks; map points are built from the frame-0 tables -----------------
+    LA = MAX_REF + 1
+    win0 = pack_window(clips, S, 0, F + LA)
+    ctx.push_frames(win0["n"], win0["recs"].numpy()[:win0["n_records"] * 40].view(T.MV_RECORD), win0["off"].numpy(),
+                    win0["flags"].numpy(), win0["grey"].numpy())
+    ctx.raster(0, F)
+    ctx.extract(0, F)
+    for b in range(N_BASE):
+        t0_tab = ctx.tracks(b, 0)
+        sp = clips[b]["spec"]
+        mp = synth.map_from_tracks(sp, t0_tab, synth.pose_at(sp, 0))
+        for s in range(b, S, N_BASE):
+            ctx.set_map_points(s, mp, len(mp) // 2)
+            ctx.set_pose(s, synth.pose_struct(synth.pose_at(sp, 0)))
+    ctx.track_poses(0, F)
+    ctx.synchronize()
+    del win0
+
+    # ---- inputs of every step: host (pinned) and device-resident copies -------------------------------------------
+    host, dev = [], []
+    for k in range(n_steps):
+        f0 = F * (k + 1) + LA
+        w = pack_window(clips, S, f0, f0 + F)
+        host.append(w)
+        dev.append({kk: (v.cuda(non_blocking=True) if hasattr(v, "cuda") else v) for kk, v in w.items()})
+    torch.cuda.synchronize()
+    h2d = int(host[0]["n_records"] * 40 + host[0]["off"].numel() * 8 + host[0]["flags"].numel() + host[0]["grey"].numel())
+    poses_out = np.zeros((S, F), T.POSE)
+    ninl_out = np.zeros((S, F), np.int32)
+    d2h = int(poses_out.nbytes + ninl_out.nbytes)
+
+    def step_device(k):
+        d = dev[k]
+        first = F * (k + 1)
+        ctx.push_frames_device(F, d["recs"].data_ptr(), d["off"].data_ptr(), d["n_records"], d["flags"].data_ptr(), d["grey"].data_ptr())
+        ctx.raster(first, F)
+        ctx.extract(first, F)
+        ctx.track_poses(first, F)
+
+    def step_host(k):
+        w = host[k]
+        first = F * (k + 1)
+        ctx.push_frames(F, w["recs"].numpy()[:w["n_records"] * 40].view(T.MV_RECORD), w["off"].numpy(), w["flags"].numpy(), w["grey"].numpy())
+        ctx.raster(first, F)
+        ctx.extract(first, F)
+        ctx.track_poses(first, F)
+        return ctx.poses(first, F)      # device->host read of the step's result (synchronises)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, label):
+        """W warm-up steps then exactly K timed steps, CUDA events on the library's stream, max over ranks."""
+        for k in range(args.warmup):
+            fn(k)
+        ctx.profile_enable(True)
+        ctx.profile_read(reset=True)
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        with torch.cuda.stream(ext):
+            e0.record()
+        for k in range(args.warmup, n_steps):
+            fn(k)
+        with torch.cuda.stream(ext):
+            e1.record()
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop()
+        stage_ms, launches = ctx.profile_read(reset=True)
+        ctx.profile_enable(False)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        log("[rank %d] %s: %.3f ms device, %.3f ms wall, stages %s" % (rank, label, ms, wall * 1e3, {k: round(v, 3) for k, v in stage_ms.items()}))
+        return float(t[0]), float(t[1]), stage_ms, launches, clocks
+
+    # the extract/pose chains are stateful: the device-resident run consumes steps 0..n-1, the host run needs its own
+    # context state, so it is measured in a second context life (same inputs, same frames)
+    dev_ms, _, stage_ms, launches, clocks = timed(step_device, "device-resident")
+    frames_total = world * S * F * args.steps
+    value = frames_total / (dev_ms / 1e3)
+
+    grid_bytes = S * F * W * H * 16.0                       # algorithmic bytes of the dominant kernel per launch
+    grid_ms = stage_ms["grid"] / max(args.steps, 1)
+    peak, peak_src = peaks()
+    achieved = grid_bytes / 1e9 / (grid_ms / 1e3)
+    roofline = {"bound": "hbm", "kernel": "grid_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": grid_bytes,
+                "launch_ms": grid_ms, "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()}}
+
+    # ---- end to end: same steps through the host-buffer API, H2D + D2H inside the timed region ------------------------
+    ctx.close()
+    ctx = lib.Context(S, W, H, max_records_per_frame=MAX_RECORDS, max_ref=MAX_REF, window_frames=F, max_tracks=MAX_TRACKS,
+                      max_map_points=2048, has_grey=True, device=local)
+    ctx.set_camera(cam, T.pose_params(), 0.5)
+    ext = torch.cuda.ExternalStream(ctx.stream_ptr, device=local)
+    win0 = pack_window(clips, S, 0, F + LA)
+    ctx.push_frames(win0["n"], win0["recs"].numpy()[:win0["n_records"] * 40].view(T.MV_RECORD), win0["off"].numpy(),
+                    win0["flags"].numpy(), win0["grey"].numpy())
+    ctx.raster(0, F)
+    ctx.extract(0, F)
+    for b in range(N_BASE):
+        sp = clips[b]["spec"]
+        mp = synth.map_from_tracks(sp, ctx.tracks(b, 0), synth.pose_at(sp, 0))
+        for s in range(b, S, N_BASE):
+            ctx.set_map_points(s, mp, len(mp) // 2)
+            ctx.set_pose(s, synth.pose_struct(synth.pose_at(sp, 0)))
+    ctx.track_poses(0, F)
+    ctx.synchronize()
+    last = {}
+
+    def step_host_keep(k):
+        last["poses"], last["ninl"] = step_host(k)
+
+    _, e2e_wall_ms, _, _, _ = timed(step_host_keep, "end-to-end")
+    e2e_value = frames_total / (e2e_wall_ms / 1e3)
+    med_inl = float(np.median(last["ninl"]))
+    ctx.close()
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu_frames = F + LA
+        cpu_fps, cpu_dt = cpu_frontend_sample(clips, cpu_frames, cores)
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "i32/f32 raster+tracks, f64 pose", "data": "synthetic", "config": config_dict(world),
+                "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_wall_ms / args.steps, "median_inliers_last_step": med_inl},
+                "gpu_launches": int(sum(launches.values())), "roofline": roofline,
+                "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                 "sample": "%d streams (one per host thread) x %d frames of the same C2 clips, %.1fs" % (cores, cpu_frames, cpu_dt)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

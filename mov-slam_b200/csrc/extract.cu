@@ -67,8 +67,64 @@ __device__ __forceinline__ Band express_band(const uint8_t *__restrict__ roi, in
 // compute_descriptor (EXPRESS.h:90-110), one warp per block. `shift` = 1 reproduces the p++-before-read
 // off-by-one of the row scans; `shift` = 0 gives the true block mask the diagonal walk reads.
 // Returns the number of out-of-band pixels; desc (bit y*rows+x, OR-ed) is uniform across the warp.
+//
+// Fast paths for the four shapes H.264 produces (compile-time rows/cols: no integer division, and the bit
+// scatter of the non-square shapes is a closed form of the ballot word); any other shape takes the generic loop.
+template <int ROWS, int COLS, bool ROWMAJOR>
+__device__ __forceinline__ int express_mask_t(const uint8_t *__restrict__ roi, int stride, Band bd, int shift,
+                                              uint32_t desc[8], int lane) {
+    constexpr int N = ROWS * COLS, ITERS = N / 32;
+    constexpr int LC = COLS == 16 ? 4 : 3;
+#pragma unroll
+    for (int i = 0; i < 8; i++) desc[i] = 0;
+    int vals[ITERS];
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {  // all loads first: ITERS independent requests in flight
+        const int p = it * 32 + lane;
+        vals[it] = roi[(p >> LC) * stride + (p & (COLS - 1)) + shift];
+    }
+    int count = 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; it++) {
+        const unsigned b = __ballot_sync(0xffffffffu, bd.low > vals[it] || bd.high < vals[it]);
+        count += __popc(b);
+        if (ROWMAJOR || ROWS == COLS) {
+            desc[it] = b;  // bit y*rows+x == raster index
+        } else if (ROWS == 16 && COLS == 8) {
+            // rows 4it..4it+3, 8 px each; bit = y*16 + x: two rows per word at offsets 0 and 16
+            desc[2 * it] = (b & 0xffu) | (((b >> 8) & 0xffu) << 16);
+            desc[2 * it + 1] = ((b >> 16) & 0xffu) | (((b >> 24) & 0xffu) << 16);
+        } else {  // ROWS == 8 && COLS == 16: bit = y*8 + x, consecutive rows overlap by 8 bits and are OR-ed
+            const unsigned c = (b & 0xffffu) | ((b >> 16) << 8);  // 24 bits starting at bit 16*it
+            if (it & 1) {
+                desc[it >> 1] |= c << 16;
+                desc[(it >> 1) + 1] |= c >> 16;
+            } else {
+                desc[it >> 1] |= c;
+            }
+        }
+    }
+    return count;
+}
+
+__device__ __forceinline__ int express_mask_generic(const uint8_t *__restrict__ roi, int stride, int rows, int cols, Band bd,
+                                                    int shift, bool rowmajor_bits, uint32_t desc[8], int lane);
+
 __device__ __forceinline__ int express_mask(const uint8_t *__restrict__ roi, int stride, int rows, int cols, Band bd,
                                             int shift, bool rowmajor_bits, uint32_t desc[8], int lane) {
+    if (rows == 16 && cols == 16) return express_mask_t<16, 16, true>(roi, stride, bd, shift, desc, lane);
+    if (rows == 8 && cols == 8) return express_mask_t<8, 8, true>(roi, stride, bd, shift, desc, lane);
+    if (rows == 16 && cols == 8)
+        return rowmajor_bits ? express_mask_t<16, 8, true>(roi, stride, bd, shift, desc, lane)
+                             : express_mask_t<16, 8, false>(roi, stride, bd, shift, desc, lane);
+    if (rows == 8 && cols == 16)
+        return rowmajor_bits ? express_mask_t<8, 16, true>(roi, stride, bd, shift, desc, lane)
+                             : express_mask_t<8, 16, false>(roi, stride, bd, shift, desc, lane);
+    return express_mask_generic(roi, stride, rows, cols, bd, shift, rowmajor_bits, desc, lane);
+}
+
+__device__ __forceinline__ int express_mask_generic(const uint8_t *__restrict__ roi, int stride, int rows, int cols, Band bd,
+                                                    int shift, bool rowmajor_bits, uint32_t desc[8], int lane) {
 #pragma unroll
     for (int i = 0; i < 8; i++) desc[i] = 0;
     int count = 0;
