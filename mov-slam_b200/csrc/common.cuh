@@ -158,6 +158,15 @@ struct ProfScope {
     }
 };
 
+// Parameters of one raster window (frames [first, first+n_in) of every stream; the first n_out are outputs).
+struct WinParams {
+    int S, n_in, n_out, K, RING, maxM, W, H;
+    int64_t first;
+    int max_hops, max_kps, max_chunks;
+};
+
+// grid.cu
+int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p);
 // raster.cu
 int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in);
 int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs, const int64_t *d_rec_off,

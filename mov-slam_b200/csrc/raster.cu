@@ -160,11 +160,7 @@ constexpr int CNT_THREADS = 512;
 constexpr int CNT_WARPS = CNT_THREADS / 32;
 constexpr int MAXCLS = MOVFE_NCLS(MOVFE_MAX_K);
 
-struct WinParams {
-    int S, n_in, n_out, K, RING, maxM, W, H;
-    int64_t first;
-    int max_hops, max_kps, max_chunks;
-};
+
 
 __global__ void __launch_bounds__(CNT_THREADS)
 count_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
@@ -378,239 +374,6 @@ __global__ void bbox_kernel(WinParams p, const HopRect *__restrict__ hop_rects, 
     if (lane == 0) chunk_bbox[(size_t)sg * p.max_chunks + warp] = (ymin & 0xffff) | (ymax << 16);
 }
 
-// -------------------------------------------------------------------------------------------------- grid -----
-constexpr int GRID_MAX_WARPS = 16;
-constexpr int GRID_LIST_CAP = 4096;   // band-list entries staged in shared memory (32 KB)
-constexpr int GRID_CHUNK_CAP = 2048;  // surviving chunk ids per band (4 KB as uint16 pairs -> stored as int)
-
-// 32x32 bit-matrix transpose across a warp: lane r ends with bit c == (lane c's input bit r).
-__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
-#pragma unroll
-    for (int j = 16; j >= 1; j >>= 1) {
-        const unsigned m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
-        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
-        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
-    }
-    return x;
-}
-
-// Running slot state of the 8 pixels (one column, 8 rows) a lane owns.
-struct TileState {
-    int s0[8], s1[8], s2[8], s3[8];
-    unsigned cnt;  // 2 bits per row: number of slots 0..2 filled
-};
-
-// Fold up to 32 candidates (lane l holds candidate l: hop index `idx`, column mask `cm`, row mask `rm`; inactive
-// lanes pass cm = 0) into the tile state. Candidates arrive in ascending hop index, so bit order == list order.
-template <bool FIRST>
-__device__ __forceinline__ void apply_chunk(TileState &st, unsigned cm, unsigned rm, int idx, int lane) {
-    const unsigned col = transpose32(cm, lane);  // bit l: candidate l covers my column
-#pragma unroll
-    for (int y = 0; y < 8; y++) {
-        const unsigned rowm = __ballot_sync(0xffffffffu, (rm >> y) & 1u);
-        const unsigned m0 = col & rowm;
-        const unsigned m1 = m0 & (m0 - 1);
-        const unsigned m2 = m1 & (m1 - 1);
-        const unsigned m3 = m2 & (m2 - 1);
-        const int v0 = __shfl_sync(0xffffffffu, idx, __ffs(m0) - 1);
-        const int v1 = __shfl_sync(0xffffffffu, idx, __ffs(m1) - 1);
-        const int v2 = __shfl_sync(0xffffffffu, idx, __ffs(m2) - 1);
-        if (FIRST) {
-            st.s0[y] = m0 ? v0 : -1;
-            st.s1[y] = m1 ? v1 : -1;
-            st.s2[y] = m2 ? v2 : -1;
-            const int vl = __shfl_sync(0xffffffffu, idx, 31 - __clz(m3));
-            st.s3[y] = m3 ? vl : -1;
-            const unsigned c = min(3, __popc(m0));
-            st.cnt |= c << (2 * y);
-        } else {
-            const unsigned c = (st.cnt >> (2 * y)) & 3u;
-            const unsigned rem = c == 0 ? m3 : c == 1 ? m2 : c == 2 ? m1 : m0;
-            const int vl = __shfl_sync(0xffffffffu, idx, 31 - __clz(rem));
-            if (c == 0) {
-                if (m0) st.s0[y] = v0;
-                if (m1) st.s1[y] = v1;
-                if (m2) st.s2[y] = v2;
-            } else if (c == 1) {
-                if (m0) st.s1[y] = v0;
-                if (m1) st.s2[y] = v1;
-            } else if (c == 2) {
-                if (m0) st.s2[y] = v0;
-            }
-            if (rem) st.s3[y] = vl;
-            const unsigned nc = min(3u, c + (unsigned)__popc(m0));
-            st.cnt = (st.cnt & ~(3u << (2 * y))) | (nc << (2 * y));
-        }
-    }
-}
-
-__device__ __forceinline__ unsigned col_mask(int x0, int x1, int tx) {
-    const int lo = max(x0 - tx, 0), hi = min(x1 - tx, 31);
-    return ((2u << (hi - lo)) - 1u) << lo;  // hi-lo in [0,31]; 2u<<31 wraps to 0 -> all ones
-}
-
-__global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 1)
-grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
-            const int32_t *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
-    extern __shared__ uint32_t smem[];
-    uint32_t *list_x = smem;                         // [CAP] x0 | x1<<16
-    uint32_t *list_i = smem + GRID_LIST_CAP;         // [CAP] hop index | rowmask<<24
-    int32_t  *clist = (int32_t *)(smem + 2 * GRID_LIST_CAP);  // [CHUNK_CAP] surviving chunk ids
-    __shared__ int32_t wcnt[GRID_MAX_WARPS];
-    __shared__ uint32_t cand[GRID_MAX_WARPS][2][64];  // per-warp candidate queue (x word, i word)
-
-    const int nwarps = blockDim.x >> 5;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const unsigned lt = lanemask_lt();
-    const int band = blockIdx.x % NB;
-    const int sg = blockIdx.x / NB;  // s*n_out + g
-    const int s = sg / p.n_out, g = sg - s * p.n_out;
-    const int ylo = band * 8, yhi = min(ylo + 7, p.H - 1);
-    const int n_h = nhops[s * p.n_in + g];
-    const HopRect *rects = hop_rects + (size_t)sg * p.max_hops;
-    const int32_t *bbox = chunk_bbox + (size_t)sg * p.max_chunks;
-    const int nchunks = (n_h + 31) >> 5;
-
-    // ---- phase 1a: ordered list of the 32-hop chunks whose y-extent touches the band --------------------------
-    int n_cl = 0;  // identical in every thread
-    for (int base = 0; base < nchunks; base += blockDim.x) {
-        const int c = base + threadIdx.x;
-        bool pred = false;
-        if (c < nchunks) {
-            const int bb = __ldg(&bbox[c]);
-            const int ymin = (int16_t)(bb & 0xffff), ymax = bb >> 16;
-            pred = ymax >= ylo && ymin <= yhi;
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, pred);
-        if (lane == 0) wcnt[warp] = __popc(b);
-        __syncthreads();
-        int before = 0, tot = 0;
-        for (int w = 0; w < nwarps; w++) {
-            const int t = wcnt[w];
-            before += w < warp ? t : 0;
-            tot += t;
-        }
-        const int pos = n_cl + before + __popc(b & lt);
-        if (pred && pos < GRID_CHUNK_CAP) clist[pos] = c;
-        n_cl += tot;
-        __syncthreads();
-    }
-    const bool chunk_overflow = n_cl > GRID_CHUNK_CAP;
-
-    // ---- phase 1b: ordered list of the hops touching the band, staged in shared memory -----------------------
-    int n_list = 0;
-    if (!chunk_overflow) {
-        for (int base = 0; base < n_cl; base += nwarps) {
-            const int ci = base + warp;
-            bool pred = false;
-            HopRect r = {0, 32767, -1, -32768};
-            int h = 0;
-            if (ci < n_cl) {
-                h = clist[ci] * 32 + lane;
-                if (h < n_h) {
-                    r = rects[h];
-                    pred = r.y1 >= ylo && r.y0 <= yhi;
-                }
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, pred);
-            if (lane == 0) wcnt[warp] = __popc(b);
-            __syncthreads();
-            int before = 0, tot = 0;
-            for (int w = 0; w < nwarps; w++) {
-                const int t = wcnt[w];
-                before += w < warp ? t : 0;
-                tot += t;
-            }
-            const int pos = n_list + before + __popc(b & lt);
-            if (pred && pos < GRID_LIST_CAP) {
-                const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
-                const unsigned rowmask = ((2u << (r1 - r0)) - 1u) << r0;
-                list_x[pos] = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
-                list_i[pos] = (uint32_t)h | (rowmask << 24);
-            }
-            n_list += tot;
-            __syncthreads();
-        }
-    }
-    const bool direct = chunk_overflow || n_list > GRID_LIST_CAP;  // pathological input: scan global memory per tile
-
-    // ---- phase 2: one warp per 32x8 tile ----------------------------------------------------------------------
-    uint32_t *qx = cand[warp][0], *qi = cand[warp][1];
-    for (int tile = warp; tile < NT; tile += nwarps) {
-        const int tx = tile * 32;
-        TileState st;
-        st.cnt = 0;
-        bool first = true;
-        int nq = 0;  // queued candidates (uniform across the warp)
-        const int n_src = direct ? n_h : n_list;
-        for (int base = 0; base < n_src; base += 32) {
-            const int e = base + lane;
-            bool pred = false;
-            uint32_t wx = 0, wi = 0;
-            if (e < n_src) {
-                if (!direct) {
-                    wx = list_x[e];
-                    wi = list_i[e];
-                    const int x0 = (int)(wx & 0xffff), x1 = (int)(wx >> 16);
-                    pred = x1 >= tx && x0 <= tx + 31;
-                } else {
-                    const HopRect r = rects[e];
-                    pred = r.y1 >= ylo && r.y0 <= yhi && r.x1 >= tx && r.x0 <= tx + 31;
-                    if (pred) {
-                        const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
-                        wx = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
-                        wi = (uint32_t)e | ((((2u << (r1 - r0)) - 1u) << r0) << 24);
-                    }
-                }
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, pred);
-            if (b == 0) continue;
-            if (pred) {
-                const int pos = nq + __popc(b & lt);
-                qx[pos] = wx;
-                qi[pos] = wi;
-            }
-            nq += __popc(b);
-            __syncwarp();
-            if (nq >= 32) {
-                const uint32_t cx = qx[lane], ci = qi[lane];
-                const unsigned cm = col_mask((int)(cx & 0xffff), (int)(cx >> 16), tx);
-                if (first) apply_chunk<true>(st, cm, ci >> 24, (int)(ci & 0xffffffu), lane);
-                else apply_chunk<false>(st, cm, ci >> 24, (int)(ci & 0xffffffu), lane);
-                first = false;
-                __syncwarp();
-                if (lane < nq - 32) {  // move the remainder to the front of the queue
-                    const uint32_t a = qx[32 + lane], c2 = qi[32 + lane];  // reads 32..62, writes 0..30: disjoint
-                    qx[lane] = a;
-                    qi[lane] = c2;
-                }
-                nq -= 32;
-                __syncwarp();
-            }
-        }
-        if (nq > 0 || first) {
-            uint32_t cx = 0, ci = 0;
-            unsigned cm = 0;
-            if (lane < nq) {
-                cx = qx[lane];
-                ci = qi[lane];
-                cm = col_mask((int)(cx & 0xffff), (int)(cx >> 16), tx);
-            }
-            const unsigned rm = lane < nq ? (ci >> 24) : 0u;
-            if (first) apply_chunk<true>(st, cm, rm, (int)(ci & 0xffffffu), lane);
-            else apply_chunk<false>(st, cm, rm, (int)(ci & 0xffffffu), lane);
-        }
-        __syncwarp();
-        const int x = tx + lane;
-        if (x < p.W) {
-            int4 *row = grid + ((size_t)sg * p.H + ylo) * p.W + x;
-#pragma unroll
-            for (int y = 0; y < 8; y++)
-                if (ylo + y < p.H) st_cs_v4(row + (size_t)y * p.W, make_int4(st.s0[y], st.s1[y], st.s2[y], st.s3[y]));
-        }
-    }
-}
-
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------- launchers -----
@@ -678,19 +441,7 @@ int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in
         bbox_kernel<<<g, 256, 0, ctx->stream>>>(p, ctx->d_hop_rect, ctx->d_nhops, ctx->d_chunk_bbox);
     }
     }
-    {
-        ProfScope prof(ctx, MOVFE_STAGE_GRID);
-        prof.launches(1);
-        // warps per CTA: the largest divisor of NT that is <= 16 keeps every warp equally loaded
-        int nw = 8;
-        for (int w = GRID_MAX_WARPS; w >= 4; w--)
-            if (ctx->NT % w == 0) { nw = w; break; }
-        const size_t smem = (2 * GRID_LIST_CAP + GRID_CHUNK_CAP) * sizeof(uint32_t);
-        MOVFE_CUDA(ctx, cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int blocks = p.S * n_out * ctx->NB;
-        grid_kernel<<<blocks, nw * 32, smem, ctx->stream>>>(p, ctx->NB, ctx->NT, ctx->d_hop_rect, ctx->d_nhops,
-                                                           ctx->d_chunk_bbox, ctx->d_grid);
-    }
+    if (int rc = movfe_grid_launch(ctx, p)) return rc;
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }

@@ -107,10 +107,12 @@ def test_random_unordered_records(orc):
 
 
 def test_deep_stacks_and_band_overflow(orc):
-    """> 32 candidates in one tile (multi-chunk path) and > 4096 hops in one band (direct path)."""
+    """> 31 candidates in one tile (multi-chunk path), > 124 in one tile (row-streaming path from the staged list)
+    and more hops in one band than the staged list holds (row-streaming path from global memory)."""
     many = [_rec((40 + (i % 7), 24 + (i % 5)), (38, 22)) for i in range(100)]
+    more = [_rec((60 + (i % 9), 30 + (i % 11)), (58, 28)) for i in range(300)]
     huge = [_rec((100 + (i % 50), 40 + (i % 3)), (90, 40), w=8, h=8) for i in range(4800)]
-    _check(orc, [_clip([[], many, huge, []])], 256, 64, window=4, max_ref=0)
+    _check(orc, [_clip([[], many, more, huge, []])], 256, 64, window=5, max_ref=0)
 
 
 def test_max_ref_10(orc):
