@@ -208,24 +208,23 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
 
     // ---- phase 2: one warp per 32x8 tile ----------------------------------------------------------------------
     uint32_t *qx = cand[warp][0], *qi = cand[warp][1];
-    for (int tile = warp; tile < NT; tile += nwarps) {
-        const int tx = tile * 32;
-        const int x = tx + lane;
-        int4 *out = grid + ((size_t)sg * p.H + ylo) * p.W + x;
-        // gather this tile's candidates (ascending hop order) into the queue
+    const int n_strips = (NT + 1) >> 1;  // a warp gathers once for a 64-px strip = two adjacent tiles
+    for (int strip = warp; strip < n_strips; strip += nwarps) {
+        const int sx = strip * 64;
+        // gather the strip's candidates (ascending hop order) into the queue
         int nq = 0;
         bool overflow = direct;
         if (!direct) {
             for (int c = 0; c < n_lc; c++) {
                 const int ext = clist[c];
-                if ((ext >> 16) < tx || (ext & 0xffff) > tx + 31) continue;  // warp-uniform
+                if ((ext >> 16) < sx || (ext & 0xffff) > sx + 63) continue;  // warp-uniform
                 const int e = c * 32 + lane;
                 bool pred = false;
                 uint32_t wx = 0, wi = 0;
                 if (e < n_list) {
                     wx = list_x[e];
                     wi = list_i[e];
-                    pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31;
+                    pred = (int)(wx >> 16) >= sx && (int)(wx & 0xffffu) <= sx + 63;
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, pred);
                 if (nq + __popc(b) > TILE_Q) {
@@ -241,36 +240,60 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
             }
         }
         __syncwarp();
+        const int nchk = (nq + 30) / 31;
+        // per-chunk lane data shared by both tiles of the strip: candidate i of chunk c sits in lane 30-i
+        uint32_t cwx[4];
+        int idx[4];
+        unsigned rm[4];
         if (!overflow) {
-            // fast path: <= 4 chunks of 31 candidates, column masks cached in registers, rows folded independently
-            unsigned col[4];
-            int idx[4];
-            unsigned rm[4];
-            const int nchk = (nq + 30) / 31;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                col[c] = 0;
+                cwx[c] = 0x0000ffffu;  // x0 = 65535 > x1 = 0: covers no column
                 idx[c] = -1;
                 rm[c] = 0;
-                if (c < nchk || c == 0) {  // warp-uniform
-                    const int e = c * 31 + (30 - lane);
-                    unsigned cm = 0;
-                    if (lane < 31 && e < nq) {
-                        const uint32_t wi = qi[e];
-                        cm = col_mask(qx[e], tx);
-                        idx[c] = (int)(wi & 0xffffffu);
-                        rm[c] = wi >> 24;
-                    }
-                    col[c] = transpose32(cm, lane);
+                const int e = c * 31 + (30 - lane);
+                if (c < nchk && lane < 31 && e < nq) {
+                    const uint32_t wi = qi[e];
+                    cwx[c] = qx[e];
+                    idx[c] = (int)(wi & 0xffffffu);
+                    rm[c] = wi >> 24;
                 }
             }
+        }
+        for (int tsub = 0; tsub < 2; tsub++) {
+        const int tx = sx + 32 * tsub;
+        if (tx >= p.W) break;
+        const int x = tx + lane;
+        int4 *out = grid + ((size_t)sg * p.H + ylo) * p.W + x;
+        if (!overflow) {
+            // fast path: <= 4 chunks of 31 candidates, column masks in registers, rows folded independently
+            const bool full = tx + 31 < p.W && ylo + 7 < p.H;  // warp-uniform: no per-store bounds test needed
+            const size_t rstride = (size_t)p.W;
+            if (nchk <= 1) {
+                const unsigned cm = (lane < 31 && (int)(cwx[0] >> 16) >= tx && (int)(cwx[0] & 0xffffu) <= tx + 31) ? col_mask(cwx[0], tx) : 0u;
+                const unsigned col0 = transpose32(cm, lane);
 #pragma unroll
-            for (int y = 0; y < 8; y++) {
-                Slots st;
-                const unsigned rowm0 = __ballot_sync(0xffffffffu, (rm[0] >> y) & 1u);
-                if (nchk <= 1) {
-                    fold<true, false>(st, col[0] & rowm0, idx[0]);
-                } else {
+                for (int y = 0; y < 8; y++) {
+                    Slots st;
+                    const unsigned rowm0 = __ballot_sync(0xffffffffu, (rm[0] >> y) & 1u);
+                    fold<true, false>(st, col0 & rowm0, idx[0]);
+                    if (full || (x < p.W && ylo + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
+                    out += rstride;
+                }
+            } else {
+                unsigned col[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    col[c] = 0;
+                    if (c < nchk) {  // warp-uniform
+                        const unsigned cm = (lane < 31 && (int)(cwx[c] >> 16) >= tx && (int)(cwx[c] & 0xffffu) <= tx + 31) ? col_mask(cwx[c], tx) : 0u;
+                        col[c] = transpose32(cm, lane);
+                    }
+                }
+#pragma unroll
+                for (int y = 0; y < 8; y++) {
+                    Slots st;
+                    const unsigned rowm0 = __ballot_sync(0xffffffffu, (rm[0] >> y) & 1u);
                     fold<true, true>(st, col[0] & rowm0, idx[0]);
 #pragma unroll
                     for (int c = 1; c < 4; c++) {
@@ -279,8 +302,9 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
                             fold<false, true>(st, col[c] & rowm, idx[c]);
                         }
                     }
+                    if (full || (x < p.W && ylo + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
+                    out += rstride;
                 }
-                if (x < p.W && ylo + y < p.H) st_cs_v4(out + (size_t)y * p.W, make_int4(st.s0, st.s1, st.s2, st.s3));
             }
         } else {
             // slow path (more than 124 candidates in one tile, or the band list did not fit): one row at a time,
@@ -289,7 +313,7 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
             for (int y = 0; y < 8; y++) {
                 if (ylo + y >= p.H) break;
                 Slots st = {-1, -1, -1, -1, 0};
-                nq = 0;
+                int nq = 0;
                 for (int base = 0; base <= n_src; base += 32) {  // one extra, empty pass flushes the queue
                     const int e = base + lane;
                     bool pred = false;
@@ -347,6 +371,7 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
             }
         }
         __syncwarp();
+        }  // tiles of the strip
     }
 }
 
@@ -355,10 +380,12 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
 int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p) {
     ProfScope prof(ctx, MOVFE_STAGE_GRID);
     prof.launches(1);
-    // warps per CTA: the largest divisor of NT that is <= 16 keeps every warp equally loaded
+    // warps per CTA: the largest divisor of the strip count (two 32-px tiles per strip) that is <= 16 keeps every
+    // warp equally loaded
+    const int n_strips = (ctx->NT + 1) / 2;
     int nw = 8;
     for (int w = GRID_MAX_WARPS; w >= 4; w--)
-        if (ctx->NT % w == 0) {
+        if (n_strips % w == 0) {
             nw = w;
             break;
         }
