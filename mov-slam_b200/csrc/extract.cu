@@ -3,16 +3,21 @@
 // streams; frames of a stream are processed in order (frame f's table is the input of frame f+1).
 // Compiled with -fmad=false (positions are binary32 sums that must round like the reference).
 //
-// Per frame, three launches:
-//   cand_kernel      one warp per previous track (in the reference's sorted order): slot-grid lookup, up to four
-//                    candidate hops scored by the Hamming distance of warp-ballot EXPRESS descriptors, move,
-//                    bounds, descriptor gate; in-bounds tracks claim their hop's kps entry with an integer
-//                    atomicMin on the sorted rank (order-independent result == the reference's first-come rule).
-//   birth_kernel     one warp per candidate-keypoint block: unclaimed + in bounds + compute_express -> descriptor.
-//   finalize_kernel  one CTA per stream: ordered compaction of the survivors, births appended in kps order with
-//                    ids ++mCurrentId, optional coverage back-fill / I-frame seeding on the 16-px lattice, then
-//                    the stable (age desc, popcount desc) order of the new table for the next frame (bitonic sort
-//                    of unique 64-bit keys in shared memory).
+// Per frame, three launches. All three are bound by the latency of dependent gathers, so the work is
+// arranged for loads in flight, not for bytes:
+//   cand_kernel      a warp takes 32 tracks (in the reference's sorted order). Thread level: each lane walks its own
+//                    track's chain order -> track -> slot-grid cell -> up to four hops. Warp level: per track, the loads
+//                    of ALL candidate patches are issued back to back, then the warp-ballot EXPRESS descriptors are
+//                    scored by Hamming distance. In-bounds tracks claim their hop's kps entry with an integer atomicMin
+//                    on the sorted rank (order-independent result == the reference's first-come rule) and write their
+//                    moved record to a staging table.
+//   birth_kernel     unclaimed in-bounds candidate-keypoint blocks: compute_express + descriptor from one pass over
+//                    the block's 17 columns.
+//   finalize_kernel  one CTA per stream: ordered compaction of the survivors (a thread owns 8 consecutive ranks, one
+//                    block scan per table), births appended in kps order with ids ++mCurrentId, optional coverage
+//                    back-fill / I-frame seeding on the 16-px lattice, then the stable (age desc, popcount desc)
+//                    order of the new table for the next frame: bitonic sort of unique 64-bit keys, register- and
+//                    shuffle-resident for all but the widest steps.
 // LK-carried features (cv::calcOpticalFlowPyrLK; MOVExtractor.cc:81-120,161-243,337-377) are host work: coverage
 // tracks and I-frame carry-over are dropped here, exactly like the oracle with lk_status == NULL.
 #include <algorithm>
@@ -26,17 +31,6 @@ constexpr int CAND_WARPS = 8;
 constexpr int FIN_THREADS = 1024;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int MAX_TRACKS_CAP = 8192;
-
-// Per previous track, produced by cand_kernel (index = sorted rank).
-struct __align__(16) Cand {
-    float pt_x, pt_y;
-    movfe_rect mb;
-    int32_t d_indx;
-    uint32_t flags;  // bit0: in bounds (may claim), bit1: passes the descriptor gate
-    uint32_t pad[2];
-    uint32_t desc[8];
-};
-static_assert(sizeof(Cand) == 64, "Cand is 64 bytes");
 
 struct ExtParams {
     int S, W, H, maxT, max_kps, max_hops, maxM, n_out, n_in, RING, TSLOTS;
@@ -229,153 +223,395 @@ __device__ __forceinline__ bool rect_in_bounds(int x, int y, int w, int h, int c
     return x >= 0 && y >= 0 && (x + w) < cols && (y + h) < rows;
 }
 
-// ------------------------------------------------------------------------------------------- cand_kernel -----
-__device__ __forceinline__ void cand_one(const ExtParams &p, int s, int i, int lane, const movfe_track *__restrict__ tracks,
-                                         const uint16_t *__restrict__ order, const int4 *__restrict__ grid,
-                                         const movfe_hop *__restrict__ hops, const uint8_t *__restrict__ grey,
-                                         Cand *__restrict__ cand, int32_t *__restrict__ claim);
+// ------------------------------------------------------------------------------------ batched patch access -----
+// The propagation kernels are bound by the latency of dependent gathers, not by bandwidth, so every global load of a
+// track's patches is ISSUED before any is consumed: patch_issue only loads, patch_words only consumes.
+template <int ROWS, int COLS>
+__device__ __forceinline__ void patch_issue(const uint8_t *__restrict__ roi, int stride, int shift, int lane,
+                                            int (&vals)[ROWS * COLS / 32], int (&cen)[4]) {
+    constexpr int LC = COLS == 16 ? 4 : 3;
+    const uint8_t *q = roi + (lane >> LC) * stride + (lane & (COLS - 1)) + shift;
+    const int step = (32 >> LC) * stride;
+#pragma unroll
+    for (int it = 0; it < ROWS * COLS / 32; it++) vals[it] = q[it * step];
+    constexpr int cr = ROWS / 2, cc = COLS / 2;  // compute_center (EXPRESS.h:79-88): at(row = cols/2, col = rows/2)
+    cen[0] = roi[cc * stride + cr];
+    cen[1] = roi[(cc - 1) * stride + (cr - 1)];
+    cen[2] = roi[cc * stride + (cr - 1)];
+    cen[3] = roi[(cc - 1) * stride + cr];
+}
 
-__global__ void __launch_bounds__(CAND_WARPS * 32)
+__device__ __forceinline__ Band band_of(const int (&cen)[4], int thr) {
+    const int center = (cen[0] + cen[1] + cen[2] + cen[3]) / 4;
+    Band b;
+    b.low = (uint8_t)(center - thr);
+    b.high = (uint8_t)(center + thr);
+    return b;
+}
+
+// out-of-band ballots of a patch, raster order: bit p of word p/32 (p = y*COLS + x)
+template <int N32>
+__device__ __forceinline__ void patch_words(const int (&vals)[N32], Band bd, uint32_t (&b)[N32]) {
+#pragma unroll
+    for (int it = 0; it < N32; it++) b[it] = __ballot_sync(0xffffffffu, bd.low > vals[it] || bd.high < vals[it]);
+}
+
+// raster-order words -> the reference's descriptor layout, bit y*rows + x, OR-ed (EXPRESS.h:90-110)
+template <int ROWS, int COLS>
+__device__ __forceinline__ void desc_layout(const uint32_t (&b)[ROWS * COLS / 32], uint32_t (&desc)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) desc[i] = 0;
+#pragma unroll
+    for (int it = 0; it < ROWS * COLS / 32; it++) {
+        if (ROWS == COLS) {
+            desc[it] = b[it];
+        } else if (ROWS == 16 && COLS == 8) {
+            desc[2 * it] = (b[it] & 0xffu) | (((b[it] >> 8) & 0xffu) << 16);
+            desc[2 * it + 1] = ((b[it] >> 16) & 0xffu) | (((b[it] >> 24) & 0xffu) << 16);
+        } else {  // ROWS == 8 && COLS == 16
+            const unsigned c = (b[it] & 0xffffu) | ((b[it] >> 16) << 8);
+            if (it & 1) {
+                desc[it >> 1] |= c << 16;
+                desc[(it >> 1) + 1] |= c >> 16;
+            } else {
+                desc[it >> 1] |= c;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- cand_kernel -----
+// A warp takes 32 consecutive tracks (sorted rank). Thread level: each lane walks its own track's dependent chain
+// order -> track -> slot-grid cell -> up to four hops, so 32 chains are in flight per warp. Warp level: the tracks that
+// need descriptors are visited one by one, all loads of all their candidate patches issued back to back.
+constexpr int CAND_THREADS = CAND_WARPS * 32;
+constexpr int CW_MXY = 0;    // [4] candidate rectangle origin, mx | my << 16
+constexpr int CW_INFO = 4;   // need (4 bits) | mw << 8 | mh << 16
+constexpr int CW_OIDX = 5;   // index of the track in the previous table
+constexpr int CW_WORDS = 6;
+
+template <int ROWS, int COLS>
+__device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int W, int thr, const int (&mxy)[4], unsigned need,
+                                         const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
+    constexpr int IT = ROWS * COLS / 32;
+    int vals[4][IT], cen[4][4];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const bool on = (need >> j) & 1u;  // candidates that are not evaluated read row 0 of the image (always valid)
+        patch_issue<ROWS, COLS>(img + (on ? (size_t)(mxy[j] >> 16) * W + (int16_t)(mxy[j] & 0xffff) : 0), on ? W : 0, on ? 1 : 0, lane,
+                                vals[j], cen[j]);
+    }
+    if (need >> 2) {  // warp-uniform
+#pragma unroll
+        for (int j = 2; j < 4; j++) {
+            const bool on = (need >> j) & 1u;
+            patch_issue<ROWS, COLS>(img + (on ? (size_t)(mxy[j] >> 16) * W + (int16_t)(mxy[j] & 0xffff) : 0), on ? W : 0, on ? 1 : 0,
+                                    lane, vals[j], cen[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 2; j < 4; j++) {
+#pragma unroll
+            for (int it = 0; it < IT; it++) vals[j][it] = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) cen[j][q] = 0;
+        }
+    }
+    int chosen = -1;
+    best = 256;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if ((need >> j) & 1u) {  // warp-uniform
+            uint32_t b[IT], d[8];
+            patch_words<IT>(vals[j], band_of(cen[j], thr), b);
+            desc_layout<ROWS, COLS>(b, d);
+            const int dist = hamming256(pd, d);
+            // :292-296 strict '<' from 256. Candidate 0 is also the default choice (:270), so taking it at dist == 256
+            // gives the reference's result (same hop, same descriptor, gate fails).
+            if (j == 0 || dist < best) {
+                best = dist;
+                chosen = j;
+#pragma unroll
+                for (int k = 0; k < 8; k++) best_d[k] = d[k];
+            }
+        }
+    }
+    return chosen;
+}
+
+// any other block shape (synthetic 4-px blocks, ...): one candidate after the other through the generic mask
+__device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, int W, int thr, int mw, int mh, const int (&mxy)[4],
+                                              unsigned need, const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
+    int chosen = -1;
+    best = 256;
+    for (int j = 0; j < 4; j++) {
+        if (!((need >> j) & 1u)) continue;
+        const uint8_t *roi = img + (size_t)(mxy[j] >> 16) * W + (int16_t)(mxy[j] & 0xffff);
+        uint32_t d[8];
+        express_mask(roi, W, mh, mw, express_band(roi, W, mh, mw, thr), 1, false, d, lane);
+        const int dist = hamming256(pd, d);
+        if (j == 0 || dist < best) {
+            best = dist;
+            chosen = j;
+#pragma unroll
+            for (int k = 0; k < 8; k++) best_d[k] = d[k];
+        }
+    }
+    return chosen;
+}
+
+__global__ void __launch_bounds__(CAND_THREADS)
 cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
             const uint16_t *__restrict__ order, const int4 *__restrict__ grid, const movfe_hop *__restrict__ hops,
-            const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, Cand *__restrict__ cand,
-            int32_t *__restrict__ claim) {
+            const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
+            int2 *__restrict__ cinfo, int32_t *__restrict__ claim) {
+    __shared__ int sm[CAND_WARPS][CW_WORDS][32];
     const int s = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_prev = ntracks[s * p.TSLOTS + p.tslot_prev];
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;  // I frame: nothing is propagated
-    for (int i = blockIdx.x * CAND_WARPS + warp; i < n_prev; i += gridDim.x * CAND_WARPS)  // i = sorted rank
-        cand_one(p, s, i, lane, tracks, order, grid, hops, grey, cand, claim);
-}
-
-__device__ __forceinline__ void cand_one(const ExtParams &p, int s, int i, int lane, const movfe_track *__restrict__ tracks,
-                                         const uint16_t *__restrict__ order, const int4 *__restrict__ grid,
-                                         const movfe_hop *__restrict__ hops, const uint8_t *__restrict__ grey,
-                                         Cand *__restrict__ cand, int32_t *__restrict__ claim) {
     const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
-    const movfe_track pvf = prev[order[(size_t)s * p.maxT + i]];
-    Cand out;
-    out.pt_x = 0.f;
-    out.pt_y = 0.f;
-    out.mb = pvf.mb;
-    out.d_indx = -1;
-    out.flags = 0;
-    out.pad[0] = out.pad[1] = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) out.desc[k] = 0;
-    Cand *dst = cand + (size_t)s * p.maxT + i;
-
+    const uint16_t *ord = order + (size_t)s * p.maxT;
     const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
     const movfe_hop *hp = hops + ((size_t)s * p.n_out + p.fi) * p.max_hops;
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H) : nullptr;
+    movfe_track *st = stage + (size_t)s * p.maxT;
+    int2 *ci = cinfo + (size_t)s * p.maxT;
+    int32_t *cl = claim + (size_t)s * p.maxM;
 
-    bool alive = !(pvf.flags & MOVFE_TRACK_COVERAGE);  // :258-262 coverage tracks go to the host LK step
-    int4 sl = make_int4(-1, -1, -1, -1);
-    if (alive) {
-        const int x = (int)pvf.pt_x, y = (int)pvf.pt_y;  // :264
-        if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
-        else sl = __ldg(&g[(size_t)y * p.W + x]);
-    }
-    if (alive && sl.x == -1) alive = false;  // :265-268
-    if (!alive) {
-        if (lane == 0) *dst = out;
-        return;
-    }
-    const int mw = pvf.mb.w, mh = pvf.mb.h;
-    const float hw = (float)(mw / 2), hh = (float)(mh / 2);
-    int indx = sl.x;  // :270
-    uint32_t best_desc[8];
-    bool have_best = false;
-    if (sl.y >= 0) {  // :272 (MV-only mode: every distance is 0, so the first in-bounds candidate wins)
-        int bestDesc = 256;
+    for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n_prev; c += gridDim.x * CAND_WARPS) {
+        const int i = c * 32 + lane;  // sorted rank
+        // ---- thread level: the track's own chain ------------------------------------------------------------------
+        const bool act = i < n_prev;
+        int oidx = 0;
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+        if (act) {
+            oidx = ord[i];
+            const uint4 *tp = reinterpret_cast<const uint4 *>(prev + oidx);
+            a0 = __ldg(tp);      // pt_x, pt_y, mb.x | mb.y << 16, mb.w | mb.h << 16
+            a1 = __ldg(tp + 1);  // track_id, age, q_indx, flags
+        }
+        const float ptx = __uint_as_float(a0.x), pty = __uint_as_float(a0.y);
+        const int mw = (int16_t)(a0.w & 0xffffu), mh = (int16_t)(a0.w >> 16);
+        bool alive = act && !(a1.w & MOVFE_TRACK_COVERAGE);  // :258-262 coverage tracks go to the host LK step
+        int4 sl = make_int4(-1, -1, -1, -1);
+        if (alive) {
+            const int x = (int)ptx, y = (int)pty;  // :264
+            if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
+            else sl = __ldg(&g[(size_t)y * p.W + x]);
+        }
+        if (sl.x == -1) alive = false;  // :265-268
         const int sj[4] = {sl.x, sl.y, sl.z, sl.w};
+        bool vj[4];
+        vj[0] = alive;
+#pragma unroll
+        for (int j = 1; j < 4; j++) vj[j] = vj[j - 1] && sj[j] != -1;  // :277-278 stop at the first empty slot
+        int4 hv[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) hv[j] = vj[j] ? __ldg(reinterpret_cast<const int4 *>(hp + sj[j])) : make_int4(0, 0, -1, 0);
+        const float hw = (float)(mw / 2), hh = (float)(mh / 2);
+        float px[4], py[4];
+        int mxy[4];
+        unsigned need = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (sj[j] == -1) break;  // :277-278
-            const movfe_hop mv = hp[sj[j]];
-            const float px = __fadd_rn(pvf.pt_x, mv.mv_x), py = __fadd_rn(pvf.pt_y, mv.mv_y);  // :283
-            const int mx = (int)__fsub_rn(px, hw), my = (int)__fsub_rn(py, hh);                // :284
-            if (rect_in_bounds(mx, my, mw, mh, p.W, p.H)) {                                    // :286
-                uint32_t d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                int dist = 0;
-                if (img) {
-                    const uint8_t *roi = img + (size_t)my * p.W + mx;
-                    const Band bd = express_band(roi, p.W, mh, mw, p.thr);
-                    express_mask(roi, p.W, mh, mw, bd, 1, false, d, lane);
-                    dist = hamming256(pvf.desc, d);
-                }
-                if (dist < bestDesc) {  // :292-296
-                    bestDesc = dist;
-                    indx = sj[j];
-                    have_best = img != nullptr;
+            px[j] = __fadd_rn(ptx, __int_as_float(hv[j].x));  // :283
+            py[j] = __fadd_rn(pty, __int_as_float(hv[j].y));
+            const int mx = (int)__fsub_rn(px[j], hw), my = (int)__fsub_rn(py[j], hh);  // :284
+            mxy[j] = (int)((uint32_t)(mx & 0xffff) | ((uint32_t)my << 16));
+            if (vj[j] && rect_in_bounds(mx, my, mw, mh, p.W, p.H)) need |= 1u << j;  // :286
+        }
+        // chosen candidate when no descriptor is involved: single-candidate pixels keep slot 0 (:270); with several
+        // candidates and a flat image every distance is 0, so the first in-bounds one wins
+        int chosen = (!img && sl.y >= 0 && need) ? __ffs(need) - 1 : 0;
+        const bool warp_job = alive && need != 0 && img != nullptr;
+        if (warp_job) {
 #pragma unroll
-                    for (int k = 0; k < 8; k++) best_desc[k] = d[k];
-                }
+            for (int j = 0; j < 4; j++) sm[warp][CW_MXY + j][lane] = mxy[j];
+            sm[warp][CW_INFO][lane] = (int)need | (mw << 8) | (mh << 16);
+            sm[warp][CW_OIDX][lane] = oidx;
+        }
+        __syncwarp();
+        // ---- warp level: descriptors of the candidate patches -------------------------------------------------------
+        uint32_t my_d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int my_best = 0;
+        unsigned todo = __ballot_sync(0xffffffffu, warp_job);
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1;
+            int cm[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cm[j] = sm[warp][CW_MXY + j][t];
+            const int info = sm[warp][CW_INFO][t];
+            const unsigned nd = info & 0xf;
+            const int tw = (info >> 8) & 0xff, th = info >> 16;
+            const uint4 *dp = reinterpret_cast<const uint4 *>(prev + sm[warp][CW_OIDX][t]) + 2;
+            const uint4 p0 = __ldg(dp), p1 = __ldg(dp + 1);
+            const uint32_t pd[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            uint32_t bd[8];
+            int best, ch;
+            if (tw == 16 && th == 16) ch = cand_eval<16, 16>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
+            else if (tw == 8 && th == 8) ch = cand_eval<8, 8>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
+            else if (tw == 8 && th == 16) ch = cand_eval<16, 8>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
+            else if (tw == 16 && th == 8) ch = cand_eval<8, 16>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
+            else ch = cand_eval_generic(img, p.W, p.thr, tw, th, cm, nd, pd, lane, bd, best);
+            if (lane == t) {
+                // single-candidate pixels never compare (:272): slot 0 stays chosen; its descriptor is the one evaluated
+                if (sl.y >= 0 && ch >= 0) chosen = ch;
+                my_best = best;
+#pragma unroll
+                for (int k = 0; k < 8; k++) my_d[k] = bd[k];
             }
         }
-    }
-    const movfe_hop mv = hp[indx];  // :301
-    const float px = __fadd_rn(pvf.pt_x, mv.mv_x), py = __fadd_rn(pvf.pt_y, mv.mv_y);
-    const int mx = (int)__fsub_rn(px, hw), my = (int)__fsub_rn(py, hh);
-    out.pt_x = px;
-    out.pt_y = py;
-    out.mb.x = (int16_t)mx;
-    out.mb.y = (int16_t)my;
-    out.d_indx = mv.d_indx;
-    if (rect_in_bounds(mx, my, mw, mh, p.W, p.H)) {  // :306 (the claim test itself happens in finalize)
-        out.flags |= 1u;
-        if (img) {
-            uint32_t d[8];
-            if (have_best) {  // indx is the candidate whose descriptor won the comparison: same rectangle, reuse it
+        __syncwarp();
+        // ---- thread level: move, bounds, gate, claim (:301-316) -------------------------------------------------------
+        if (act) {
+            float cx = px[0], cy = py[0];
+            int cxy = mxy[0], cd = hv[0].z;
 #pragma unroll
-                for (int k = 0; k < 8; k++) d[k] = best_desc[k];
-            } else {  // single-candidate pixel: no descriptor was evaluated yet
-                const uint8_t *roi = img + (size_t)my * p.W + mx;
-                const Band bd = express_band(roi, p.W, mh, mw, p.thr);
-                express_mask(roi, p.W, mh, mw, bd, 1, false, d, lane);
+            for (int j = 1; j < 4; j++)
+                if (chosen == j) {
+                    cx = px[j];
+                    cy = py[j];
+                    cxy = mxy[j];
+                    cd = hv[j].z;
+                }
+            const bool inb = alive && ((need >> chosen) & 1u);  // :306 (the claim test itself happens in finalize)
+            int fl = 0;
+            if (inb) {
+                fl = 1;
+                // with an image the chosen candidate's descriptor was evaluated above (need bit set => warp job)
+                if (!img || my_best <= 40) fl |= 2;  // :311-316
+                uint4 *o = reinterpret_cast<uint4 *>(st + i);
+                o[0] = make_uint4(__float_as_uint(cx), __float_as_uint(cy), (uint32_t)cxy, a0.w);
+                o[1] = make_uint4(a1.x, a1.y + 1, (uint32_t)i, 0u);  // trackId, age + 1, qIndx, flags
+                o[2] = make_uint4(my_d[0], my_d[1], my_d[2], my_d[3]);
+                o[3] = make_uint4(my_d[4], my_d[5], my_d[6], my_d[7]);
+                if (cd >= 0 && cd < p.maxM) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
             }
-            const int dist = hamming256(pvf.desc, d);  // :311-316
-            if (dist <= 40) out.flags |= 2u;
-#pragma unroll
-            for (int k = 0; k < 8; k++) out.desc[k] = d[k];
-        } else {
-            out.flags |= 2u;  // MV-only mode: flat image, every distance is 0
+            ci[i] = make_int2(alive ? cd : -1, fl);
         }
-        if (lane == 0 && mv.d_indx >= 0 && mv.d_indx < p.maxM)
-            atomicMin(&claim[(size_t)s * p.maxM + mv.d_indx], i);  // first-come in sorted order (:306-309)
     }
-    if (lane == 0) *dst = out;
 }
 
 // ------------------------------------------------------------------------------------------ birth_kernel -----
-__global__ void __launch_bounds__(CAND_WARPS * 32)
+// compute_express (EXPRESS.h:117-192) + descriptor of one block from ONE pass over its 17 columns: the true block mask
+// (diagonal walk) and the p++-shifted mask (pre-check, descriptor) differ by one column.
+template <int ROWS, int COLS>
+__device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ roi, int stride, int thr, uint32_t *smem8, int lane,
+                                              uint32_t (&desc)[8]) {
+    constexpr int IT = ROWS * COLS / 32;
+    int v0[IT], cen[4];
+    patch_issue<ROWS, COLS>(roi, stride, 0, lane, v0, cen);
+    const int vx = lane < ROWS ? (int)roi[lane * stride + COLS] : 0;  // column COLS: in bounds because x + w < cols (:388)
+    const Band bd = band_of(cen, thr);
+    uint32_t m0[IT], m1[IT];
+    patch_words<IT>(v0, bd, m0);
+    const unsigned cx = __ballot_sync(0xffffffffu, lane < ROWS && (bd.low > vx || bd.high < vx));
+    int f = 0;
+#pragma unroll
+    for (int it = 0; it < IT; it++) {
+        if (COLS == 16) {
+            m1[it] = ((m0[it] >> 1) & 0x7fff7fffu) | (((cx >> (2 * it)) & 1u) << 15) | (((cx >> (2 * it + 1)) & 1u) << 31);
+        } else {
+            m1[it] = (m0[it] >> 1) & 0x7f7f7f7fu;
+#pragma unroll
+            for (int k = 0; k < 4; k++) m1[it] |= ((cx >> (4 * it + k)) & 1u) << (8 * k + 7);
+        }
+        f += __popc(m1[it]);
+    }
+    // pre-check (:122-139): the running count only grows and is tested per row, so "reaches precheck at some row end" ==
+    // "total >= precheck" (the uint8 counter cannot wrap before the break)
+    constexpr int precheck = ROWS * COLS / 8;
+    if (f < precheck) return false;
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < IT; it++)
+        if (lane == it) smem8[it] = m0[it];
+    __syncwarp();
+    constexpr int slices = ROWS + COLS - 1;
+    constexpr int rounds = slices == 31 ? 8 : slices == 23 ? 6 : 4;  // roundf(slices * .25f)
+    constexpr uint32_t valid = slices >= 32 ? 0xffffffffu : ((1u << slices) - 1u);
+    bool ok = false;
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+        const bool direction = a == 0;
+        bool winbit = false;
+        if (lane < slices) {
+            const int d = lane;
+            const int len = min(min(d + 1, ROWS), min(COLS, slices - d));
+            const int r0 = max(ROWS - 1 - d, 0);
+            const int c1 = max(0, d - (ROWS - 1));
+            const int c0 = direction ? c1 : COLS - 1 - c1;
+            const int dc = direction ? 1 : -1;
+            int win = 0;
+            for (int r = 0; r < len; r++) {
+                const int bit = (r0 + r) * COLS + (c0 + dc * r);
+                win += (smem8[bit >> 5] >> (bit & 31)) & 1u;
+            }
+            winbit = win >= len - win;
+        }
+        const uint32_t wb = __ballot_sync(0xffffffffu, winbit) & valid;
+        if (has_run(wb, rounds) && has_run(~wb & valid, rounds)) ok = true;
+    }
+    __syncwarp();
+    if (ok) desc_layout<ROWS, COLS>(m1, desc);
+    return ok;
+}
+
+__global__ void __launch_bounds__(CAND_THREADS)
 birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
              const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
              uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
     __shared__ uint32_t scratch[CAND_WARPS][8];
+    __shared__ int sm[CAND_WARPS][2][32];
     const int s = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = nkps[s * p.n_in + p.fi];
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;
-    for (int i = blockIdx.x * CAND_WARPS + warp; i < n; i += gridDim.x * CAND_WARPS) {
-    bool pass = false;
-    const movfe_rect mb = kps[((size_t)s * p.n_out + p.fi) * p.max_kps + i];
-    const bool claimed = i < p.maxM && claim[(size_t)s * p.maxM + i] != 0x7fffffff;  // lbFound[i] (:381)
-    uint32_t d[8];
-    if (!claimed && rect_in_bounds(mb.x, mb.y, mb.w, mb.h, p.W, p.H)) {  // :388
-        const uint8_t *roi = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H) + (size_t)mb.y * p.W + mb.x;
-        if (express_test(roi, p.W, mb.h, mb.w, p.thr, scratch[warp], lane)) {  // :391
-            const Band bd = express_band(roi, p.W, mb.h, mb.w, p.thr);
-            express_mask(roi, p.W, mb.h, mb.w, bd, 1, false, d, lane);
-            pass = true;
+    const uint8_t *img = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H);
+    const movfe_rect *kp = kps + ((size_t)s * p.n_out + p.fi) * p.max_kps;
+    for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n; c += gridDim.x * CAND_WARPS) {
+        const int i = c * 32 + lane;
+        // thread level: which blocks are unclaimed and inside the image (:381,:388)
+        bool job = false;
+        int2 r = make_int2(0, 0);
+        if (i < n) {
+            r = __ldg(reinterpret_cast<const int2 *>(kp + i));  // x | y << 16, w | h << 16
+            const int x = (int16_t)(r.x & 0xffff), y = r.x >> 16, w = (int16_t)(r.y & 0xffff), h = r.y >> 16;
+            const bool claimed = i < p.maxM && claim[(size_t)s * p.maxM + i] != 0x7fffffff;  // lbFound[i]
+            job = !claimed && rect_in_bounds(x, y, w, h, p.W, p.H);
+            birth_flag[(size_t)s * p.max_kps + i] = 0;
         }
-    }
-    if (lane == 0) birth_flag[(size_t)s * p.max_kps + i] = pass ? 1 : 0;
-    if (pass) {
+        sm[warp][0][lane] = r.x;
+        sm[warp][1][lane] = r.y;
+        __syncwarp();
+        unsigned todo = __ballot_sync(0xffffffffu, job);
+        while (todo) {
+            const int t = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int rx = sm[warp][0][t], ry = sm[warp][1][t];
+            const int x = (int16_t)(rx & 0xffff), y = rx >> 16, w = (int16_t)(ry & 0xffff), h = ry >> 16;
+            const uint8_t *roi = img + (size_t)y * p.W + x;
+            uint32_t d[8];
+            bool pass;
+            if (w == 16 && h == 16) pass = express_birth<16, 16>(roi, p.W, p.thr, scratch[warp], lane, d);
+            else if (w == 8 && h == 8) pass = express_birth<8, 8>(roi, p.W, p.thr, scratch[warp], lane, d);
+            else if (w == 8 && h == 16) pass = express_birth<16, 8>(roi, p.W, p.thr, scratch[warp], lane, d);
+            else if (w == 16 && h == 8) pass = express_birth<8, 16>(roi, p.W, p.thr, scratch[warp], lane, d);
+            else {
+                pass = express_test(roi, p.W, h, w, p.thr, scratch[warp], lane);  // :391
+                if (pass) express_mask(roi, p.W, h, w, express_band(roi, p.W, h, w, p.thr), 1, false, d, lane);
+            }
+            if (pass) {
+                const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
+                if (lane == 0) birth_flag[o] = 1;
 #pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (lane == k) birth_desc[((size_t)s * p.max_kps + i) * 8 + k] = d[k];
-    }
+                for (int k = 0; k < 8; k++)
+                    if (lane == k) birth_desc[o * 8 + k] = d[k];
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -414,45 +650,158 @@ __device__ __forceinline__ int popc256(const uint32_t d[8]) {
     return c;
 }
 
-// Stable (age desc, popcount desc) order of a table: bitonic sort of unique 64-bit keys in shared memory.
-__device__ void sort_table(const movfe_track *__restrict__ tab, int n, unsigned long long *keys, uint16_t *__restrict__ order_out) {
-    int N = 1;
-    while (N < n) N <<= 1;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        unsigned long long k = ~0ull;
-        if (i < n) {
-            const movfe_track &t = tab[i];
-            const uint32_t a = 0x7fffffffu - (uint32_t)max(t.age, 0);
-            k = ((unsigned long long)a << 32) | ((unsigned long long)(256 - popc256(t.desc)) << 16) | (unsigned)i;
-        }
-        keys[i] = k;
+// Sort key of table entry `idx`: the reference orders prev->mvVF by age descending, then descriptor popcount descending
+// (MOVExtractor.cc:249-252), canonicalised to a stable sort — ascending unique 64-bit keys.
+__device__ __forceinline__ unsigned long long sort_key(int age, int popc, int idx) {
+    const uint32_t a = 0x7fffffffu - (uint32_t)max(age, 0);
+    return ((unsigned long long)a << 32) | ((unsigned long long)(256 - popc) << 16) | (unsigned)idx;
+}
+
+constexpr int SORT_MIN_N = 256;  // keys are padded to at least this many (one full warp at E = 8)
+
+// Bitonic sort (ascending) of N = 2^m >= SORT_MIN_N unique 64-bit keys in shared memory by the whole CTA. Thread t owns
+// the E consecutive keys [tE, tE+E): compare-exchange steps with partner distance j < E stay in registers, j < 32E go
+// through warp shuffles, only the rest (15 of 78 steps at N = 4096) goes through shared memory and a barrier.
+template <int E>
+__device__ void bitonic_sort(unsigned long long *keys, int N) {
+    const int t = threadIdx.x, lane = t & 31;
+    const bool act = t * E < N;  // whole warps (N >= 32E)
+    unsigned long long k[E];
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < E; e++) k[e] = keys[t * E + e];
     }
-    __syncthreads();
-    for (int k = 2; k <= N; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < N; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        keys[i] = b;
-                        keys[ixj] = a;
+    for (int kk = 2; kk <= N; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            if (j < E) {
+                if (act) {
+#pragma unroll
+                    for (int jj = E >> 1; jj > 0; jj >>= 1) {
+                        if (j == jj) {
+#pragma unroll
+                            for (int e = 0; e < E; e++) {
+                                if ((e & jj) == 0) {
+                                    const bool up = ((t * E + e) & kk) == 0;
+                                    const unsigned long long a = k[e], b = k[e | jj];
+                                    if ((a > b) == up) {
+                                        k[e] = b;
+                                        k[e | jj] = a;
+                                    }
+                                }
+                            }
+                        }
                     }
                 }
+            } else if (j < 32 * E) {
+                if (act) {
+                    const int lj = j / E;
+                    const bool keep_min = ((lane & lj) == 0) == (((t * E) & kk) == 0);
+#pragma unroll
+                    for (int e = 0; e < E; e++) {
+                        const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[e], lj);
+                        k[e] = keep_min ? (k[e] < o ? k[e] : o) : (k[e] > o ? k[e] : o);
+                    }
+                }
+            } else {
+                if (act) {
+#pragma unroll
+                    for (int e = 0; e < E; e++) keys[t * E + e] = k[e];
+                }
+                __syncthreads();
+                if (act) {
+                    const int tj = j / E;
+                    const bool keep_min = ((t & tj) == 0) == (((t * E) & kk) == 0);
+                    const unsigned long long *o = keys + (t ^ tj) * E;
+#pragma unroll
+                    for (int e = 0; e < E; e++) k[e] = keep_min ? (k[e] < o[e] ? k[e] : o[e]) : (k[e] > o[e] ? k[e] : o[e]);
+                }
+                __syncthreads();
             }
-            __syncthreads();
         }
     }
+    if (act) {
+#pragma unroll
+        for (int e = 0; e < E; e++) keys[t * E + e] = k[e];
+    }
+    __syncthreads();
+}
+
+// Sorts keys[0..n) (already filled; n <= capacity of the shared array) and writes the permutation.
+__device__ void sort_keys(unsigned long long *keys, int n, uint16_t *__restrict__ order_out) {
+    int N = SORT_MIN_N;
+    while (N < n) N <<= 1;
+    for (int i = n + threadIdx.x; i < N; i += blockDim.x) keys[i] = ~0ull;
+    __syncthreads();
+    if (N <= 4 * FIN_THREADS) bitonic_sort<4>(keys, N);
+    else bitonic_sort<8>(keys, N);
     for (int i = threadIdx.x; i < n; i += blockDim.x) order_out[i] = (uint16_t)(keys[i] & 0xffffu);
     __syncthreads();
 }
 
+// keys of entries [from, n) from the table in global memory (entries written outside the fused copy paths)
+__device__ void fill_keys(const movfe_track *__restrict__ tab, int from, int n, unsigned long long *keys) {
+    for (int i = from + threadIdx.x; i < n; i += blockDim.x) {
+        const movfe_track &t = tab[i];
+        keys[i] = sort_key(t.age, popc256(t.desc), i);
+    }
+    __syncthreads();
+}
+
+// 16-px lattice walk shared by the coverage back-fill (:418-451) and the I-frame seeding (:123-157).
+__device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img, const int4 *__restrict__ g, bool need_uncovered,
+                             uint32_t track_flags, movfe_track *__restrict__ cur, int &n_out, int &id, uint32_t (*scratch)[8],
+                             int *lat_flag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gw = (p.W - 16 + 15) / 16, gh = (p.H - 16 + 15) / 16;  // x = 8,24,.. < W-8
+    const int nb = gw * gh;
+    for (int base = 0; base < nb; base += FIN_WARPS) {
+        const int b = base + warp;
+        bool pass = false;
+        uint32_t d[8];
+        int x = 0, y = 0;
+        if (b < nb) {
+            y = 8 + 16 * (b / gw);
+            x = 8 + 16 * (b % gw);
+            if (rect_in_bounds(x - 8, y - 8, 16, 16, p.W, p.H)) {
+                const uint8_t *roi = img + (size_t)(y - 8) * p.W + (x - 8);
+                if (express_birth<16, 16>(roi, p.W, p.thr, scratch[warp], lane, d) &&
+                    !(need_uncovered && __ldg(&g[(size_t)y * p.W + x]).x >= 0))
+                    pass = true;
+            }
+        }
+        if (lane == 0) lat_flag[warp] = pass;
+        __syncthreads();
+        int before = 0, tot = 0;
+        for (int w = 0; w < FIN_WARPS; w++) {
+            before += w < warp ? lat_flag[w] : 0;
+            tot += lat_flag[w];
+        }
+        if (pass && n_out + before < p.maxT && lane == 0) {
+            movfe_track t;
+            t.pt_x = (float)x;
+            t.pt_y = (float)y;
+            t.mb = {(int16_t)(x - 8), (int16_t)(y - 8), 16, 16};
+            t.track_id = id + before + 1;
+            t.age = 0;
+            t.q_indx = -1;
+            t.flags = track_flags;
+#pragma unroll
+            for (int k = 0; k < 8; k++) t.desc[k] = d[k];
+            cur[n_out + before] = t;
+        }
+        n_out += tot;
+        id += tot;
+        __syncthreads();
+    }
+}
+
+constexpr int FIN_IPT = 8;  // consecutive entries a thread owns per round of the ordered compactions
+
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restrict__ ntracks,
-                int32_t *__restrict__ cur_id, uint16_t *__restrict__ order, const Cand *__restrict__ cand,
-                int32_t *__restrict__ claim, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
-                const double *__restrict__ cov, const uint8_t *__restrict__ birth_flag,
+                int32_t *__restrict__ cur_id, uint16_t *__restrict__ order, const movfe_track *__restrict__ stage,
+                const int2 *__restrict__ cinfo, int32_t *__restrict__ claim, const movfe_rect *__restrict__ kps,
+                const int32_t *__restrict__ nkps, const double *__restrict__ cov, const uint8_t *__restrict__ birth_flag,
                 const uint32_t *__restrict__ birth_desc, const int4 *__restrict__ grid,
                 const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags) {
     extern __shared__ unsigned long long keys[];
@@ -460,181 +809,118 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     __shared__ uint32_t scratch[FIN_WARPS][8];
     __shared__ int lat_flag[FIN_WARPS];
     const int s = blockIdx.x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
     movfe_track *cur = tracks + ((size_t)s * p.TSLOTS + p.tslot_cur) * p.maxT;
-    const uint16_t *ord = order + (size_t)s * p.maxT;
-    const Cand *cd = cand + (size_t)s * p.maxT;
+    const movfe_track *st = stage + (size_t)s * p.maxT;
+    const int2 *ci = cinfo + (size_t)s * p.maxT;
     int32_t *cl = claim + (size_t)s * p.maxM;
     const int n_prev = ntracks[s * p.TSLOTS + p.tslot_prev];
     const uint8_t ff = fflags[s * p.RING + p.gslot];
     const bool is_p = ff & MOVFE_FRAME_P;
     const int n_kps = nkps[s * p.n_in + p.fi];
     int id = cur_id[s * p.TSLOTS + p.tslot_prev];
-    int n_out = 0;  // logical size of the new table (entries beyond maxT are dropped)
+    int n_out = 0;    // logical size of the new table (entries beyond maxT are dropped)
+    int n_keyed = 0;  // entries whose sort key is already in shared memory
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H) : nullptr;
     const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
 
     if (is_p) {
-        // survivors in sorted order (:254-334)
-        for (int base = 0; base < n_prev; base += FIN_THREADS) {
-            const int i = base + threadIdx.x;
-            bool acc = false;
-            Cand c;
-            if (i < n_prev) {
-                c = cd[i];
-                const bool mine = c.d_indx < 0 || c.d_indx >= p.maxM || cl[c.d_indx] == i;  // !lbFound at my turn
-                acc = (c.flags & 1u) && mine && (c.flags & 2u);
+        // survivors in sorted order (:254-334): a thread owns FIN_IPT consecutive ranks, so one block scan orders a round
+        for (int base = 0; base < n_prev; base += FIN_THREADS * FIN_IPT) {
+            const int i0 = base + threadIdx.x * FIN_IPT;
+            int2 c[FIN_IPT];
+#pragma unroll
+            for (int e = 0; e < FIN_IPT; e++) c[e] = i0 + e < n_prev ? ci[i0 + e] : make_int2(-1, 0);
+            unsigned accm = 0;
+#pragma unroll
+            for (int e = 0; e < FIN_IPT; e++) {
+                if ((c[e].y & 3) == 3) {  // in bounds and through the descriptor gate
+                    const bool mine = c[e].x < 0 || c[e].x >= p.maxM || cl[c[e].x] == i0 + e;  // !lbFound at my turn
+                    if (mine) accm |= 1u << e;
+                }
             }
             int tot;
-            const int pos = n_out + block_excl_scan(acc ? 1 : 0, wsum, tot);
-            if (acc && pos < p.maxT) {
-                const movfe_track &pv = prev[ord[i]];
-                movfe_track t;
-                t.pt_x = c.pt_x;
-                t.pt_y = c.pt_y;
-                t.mb = c.mb;
-                t.track_id = pv.track_id;
-                t.age = pv.age + 1;
-                t.q_indx = i;
-                t.flags = 0;
+            int pos = n_out + block_excl_scan(__popc(accm), wsum, tot);  // barriers: every claim test is done
 #pragma unroll
-                for (int k = 0; k < 8; k++) t.desc[k] = c.desc[k];
-                cur[pos] = t;
+            for (int e = 0; e < FIN_IPT; e++) {
+                if ((c[e].y & 1) && c[e].x >= 0 && c[e].x < p.maxM) cl[c[e].x] = 0x7fffffff;  // claims are per frame
+                if ((accm >> e) & 1u) {
+                    if (pos < p.maxT) {
+                        const uint4 *src = reinterpret_cast<const uint4 *>(st + i0 + e);
+                        const uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3];
+                        uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
+                        dst[0] = r0;
+                        dst[1] = r1;
+                        dst[2] = r2;
+                        dst[3] = r3;
+                        const int pc = __popc(r2.x) + __popc(r2.y) + __popc(r2.z) + __popc(r2.w) + __popc(r3.x) + __popc(r3.y) +
+                                       __popc(r3.z) + __popc(r3.w);
+                        keys[pos] = sort_key((int)r1.y, pc, pos);
+                    }
+                    pos++;
+                }
             }
             n_out += tot;
         }
         // births in kps order (:379-416)
         int mov_cnt = 0;
         if (img) {
-            for (int base = 0; base < n_kps; base += FIN_THREADS) {
-                const int i = base + threadIdx.x;
-                const bool b = i < n_kps && birth_flag[(size_t)s * p.max_kps + i];
-                int tot;
-                const int r = block_excl_scan(b ? 1 : 0, wsum, tot);
-                if (b && n_out + r < p.maxT) {
-                    const movfe_rect mb = kps[((size_t)s * p.n_out + p.fi) * p.max_kps + i];
-                    movfe_track t;
-                    // (mb.br() + mb.tl()) * 0.5 on Point_<int>: saturate_cast<int>(double) rounds half to even (:385)
-                    t.pt_x = (float)__double2int_rn((mb.x + mb.w + mb.x) * 0.5);
-                    t.pt_y = (float)__double2int_rn((mb.y + mb.h + mb.y) * 0.5);
-                    t.mb = mb;
-                    t.track_id = id + r + 1;  // ++mCurrentId
-                    t.age = 0;
-                    t.q_indx = -1;
-                    t.flags = 0;
+            const movfe_rect *kp = kps + ((size_t)s * p.n_out + p.fi) * p.max_kps;
+            const uint8_t *bf = birth_flag + (size_t)s * p.max_kps;
+            for (int base = 0; base < n_kps; base += FIN_THREADS * FIN_IPT) {
+                const int i0 = base + threadIdx.x * FIN_IPT;
+                unsigned bm = 0;
 #pragma unroll
-                    for (int k = 0; k < 8; k++) t.desc[k] = birth_desc[((size_t)s * p.max_kps + i) * 8 + k];
-                    cur[n_out + r] = t;
+                for (int e = 0; e < FIN_IPT; e++)
+                    if (i0 + e < n_kps && bf[i0 + e]) bm |= 1u << e;
+                int tot;
+                int r = block_excl_scan(__popc(bm), wsum, tot);
+#pragma unroll
+                for (int e = 0; e < FIN_IPT; e++) {
+                    if ((bm >> e) & 1u) {
+                        const int pos = n_out + r;
+                        if (pos < p.maxT) {
+                            const int i = i0 + e;
+                            const movfe_rect mb = kp[i];
+                            const uint4 *dp = reinterpret_cast<const uint4 *>(birth_desc + ((size_t)s * p.max_kps + i) * 8);
+                            const uint4 d0 = dp[0], d1 = dp[1];
+                            // (mb.br() + mb.tl()) * 0.5 on Point_<int>: saturate_cast<int>(double) rounds half to even (:385)
+                            const float fx = (float)__double2int_rn((mb.x + mb.w + mb.x) * 0.5);
+                            const float fy = (float)__double2int_rn((mb.y + mb.h + mb.y) * 0.5);
+                            uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
+                            dst[0] = make_uint4(__float_as_uint(fx), __float_as_uint(fy), (uint32_t)(uint16_t)mb.x | ((uint32_t)(uint16_t)mb.y << 16),
+                                                (uint32_t)(uint16_t)mb.w | ((uint32_t)(uint16_t)mb.h << 16));
+                            dst[1] = make_uint4((uint32_t)(id + r + 1), 0u, (uint32_t)-1, 0u);  // ++mCurrentId, age 0, qIndx -1
+                            dst[2] = d0;
+                            dst[3] = d1;
+                            const int pc = __popc(d0.x) + __popc(d0.y) + __popc(d0.z) + __popc(d0.w) + __popc(d1.x) + __popc(d1.y) +
+                                           __popc(d1.z) + __popc(d1.w);
+                            keys[pos] = sort_key(0, pc, pos);
+                        }
+                        r++;
+                    }
                 }
                 n_out += tot;
                 id += tot;
                 mov_cnt += tot;
             }
         }
-        // reset the claims this frame used (own kps only) for the next frame
-        for (int i = threadIdx.x; i < p.maxM; i += FIN_THREADS) cl[i] = 0x7fffffff;
-        // lattice pass: coverage back-fill (:418-451); I-frame seeding below shares the walker
-        const bool backfill = img && (cov[s * p.n_in + p.fi] < p.cov_thr || mov_cnt < 60);
-        if (backfill) {
-            const int gw = (p.W - 16 + 15) / 16, gh = (p.H - 16 + 15) / 16;  // x = 8,24,.. < W-8
-            const int nb = gw * gh;
-            for (int base = 0; base < nb; base += FIN_WARPS) {
-                const int b = base + warp;
-                bool pass = false;
-                uint32_t d[8];
-                int x = 0, y = 0;
-                if (b < nb) {
-                    y = 8 + 16 * (b / gw);
-                    x = 8 + 16 * (b % gw);
-                    if (rect_in_bounds(x - 8, y - 8, 16, 16, p.W, p.H)) {
-                        const uint8_t *roi = img + (size_t)(y - 8) * p.W + (x - 8);
-                        if (express_test(roi, p.W, 16, 16, p.thr, scratch[warp], lane) && !(__ldg(&g[(size_t)y * p.W + x]).x >= 0)) {
-                            const Band bd = express_band(roi, p.W, 16, 16, p.thr);
-                            express_mask(roi, p.W, 16, 16, bd, 1, false, d, lane);
-                            pass = true;
-                        }
-                    }
-                }
-                if (lane == 0) lat_flag[warp] = pass;
-                __syncthreads();
-                int before = 0, tot = 0;
-                for (int w = 0; w < FIN_WARPS; w++) {
-                    before += w < warp ? lat_flag[w] : 0;
-                    tot += lat_flag[w];
-                }
-                if (pass && n_out + before < p.maxT && lane == 0) {
-                    movfe_track t;
-                    t.pt_x = (float)x;
-                    t.pt_y = (float)y;
-                    t.mb = {(int16_t)(x - 8), (int16_t)(y - 8), 16, 16};
-                    t.track_id = id + before + 1;
-                    t.age = 0;
-                    t.q_indx = -1;
-                    t.flags = MOVFE_TRACK_COVERAGE;
-#pragma unroll
-                    for (int k = 0; k < 8; k++) t.desc[k] = d[k];
-                    cur[n_out + before] = t;
-                }
-                n_out += tot;
-                id += tot;
-                __syncthreads();
-            }
-        }
+        n_keyed = min(n_out, p.maxT);
+        // coverage back-fill (:418-451)
+        if (img && (cov[s * p.n_in + p.fi] < p.cov_thr || mov_cnt < 60))
+            lattice_pass(p, img, g, true, MOVFE_TRACK_COVERAGE, cur, n_out, id, scratch, lat_flag);
     } else if (n_prev == 0 && img) {
         // I frame without previous features: seeding on the 16-px lattice (:123-157). With previous features the
         // reference carries them by LK (:81-120) — host work, dropped here.
-        const int gw = (p.W - 16 + 15) / 16, gh = (p.H - 16 + 15) / 16;
-        const int nb = gw * gh;
-        for (int base = 0; base < nb; base += FIN_WARPS) {
-            const int b = base + warp;
-            bool pass = false;
-            uint32_t d[8];
-            int x = 0, y = 0;
-            if (b < nb) {
-                y = 8 + 16 * (b / gw);
-                x = 8 + 16 * (b % gw);
-                if (rect_in_bounds(x - 8, y - 8, 16, 16, p.W, p.H)) {
-                    const uint8_t *roi = img + (size_t)(y - 8) * p.W + (x - 8);
-                    if (express_test(roi, p.W, 16, 16, p.thr, scratch[warp], lane)) {
-                        const Band bd = express_band(roi, p.W, 16, 16, p.thr);
-                        express_mask(roi, p.W, 16, 16, bd, 1, false, d, lane);
-                        pass = true;
-                    }
-                }
-            }
-            if (lane == 0) lat_flag[warp] = pass;
-            __syncthreads();
-            int before = 0, tot = 0;
-            for (int w = 0; w < FIN_WARPS; w++) {
-                before += w < warp ? lat_flag[w] : 0;
-                tot += lat_flag[w];
-            }
-            if (pass && n_out + before < p.maxT && lane == 0) {
-                movfe_track t;
-                t.pt_x = (float)x;
-                t.pt_y = (float)y;
-                t.mb = {(int16_t)(x - 8), (int16_t)(y - 8), 16, 16};
-                t.track_id = id + before + 1;
-                t.age = 0;
-                t.q_indx = -1;
-                t.flags = 0;
-#pragma unroll
-                for (int k = 0; k < 8; k++) t.desc[k] = d[k];
-                cur[n_out + before] = t;
-            }
-            n_out += tot;
-            id += tot;
-            __syncthreads();
-        }
+        lattice_pass(p, img, g, false, 0u, cur, n_out, id, scratch, lat_flag);
     }
     const int n_new = min(n_out, p.maxT);
     if (threadIdx.x == 0) {
         ntracks[s * p.TSLOTS + p.tslot_cur] = n_new;
         cur_id[s * p.TSLOTS + p.tslot_cur] = id;
     }
-    __syncthreads();  // cur[] writes visible to the whole CTA before the sort reads them
-    sort_table(cur, n_new, keys, order + (size_t)s * p.maxT);
+    __syncthreads();  // cur[] and keys[] writes visible to the whole CTA
+    fill_keys(cur, n_keyed, n_new, keys);
+    sort_keys(keys, n_new, order + (size_t)s * p.maxT);
 }
 
 // Sorts a table that was installed from the host (movfe_set_tracks).
@@ -643,7 +929,9 @@ sort_only_kernel(int maxT, int TSLOTS, int tslot, int stream, const movfe_track 
                  const int32_t *__restrict__ ntracks, uint16_t *__restrict__ order) {
     extern __shared__ unsigned long long keys[];
     const int s = stream;
-    sort_table(tracks + ((size_t)s * TSLOTS + tslot) * maxT, ntracks[s * TSLOTS + tslot], keys, order + (size_t)s * maxT);
+    const int n = ntracks[s * TSLOTS + tslot];
+    fill_keys(tracks + ((size_t)s * TSLOTS + tslot) * maxT, 0, n, keys);
+    sort_keys(keys, n, order + (size_t)s * maxT);
 }
 
 __global__ void fill_i32(int32_t *p, size_t n, int32_t v) {
@@ -652,7 +940,8 @@ __global__ void fill_i32(int32_t *p, size_t n, int32_t v) {
 }
 
 struct ExtScratch {
-    Cand *cand;
+    movfe_track *stage;  // [S][maxT] moved tracks by sorted rank, written by cand_kernel for in-bounds tracks
+    int2 *cinfo;         // [S][maxT] {hop's kps index, bit0 in bounds | bit1 through the descriptor gate}
     int32_t *claim;
     uint8_t *birth_flag;
     uint32_t *birth_desc;
@@ -667,8 +956,10 @@ ExtScratch carve(const movfe_ctx *ctx, size_t *total) {
     uint8_t *base = (uint8_t *)ctx->d_ext_scratch;
     size_t off = 0;
     ExtScratch e;
-    e.cand = (Cand *)(base + off);
-    off += align256(S * c.max_tracks * sizeof(Cand));
+    e.stage = (movfe_track *)(base + off);
+    off += align256(S * c.max_tracks * sizeof(movfe_track));
+    e.cinfo = (int2 *)(base + off);
+    off += align256(S * c.max_tracks * sizeof(int2));
     e.claim = (int32_t *)(base + off);
     off += align256(S * c.max_records_per_frame * sizeof(int32_t));
     e.birth_flag = (uint8_t *)(base + off);
@@ -682,7 +973,7 @@ ExtScratch carve(const movfe_ctx *ctx, size_t *total) {
 }
 
 size_t sort_smem(int maxT) {
-    int N = 1;
+    int N = SORT_MIN_N;
     while (N < maxT) N <<= 1;
     return (size_t)N * sizeof(unsigned long long);
 }
@@ -740,18 +1031,18 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.cov_thr = c.coverage_threshold;
         // grid-stride over tracks / kps: enough CTAs to fill the chip, never one CTA per (mostly empty) capacity slot
         const int bps = std::max(4, (8 * ctx->sm_count + c.n_streams - 1) / c.n_streams);
-        dim3 gc(std::min((c.max_tracks + CAND_WARPS - 1) / CAND_WARPS, bps), c.n_streams);
+        dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), c.n_streams);  // a warp takes 32 tracks
         cand_kernel<<<gc, CAND_WARPS * 32, 0, ctx->stream>>>(p, ctx->d_tracks, ctx->d_ntracks, e.order, ctx->d_grid,
-                                                            ctx->d_hops, ctx->d_grey, ctx->d_fflags, e.cand, e.claim);
+                                                            ctx->d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim);
         int nl = 2;
         if (c.has_grey) {
-            dim3 gb(std::min((ctx->max_kps + CAND_WARPS - 1) / CAND_WARPS, bps), c.n_streams);
+            dim3 gb(std::min((ctx->max_kps + CAND_THREADS - 1) / CAND_THREADS, bps), c.n_streams);
             birth_kernel<<<gb, CAND_WARPS * 32, 0, ctx->stream>>>(p, ctx->d_kps, ctx->d_nkps, ctx->d_grey, ctx->d_fflags,
                                                                  e.claim, e.birth_flag, e.birth_desc);
             nl = 3;
         }
         finalize_kernel<<<c.n_streams, FIN_THREADS, sort_smem(c.max_tracks), ctx->stream>>>(
-            p, ctx->d_tracks, ctx->d_ntracks, ctx->d_cur_id, e.order, e.cand, e.claim, ctx->d_kps, ctx->d_nkps, ctx->d_cov,
+            p, ctx->d_tracks, ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, ctx->d_kps, ctx->d_nkps, ctx->d_cov,
             e.birth_flag, e.birth_desc, ctx->d_grid, ctx->d_grey, ctx->d_fflags);
         prof.launches(nl);
     }
