@@ -24,8 +24,9 @@ static cudaError_t dalloc(T **p, size_t n) {
 extern "C" void movfe_destroy(movfe_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *bufs[] = {ctx->d_stage, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected, ctx->d_cls_cnt,
+    void *bufs[] = {ctx->d_stage[0], ctx->d_stage[1], ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected, ctx->d_cls_cnt,
                     ctx->d_area, ctx->d_hop_base, ctx->d_kps_base, ctx->d_nhops, ctx->d_nkps, ctx->d_cov, ctx->d_hops,
                     ctx->d_hop_rect, ctx->d_kps, ctx->d_chunk_bbox, ctx->d_grid, ctx->d_tracks, ctx->d_ntracks,
                     ctx->d_cur_id, ctx->d_ext_scratch, ctx->d_map, ctx->d_nmap, ctx->d_nkf, ctx->d_pose_cur,
@@ -34,6 +35,11 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
         if (b) cudaFree(b);
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
+        if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -81,6 +87,13 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(cudaGetDeviceProperties(&prop, c.device));
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming));
+    }
+    ctx->grey_pitch = 1024;
+    while (ctx->grey_pitch < c.width) ctx->grey_pitch <<= 1;
 
     ctx->K = c.max_ref;
     ctx->LA = ctx->K + 1;
@@ -100,7 +113,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(dalloc(&ctx->d_rec, S * RING * c.max_records_per_frame));
     CK(dalloc(&ctx->d_rec_cnt, S * RING));
     CK(dalloc(&ctx->d_fflags, S * RING));
-    if (c.has_grey) CK(dalloc(&ctx->d_grey, S * RING * plane));
+    if (c.has_grey) CK(dalloc(&ctx->d_grey, S * RING * (size_t)c.height * ctx->grey_pitch));
     CK(dalloc(&ctx->d_rejected, 1));
     CK(cudaMemset(ctx->d_rejected, 0, sizeof(unsigned long long)));
     CK(cudaMemset(ctx->d_rec_cnt, 0, S * RING * sizeof(int32_t)));
@@ -171,15 +184,16 @@ extern "C" int movfe_synchronize(movfe_ctx *ctx) {
 extern "C" void *movfe_cuda_stream(movfe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 extern "C" int64_t movfe_frames_pushed(const movfe_ctx *ctx) { return ctx ? ctx->pushed : -1; }
 
-static int ensure_stage(movfe_ctx *ctx, size_t bytes) {
-    if (bytes <= ctx->stage_bytes) return MOVFE_OK;
+static int ensure_stage(movfe_ctx *ctx, int b, size_t bytes) {
+    if (bytes <= ctx->stage_bytes[b]) return MOVFE_OK;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->d_stage) cudaFree(ctx->d_stage);
-    ctx->d_stage = nullptr;
-    ctx->stage_bytes = 0;
+    if (ctx->d_stage[b]) cudaFree(ctx->d_stage[b]);
+    ctx->d_stage[b] = nullptr;
+    ctx->stage_bytes[b] = 0;
     const size_t want = bytes + bytes / 4 + 4096;
-    MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_stage, want));
-    ctx->stage_bytes = want;
+    MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_stage[b], want));
+    ctx->stage_bytes[b] = want;
     return MOVFE_OK;
 }
 
@@ -226,20 +240,38 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
     const size_t n_seg = (size_t)ctx->cfg.n_streams * n_frames;
     const int64_t n_records = rec_off[n_seg];
     if (n_records < 0 || (n_records > 0 && !recs)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: bad record offsets");
-    // staging layout: [records, padded to 16 B][offsets][flags]
+    // staging layout: [records, padded to 16 B][offsets][flags, padded to 16 B][grey planes]
     const size_t rec_bytes = ((size_t)n_records * sizeof(movfe_mv_record) + 15) & ~(size_t)15;
     const size_t off_bytes = ((n_seg + 1) * sizeof(int64_t) + 15) & ~(size_t)15;
-    const size_t total = rec_bytes + off_bytes + n_seg + 16;
-    rc = ensure_stage(ctx, total);
+    const size_t flag_bytes = (n_seg + 15) & ~(size_t)15;
+    const bool with_grey = ctx->cfg.has_grey && grey;
+    const size_t grey_bytes = with_grey ? n_seg * (size_t)ctx->cfg.width * ctx->cfg.height : 0;
+    const size_t total = rec_bytes + off_bytes + flag_bytes + grey_bytes + 16;
+    const int b = ctx->push_parity;
+    rc = ensure_stage(ctx, b, total);
     if (rc) return rc;
-    uint8_t *base = (uint8_t *)ctx->d_stage;
+    // the copies run on copy_stream so that they overlap the kernels of the previous window; the buffer must have been
+    // consumed by the ingest kernels of the push two calls ago
+    if (ctx->stage_used[b]) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[b], 0));
+    uint8_t *base = (uint8_t *)ctx->d_stage[b];
+    cudaStream_t cs = ctx->copy_stream;
     if (n_records > 0)
-        MOVFE_CUDA(ctx, cudaMemcpyAsync(base, recs, (size_t)n_records * sizeof(movfe_mv_record), cudaMemcpyHostToDevice, ctx->stream));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes, rec_off, (n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes + off_bytes, frame_flags, n_seg, cudaMemcpyHostToDevice, ctx->stream));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(base, recs, (size_t)n_records * sizeof(movfe_mv_record), cudaMemcpyHostToDevice, cs));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes, rec_off, (n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes + off_bytes, frame_flags, n_seg, cudaMemcpyHostToDevice, cs));
+    uint8_t *d_grey = nullptr;
+    if (with_grey) {
+        d_grey = base + rec_bytes + off_bytes + flag_bytes;
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_grey, grey, grey_bytes, cudaMemcpyHostToDevice, cs));
+    }
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
     rc = movfe_ingest_launch(ctx, n_frames, (const movfe_mv_record *)base, (const int64_t *)(base + rec_bytes), n_records,
-                             base + rec_bytes + off_bytes, grey);
+                             base + rec_bytes + off_bytes, d_grey);
     if (rc) return rc;
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+    ctx->stage_used[b] = true;
+    ctx->push_parity ^= 1;
     ctx->pushed += n_frames;
     return MOVFE_OK;
 }

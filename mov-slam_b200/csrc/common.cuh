@@ -54,15 +54,22 @@ struct movfe_ctx {
     int64_t pose_first = -1;
     int     pose_n = 0;
 
-    // staging for host pushes (grown on demand)
-    void   *d_stage = nullptr;
-    size_t  stage_bytes = 0;
+    // staging for host pushes (grown on demand), double-buffered: the host->device copies of push k+1 run on
+    // copy_stream while the kernels of window k run on `stream`; events order buffer reuse
+    cudaStream_t copy_stream = nullptr;
+    void   *d_stage[2] = {nullptr, nullptr};
+    size_t  stage_bytes[2] = {0, 0};
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // recorded on copy_stream after the copies into d_stage[b]
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // recorded on stream after the ingest kernels read d_stage[b]
+    bool    stage_used[2] = {false, false};
+    int     push_parity = 0;
+    int     grey_pitch = 0;        // row pitch of the grey ring: power of two >= width (compile-time strides in extract.cu)
 
     // record / image ring, slot = absolute frame % RING
     Rec16   *d_rec = nullptr;      // [S][RING][max_records]
     int32_t *d_rec_cnt = nullptr;  // [S][RING]
     uint8_t *d_fflags = nullptr;   // [S][RING]
-    uint8_t *d_grey = nullptr;     // [S][RING][H*W]   (has_grey)
+    uint8_t *d_grey = nullptr;     // [S][RING][H*grey_pitch]   (has_grey)
     unsigned long long *d_rejected = nullptr;
 
     // raster window (window-local frame index fi = frame - win_first)

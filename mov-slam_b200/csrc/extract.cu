@@ -34,6 +34,7 @@ constexpr int MAX_TRACKS_CAP = 8192;
 
 struct ExtParams {
     int S, W, H, maxT, max_kps, max_hops, maxM, n_out, n_in, RING, TSLOTS;
+    int P;           // row pitch of the grey ring (power of two >= W)
     int fi;          // raster-window slot of this frame
     int gslot;       // ring slot of this frame (grey, flags)
     int tslot_prev, tslot_cur;
@@ -226,19 +227,22 @@ __device__ __forceinline__ bool rect_in_bounds(int x, int y, int w, int h, int c
 // ------------------------------------------------------------------------------------ batched patch access -----
 // The propagation kernels are bound by the latency of dependent gathers, not by bandwidth, so every global load of a
 // track's patches is ISSUED before any is consumed: patch_issue only loads, patch_words only consumes.
-template <int ROWS, int COLS>
-__device__ __forceinline__ void patch_issue(const uint8_t *__restrict__ roi, int stride, int shift, int lane,
+template <int ROWS, int COLS, int STRIDE>
+__device__ __forceinline__ void patch_issue(const uint8_t *__restrict__ img, unsigned origin, int stride_rt, int shift, int lane,
                                             int (&vals)[ROWS * COLS / 32], int (&cen)[4]) {
+    const int stride = STRIDE ? STRIDE : stride_rt;  // compile-time pitch: every row offset below is an immediate
+    // one 64-bit address per patch and lane; with a compile-time pitch every load below is [base + immediate]
     constexpr int LC = COLS == 16 ? 4 : 3;
-    const uint8_t *q = roi + (lane >> LC) * stride + (lane & (COLS - 1)) + shift;
+    const uint8_t *pc = img + origin;
+    const uint8_t *pq = pc + ((lane >> LC) * stride + (lane & (COLS - 1)) + shift);
     const int step = (32 >> LC) * stride;
 #pragma unroll
-    for (int it = 0; it < ROWS * COLS / 32; it++) vals[it] = q[it * step];
+    for (int it = 0; it < ROWS * COLS / 32; it++) vals[it] = pq[it * step];
     constexpr int cr = ROWS / 2, cc = COLS / 2;  // compute_center (EXPRESS.h:79-88): at(row = cols/2, col = rows/2)
-    cen[0] = roi[cc * stride + cr];
-    cen[1] = roi[(cc - 1) * stride + (cr - 1)];
-    cen[2] = roi[cc * stride + (cr - 1)];
-    cen[3] = roi[(cc - 1) * stride + cr];
+    cen[0] = pc[cc * stride + cr];
+    cen[1] = pc[(cc - 1) * stride + (cr - 1)];
+    cen[2] = pc[cc * stride + (cr - 1)];
+    cen[3] = pc[(cc - 1) * stride + cr];
 }
 
 __device__ __forceinline__ Band band_of(const int (&cen)[4], int thr) {
@@ -290,23 +294,24 @@ constexpr int CW_INFO = 4;   // need (4 bits) | mw << 8 | mh << 16
 constexpr int CW_OIDX = 5;   // index of the track in the previous table
 constexpr int CW_WORDS = 6;
 
-template <int ROWS, int COLS>
-__device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int W, int thr, const int (&mxy)[4], unsigned need,
+template <int ROWS, int COLS, int STRIDE>
+__device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int stride_rt, int thr, const int (&mxy)[4], unsigned need,
                                          const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
     constexpr int IT = ROWS * COLS / 32;
     int vals[4][IT], cen[4][4];
+    const int stride = STRIDE ? STRIDE : stride_rt;
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-        const bool on = (need >> j) & 1u;  // candidates that are not evaluated read row 0 of the image (always valid)
-        patch_issue<ROWS, COLS>(img + (on ? (size_t)(mxy[j] >> 16) * W + (int16_t)(mxy[j] & 0xffff) : 0), on ? W : 0, on ? 1 : 0, lane,
-                                vals[j], cen[j]);
+        const bool on = (need >> j) & 1u;  // candidates that are not evaluated read the block at (0,0) (always valid)
+        patch_issue<ROWS, COLS, STRIDE>(img, on ? (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)) : 0u, stride_rt, 1, lane,
+                                        vals[j], cen[j]);
     }
     if (need >> 2) {  // warp-uniform
 #pragma unroll
         for (int j = 2; j < 4; j++) {
             const bool on = (need >> j) & 1u;
-            patch_issue<ROWS, COLS>(img + (on ? (size_t)(mxy[j] >> 16) * W + (int16_t)(mxy[j] & 0xffff) : 0), on ? W : 0, on ? 1 : 0,
-                                    lane, vals[j], cen[j]);
+            patch_issue<ROWS, COLS, STRIDE>(img, on ? (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)) : 0u, stride_rt, 1,
+                                            lane, vals[j], cen[j]);
         }
     } else {
 #pragma unroll
@@ -340,15 +345,15 @@ __device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int W,
 }
 
 // any other block shape (synthetic 4-px blocks, ...): one candidate after the other through the generic mask
-__device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, int W, int thr, int mw, int mh, const int (&mxy)[4],
+__device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, int stride, int thr, int mw, int mh, const int (&mxy)[4],
                                               unsigned need, const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
     int chosen = -1;
     best = 256;
     for (int j = 0; j < 4; j++) {
         if (!((need >> j) & 1u)) continue;
-        const uint8_t *roi = img + (size_t)(mxy[j] >> 16) * W + (int16_t)(mxy[j] & 0xffff);
+        const uint8_t *roi = img + (size_t)(mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff);
         uint32_t d[8];
-        express_mask(roi, W, mh, mw, express_band(roi, W, mh, mw, thr), 1, false, d, lane);
+        express_mask(roi, stride, mh, mw, express_band(roi, stride, mh, mw, thr), 1, false, d, lane);
         const int dist = hamming256(pd, d);
         if (j == 0 || dist < best) {
             best = dist;
@@ -360,6 +365,7 @@ __device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, i
     return chosen;
 }
 
+template <int PITCH>
 __global__ void __launch_bounds__(CAND_THREADS)
 cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
             const uint16_t *__restrict__ order, const int4 *__restrict__ grid, const movfe_hop *__restrict__ hops,
@@ -374,7 +380,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
     const uint16_t *ord = order + (size_t)s * p.maxT;
     const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
     const movfe_hop *hp = hops + ((size_t)s * p.n_out + p.fi) * p.max_hops;
-    const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H) : nullptr;
+    const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     movfe_track *st = stage + (size_t)s * p.maxT;
     int2 *ci = cinfo + (size_t)s * p.maxT;
     int32_t *cl = claim + (size_t)s * p.maxM;
@@ -450,11 +456,11 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             const uint32_t pd[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
             uint32_t bd[8];
             int best, ch;
-            if (tw == 16 && th == 16) ch = cand_eval<16, 16>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
-            else if (tw == 8 && th == 8) ch = cand_eval<8, 8>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
-            else if (tw == 8 && th == 16) ch = cand_eval<16, 8>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
-            else if (tw == 16 && th == 8) ch = cand_eval<8, 16>(img, p.W, p.thr, cm, nd, pd, lane, bd, best);
-            else ch = cand_eval_generic(img, p.W, p.thr, tw, th, cm, nd, pd, lane, bd, best);
+            if (tw == 16 && th == 16) ch = cand_eval<16, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
+            else if (tw == 8 && th == 8) ch = cand_eval<8, 8, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
+            else if (tw == 8 && th == 16) ch = cand_eval<16, 8, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
+            else if (tw == 16 && th == 8) ch = cand_eval<8, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
+            else ch = cand_eval_generic(img, p.P, p.thr, tw, th, cm, nd, pd, lane, bd, best);
             if (lane == t) {
                 // single-candidate pixels never compare (:272): slot 0 stays chosen; its descriptor is the one evaluated
                 if (sl.y >= 0 && ch >= 0) chosen = ch;
@@ -497,13 +503,25 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
 // ------------------------------------------------------------------------------------------ birth_kernel -----
 // compute_express (EXPRESS.h:117-192) + descriptor of one block from ONE pass over its 17 columns: the true block mask
 // (diagonal walk) and the p++-shifted mask (pre-check, descriptor) differ by one column.
-template <int ROWS, int COLS>
-__device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ roi, int stride, int thr, uint32_t *smem8, int lane,
-                                              uint32_t (&desc)[8]) {
+// 32x32 bit-matrix transpose across a warp: lane r ends with bit c == (lane c's input bit r).
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int j = 16; j >= 1; j >>= 1) {
+        const unsigned m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+    }
+    return x;
+}
+
+template <int ROWS, int COLS, int STRIDE>
+__device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ img, unsigned origin, int stride_rt, int thr, uint32_t *smem8,
+                                              int lane, uint32_t (&desc)[8]) {
     constexpr int IT = ROWS * COLS / 32;
+    const int stride = STRIDE ? STRIDE : stride_rt;
     int v0[IT], cen[4];
-    patch_issue<ROWS, COLS>(roi, stride, 0, lane, v0, cen);
-    const int vx = lane < ROWS ? (int)roi[lane * stride + COLS] : 0;  // column COLS: in bounds because x + w < cols (:388)
+    patch_issue<ROWS, COLS, STRIDE>(img, origin, stride_rt, 0, lane, v0, cen);
+    const int vx = lane < ROWS ? (int)img[origin + (unsigned)(lane * stride + COLS)] : 0;  // column COLS: in bounds, x + w < cols (:388)
     const Band bd = band_of(cen, thr);
     uint32_t m0[IT], m1[IT];
     patch_words<IT>(v0, bd, m0);
@@ -524,34 +542,31 @@ __device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ roi, i
     // "total >= precheck" (the uint8 counter cannot wrap before the break)
     constexpr int precheck = ROWS * COLS / 8;
     if (f < precheck) return false;
+    // diagonal walk (:141-190). A block diagonal is the set of cells with constant c - r (direction 1, closed form of the
+    // tables EXPRESS.h:20-38: d = c - r + ROWS-1) or constant c + r (direction 0, the same on the column-reversed row).
+    // Lane r shifts its row left by ROWS-1-r so that diagonal d sits in bit d of every lane; one 32x32 bit transpose then
+    // hands lane d the cells of diagonal d, and the win count is a popcount.
     __syncwarp();
 #pragma unroll
     for (int it = 0; it < IT; it++)
         if (lane == it) smem8[it] = m0[it];
     __syncwarp();
+    unsigned row = 0;
+    if (lane < ROWS) row = COLS == 16 ? reinterpret_cast<const uint16_t *>(smem8)[lane] : reinterpret_cast<const uint8_t *>(smem8)[lane];
     constexpr int slices = ROWS + COLS - 1;
     constexpr int rounds = slices == 31 ? 8 : slices == 23 ? 6 : 4;  // roundf(slices * .25f)
-    constexpr uint32_t valid = slices >= 32 ? 0xffffffffu : ((1u << slices) - 1u);
+    constexpr uint32_t valid = (1u << slices) - 1u;
+    const int len = min(min(lane + 1, ROWS), min(COLS, slices - lane));
     bool ok = false;
 #pragma unroll
     for (int a = 0; a < 2; a++) {
-        const bool direction = a == 0;
-        bool winbit = false;
-        if (lane < slices) {
-            const int d = lane;
-            const int len = min(min(d + 1, ROWS), min(COLS, slices - d));
-            const int r0 = max(ROWS - 1 - d, 0);
-            const int c1 = max(0, d - (ROWS - 1));
-            const int c0 = direction ? c1 : COLS - 1 - c1;
-            const int dc = direction ? 1 : -1;
-            int win = 0;
-            for (int r = 0; r < len; r++) {
-                const int bit = (r0 + r) * COLS + (c0 + dc * r);
-                win += (smem8[bit >> 5] >> (bit & 31)) & 1u;
-            }
-            winbit = win >= len - win;
-        }
+        const unsigned bits = a == 0 ? row : (__brev(row) >> (32 - COLS));
+        const unsigned diag = transpose32(lane < ROWS ? bits << (ROWS - 1 - lane) : 0u, lane);
+        const int win = __popc(diag);
+        const bool winbit = lane < slices && win >= len - win;  // win >= loss (:171); "loss > win" is its complement (:179)
         const uint32_t wb = __ballot_sync(0xffffffffu, winbit) & valid;
+        // sticky run counters (:169-184): wins reaches `rounds` iff `rounds` consecutive win diagonals exist; the
+        // early break (:185) only fires when the verdict is already false.
         if (has_run(wb, rounds) && has_run(~wb & valid, rounds)) ok = true;
     }
     __syncwarp();
@@ -559,6 +574,7 @@ __device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ roi, i
     return ok;
 }
 
+template <int PITCH>
 __global__ void __launch_bounds__(CAND_THREADS)
 birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
              const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
@@ -569,7 +585,7 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = nkps[s * p.n_in + p.fi];
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;
-    const uint8_t *img = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H);
+    const uint8_t *img = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H);
     const movfe_rect *kp = kps + ((size_t)s * p.n_out + p.fi) * p.max_kps;
     for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n; c += gridDim.x * CAND_WARPS) {
         const int i = c * 32 + lane;
@@ -592,23 +608,27 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
             todo &= todo - 1;
             const int rx = sm[warp][0][t], ry = sm[warp][1][t];
             const int x = (int16_t)(rx & 0xffff), y = rx >> 16, w = (int16_t)(ry & 0xffff), h = ry >> 16;
-            const uint8_t *roi = img + (size_t)y * p.W + x;
+            const int stride = PITCH ? PITCH : p.P;
+            const unsigned origin = (unsigned)(y * stride + x);
+            const uint8_t *roi = img + origin;
             uint32_t d[8];
             bool pass;
-            if (w == 16 && h == 16) pass = express_birth<16, 16>(roi, p.W, p.thr, scratch[warp], lane, d);
-            else if (w == 8 && h == 8) pass = express_birth<8, 8>(roi, p.W, p.thr, scratch[warp], lane, d);
-            else if (w == 8 && h == 16) pass = express_birth<16, 8>(roi, p.W, p.thr, scratch[warp], lane, d);
-            else if (w == 16 && h == 8) pass = express_birth<8, 16>(roi, p.W, p.thr, scratch[warp], lane, d);
+            if (w == 16 && h == 16) pass = express_birth<16, 16, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
+            else if (w == 8 && h == 8) pass = express_birth<8, 8, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
+            else if (w == 8 && h == 16) pass = express_birth<16, 8, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
+            else if (w == 16 && h == 8) pass = express_birth<8, 16, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
             else {
-                pass = express_test(roi, p.W, h, w, p.thr, scratch[warp], lane);  // :391
-                if (pass) express_mask(roi, p.W, h, w, express_band(roi, p.W, h, w, p.thr), 1, false, d, lane);
+                pass = express_test(roi, stride, h, w, p.thr, scratch[warp], lane);  // :391
+                if (pass) express_mask(roi, stride, h, w, express_band(roi, stride, h, w, p.thr), 1, false, d, lane);
             }
             if (pass) {
                 const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
-                if (lane == 0) birth_flag[o] = 1;
-#pragma unroll
-                for (int k = 0; k < 8; k++)
-                    if (lane == k) birth_desc[o * 8 + k] = d[k];
+                if (lane == 0) {
+                    birth_flag[o] = 1;
+                    uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
+                    bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
+                    bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
+                }
             }
         }
         __syncwarp();
@@ -763,8 +783,7 @@ __device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img
             y = 8 + 16 * (b / gw);
             x = 8 + 16 * (b % gw);
             if (rect_in_bounds(x - 8, y - 8, 16, 16, p.W, p.H)) {
-                const uint8_t *roi = img + (size_t)(y - 8) * p.W + (x - 8);
-                if (express_birth<16, 16>(roi, p.W, p.thr, scratch[warp], lane, d) &&
+                if (express_birth<16, 16, 0>(img, (unsigned)((y - 8) * p.P + (x - 8)), p.P, p.thr, scratch[warp], lane, d) &&
                     !(need_uncovered && __ldg(&g[(size_t)y * p.W + x]).x >= 0))
                     pass = true;
             }
@@ -820,7 +839,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     int id = cur_id[s * p.TSLOTS + p.tslot_prev];
     int n_out = 0;    // logical size of the new table (entries beyond maxT are dropped)
     int n_keyed = 0;  // entries whose sort key is already in shared memory
-    const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.W * p.H) : nullptr;
+    const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
 
     if (is_p) {
@@ -1028,17 +1047,32 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.tslot_cur = tslot_of(ctx, a);
         p.thr = c.express_threshold;
         p.has_grey = c.has_grey;
+        p.P = ctx->grey_pitch;
         p.cov_thr = c.coverage_threshold;
         // grid-stride over tracks / kps: enough CTAs to fill the chip, never one CTA per (mostly empty) capacity slot
         const int bps = std::max(4, (8 * ctx->sm_count + c.n_streams - 1) / c.n_streams);
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), c.n_streams);  // a warp takes 32 tracks
-        cand_kernel<<<gc, CAND_WARPS * 32, 0, ctx->stream>>>(p, ctx->d_tracks, ctx->d_ntracks, e.order, ctx->d_grid,
-                                                            ctx->d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim);
+#define MOVFE_CAND(PITCH)                                                                                              \
+    cand_kernel<PITCH><<<gc, CAND_THREADS, 0, ctx->stream>>>(p, ctx->d_tracks, ctx->d_ntracks, e.order, ctx->d_grid, ctx->d_hops, \
+                                                             ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim)
+        switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
+            case 1024: MOVFE_CAND(1024); break;
+            case 2048: MOVFE_CAND(2048); break;
+            default: MOVFE_CAND(0); break;
+        }
+#undef MOVFE_CAND
         int nl = 2;
         if (c.has_grey) {
             dim3 gb(std::min((ctx->max_kps + CAND_THREADS - 1) / CAND_THREADS, bps), c.n_streams);
-            birth_kernel<<<gb, CAND_WARPS * 32, 0, ctx->stream>>>(p, ctx->d_kps, ctx->d_nkps, ctx->d_grey, ctx->d_fflags,
-                                                                 e.claim, e.birth_flag, e.birth_desc);
+#define MOVFE_BIRTH(PITCH)                                                                                             \
+    birth_kernel<PITCH><<<gb, CAND_THREADS, 0, ctx->stream>>>(p, ctx->d_kps, ctx->d_nkps, ctx->d_grey, ctx->d_fflags, e.claim,    \
+                                                              e.birth_flag, e.birth_desc)
+            switch (ctx->grey_pitch) {
+                case 1024: MOVFE_BIRTH(1024); break;
+                case 2048: MOVFE_BIRTH(2048); break;
+                default: MOVFE_BIRTH(0); break;
+            }
+#undef MOVFE_BIRTH
             nl = 3;
         }
         finalize_kernel<<<c.n_streams, FIN_THREADS, sort_smem(c.max_tracks), ctx->stream>>>(

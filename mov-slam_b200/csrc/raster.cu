@@ -17,6 +17,7 @@
 //                   transpose, row masks by ballots, slots 0..2 = three lowest set bits, slot 3 = highest of the
 //                   rest. Every pixel is written exactly once with one 128-bit streaming store (no atomics,
 //                   no read-modify-write, the -1 fill is implicit).
+#include <algorithm>
 #include <cstdio>
 
 #include "common.cuh"
@@ -88,6 +89,26 @@ __global__ void ingest_meta_kernel(const int64_t *__restrict__ rec_off, const ui
     const int64_t n = rec_off[seg + 1] - rec_off[seg];
     rec_cnt[s * RING + slot] = (int32_t)(n < maxM ? n : maxM);
     fflags[s * RING + slot] = flags[seg];
+}
+
+// Grey planes [segment][H][W] (packed, as the decoder hands them over) -> the ring [S][slot][H][pitch]. The power-of-two
+// pitch makes every row offset inside a patch a compile-time constant for the propagation kernels (extract.cu).
+__global__ void grey_ingest_kernel(const uint8_t *__restrict__ src, int n_seg, int n_frames, int W, int H, int pitch, int vec,
+                                   int64_t first_abs, int RING, uint8_t *__restrict__ ring) {
+    const int wv = W / vec;
+    const int64_t total = (int64_t)n_seg * H * wv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % wv);
+        const int64_t row = i / wv;
+        const int y = (int)(row % H);
+        const int seg = (int)(row / H);
+        const int s = seg / n_frames, f = seg - s * n_frames;
+        const int slot = (int)((first_abs + f) % RING);
+        const size_t so = ((size_t)seg * H + y) * W + (size_t)x * vec;
+        const size_t dof = (((size_t)s * RING + slot) * H + y) * pitch + (size_t)x * vec;
+        if (vec == 16) *reinterpret_cast<uint4 *>(ring + dof) = __ldg(reinterpret_cast<const uint4 *>(src + so));
+        else ring[dof] = src[so];
+    }
 }
 
 // ------------------------------------------------------------------------------------------ record classes ---
@@ -394,18 +415,12 @@ int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_r
                                                                      ctx->RING, c.max_records_per_frame,
                                                                      ctx->d_rec_cnt, ctx->d_fflags);
     if (c.has_grey && d_grey) {
-        const size_t plane = (size_t)c.width * c.height;
-        for (int s = 0; s < c.n_streams; s++) {
-            int f = 0;
-            while (f < n_frames) {  // contiguous run of ring slots
-                const int slot = (int)((ctx->pushed + f) % ctx->RING);
-                const int run = std::min(n_frames - f, ctx->RING - slot);
-                MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_grey + ((size_t)s * ctx->RING + slot) * plane,
-                                                d_grey + ((size_t)s * n_frames + f) * plane, plane * run,
-                                                cudaMemcpyDefault, ctx->stream));
-                f += run;
-            }
-        }
+        const int vec = (c.width % 16 == 0 && ((uintptr_t)d_grey & 15) == 0) ? 16 : 1;
+        const int64_t total = (int64_t)n_seg * c.height * (c.width / vec);
+        const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
+        grey_ingest_kernel<<<blocks, 256, 0, ctx->stream>>>(d_grey, n_seg, n_frames, c.width, c.height, ctx->grey_pitch, vec, ctx->pushed,
+                                                          ctx->RING, ctx->d_grey);
+        prof.launches(1);
     }
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
