@@ -184,17 +184,15 @@ __device__ __forceinline__ int hash_find(int id, const int *keys, const int *val
 }
 
 // ------------------------------------------------------------------------------------------------ solver -----
-__device__ __forceinline__ double shfl_xor_d(double v, int o) {
-    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o), __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
-}
-
 // g2o SE3Quat::exp, update = [omega, upsilon]
 __device__ void se3_exp_d(const double dx[6], double R[9], double t[3]) {
     const double wx = dx[0], wy = dx[1], wz = dx[2];
     const double theta = sqrt(wx * wx + wy * wy + wz * wz);
     const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
     double O2[9];
+#pragma unroll
     for (int i = 0; i < 3; i++)
+#pragma unroll
         for (int j = 0; j < 3; j++) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
     double a, b, c;
     if (theta < 0.00001) {
@@ -202,56 +200,79 @@ __device__ void se3_exp_d(const double dx[6], double R[9], double t[3]) {
         b = 0.5;
         c = 1.0 / 6.0;
     } else {
-        a = sin(theta) / theta;
-        b = (1 - cos(theta)) / (theta * theta);
-        c = (theta - sin(theta)) / (theta * theta * theta);
+        double sn, cs;
+        sincos(theta, &sn, &cs);
+        const double it = 1.0 / theta;
+        a = sn * it;
+        b = (1 - cs) * it * it;
+        c = (theta - sn) * it * it * it;
     }
     double V[9];
+#pragma unroll
     for (int i = 0; i < 9; i++) {
         const double I = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
         R[i] = I + a * O[i] + b * O2[i];
         V[i] = I + b * O[i] + c * O2[i];
     }
+#pragma unroll
     for (int i = 0; i < 3; i++) t[i] = V[i * 3] * dx[3] + V[i * 3 + 1] * dx[4] + V[i * 3 + 2] * dx[5];
 }
 
-// 6x6 Cholesky solve; H given as its 21 upper-triangle entries in row order. Same pivot rule as the oracle.
-__device__ bool solve6_d(const double *Hu, const double b[6], double x[6]) {
-    double H[36];
-    int k = 0;
-    for (int a = 0; a < 6; a++)
-        for (int c = a; c < 6; c++) {
-            H[a * 6 + c] = Hu[k];
-            H[c * 6 + a] = Hu[k];
-            k++;
-        }
-    double L[36];
-    for (int i = 0; i < 36; i++) L[i] = 0;
+// 6x6 Cholesky solve; H given as its 21 upper-triangle entries in row order. Same pivot rule as the oracle. Fully
+// unrolled (everything stays in registers) with one reciprocal per pivot: this runs on one thread between two barriers,
+// so its dependent-operation chain is on the critical path of every Gauss-Newton iteration.
+__device__ __forceinline__ bool solve6_d(const double *Hu, const double *b, double (&x)[6]) {
+    double H[6][6];
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int c = a; c < 6; c++) {
+                H[a][c] = Hu[k];
+                H[c][a] = Hu[k];
+                k++;
+            }
+    }
     double maxd = 0;
-    for (int i = 0; i < 6; i++) maxd = fmax(maxd, fabs(H[i * 6 + i]));
+#pragma unroll
+    for (int i = 0; i < 6; i++) maxd = fmax(maxd, fabs(H[i][i]));
     if (!(maxd > 0)) return false;
     const double tiny = 1e-13 * maxd;
+    double L[6][6], inv[6];
+    bool ok = true;
+#pragma unroll
     for (int j = 0; j < 6; j++) {
-        double d = H[j * 6 + j];
-        for (int q = 0; q < j; q++) d -= L[j * 6 + q] * L[j * 6 + q];
-        if (!(d > tiny)) return false;
-        L[j * 6 + j] = sqrt(d);
+        double d = H[j][j];
+#pragma unroll
+        for (int q = 0; q < j; q++) d -= L[j][q] * L[j][q];
+        if (!(d > tiny)) ok = false;
+        const double r = rsqrt(d);
+        inv[j] = r;
+        L[j][j] = d * r;
+#pragma unroll
         for (int i = j + 1; i < 6; i++) {
-            double s = H[i * 6 + j];
-            for (int q = 0; q < j; q++) s -= L[i * 6 + q] * L[j * 6 + q];
-            L[i * 6 + j] = s / L[j * 6 + j];
+            double s = H[i][j];
+#pragma unroll
+            for (int q = 0; q < j; q++) s -= L[i][q] * L[j][q];
+            L[i][j] = s * r;
         }
     }
+    if (!ok) return false;
     double y[6];
+#pragma unroll
     for (int i = 0; i < 6; i++) {
         double s = b[i];
-        for (int q = 0; q < i; q++) s -= L[i * 6 + q] * y[q];
-        y[i] = s / L[i * 6 + i];
+#pragma unroll
+        for (int q = 0; q < i; q++) s -= L[i][q] * y[q];
+        y[i] = s * inv[i];
     }
+#pragma unroll
     for (int i = 5; i >= 0; i--) {
         double s = y[i];
-        for (int q = i + 1; q < 6; q++) s -= L[q * 6 + i] * x[q];
-        x[i] = s / L[i * 6 + i];
+#pragma unroll
+        for (int q = i + 1; q < 6; q++) s -= L[q][i] * x[q];
+        x[i] = s * inv[i];
     }
     return true;
 }
@@ -261,48 +282,80 @@ struct SolverShared {
     double part[TP_WARPS][28];  // per-warp partial sums: 21 JtJ + 6 Jtr (+1 pad)
     int    ipart[TP_WARPS];
     int    flag;                // 0 continue, 1 converged, 2 solver failure
-    int    n_bad;
     int    stats[4];
 };
 
-// One correspondence: residual, Huber weight, 2x6 Jacobian -> 27 sums.
+// One correspondence: residual, Huber weight, 2x6 Jacobian -> 27 sums. Explicit fma(): this translation unit is compiled
+// with -fmad=false for the frustum's binary32 parity; the solver's tolerance is 1e-5 relative, not bit-exactness.
 __device__ __forceinline__ void accumulate_point(const CamD &cam, const double *R, const double *t, float X0, float X1, float X2,
-                                                 float ou, float ov, bool robust, double delta, double acc[27]) {
+                                                 float ou, float ov, bool robust, double delta, double (&acc)[27]) {
     const double X[3] = {X0, X1, X2};
     double Xc[3];
-    for (int r = 0; r < 3; r++) Xc[r] = R[r * 3] * X[0] + R[r * 3 + 1] * X[1] + R[r * 3 + 2] * X[2] + t[r];
-    if (!(Xc[2] > 0.0)) return;  // isDepthPositive (OptimizableTypes.h:48-52)
-    double u, v;
-    project_d(cam, Xc[0], Xc[1], Xc[2], u, v);
-    const double e0 = (double)ou - u, e1 = (double)ov - v;  // OptimizableTypes.h:41-46
-    const double chi2 = e0 * e0 + e1 * e1;
-    const double w = (robust && chi2 > delta * delta) ? delta / sqrt(chi2) : 1.0;  // RobustKernelHuber rho'
-    double Jp[6];
-    project_jac_d(cam, Xc[0], Xc[1], Xc[2], Jp);
-    const double x = Xc[0], y = Xc[1], z = Xc[2];
-    // J = -Jp * [ -[Xc]x | I ]  (OptimizableTypes.cpp:63-68)
-    const double D[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
-    double J0[6], J1[6];
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
-        J0[k] = -(Jp[0] * D[0][k] + Jp[1] * D[1][k] + Jp[2] * D[2][k]);
-        J1[k] = -(Jp[3] * D[0][k] + Jp[4] * D[1][k] + Jp[5] * D[2][k]);
+    for (int r = 0; r < 3; r++) Xc[r] = fma(R[r * 3], X[0], fma(R[r * 3 + 1], X[1], fma(R[r * 3 + 2], X[2], t[r])));
+    if (!(Xc[2] > 0.0)) return;  // isDepthPositive (OptimizableTypes.h:48-52)
+    const double x = Xc[0], y = Xc[1], z = Xc[2];
+    double u, v, J0[6], J1[6];
+    if (cam.model == MOVFE_CAM_FISHEYE) {
+        double Jp[6];
+        project_d(cam, x, y, z, u, v);
+        project_jac_d(cam, x, y, z, Jp);
+        // J = -Jp * [ -[Xc]x | I ]  (OptimizableTypes.cpp:63-68)
+        const double D[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            J0[k] = -(Jp[0] * D[0][k] + Jp[1] * D[1][k] + Jp[2] * D[2][k]);
+            J1[k] = -(Jp[3] * D[0][k] + Jp[4] * D[1][k] + Jp[5] * D[2][k]);
+        }
+    } else {
+        // Pinhole (Pinhole.cpp:37-43, 77-88) with the zero entries of Jp folded away
+        const double iz = 1.0 / z;
+        const double a = cam.fx * iz, b = cam.fy * iz;  // Jp[0], Jp[4]
+        const double xz = x * iz, yz = y * iz;
+        u = fma(cam.fx, xz, cam.cx);
+        v = fma(cam.fy, yz, cam.cy);
+        const double c = -a * xz, d = -b * yz;  // Jp[2], Jp[5]
+        J0[0] = -(c * y);
+        J0[1] = -(a * z - c * x);
+        J0[2] = a * y;
+        J0[3] = -a;
+        J0[4] = 0.0;
+        J0[5] = -c;
+        J1[0] = -(d * y - b * z);
+        J1[1] = d * x;
+        J1[2] = -(b * x);
+        J1[3] = 0.0;
+        J1[4] = -b;
+        J1[5] = -d;
+    }
+    const double e0 = (double)ou - u, e1 = (double)ov - v;  // OptimizableTypes.h:41-46
+    const double chi2 = fma(e0, e0, e1 * e1);
+    const double w = (robust && chi2 > delta * delta) ? delta * rsqrt(chi2) : 1.0;  // RobustKernelHuber rho'
+    double wJ0[6], wJ1[6];
+#pragma unroll
+    for (int a = 0; a < 6; a++) {
+        wJ0[a] = w * J0[a];
+        wJ1[a] = w * J1[a];
     }
     int q = 0;
 #pragma unroll
     for (int a = 0; a < 6; a++) {
 #pragma unroll
-        for (int c = a; c < 6; c++) acc[q++] += w * (J0[a] * J0[c] + J1[a] * J1[c]);
+        for (int c = a; c < 6; c++) {
+            acc[q] = fma(wJ0[a], J0[c], fma(wJ1[a], J1[c], acc[q]));
+            q++;
+        }
     }
 #pragma unroll
-    for (int a = 0; a < 6; a++) acc[21 + a] -= w * (J0[a] * e0 + J1[a] * e1);
+    for (int a = 0; a < 6; a++) acc[21 + a] -= fma(wJ0[a], e0, wJ1[a] * e1);
 }
 
 __device__ __forceinline__ bool classify_point(const CamD &cam, const double *R, const double *t, float X0, float X1, float X2,
                                                float ou, float ov, double chi2thr) {
     const double X[3] = {X0, X1, X2};
     double Xc[3];
-    for (int r = 0; r < 3; r++) Xc[r] = R[r * 3] * X[0] + R[r * 3 + 1] * X[1] + R[r * 3 + 2] * X[2] + t[r];
+#pragma unroll
+    for (int r = 0; r < 3; r++) Xc[r] = fma(R[r * 3], X[0], fma(R[r * 3 + 1], X[1], fma(R[r * 3 + 2], X[2], t[r])));
     if (!(Xc[2] > 0.0)) return true;
     double u, v;
     project_d(cam, Xc[0], Xc[1], Xc[2], u, v);
@@ -310,9 +363,39 @@ __device__ __forceinline__ bool classify_point(const CamD &cam, const double *R,
     return (e0 * e0 + e1 * e1) > chi2thr;
 }
 
-// CTA-cooperative PoseOptimization. `Src` yields correspondence i of n slots: valid(i), X(i), obs(i).
-// outlier[i] is written for every slot: 1 = unmatched or outlier, 0 = inlier (== Frame::mvbOutlier, Optimizer.cc:452-456).
-// pose (global) is read and, unless fewer than 4 valid correspondences exist, overwritten. Returns the inlier count.
+// Sum of 27 per-lane doubles over the warp by recursive halving: at every step a lane keeps one half of its values and
+// trades the other half with its partner, so 16+8+4+2+1 values cross the warp instead of 27 x 5. On return lane l holds
+// the warp total of value slot_of(l) (bit-reversed index), or nothing for slots >= 27.
+__device__ __forceinline__ double shfl_xor_d(double v, int o) {
+    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o), __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+}
+
+template <int HALF>
+__device__ __forceinline__ void halve(double (&v)[32], int lane) {
+    const bool upper = lane & HALF;
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+        const double keep = upper ? v[i + HALF] : v[i];
+        const double send = upper ? v[i] : v[i + HALF];
+        v[i] = keep + shfl_xor_d(send, HALF);
+    }
+}
+
+__device__ __forceinline__ double warp_reduce27(const double (&acc)[27], int lane) {
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = i < 27 ? acc[i] : 0.0;
+    halve<16>(v, lane);
+    halve<8>(v, lane);
+    halve<4>(v, lane);
+    halve<2>(v, lane);
+    halve<1>(v, lane);
+    return v[0];  // slot (lane&16) + (lane&8) + ... : the lane's own index
+}
+
+// CTA-cooperative PoseOptimization. `Src` yields correspondence i of n: X(i), obs(i); every one is valid.
+// outlier[i]: 1 = outlier, 0 = inlier. pose (global) is read and, unless fewer than 4 correspondences exist, overwritten.
+// Only ceil(n/32) warps (at most the CTA) take part in the per-point passes. Returns the inlier count.
 template <typename Src>
 __device__ int pose_solve(const Src &src, int n, const movfe_camera &cam_, const movfe_pose_params &pp, movfe_pose *pose,
                           uint8_t *outlier, int32_t *stats_out, SolverShared &sh) {
@@ -321,24 +404,15 @@ __device__ int pose_solve(const Src &src, int n, const movfe_camera &cam_, const
     const float repErrorF = pp.is_lost ? (float)pp.reprojection_error_lost : (float)pp.reprojection_error;  // Optimizer.cc:423-427
     const double delta = repErrorF, chi2thr = delta * delta;
     const int its = pp.iteration_count / 4 > 1 ? pp.iteration_count / 4 : 1;
+    const int nw = min((n + 31) >> 5, (int)(blockDim.x >> 5));  // warps that own points
+    const int nthr = nw * 32;
 
-    // count valid correspondences, initialise outlier flags
-    int cnt = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const bool v = src.valid(i);
-        outlier[i] = v ? 0 : 1;
-        cnt += v;
-    }
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-    if (lane == 0) sh.ipart[warp] = cnt;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) outlier[i] = 0;
     if (threadIdx.x < 9) sh.R[threadIdx.x] = pose->R[threadIdx.x];
     if (threadIdx.x < 3) sh.t[threadIdx.x] = pose->t[threadIdx.x];
     if (threadIdx.x < 4) sh.stats[threadIdx.x] = 0;
     __syncthreads();
-    int P = 0;
-    for (int w = 0; w < TP_WARPS; w++) P += sh.ipart[w];
-    __syncthreads();
-    if (P < 4) {  // Optimizer.cc:415-418
+    if (n < 4) {  // Optimizer.cc:415-418
         if (stats_out && threadIdx.x < 4) stats_out[threadIdx.x] = 0;
         return 0;
     }
@@ -346,25 +420,23 @@ __device__ int pose_solve(const Src &src, int n, const movfe_camera &cam_, const
     for (int round = 0; round < 4; round++) {
         const bool robust = round < 3;
         for (int it = 0; it < its; it++) {
-            double acc[27];
+            if (warp < nw) {
+                double acc[27];
 #pragma unroll
-            for (int q = 0; q < 27; q++) acc[q] = 0.0;
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                if (!src.valid(i) || outlier[i]) continue;
-                float X0, X1, X2, ou, ov;
-                src.get(i, X0, X1, X2, ou, ov);
-                accumulate_point(cam, sh.R, sh.t, X0, X1, X2, ou, ov, robust, delta, acc);
-            }
-#pragma unroll
-            for (int q = 0; q < 27; q++) {
-                double v = acc[q];
-                for (int o = 16; o; o >>= 1) v += shfl_xor_d(v, o);
-                if (lane == 0) sh.part[warp][q] = v;
+                for (int q = 0; q < 27; q++) acc[q] = 0.0;
+                for (int i = threadIdx.x; i < n; i += nthr) {
+                    if (outlier[i]) continue;
+                    float X0, X1, X2, ou, ov;
+                    src.get(i, X0, X1, X2, ou, ov);
+                    accumulate_point(cam, sh.R, sh.t, X0, X1, X2, ou, ov, robust, delta, acc);
+                }
+                const double v = warp_reduce27(acc, lane);
+                if (lane < 27) sh.part[warp][lane] = v;
             }
             __syncthreads();
             if (threadIdx.x < 27) {
                 double v = 0;
-                for (int w = 0; w < TP_WARPS; w++) v += sh.part[w][threadIdx.x];
+                for (int w = 0; w < nw; w++) v += sh.part[w][threadIdx.x];
                 sh.part[0][threadIdx.x] = v;  // only thread q touches column q
             }
             __syncthreads();
@@ -378,13 +450,19 @@ __device__ int pose_solve(const Src &src, int n, const movfe_camera &cam_, const
                 } else {
                     double dR[9], dt[3], Rn[9], tn[3];
                     se3_exp_d(dx, dR, dt);
+#pragma unroll
                     for (int i = 0; i < 3; i++)
+#pragma unroll
                         for (int j = 0; j < 3; j++)
                             Rn[i * 3 + j] = dR[i * 3] * sh.R[j] + dR[i * 3 + 1] * sh.R[3 + j] + dR[i * 3 + 2] * sh.R[6 + j];
+#pragma unroll
                     for (int r = 0; r < 3; r++) tn[r] = dR[r * 3] * sh.t[0] + dR[r * 3 + 1] * sh.t[1] + dR[r * 3 + 2] * sh.t[2] + dt[r];
+#pragma unroll
                     for (int i = 0; i < 9; i++) sh.R[i] = Rn[i];
+#pragma unroll
                     for (int i = 0; i < 3; i++) sh.t[i] = tn[i];
                     double m = 0;
+#pragma unroll
                     for (int a = 0; a < 6; a++) m = fmax(m, fabs(dx[a]));
                     sh.flag = m < 1e-10 ? 1 : 0;
                 }
@@ -393,40 +471,40 @@ __device__ int pose_solve(const Src &src, int n, const movfe_camera &cam_, const
             const int flag = sh.flag;
             if (flag) break;
         }
-        // re-classification of every valid correspondence
+        // re-classification of every correspondence
         int bad = 0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            if (!src.valid(i)) continue;
-            float X0, X1, X2, ou, ov;
-            src.get(i, X0, X1, X2, ou, ov);
-            const bool b = classify_point(cam, sh.R, sh.t, X0, X1, X2, ou, ov, chi2thr);
-            outlier[i] = b ? 1 : 0;
-            bad += b;
+        if (warp < nw) {
+            for (int i = threadIdx.x; i < n; i += nthr) {
+                float X0, X1, X2, ou, ov;
+                src.get(i, X0, X1, X2, ou, ov);
+                const bool b = classify_point(cam, sh.R, sh.t, X0, X1, X2, ou, ov, chi2thr);
+                outlier[i] = b ? 1 : 0;
+                bad += b;
+            }
+            for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
         }
-        for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
         __syncthreads();  // everyone is past the flag read / previous ipart use
-        if (lane == 0) sh.ipart[warp] = bad;
+        if (lane == 0 && warp < nw) sh.ipart[warp] = bad;
         if (threadIdx.x == 0) {
             sh.stats[1]++;
             sh.stats[2]++;
         }
         __syncthreads();
         n_bad = 0;
-        for (int w = 0; w < TP_WARPS; w++) n_bad += sh.ipart[w];
-        if (P - n_bad < 3) break;
+        for (int w = 0; w < nw; w++) n_bad += sh.ipart[w];
+        if (n - n_bad < 3) break;
     }
     __syncthreads();
     if (threadIdx.x < 9) pose->R[threadIdx.x] = sh.R[threadIdx.x];
     if (threadIdx.x < 3) pose->t[threadIdx.x] = sh.t[threadIdx.x];
     if (stats_out && threadIdx.x < 4) stats_out[threadIdx.x] = sh.stats[threadIdx.x];
     __syncthreads();
-    return P - n_bad;
+    return n - n_bad;
 }
 
 // correspondence sources
-struct DirectSrc {
+struct DirectSrc {  // packed global arrays (movfe_pose_optimize)
     const float *pts, *obs;
-    __device__ bool valid(int) const { return true; }
     __device__ void get(int i, float &X0, float &X1, float &X2, float &u, float &v) const {
         X0 = pts[3 * i];
         X1 = pts[3 * i + 1];
@@ -436,19 +514,16 @@ struct DirectSrc {
     }
 };
 
-// Optimizer.cc:404-413: for every keypoint i with a map point: (GetWorldPos(), mvKeys[i].pt)
-struct FrameSrc {
-    const movfe_track *tracks;
-    const int32_t *match;
-    const movfe_map_point *map;
-    __device__ bool valid(int i) const { return match[i] >= 0; }
-    __device__ void get(int i, float &X0, float &X1, float &X2, float &u, float &v) const {
-        const movfe_map_point &mp = map[match[i]];
-        X0 = mp.pos[0];
-        X1 = mp.pos[1];
-        X2 = mp.pos[2];
-        u = tracks[i].pt_x;
-        v = tracks[i].pt_y;
+// Optimizer.cc:404-413 gathers, for every keypoint with a map point, (GetWorldPos(), mvKeys[i].pt). The persistent
+// driver compacts them once per solve into shared memory (keypoint order), so the passes never touch global memory.
+struct CompactSrc {
+    const float *x, *y, *z, *u, *v;
+    __device__ void get(int i, float &X0, float &X1, float &X2, float &ou, float &ov) const {
+        X0 = x[i];
+        X1 = y[i];
+        X2 = z[i];
+        ou = u[i];
+        ov = v[i];
     }
 };
 
@@ -463,19 +538,72 @@ struct TrackPoseParams {
     movfe_pose_params pp;
 };
 
+// Exclusive scan of one int per thread over the CTA (TP_THREADS); wsum: TP_WARPS ints of shared memory.
+__device__ __forceinline__ int tp_excl_scan(int v, int *wsum, int &total) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < TP_WARPS; w++) {
+        const int c = wsum[w];
+        before += w < warp ? c : 0;
+        tot += c;
+    }
+    total = tot;
+    __syncthreads();
+    return before + x - v;
+}
+
+// Optimizer.cc:404-413: the frame's (map point, keypoint) pairs in keypoint order -> shared memory. Returns the count.
+__device__ int gather_pairs(const movfe_track *__restrict__ tr, int n, const int32_t *__restrict__ match,
+                            const movfe_map_point *__restrict__ mp, float *cx, float *cy, float *cz, float *cu, float *cv, int *cidx,
+                            int cap, int *wsum) {
+    int n_pairs = 0;
+    for (int base = 0; base < n; base += TP_THREADS) {
+        const int t = base + threadIdx.x;
+        const int m = t < n ? match[t] : -1;
+        int tot;
+        const int pos = n_pairs + tp_excl_scan(m >= 0 ? 1 : 0, wsum, tot);
+        if (m >= 0 && pos < cap) {
+            cx[pos] = mp[m].pos[0];
+            cy[pos] = mp[m].pos[1];
+            cz[pos] = mp[m].pos[2];
+            const float2 pt = *reinterpret_cast<const float2 *>(&tr[t].pt_x);
+            cu[pos] = pt.x;
+            cv[pos] = pt.y;
+            cidx[pos] = t;
+        }
+        n_pairs += tot;
+    }
+    __syncthreads();
+    return min(n_pairs, cap);
+}
+
 __global__ void __launch_bounds__(TP_THREADS)
 track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
                    const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
                    movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses, int32_t *__restrict__ ninl,
                    int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out, int32_t *__restrict__ skip_tag) {
-    extern __shared__ int hsm[];  // keys[cap] vals[cap] hit[maxT]
+    extern __shared__ int hsm[];  // keys[cap] vals[cap] hit[maxT] | pairs: x y z u v idx [maxMap] out[maxMap]
     __shared__ SolverShared sh;
+    __shared__ int wsum[TP_WARPS];
     int *keys = hsm, *vals = hsm + p.hash_cap, *hit = hsm + 2 * p.hash_cap;
+    float *cx = reinterpret_cast<float *>(hit + p.maxT), *cy = cx + p.maxMap, *cz = cy + p.maxMap, *cu = cz + p.maxMap, *cv = cu + p.maxMap;
+    int *cidx = reinterpret_cast<int *>(cv + p.maxMap);
+    uint8_t *cout = reinterpret_cast<uint8_t *>(cidx + p.maxMap);
     const int s = blockIdx.x;
     const movfe_map_point *mp = map + (size_t)s * p.maxMap;
     const int n_map = nmap[s], n_kf = min(nkf[s], n_map);
     int32_t *tag = skip_tag + (size_t)s * p.maxMap;
     movfe_pose *pc = pose_cur + s;
+    const CompactSrc src{cx, cy, cz, cu, cv};
 
     for (int k = 0; k < p.n_frames; k++) {
         const int ts = (p.tslot0 + k) % p.TSLOTS;
@@ -499,27 +627,35 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
             __syncthreads();
             for (int t = threadIdx.x; t < n; t += blockDim.x) match[t] = hit[t];
             __syncthreads();
-            FrameSrc src{tr, match, mp};
-            pose_solve(src, n, p.cam, p.pp, pc, outl, nullptr, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
+            int np = gather_pairs(tr, n, match, mp, cx, cy, cz, cu, cv, cidx, p.maxMap, wsum);
+            pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
             // --- TrackLocalMap / SearchLocalPoints (Tracking.cc:1109-1158)
             const int frame_tag = 1;  // tags are cleared again below, so one value is enough
-            for (int t = threadIdx.x; t < n; t += blockDim.x)
-                if (match[t] >= 0) tag[match[t]] = frame_tag;  // mnLastFrameSeen = current frame
+            for (int i = threadIdx.x; i < np; i += blockDim.x) tag[match[cidx[i]]] = frame_tag;  // mnLastFrameSeen = current frame
             __syncthreads();
             const FrustumPose fp = frustum_pose(*pc);
             for (int t = threadIdx.x; t < n; t += blockDim.x) hit[t] = -1;
             __syncthreads();
             for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
-                const movfe_projection pr = frustum_point(fp, p.cam, p.W, p.H, p.view_cos, mp[i], tag[i] == frame_tag);
-                if (!pr.in_view || (mp[i].flags & MOVFE_MP_BAD)) continue;  // MOVMatcher.h:43-49 (far-point filter off)
-                const int t = hash_find(mp[i].track_id, keys, vals, cap);
+                const movfe_map_point m = mp[i];
+                const movfe_projection pr = frustum_point(fp, p.cam, p.W, p.H, p.view_cos, m, tag[i] == frame_tag);
+                if (!pr.in_view || (m.flags & MOVFE_MP_BAD)) continue;  // MOVMatcher.h:43-49 (far-point filter off)
+                const int t = hash_find(m.track_id, keys, vals, cap);
                 if (t >= 0) atomicMax(&hit[t], i);
             }
             __syncthreads();
             for (int t = threadIdx.x; t < n; t += blockDim.x)
                 if (hit[t] >= 0) match[t] = hit[t];
             __syncthreads();
-            n_inl = pose_solve(src, n, p.cam, p.pp, pc, outl, nullptr, sh);
+            np = gather_pairs(tr, n, match, mp, cx, cy, cz, cu, cv, cidx, p.maxMap, wsum);
+            n_inl = pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);
+            // Frame::mvbOutlier (Optimizer.cc:452-456): true everywhere, false for the inliers
+            for (int t = threadIdx.x; t < n; t += blockDim.x) outl[t] = 1;
+            __syncthreads();
+            if (np >= 4)
+                for (int i = threadIdx.x; i < np; i += blockDim.x) outl[cidx[i]] = cout[i];
+            else
+                for (int i = threadIdx.x; i < np; i += blockDim.x) outl[cidx[i]] = 0;  // <4 pairs: the frame is left untouched
             for (int i = threadIdx.x; i < n_map; i += blockDim.x) tag[i] = 0;  // leave the tags clean for the next launch
             __syncthreads();
         } else {
@@ -626,7 +762,10 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     p.view_cos = ctx->view_cos;
     p.cam = ctx->cam;
     p.pp = ctx->pp;
-    const size_t smem = ((size_t)2 * p.hash_cap + c.max_tracks) * sizeof(int);
+    const size_t smem = ((size_t)2 * p.hash_cap + c.max_tracks) * sizeof(int) + (size_t)p.maxMap * 25;
+    if (smem > 200 * 1024)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_poses: max_tracks=%d / max_map_points=%d need %zu bytes of shared memory per stream (limit 204800)",
+                   c.max_tracks, c.max_map_points, smem);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(track_poses_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(ctx, MOVFE_STAGE_POSE);
     prof.launches(1);
