@@ -12,7 +12,7 @@
  *    per host thread / GPU (streams shard across GPUs with no collective).
  *  - Work is batched over the context's n_streams independent video streams. All batched arrays are
  *    stream-major: element (stream s, frame f) of a call with n frames lives at index s*n + f.
- *  - Calls enqueue work on the context's stream and return; movfe_synchronize() or any download waits.
+ *  - Calls enqueue work on the context's streams and return; movfe_synchronize() or any download waits.
  *  - There is no CPU fallback: without a CUDA device movfe_create fails with MOVFE_E_CUDA.
  */
 #ifndef MOVFE_H
@@ -53,8 +53,14 @@ typedef struct movfe_config {
 int         movfe_create(const movfe_config *cfg, movfe_ctx **out);
 void        movfe_destroy(movfe_ctx *ctx);
 const char *movfe_last_error(const movfe_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
-int         movfe_synchronize(movfe_ctx *ctx);
-void       *movfe_cuda_stream(movfe_ctx *ctx);        /* the cudaStream_t work is enqueued on */
+int         movfe_synchronize(movfe_ctx *ctx);        /* waits for all of the context's streams */
+void       *movfe_cuda_stream(movfe_ctx *ctx);        /* the primary cudaStream_t (ingest, raster, propagation) */
+/* The context also owns a copy stream (host->device staging of movfe_push_frames) and a pose stream (movfe_track_poses
+ * runs beside raster/propagation of the next window). movfe_fence makes the primary stream wait, on the device, for
+ * everything enqueued so far on the pose stream - call it before recording a timing event or enqueueing dependent work
+ * on movfe_cuda_stream(). Host buffers handed to movfe_push_frames must stay unchanged until the next call that
+ * synchronises (any download, movfe_synchronize) or until the second following push. */
+int         movfe_fence(movfe_ctx *ctx);
 const char *movfe_version(void);
 
 /* -- ingest: replaces av_frame_get_side_data -> the loop head of VideoDecoder::NextImage

@@ -25,6 +25,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->pose_stream) cudaStreamSynchronize(ctx->pose_stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     void *bufs[] = {ctx->d_stage[0], ctx->d_stage[1], ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected, ctx->d_cls_cnt,
                     ctx->d_area, ctx->d_hop_base, ctx->d_kps_base, ctx->d_nhops, ctx->d_nkps, ctx->d_cov, ctx->d_hops,
@@ -39,7 +40,13 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
         if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
         if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
     }
+    if (ctx->ev_tables) cudaEventDestroy(ctx->ev_tables);
+    for (auto e : ctx->ev_frame)
+        if (e) cudaEventDestroy(e);
+    for (auto &pl : ctx->pose_launches)
+        if (pl.done) cudaEventDestroy(pl.done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->pose_stream) cudaStreamDestroy(ctx->pose_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -88,6 +95,15 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->pose_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming));
+    ctx->ev_frame.resize(c.window_frames, nullptr);
+    for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &pl : ctx->pose_launches) {
+        pl.first = -1;
+        pl.n = 0;
+        CK(cudaEventCreateWithFlags(&pl.done, cudaEventDisableTiming));
+    }
     for (int b = 0; b < 2; b++) {
         CK(cudaEventCreateWithFlags(&ctx->ev_copied[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_consumed[b], cudaEventDisableTiming));
@@ -131,11 +147,13 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(dalloc(&ctx->d_chunk_bbox, S * F * ctx->max_chunks));
     CK(dalloc(&ctx->d_grid, S * F * plane));
     // track tables
-    CK(dalloc(&ctx->d_tracks, S * (F + 1) * c.max_tracks));
-    CK(dalloc(&ctx->d_ntracks, S * (F + 1)));
-    CK(dalloc(&ctx->d_cur_id, S * (F + 1)));
-    CK(cudaMemset(ctx->d_ntracks, 0, S * (F + 1) * sizeof(int32_t)));
-    CK(cudaMemset(ctx->d_cur_id, 0, S * (F + 1) * sizeof(int32_t)));
+    ctx->TSLOTS = 2 * c.window_frames + 1;
+    const size_t TS = ctx->TSLOTS;
+    CK(dalloc(&ctx->d_tracks, S * TS * c.max_tracks));
+    CK(dalloc(&ctx->d_ntracks, S * TS));
+    CK(dalloc(&ctx->d_cur_id, S * TS));
+    CK(cudaMemset(ctx->d_ntracks, 0, S * TS * sizeof(int32_t)));
+    CK(cudaMemset(ctx->d_cur_id, 0, S * TS * sizeof(int32_t)));
     ctx->ext_scratch_bytes = movfe_extract_scratch_bytes(ctx);
     CK(cudaMalloc(&ctx->d_ext_scratch, std::max<size_t>(ctx->ext_scratch_bytes, 16)));
     if (int rc = movfe_extract_init(ctx)) return fail(rc);
@@ -178,6 +196,16 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
 extern "C" int movfe_synchronize(movfe_ctx *ctx) {
     if (!ctx) return MOVFE_E_INVALID;
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_fence(movfe_ctx *ctx) {
+    if (!ctx) return MOVFE_E_INVALID;
+    // device-side join: everything enqueued so far on the pose stream precedes whatever the caller enqueues next on the
+    // primary stream (an event record for timing, a dependent kernel)
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tables, 0));
     return MOVFE_OK;
 }
 
@@ -376,6 +404,7 @@ extern "C" int movfe_profile_enable(movfe_ctx *ctx, int on) {
 extern "C" int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset) {
     if (!ctx) return MOVFE_E_INVALID;
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     for (auto &sp : ctx->prof_spans) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ctx->prof_ms[sp.stage] += t;

@@ -44,6 +44,15 @@ struct movfe_ctx {
     int max_hops = 0, max_kps = 0, max_chunks = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    // join / frustum / pose of a window run on their own stream, concurrently with raster + propagation of the next
+    // window (the chains are independent once a window's track tables exist)
+    cudaStream_t pose_stream = nullptr;
+    cudaEvent_t ev_tables = nullptr;   // scratch event of movfe_fence
+    std::vector<cudaEvent_t> ev_frame; // [window_frames] recorded on `stream` after the finalize of frame f (index f % F)
+    struct PoseLaunch { int64_t first; int n; cudaEvent_t done; };
+    PoseLaunch pose_launches[4] = {};  // ring of the last pose launches (events created at movfe_create)
+    int     pose_launch_head = 0;
+    int     TSLOTS = 0;                // track-table slots per stream: 2*window_frames + 1
     std::string err;
 
     int64_t pushed = 0;            // frames pushed per stream so far
@@ -86,10 +95,11 @@ struct movfe_ctx {
     int32_t *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  (ymin | ymax<<16)
     int4    *d_grid = nullptr;      // [S][F][H*W]
 
-    // track tables: [S][F+1][max_tracks]; slot 0 of a window holds the previous window's last table
+    // track tables: [S][TSLOTS][max_tracks], slot = frame % TSLOTS; two windows are resident so that the pose stream can
+    // still read window k while propagation writes window k+1
     movfe_track *d_tracks = nullptr;
-    int32_t *d_ntracks = nullptr;   // [S][F+1]
-    int32_t *d_cur_id = nullptr;    // [S][F+1]  mCurrentId after each frame
+    int32_t *d_ntracks = nullptr;   // [S][TSLOTS]
+    int32_t *d_cur_id = nullptr;    // [S][TSLOTS]  mCurrentId after each frame
     void    *d_ext_scratch = nullptr;
     size_t   ext_scratch_bytes = 0;
 
@@ -156,12 +166,13 @@ struct ProfScope {
         cudaEventCreate(&e);
         return e;
     }
-    ProfScope(movfe_ctx *c, int st) : ctx(c), stage(st) {
-        if (ctx->prof_on) { a = get(ctx); b = get(ctx); cudaEventRecord(a, ctx->stream); }
+    cudaStream_t on;
+    ProfScope(movfe_ctx *c, int st, cudaStream_t s = nullptr) : ctx(c), stage(st), on(s ? s : c->stream) {
+        if (ctx->prof_on) { a = get(ctx); b = get(ctx); cudaEventRecord(a, on); }
     }
     void launches(int n) { ctx->prof_launches[stage] += n; }
     ~ProfScope() {
-        if (a) { cudaEventRecord(b, ctx->stream); ctx->prof_spans.push_back({stage, a, b}); }
+        if (a) { cudaEventRecord(b, on); ctx->prof_spans.push_back({stage, a, b}); }
     }
 };
 

@@ -1006,7 +1006,7 @@ size_t movfe_extract_scratch_bytes(const movfe_ctx *ctx) {
 }
 
 static int tslot_of(const movfe_ctx *ctx, int64_t frame) {
-    const int T = ctx->cfg.window_frames + 1;
+    const int T = ctx->TSLOTS;
     return (int)(((frame % T) + T) % T);
 }
 
@@ -1026,6 +1026,10 @@ int movfe_extract_init(movfe_ctx *ctx) {
 int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
     const movfe_config &c = ctx->cfg;
     ExtScratch e = carve(ctx, nullptr);
+    // frames [first, first+n) overwrite the tables of frames TSLOTS earlier: a pose launch still reading those must finish
+    for (const auto &pl : ctx->pose_launches)
+        if (pl.first >= 0 && pl.first <= first_frame + n_frames - 1 - ctx->TSLOTS)
+            MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl.done, 0));
     ProfScope prof(ctx, MOVFE_STAGE_EXTRACT);
     for (int k = 0; k < n_frames; k++) {
         const int64_t a = first_frame + k;
@@ -1040,7 +1044,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.n_out = ctx->win_nout;
         p.n_in = ctx->win_nin;
         p.RING = ctx->RING;
-        p.TSLOTS = c.window_frames + 1;
+        p.TSLOTS = ctx->TSLOTS;
         p.fi = (int)(a - ctx->win_first);
         p.gslot = (int)(a % ctx->RING);
         p.tslot_prev = tslot_of(ctx, a - 1);
@@ -1079,6 +1083,8 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
             p, ctx->d_tracks, ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, ctx->d_kps, ctx->d_nkps, ctx->d_cov,
             e.birth_flag, e.birth_desc, ctx->d_grid, ctx->d_grey, ctx->d_fflags);
         prof.launches(nl);
+        // frame a's table is complete: the pose stream may start on it while propagation goes on with frame a+1
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_frame[a % c.window_frames], ctx->stream));
     }
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
@@ -1093,7 +1099,7 @@ extern "C" int movfe_set_tracks(movfe_ctx *ctx, int stream, const movfe_track *t
     MOVFE_CUDA(ctx, cudaSetDevice(c.device));
     const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
     const int ts = tslot_of(ctx, next - 1);
-    const int T = c.window_frames + 1;
+    const int T = ctx->TSLOTS;
     if (n > 0)
         MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_tracks + ((size_t)stream * T + ts) * c.max_tracks, tracks, (size_t)n * sizeof(movfe_track),
                                         cudaMemcpyHostToDevice, ctx->stream));
@@ -1138,7 +1144,7 @@ extern "C" int movfe_track_count(movfe_ctx *ctx, int stream, int64_t frame, int3
     int ts;
     int rc = track_slot(ctx, stream, frame, &ts);
     if (rc) return rc;
-    const int T = ctx->cfg.window_frames + 1;
+    const int T = ctx->TSLOTS;
     if (n_tracks) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_tracks, ctx->d_ntracks + stream * T + ts, 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (current_id) MOVFE_CUDA(ctx, cudaMemcpyAsync(current_id, ctx->d_cur_id + stream * T + ts, 4, cudaMemcpyDeviceToHost, ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1152,7 +1158,7 @@ extern "C" int movfe_download_tracks(movfe_ctx *ctx, int stream, int64_t frame, 
     rc = movfe_track_count(ctx, stream, frame, &n, nullptr);
     if (rc) return rc;
     if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_tracks: %d tracks, capacity %d", n, capacity);
-    const int T = ctx->cfg.window_frames + 1;
+    const int T = ctx->TSLOTS;
     if (n > 0) {
         MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_tracks + ((size_t)stream * T + ts) * ctx->cfg.max_tracks, (size_t)n * sizeof(movfe_track),
                                         cudaMemcpyDeviceToHost, ctx->stream));

@@ -17,7 +17,7 @@
 
 namespace {
 
-constexpr int TP_THREADS = 512;
+constexpr int TP_THREADS = 256;  // 256 x 128 registers: half an SM's register file, so propagation CTAs co-reside
 constexpr int TP_WARPS = TP_THREADS / 32;
 constexpr int HASH_EMPTY = (int)0x80000000;
 
@@ -586,16 +586,58 @@ __device__ int gather_pairs(const movfe_track *__restrict__ tr, int n, const int
     return min(n_pairs, cap);
 }
 
-__global__ void __launch_bounds__(TP_THREADS)
+// One join of the frame (MOVMatcher.h:35-103) with the hash on the PROBE side, so shared memory scales with the map
+// points (hundreds) and not with the track table (thousands): key = track id, value = the last eligible map point with
+// that id (list order, last wins). Every track then looks its id up; of several tracks with one id only the first owns
+// the match (F.mvVFMap is first-wins, MOVExtractor.cc:330) - resolved by an integer atomicMin per map point.
+// reset: SearchByVideoFeature(KF, F, out) starts from an all-NULL vector; the Frame overload keeps earlier matches.
+template <typename Elig>
+__device__ void join_frame(const movfe_track *__restrict__ tr, int n, const movfe_map_point *__restrict__ mp, int n_pts, Elig elig,
+                           bool reset, int *keys, int *vals, int cap, int *first, int32_t *__restrict__ match) {
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        keys[i] = HASH_EMPTY;
+        vals[i] = -1;
+    }
+    for (int i = threadIdx.x; i < n_pts; i += blockDim.x) first[i] = 0x7fffffff;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pts; i += blockDim.x) {
+        if (!elig(i)) continue;
+        const int id = mp[i].track_id;
+        if (id == HASH_EMPTY) continue;
+        unsigned h = hash_id(id) & (cap - 1);
+        while (true) {
+            const int prev = atomicCAS(&keys[h], HASH_EMPTY, id);
+            if (prev == HASH_EMPTY || prev == id) {
+                atomicMax(&vals[h], i);
+                break;
+            }
+            h = (h + 1) & (cap - 1);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int m = hash_find(tr[t].track_id, keys, vals, cap);
+        if (m >= 0) atomicMin(&first[m], t);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int m = hash_find(tr[t].track_id, keys, vals, cap);
+        if (m >= 0 && first[m] == t) match[t] = m;
+        else if (reset) match[t] = -1;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 2)
 track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
                    const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
                    movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses, int32_t *__restrict__ ninl,
                    int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out, int32_t *__restrict__ skip_tag) {
-    extern __shared__ int hsm[];  // keys[cap] vals[cap] hit[maxT] | pairs: x y z u v idx [maxMap] out[maxMap]
+    extern __shared__ int hsm[];  // keys[cap] vals[cap] first[maxMap] | pairs: x y z u v idx [maxMap] out[maxMap]
     __shared__ SolverShared sh;
     __shared__ int wsum[TP_WARPS];
-    int *keys = hsm, *vals = hsm + p.hash_cap, *hit = hsm + 2 * p.hash_cap;
-    float *cx = reinterpret_cast<float *>(hit + p.maxT), *cy = cx + p.maxMap, *cz = cy + p.maxMap, *cu = cz + p.maxMap, *cv = cu + p.maxMap;
+    int *keys = hsm, *vals = hsm + p.hash_cap, *first = hsm + 2 * p.hash_cap;
+    float *cx = reinterpret_cast<float *>(first + p.maxMap), *cy = cx + p.maxMap, *cz = cy + p.maxMap, *cu = cz + p.maxMap, *cv = cu + p.maxMap;
     int *cidx = reinterpret_cast<int *>(cv + p.maxMap);
     uint8_t *cout = reinterpret_cast<uint8_t *>(cidx + p.maxMap);
     const int s = blockIdx.x;
@@ -604,6 +646,8 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
     int32_t *tag = skip_tag + (size_t)s * p.maxMap;
     movfe_pose *pc = pose_cur + s;
     const CompactSrc src{cx, cy, cz, cu, cv};
+    int cap = 2;
+    while (cap < 2 * n_map) cap <<= 1;
 
     for (int k = 0; k < p.n_frames; k++) {
         const int ts = (p.tslot0 + k) % p.TSLOTS;
@@ -613,20 +657,9 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
         uint8_t *outl = outlier_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
         int n_inl = 0;
         if (n > 0 && n_map > 0) {
-            int cap = 2;
-            while (cap < 2 * n) cap <<= 1;
-            hash_build([&](int t) { return tr[t].track_id; }, n, keys, vals, cap);
             // --- TrackReferenceKeyFrame: SearchByVideoFeature(KF, F, matches) (MOVMatcher.h:70-103)
-            for (int t = threadIdx.x; t < n; t += blockDim.x) hit[t] = -1;
-            __syncthreads();
-            for (int i = threadIdx.x; i < n_kf; i += blockDim.x) {
-                if (mp[i].flags & (MOVFE_MP_NULL | MOVFE_MP_BAD)) continue;
-                const int t = hash_find(mp[i].track_id, keys, vals, cap);
-                if (t >= 0) atomicMax(&hit[t], i);  // last map point in list order wins
-            }
-            __syncthreads();
-            for (int t = threadIdx.x; t < n; t += blockDim.x) match[t] = hit[t];
-            __syncthreads();
+            join_frame(tr, n, mp, n_kf, [&](int i) { return !(mp[i].flags & (MOVFE_MP_NULL | MOVFE_MP_BAD)); }, true, keys, vals, cap,
+                       first, match);
             int np = gather_pairs(tr, n, match, mp, cx, cy, cz, cu, cv, cidx, p.maxMap, wsum);
             pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
             // --- TrackLocalMap / SearchLocalPoints (Tracking.cc:1109-1158)
@@ -634,19 +667,14 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
             for (int i = threadIdx.x; i < np; i += blockDim.x) tag[match[cidx[i]]] = frame_tag;  // mnLastFrameSeen = current frame
             __syncthreads();
             const FrustumPose fp = frustum_pose(*pc);
-            for (int t = threadIdx.x; t < n; t += blockDim.x) hit[t] = -1;
-            __syncthreads();
+            // isInFrustum for every local point (:1136-1151); in view and not bad -> eligible (MOVMatcher.h:43-49, far filter off)
             for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
                 const movfe_map_point m = mp[i];
                 const movfe_projection pr = frustum_point(fp, p.cam, p.W, p.H, p.view_cos, m, tag[i] == frame_tag);
-                if (!pr.in_view || (m.flags & MOVFE_MP_BAD)) continue;  // MOVMatcher.h:43-49 (far-point filter off)
-                const int t = hash_find(m.track_id, keys, vals, cap);
-                if (t >= 0) atomicMax(&hit[t], i);
+                cout[i] = pr.in_view && !(m.flags & MOVFE_MP_BAD);
             }
             __syncthreads();
-            for (int t = threadIdx.x; t < n; t += blockDim.x)
-                if (hit[t] >= 0) match[t] = hit[t];
-            __syncthreads();
+            join_frame(tr, n, mp, n_map, [&](int i) { return cout[i] != 0; }, false, keys, vals, cap, first, match);
             np = gather_pairs(tr, n, match, mp, cx, cy, cz, cu, cv, cidx, p.maxMap, wsum);
             n_inl = pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);
             // Frame::mvbOutlier (Optimizer.cc:452-456): true everywhere, false for the inliers
@@ -753,25 +781,42 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     p.H = c.height;
     p.maxT = c.max_tracks;
     p.maxMap = std::max(c.max_map_points, 1);
-    p.TSLOTS = c.window_frames + 1;
+    p.TSLOTS = ctx->TSLOTS;
     p.F = c.window_frames;
-    p.hash_cap = pow2_at_least(2 * c.max_tracks);
+    p.hash_cap = pow2_at_least(2 * p.maxMap);
     p.n_frames = n_frames;
-    p.tslot0 = (int)(first_frame % p.TSLOTS);
+    p.tslot0 = (int)(first_frame % p.TSLOTS);  // == tslot_of(first_frame) in extract.cu
     p.out0 = 0;
     p.view_cos = ctx->view_cos;
     p.cam = ctx->cam;
     p.pp = ctx->pp;
-    const size_t smem = ((size_t)2 * p.hash_cap + c.max_tracks) * sizeof(int) + (size_t)p.maxMap * 25;
-    if (smem > 200 * 1024)
-        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_poses: max_tracks=%d / max_map_points=%d need %zu bytes of shared memory per stream (limit 204800)",
-                   c.max_tracks, c.max_map_points, smem);
+    const size_t smem = ((size_t)2 * p.hash_cap + p.maxMap) * sizeof(int) + (size_t)p.maxMap * 25;
+    int optin = 0;
+    cudaFuncAttributes fa;
+    MOVFE_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
+    MOVFE_CUDA(ctx, cudaFuncGetAttributes(&fa, track_poses_kernel));
+    if (smem + fa.sharedSizeBytes > (size_t)optin)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_poses: max_tracks=%d / max_map_points=%d need %zu bytes of shared memory per stream (limit %zu)",
+                   c.max_tracks, c.max_map_points, smem, (size_t)optin - fa.sharedSizeBytes);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(track_poses_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ProfScope prof(ctx, MOVFE_STAGE_POSE);
-    prof.launches(1);
-    track_poses_kernel<<<c.n_streams, TP_THREADS, smem, ctx->stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap,
-                                                                       ctx->d_nkf, ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl,
-                                                                       ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch);
+    // one launch per frame, each released by the event recorded after that frame's finalize: the pose chain of frame f
+    // runs beside the propagation of frame f+1 instead of after the window
+    for (int k = 0; k < n_frames; k++) {
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(first_frame + k) % c.window_frames], 0));
+        p.n_frames = 1;
+        p.tslot0 = (int)((first_frame + k) % p.TSLOTS);
+        p.out0 = k;
+        ProfScope prof(ctx, MOVFE_STAGE_POSE, ctx->pose_stream);
+        prof.launches(1);
+        track_poses_kernel<<<c.n_streams, TP_THREADS, smem, ctx->pose_stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap,
+                                                                                ctx->d_nkf, ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl,
+                                                                                ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch);
+    }
+    movfe_ctx::PoseLaunch &pl = ctx->pose_launches[ctx->pose_launch_head];
+    ctx->pose_launch_head = (ctx->pose_launch_head + 1) % 4;
+    pl.first = first_frame;
+    pl.n = n_frames;
+    MOVFE_CUDA(ctx, cudaEventRecord(pl.done, ctx->pose_stream));
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
@@ -795,11 +840,11 @@ extern "C" int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_
     MOVFE_CUDA(ctx, cudaSetDevice(c.device));
     if (n > 0)
         MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_map + (size_t)stream * std::max(c.max_map_points, 1), pts, (size_t)n * sizeof(movfe_map_point),
-                                        cudaMemcpyHostToDevice, ctx->stream));
+                                        cudaMemcpyHostToDevice, ctx->pose_stream));
     const int32_t nn = n, nk = std::min(n_keyframe_points, n);
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nmap + stream, &nn, 4, cudaMemcpyHostToDevice, ctx->stream));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkf + stream, &nk, 4, cudaMemcpyHostToDevice, ctx->stream));
-    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nmap + stream, &nn, 4, cudaMemcpyHostToDevice, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkf + stream, &nk, 4, cudaMemcpyHostToDevice, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     return MOVFE_OK;
 }
 
@@ -807,8 +852,8 @@ extern "C" int movfe_set_pose(movfe_ctx *ctx, int stream, const movfe_pose *pose
     if (!ctx || !pose) return MOVFE_E_INVALID;
     if (stream < 0 || stream >= ctx->cfg.n_streams) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "stream %d out of range", stream);
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_pose_cur + stream, pose, sizeof(movfe_pose), cudaMemcpyHostToDevice, ctx->stream));
-    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_pose_cur + stream, pose, sizeof(movfe_pose), cudaMemcpyHostToDevice, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     return MOVFE_OK;
 }
 
@@ -836,11 +881,11 @@ extern "C" int movfe_download_poses(movfe_ctx *ctx, int64_t first_frame, int n_f
     const int S = ctx->cfg.n_streams, F = ctx->cfg.window_frames;
     const int o = (int)(first_frame - ctx->pose_first);
     MOVFE_CUDA(ctx, cudaMemcpy2DAsync(poses, (size_t)n_frames * sizeof(movfe_pose), ctx->d_poses + o, (size_t)F * sizeof(movfe_pose),
-                                      (size_t)n_frames * sizeof(movfe_pose), S, cudaMemcpyDeviceToHost, ctx->stream));
+                                      (size_t)n_frames * sizeof(movfe_pose), S, cudaMemcpyDeviceToHost, ctx->pose_stream));
     if (n_inliers)
         MOVFE_CUDA(ctx, cudaMemcpy2DAsync(n_inliers, (size_t)n_frames * 4, ctx->d_ninl + o, (size_t)F * 4, (size_t)n_frames * 4, S,
-                                          cudaMemcpyDeviceToHost, ctx->stream));
-    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                                          cudaMemcpyDeviceToHost, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     return MOVFE_OK;
 }
 
@@ -855,9 +900,9 @@ extern "C" int movfe_download_matches(movfe_ctx *ctx, int stream, int64_t frame,
     if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_matches: %d tracks, capacity %d", n, capacity);
     const size_t o = ((size_t)stream * ctx->cfg.window_frames + (frame - ctx->pose_first)) * ctx->cfg.max_tracks;
     if (n > 0) {
-        if (match) MOVFE_CUDA(ctx, cudaMemcpyAsync(match, ctx->d_match + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (outlier) MOVFE_CUDA(ctx, cudaMemcpyAsync(outlier, ctx->d_outlier + o, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (match) MOVFE_CUDA(ctx, cudaMemcpyAsync(match, ctx->d_match + o, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->pose_stream));
+        if (outlier) MOVFE_CUDA(ctx, cudaMemcpyAsync(outlier, ctx->d_outlier + o, (size_t)n, cudaMemcpyDeviceToHost, ctx->pose_stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     }
     return n;
 }

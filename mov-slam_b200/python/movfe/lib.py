@@ -41,6 +41,7 @@ def load():
     L.movfe_last_error.argtypes = [vp]
     L.movfe_version.restype = C.c_char_p
     L.movfe_synchronize.argtypes = [vp]
+    L.movfe_fence.argtypes = [vp]
     L.movfe_cuda_stream.restype = vp
     L.movfe_cuda_stream.argtypes = [vp]
     L.movfe_push_frames.argtypes = [vp, i32, vp, vp, vp, vp]
@@ -73,7 +74,7 @@ def load():
     return L
 
 
-EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchronize", "movfe_cuda_stream",
+EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchronize", "movfe_fence", "movfe_cuda_stream",
            "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_frames_pushed", "movfe_raster",
            "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
            "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_track_count",
@@ -119,6 +120,10 @@ class Context:
 
     def synchronize(self):
         self._ck(self.L.movfe_synchronize(self.h))
+
+    def fence(self):
+        """Primary stream waits (on the device) for the pose stream."""
+        self._ck(self.L.movfe_fence(self.h))
 
     @property
     def stream_ptr(self):
