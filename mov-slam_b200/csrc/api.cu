@@ -120,8 +120,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->max_hops = c.max_records_per_frame * (ctx->K + 1);
     ctx->max_kps = c.max_records_per_frame * (ctx->K + 1);
     ctx->max_chunks = (ctx->max_hops + 31) / 32;
-    if (ctx->max_hops >= (1 << 24)) {
-        ctx->err = "movfe_create: max_records_per_frame*(max_ref+1) must stay below 2^24";
+    if (ctx->max_hops >= (1 << 22)) {
+        ctx->err = "movfe_create: max_records_per_frame*(max_ref+1) must stay below 2^22";
         return fail(MOVFE_E_INVALID);
     }
     const size_t S = c.n_streams, F = c.window_frames, NIN = ctx->NIN, RING = ctx->RING;

@@ -22,7 +22,7 @@
 namespace {
 
 constexpr int GRID_MAX_WARPS = 16;
-constexpr int GRID_LIST_CAP = 2048;    // band-list entries staged in shared memory (2 words each = 16 KB)
+constexpr int GRID_LIST_CAP = 2048;    // band-list entries staged in shared memory (2 words each = 16 KB); multiple of 32
 constexpr int GRID_CHUNK_CAP = 1024;   // surviving 32-hop chunk ids per band
 constexpr int TILE_Q = 124;            // a tile's candidate queue: 4 chunks of 31
 
@@ -110,23 +110,33 @@ __device__ __forceinline__ void warp_counts_prefix(const int *wcnt, int nwarps, 
     before = __shfl_sync(0xffffffffu, incl - v, warp);
 }
 
+constexpr int SB_ROWS = 32;  // rows a CTA owns: four 8-row bands share one staged hop list
+
+// list_i word: hop index (22 bits) | first row (5 bits) << 22 | last row (5 bits) << 27, rows relative to the CTA's band
+__device__ __forceinline__ unsigned row_mask8(uint32_t wi, int sub) {
+    const int r0 = (int)((wi >> 22) & 31u) - 8 * sub, r1 = (int)(wi >> 27) - 8 * sub;
+    const int a = max(r0, 0), b = min(r1, 7);
+    return b >= a ? ((2u << (b - a)) - 1u) << a : 0u;
+}
+
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
-grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
+grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
             const int32_t *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
     extern __shared__ uint32_t smem[];
     uint32_t *list_x = smem;                                   // [CAP] x0 | x1<<16
-    uint32_t *list_i = smem + GRID_LIST_CAP;                   // [CAP] hop index | rowmask<<24
+    uint32_t *list_i = smem + GRID_LIST_CAP;                   // [CAP] hop index | r0<<22 | r1<<27
     int32_t  *clist = (int32_t *)(smem + 2 * GRID_LIST_CAP);   // [CHUNK_CAP] surviving chunk ids; reused as x-extents
     __shared__ int32_t wcnt[GRID_MAX_WARPS];
+    __shared__ uint32_t cext[GRID_LIST_CAP / 32];              // per list chunk: rows touched, bit r = some entry covers row r
     __shared__ uint32_t cand[GRID_MAX_WARPS][2][TILE_Q + 36];  // per-warp candidate queue (x word, i word)
 
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
-    const int band = blockIdx.x % NB;
-    const int sg = blockIdx.x / NB;  // s*n_out + g
+    const int band = blockIdx.x % NSB;
+    const int sg = blockIdx.x / NSB;  // s*n_out + g
     const int s = sg / p.n_out, g = sg - s * p.n_out;
-    const int ylo = band * 8, yhi = min(ylo + 7, p.H - 1);
+    const int ylo = band * SB_ROWS, yhi = min(ylo + SB_ROWS - 1, p.H - 1);
     const int n_h = nhops[s * p.n_in + g];
     const HopRect *rects = hop_rects + (size_t)sg * p.max_hops;
     const int32_t *bbox = chunk_bbox + (size_t)sg * p.max_chunks;
@@ -177,9 +187,8 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
             const int pos = n_list + before + __popc(b & lt);
             if (pred && pos < GRID_LIST_CAP) {
                 const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
-                const unsigned rowmask = ((2u << (r1 - r0)) - 1u) << r0;
                 list_x[pos] = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
-                list_i[pos] = (uint32_t)h | (rowmask << 24);
+                list_i[pos] = (uint32_t)h | ((uint32_t)r0 << 22) | ((uint32_t)r1 << 27);
             }
             n_list += tot;
             __syncthreads();
@@ -187,44 +196,55 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
     }
     const bool direct = chunk_overflow || n_list > GRID_LIST_CAP;  // pathological input: tiles scan global memory
 
-    // ---- phase 1c: x-extent of every 32-entry chunk of the staged list (reuses clist) -------------------------
+    // ---- phase 1c: x-extent and touched rows of every 32-entry chunk of the staged list (reuses clist) --------
     const int n_lc = direct ? 0 : (n_list + 31) >> 5;
     for (int c = warp; c < n_lc; c += nwarps) {
         const int e = c * 32 + lane;
         int xmin = 65535, xmax = -1;
+        unsigned rows = 0;
         if (e < n_list) {
-            const uint32_t wx = list_x[e];
+            const uint32_t wx = list_x[e], wi = list_i[e];
             xmin = (int)(wx & 0xffffu);
             xmax = (int)(wx >> 16);
+            const int r0 = (wi >> 22) & 31u, r1 = wi >> 27;
+            rows = ((2u << (r1 - r0)) - 1u) << r0;
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
             xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+            rows |= __shfl_xor_sync(0xffffffffu, rows, o);
         }
-        if (lane == 0) clist[c] = xmin | (xmax << 16);
+        if (lane == 0) {
+            clist[c] = xmin | (xmax << 16);
+            cext[c] = rows;
+        }
     }
     __syncthreads();
 
-    // ---- phase 2: one warp per 32x8 tile ----------------------------------------------------------------------
+    // ---- phase 2: a warp takes (8-row band, 64-px strip) items; no barrier from here on ------------------------
     uint32_t *qx = cand[warp][0], *qi = cand[warp][1];
     const int n_strips = (NT + 1) >> 1;  // a warp gathers once for a 64-px strip = two adjacent tiles
-    for (int strip = warp; strip < n_strips; strip += nwarps) {
+    const int n_sub = (yhi - ylo + 8) >> 3;
+    for (int item = warp; item < n_sub * n_strips; item += nwarps) {
+        const int sub = item / n_strips, strip = item - sub * n_strips;
         const int sx = strip * 64;
+        const int by = ylo + 8 * sub;  // first row of this 8-row band
+        const unsigned submask = 0xffu << (8 * sub);
         // gather the strip's candidates (ascending hop order) into the queue
         int nq = 0;
         bool overflow = direct;
         if (!direct) {
             for (int c = 0; c < n_lc; c++) {
                 const int ext = clist[c];
-                if ((ext >> 16) < sx || (ext & 0xffff) > sx + 63) continue;  // warp-uniform
+                if ((ext >> 16) < sx || (ext & 0xffff) > sx + 63 || !(cext[c] & submask)) continue;  // warp-uniform
                 const int e = c * 32 + lane;
                 bool pred = false;
                 uint32_t wx = 0, wi = 0;
                 if (e < n_list) {
                     wx = list_x[e];
                     wi = list_i[e];
-                    pred = (int)(wx >> 16) >= sx && (int)(wx & 0xffffu) <= sx + 63;
+                    pred = (int)(wx >> 16) >= sx && (int)(wx & 0xffffu) <= sx + 63 && row_mask8(wi, sub) != 0;
                 }
                 const unsigned b = __ballot_sync(0xffffffffu, pred);
                 if (nq + __popc(b) > TILE_Q) {
@@ -255,8 +275,8 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
                 if (c < nchk && lane < 31 && e < nq) {
                     const uint32_t wi = qi[e];
                     cwx[c] = qx[e];
-                    idx[c] = (int)(wi & 0xffffffu);
-                    rm[c] = wi >> 24;
+                    idx[c] = (int)(wi & 0x3fffffu);
+                    rm[c] = row_mask8(wi, sub);
                 }
             }
         }
@@ -264,20 +284,25 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
         const int tx = sx + 32 * tsub;
         if (tx >= p.W) break;
         const int x = tx + lane;
-        int4 *out = grid + ((size_t)sg * p.H + ylo) * p.W + x;
+        int4 *out = grid + ((size_t)sg * p.H + by) * p.W + x;
         if (!overflow) {
-            // fast path: <= 4 chunks of 31 candidates, column masks in registers, rows folded independently
-            const bool full = tx + 31 < p.W && ylo + 7 < p.H;  // warp-uniform: no per-store bounds test needed
+            // fast path: <= 4 chunks of 31 candidates, column masks in registers. Rows are folded independently, and a
+            // row whose covering set equals the previous row's (block edges are sparse) reuses its slots.
+            const bool full = tx + 31 < p.W && by + 7 < p.H;  // warp-uniform: no per-store bounds test needed
             const size_t rstride = (size_t)p.W;
             if (nchk <= 1) {
                 const unsigned cm = (lane < 31 && (int)(cwx[0] >> 16) >= tx && (int)(cwx[0] & 0xffffu) <= tx + 31) ? col_mask(cwx[0], tx) : 0u;
                 const unsigned col0 = transpose32(cm, lane);
+                Slots st = {-1, -1, -1, -1, 0};
+                unsigned prev0 = 0;
 #pragma unroll
                 for (int y = 0; y < 8; y++) {
-                    Slots st;
                     const unsigned rowm0 = __ballot_sync(0xffffffffu, (rm[0] >> y) & 1u);
-                    fold<true, false>(st, col0 & rowm0, idx[0]);
-                    if (full || (x < p.W && ylo + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
+                    if (y == 0 || rowm0 != prev0) {  // warp-uniform
+                        fold<true, false>(st, col0 & rowm0, idx[0]);
+                        prev0 = rowm0;
+                    }
+                    if (full || (x < p.W && by + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
                     out += rstride;
                 }
             } else {
@@ -290,19 +315,26 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
                         col[c] = transpose32(cm, lane);
                     }
                 }
+                Slots st = {-1, -1, -1, -1, 0};
+                unsigned prev[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int y = 0; y < 8; y++) {
-                    Slots st;
-                    const unsigned rowm0 = __ballot_sync(0xffffffffu, (rm[0] >> y) & 1u);
-                    fold<true, true>(st, col[0] & rowm0, idx[0]);
+                    unsigned rowm[4];
+                    bool same = y != 0;
 #pragma unroll
-                    for (int c = 1; c < 4; c++) {
-                        if (c < nchk) {
-                            const unsigned rowm = __ballot_sync(0xffffffffu, (rm[c] >> y) & 1u);
-                            fold<false, true>(st, col[c] & rowm, idx[c]);
-                        }
+                    for (int c = 0; c < 4; c++) {
+                        rowm[c] = c < nchk ? __ballot_sync(0xffffffffu, (rm[c] >> y) & 1u) : 0u;
+                        same = same && rowm[c] == prev[c];
                     }
-                    if (full || (x < p.W && ylo + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
+                    if (!same) {  // warp-uniform
+                        fold<true, true>(st, col[0] & rowm[0], idx[0]);
+#pragma unroll
+                        for (int c = 1; c < 4; c++)
+                            if (c < nchk) fold<false, true>(st, col[c] & rowm[c], idx[c]);
+#pragma unroll
+                        for (int c = 0; c < 4; c++) prev[c] = rowm[c];
+                    }
+                    if (full || (x < p.W && by + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
                     out += rstride;
                 }
             }
@@ -311,7 +343,7 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
             // streaming every source entry again and folding 31 candidates per step.
             const int n_src = direct ? n_h : n_list;
             for (int y = 0; y < 8; y++) {
-                if (ylo + y >= p.H) break;
+                if (by + y >= p.H) break;
                 Slots st = {-1, -1, -1, -1, 0};
                 int nq = 0;
                 for (int base = 0; base <= n_src; base += 32) {  // one extra, empty pass flushes the queue
@@ -322,10 +354,11 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
                         if (!direct) {
                             wx = list_x[e];
                             wi = list_i[e];
-                            pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31 && ((wi >> (24 + y)) & 1u);
+                            pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31 && ((row_mask8(wi, sub) >> y) & 1u);
+                            wi &= 0x3fffffu;
                         } else {
                             const HopRect r = rects[e];
-                            pred = r.y1 >= ylo + y && r.y0 <= ylo + y && r.x1 >= tx && r.x0 <= tx + 31;
+                            pred = r.y1 >= by + y && r.y0 <= by + y && r.x1 >= tx && r.x0 <= tx + 31;
                             wx = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
                             wi = (uint32_t)e;
                         }
@@ -346,7 +379,7 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
                         int id = -1;
                         if (lane < 31 && e2 < take) {
                             cm = col_mask(qx[e2], tx);
-                            id = (int)(qi[e2] & 0xffffffu);
+                            id = (int)qi[e2];
                         }
                         const unsigned colm = transpose32(cm, lane);
                         fold<false, true>(st, colm, id);
@@ -380,19 +413,20 @@ grid_kernel(WinParams p, int NB, int NT, const HopRect *__restrict__ hop_rects, 
 int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p) {
     ProfScope prof(ctx, MOVFE_STAGE_GRID);
     prof.launches(1);
-    // warps per CTA: the largest divisor of the strip count (two 32-px tiles per strip) that is <= 16 keeps every
-    // warp equally loaded
+    // a CTA owns a 32-row band = 4 x n_strips (8-row band, 64-px strip) items; warps per CTA: the largest divisor of the
+    // item count that is <= 16 keeps every warp equally loaded
     const int n_strips = (ctx->NT + 1) / 2;
+    const int nsb = (p.H + SB_ROWS - 1) / SB_ROWS;
     int nw = 8;
     for (int w = GRID_MAX_WARPS; w >= 4; w--)
-        if (n_strips % w == 0) {
+        if ((4 * n_strips) % w == 0) {
             nw = w;
             break;
         }
     const size_t smem = (2 * GRID_LIST_CAP + GRID_CHUNK_CAP) * sizeof(uint32_t);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = p.S * p.n_out * ctx->NB;
-    grid_kernel<<<blocks, nw * 32, smem, ctx->stream>>>(p, ctx->NB, ctx->NT, ctx->d_hop_rect, ctx->d_nhops, ctx->d_chunk_bbox,
+    const int blocks = p.S * p.n_out * nsb;
+    grid_kernel<<<blocks, nw * 32, smem, ctx->stream>>>(p, nsb, ctx->NT, ctx->d_hop_rect, ctx->d_nhops, ctx->d_chunk_bbox,
                                                        ctx->d_grid);
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
