@@ -125,6 +125,15 @@ int movfe_profile_enable(movfe_ctx *ctx, int on);
 int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset);
 
 /* -- single-shot operators (batch of independent problems; used by the drop-in shims and the parity tests) --- */
+/* MOVExtractor::operator() (include/MOVExtractor.h:36-37) for ONE frame whose raster results the caller holds on the
+ * host: grid = VideoImage::mvi (height*width*4 int32), hops = mvs, kps, coverage_area, frame_flags = MOVFE_FRAME_*,
+ * grey = imGray (height*width, or NULL for a context created with has_grey = 0); prev/n_prev = prev->mvVF (any order:
+ * the reference's stable sort is applied); *current_id = MOVExtractor::mCurrentId, read and updated. Writes the new
+ * frame's table to out and returns its size. The context must have n_streams == 1 and must not be mixed with the
+ * batched push/raster/extract calls. */
+int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const uint8_t *grey, const int32_t *grid,
+                        const movfe_hop *hops, int n_hops, const movfe_rect *kps, int n_kps, double coverage_area,
+                        const movfe_track *prev, int n_prev, int32_t *current_id, movfe_track *out, int capacity);
 /* Frame::isInFrustum for n_problems point sets. pts/out are packed; off has n_problems+1 entries. */
 int movfe_frustum(movfe_ctx *ctx, int n_problems, const movfe_pose *poses, const movfe_map_point *pts,
                   const int32_t *off, movfe_projection *out);

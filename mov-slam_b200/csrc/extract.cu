@@ -383,7 +383,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     movfe_track *st = stage + (size_t)s * p.maxT;
     int2 *ci = cinfo + (size_t)s * p.maxT;
-    int32_t *cl = claim + (size_t)s * p.maxM;
+    int32_t *cl = claim + (size_t)s * p.max_kps;  // lbFound (MOVExtractor.cc:253), one entry per kps of the frame
 
     for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n_prev; c += gridDim.x * CAND_WARPS) {
         const int i = c * 32 + lane;  // sorted rank
@@ -493,7 +493,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
                 o[1] = make_uint4(a1.x, a1.y + 1, (uint32_t)i, 0u);  // trackId, age + 1, qIndx, flags
                 o[2] = make_uint4(my_d[0], my_d[1], my_d[2], my_d[3]);
                 o[3] = make_uint4(my_d[4], my_d[5], my_d[6], my_d[7]);
-                if (cd >= 0 && cd < p.maxM) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
+                if (cd >= 0 && cd < p.max_kps) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
             }
             ci[i] = make_int2(alive ? cd : -1, fl);
         }
@@ -595,7 +595,7 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
         if (i < n) {
             r = __ldg(reinterpret_cast<const int2 *>(kp + i));  // x | y << 16, w | h << 16
             const int x = (int16_t)(r.x & 0xffff), y = r.x >> 16, w = (int16_t)(r.y & 0xffff), h = r.y >> 16;
-            const bool claimed = i < p.maxM && claim[(size_t)s * p.maxM + i] != 0x7fffffff;  // lbFound[i]
+            const bool claimed = claim[(size_t)s * p.max_kps + i] != 0x7fffffff;  // lbFound[i]
             job = !claimed && rect_in_bounds(x, y, w, h, p.W, p.H);
             birth_flag[(size_t)s * p.max_kps + i] = 0;
         }
@@ -831,7 +831,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     movfe_track *cur = tracks + ((size_t)s * p.TSLOTS + p.tslot_cur) * p.maxT;
     const movfe_track *st = stage + (size_t)s * p.maxT;
     const int2 *ci = cinfo + (size_t)s * p.maxT;
-    int32_t *cl = claim + (size_t)s * p.maxM;
+    int32_t *cl = claim + (size_t)s * p.max_kps;  // lbFound (MOVExtractor.cc:253), one entry per kps of the frame
     const int n_prev = ntracks[s * p.TSLOTS + p.tslot_prev];
     const uint8_t ff = fflags[s * p.RING + p.gslot];
     const bool is_p = ff & MOVFE_FRAME_P;
@@ -853,7 +853,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
 #pragma unroll
             for (int e = 0; e < FIN_IPT; e++) {
                 if ((c[e].y & 3) == 3) {  // in bounds and through the descriptor gate
-                    const bool mine = c[e].x < 0 || c[e].x >= p.maxM || cl[c[e].x] == i0 + e;  // !lbFound at my turn
+                    const bool mine = c[e].x < 0 || c[e].x >= p.max_kps || cl[c[e].x] == i0 + e;  // !lbFound at my turn
                     if (mine) accm |= 1u << e;
                 }
             }
@@ -861,7 +861,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
             int pos = n_out + block_excl_scan(__popc(accm), wsum, tot);  // barriers: every claim test is done
 #pragma unroll
             for (int e = 0; e < FIN_IPT; e++) {
-                if ((c[e].y & 1) && c[e].x >= 0 && c[e].x < p.maxM) cl[c[e].x] = 0x7fffffff;  // claims are per frame
+                if ((c[e].y & 1) && c[e].x >= 0 && c[e].x < p.max_kps) cl[c[e].x] = 0x7fffffff;  // claims are per frame
                 if ((accm >> e) & 1u) {
                     if (pos < p.maxT) {
                         const uint4 *src = reinterpret_cast<const uint4 *>(st + i0 + e);
@@ -980,7 +980,7 @@ ExtScratch carve(const movfe_ctx *ctx, size_t *total) {
     e.cinfo = (int2 *)(base + off);
     off += align256(S * c.max_tracks * sizeof(int2));
     e.claim = (int32_t *)(base + off);
-    off += align256(S * c.max_records_per_frame * sizeof(int32_t));
+    off += align256(S * (size_t)ctx->max_kps * sizeof(int32_t));
     e.birth_flag = (uint8_t *)(base + off);
     off += align256(S * (size_t)ctx->max_kps);
     e.birth_desc = (uint32_t *)(base + off);
@@ -1014,7 +1014,7 @@ int movfe_extract_init(movfe_ctx *ctx) {
     const movfe_config &c = ctx->cfg;
     if (c.max_tracks > MAX_TRACKS_CAP) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "max_tracks must be <= %d", MAX_TRACKS_CAP);
     ExtScratch e = carve(ctx, nullptr);
-    const size_t n = (size_t)c.n_streams * c.max_records_per_frame;
+    const size_t n = (size_t)c.n_streams * ctx->max_kps;
     fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(e.claim, n, 0x7fffffff);
     MOVFE_CUDA(ctx, cudaMemsetAsync(e.order, 0, (size_t)c.n_streams * c.max_tracks * sizeof(uint16_t), ctx->stream));
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
@@ -1165,4 +1165,65 @@ extern "C" int movfe_download_tracks(movfe_ctx *ctx, int stream, int64_t frame, 
         MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
     return n;
+}
+
+// Single-shot MOVExtractor::operator() for callers that hold one frame's raster results on the host (the drop-in shim
+// when only MOVExtractor is replaced; the parity tests of propagation in isolation). One-stream contexts only; every call
+// is one new frame, so it must not be mixed with the batched push / raster / extract calls on the same context.
+int movfe_grey_upload(movfe_ctx *ctx, const uint8_t *d_src, int slot);  // raster.cu
+
+extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const uint8_t *grey, const int32_t *grid,
+                                   const movfe_hop *hops, int n_hops, const movfe_rect *kps, int n_kps, double coverage_area,
+                                   const movfe_track *prev, int n_prev, int32_t *current_id, movfe_track *out, int capacity) {
+    if (!ctx) return MOVFE_E_INVALID;
+    const movfe_config &c = ctx->cfg;
+    if (c.n_streams != 1) MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract_frame: the context must have exactly one stream");
+    if (!grid || !current_id || !out || n_hops < 0 || n_kps < 0 || n_prev < 0 || (n_hops && !hops) || (n_kps && !kps) || (n_prev && !prev))
+        MOVFE_FAIL(ctx, MOVFE_E_INVALID, "extract_frame: bad argument");
+    if ((c.has_grey != 0) != (grey != nullptr))
+        MOVFE_FAIL(ctx, MOVFE_E_INVALID, "extract_frame: grey plane %s but the context was created with has_grey=%d", grey ? "given" : "missing", c.has_grey);
+    if (n_hops > ctx->max_hops || n_kps > ctx->max_kps)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "extract_frame: %d hops / %d kps exceed the context's capacity (%d / %d)", n_hops, n_kps, ctx->max_hops, ctx->max_kps);
+    const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
+    if (next != ctx->pushed) MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract_frame: mixed with the batched calls on this context");
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    int rc = movfe_set_tracks(ctx, 0, prev, n_prev, *current_id);
+    if (rc) return rc;
+    const int64_t a = ctx->pushed;
+    const int slot = (int)(a % ctx->RING);
+    const size_t plane = (size_t)c.width * c.height;
+    cudaStream_t st = ctx->stream;
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid, grid, plane * sizeof(int4), cudaMemcpyHostToDevice, st));
+    if (n_hops) MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_hops, hops, (size_t)n_hops * sizeof(movfe_hop), cudaMemcpyHostToDevice, st));
+    if (n_kps) MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_kps, kps, (size_t)n_kps * sizeof(movfe_rect), cudaMemcpyHostToDevice, st));
+    const int32_t nh = n_hops, nk = n_kps;
+    const uint8_t ff = (uint8_t)frame_flags;
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nhops, &nh, 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkps, &nk, 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cov, &coverage_area, 8, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_fflags + slot, &ff, 1, cudaMemcpyHostToDevice, st));
+    if (grey) {
+        if (ctx->stage_bytes[0] < plane + 16) {
+            MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+            if (ctx->d_stage[0]) cudaFree(ctx->d_stage[0]);
+            ctx->d_stage[0] = nullptr;
+            ctx->stage_bytes[0] = 0;
+            MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_stage[0], plane + 4096));
+            ctx->stage_bytes[0] = plane + 4096;
+        }
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[0], grey, plane, cudaMemcpyHostToDevice, st));
+        rc = movfe_grey_upload(ctx, (const uint8_t *)ctx->d_stage[0], slot);
+        if (rc) return rc;
+    }
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // nh / nk / ff live on this stack frame
+    ctx->pushed = a + 1;
+    ctx->win_first = a;
+    ctx->win_nout = 1;
+    ctx->win_nin = 1;
+    rc = movfe_extract(ctx, a, 1);
+    if (rc) return rc;
+    int32_t n = 0;
+    rc = movfe_track_count(ctx, 0, a, &n, current_id);
+    if (rc) return rc;
+    return movfe_download_tracks(ctx, 0, a, out, capacity);
 }

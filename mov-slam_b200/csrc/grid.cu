@@ -235,28 +235,39 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
         int nq = 0;
         bool overflow = direct;
         if (!direct) {
-            for (int c = 0; c < n_lc; c++) {
-                const int ext = clist[c];
-                if ((ext >> 16) < sx || (ext & 0xffff) > sx + 63 || !(cext[c] & submask)) continue;  // warp-uniform
-                const int e = c * 32 + lane;
-                bool pred = false;
-                uint32_t wx = 0, wi = 0;
-                if (e < n_list) {
-                    wx = list_x[e];
-                    wi = list_i[e];
-                    pred = (int)(wx >> 16) >= sx && (int)(wx & 0xffffu) <= sx + 63 && row_mask8(wi, sub) != 0;
+            // list chunks that can matter to this item (x-extent meets the strip, some entry covers one of its rows): 32
+            // chunks are tested per ballot, only the survivors are visited, in ascending order
+            for (int cb = 0; cb < n_lc && !overflow; cb += 32) {
+                const int cc = cb + lane;
+                bool rel = false;
+                if (cc < n_lc) {
+                    const int ext = clist[cc];
+                    rel = (ext >> 16) >= sx && (ext & 0xffff) <= sx + 63 && (cext[cc] & submask);
                 }
-                const unsigned b = __ballot_sync(0xffffffffu, pred);
-                if (nq + __popc(b) > TILE_Q) {
-                    overflow = true;
-                    break;
+                unsigned todo = __ballot_sync(0xffffffffu, rel);
+                while (todo) {
+                    const int c = cb + __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int e = c * 32 + lane;
+                    bool pred = false;
+                    uint32_t wx = 0, wi = 0;
+                    if (e < n_list) {
+                        wx = list_x[e];
+                        wi = list_i[e];
+                        pred = (int)(wx >> 16) >= sx && (int)(wx & 0xffffu) <= sx + 63 && row_mask8(wi, sub) != 0;
+                    }
+                    const unsigned b = __ballot_sync(0xffffffffu, pred);
+                    if (nq + __popc(b) > TILE_Q) {
+                        overflow = true;
+                        break;
+                    }
+                    if (pred) {
+                        const int pos = nq + __popc(b & lt);
+                        qx[pos] = wx;
+                        qi[pos] = wi;
+                    }
+                    nq += __popc(b);
                 }
-                if (pred) {
-                    const int pos = nq + __popc(b & lt);
-                    qx[pos] = wx;
-                    qi[pos] = wi;
-                }
-                nq += __popc(b);
             }
         }
         __syncwarp();

@@ -426,6 +426,17 @@ int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_r
     return MOVFE_OK;
 }
 
+// one packed plane (device memory) -> ring slot `slot` of stream 0 (movfe_extract_frame)
+int movfe_grey_upload(movfe_ctx *ctx, const uint8_t *d_src, int slot) {
+    const movfe_config &c = ctx->cfg;
+    const int vec = (c.width % 16 == 0 && ((uintptr_t)d_src & 15) == 0) ? 16 : 1;
+    const int64_t total = (int64_t)c.height * (c.width / vec);
+    grey_ingest_kernel<<<(int)((total + 255) / 256), 256, 0, ctx->stream>>>(d_src, 1, 1, c.width, c.height, ctx->grey_pitch, vec, slot, ctx->RING,
+                                                                      ctx->d_grey);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    return MOVFE_OK;
+}
+
 int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in) {
     const movfe_config &c = ctx->cfg;
     WinParams p;

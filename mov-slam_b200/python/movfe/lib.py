@@ -57,6 +57,7 @@ def load():
     L.movfe_rejected_records.argtypes = [vp]
     L.movfe_set_tracks.argtypes = [vp, i32, vp, i32, i32]
     L.movfe_extract.argtypes = [vp, i64, i32]
+    L.movfe_extract_frame.argtypes = [vp, C.c_uint32, vp, vp, vp, i32, vp, i32, C.c_double, vp, i32, vp, vp, i32]
     L.movfe_track_count.argtypes = [vp, i32, i64, vp, vp]
     L.movfe_download_tracks.argtypes = [vp, i32, i64, vp, i32]
     L.movfe_set_camera.argtypes = [vp, vp, vp, C.c_float]
@@ -77,7 +78,7 @@ def load():
 EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchronize", "movfe_fence", "movfe_cuda_stream",
            "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_frames_pushed", "movfe_raster",
            "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
-           "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_track_count",
+           "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read"]
@@ -195,6 +196,20 @@ class Context:
 
     def extract(self, first_frame, n_frames):
         self._ck(self.L.movfe_extract(self.h, first_frame, n_frames))
+
+    def extract_frame(self, frame_flags, grey, grid, hops, kps, coverage_area, prev, current_id):
+        """Single-shot MOVExtractor::operator() on host raster results -> (tracks, current_id)."""
+        grid = np.ascontiguousarray(grid, np.int32)
+        hops = np.ascontiguousarray(hops, T.HOP)
+        kps = np.ascontiguousarray(kps, T.RECT)
+        prev = np.ascontiguousarray(prev, T.TRACK)
+        if grey is not None:
+            grey = np.ascontiguousarray(grey, np.uint8)
+        cid = C.c_int32(current_id)
+        out = np.zeros(self.cfg.max_tracks, T.TRACK)
+        n = self._ck(self.L.movfe_extract_frame(self.h, int(frame_flags), _p(grey), _p(grid), _p(hops), len(hops), _p(kps), len(kps),
+                                                float(coverage_area), _p(prev), len(prev), C.byref(cid), _p(out), len(out)))
+        return out[:n], cid.value
 
     def track_count(self, stream, frame):
         n, cid = C.c_int32(), C.c_int32()

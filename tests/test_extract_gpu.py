@@ -61,3 +61,23 @@ def test_dense4x4_mv_only(orc):
     for f in range(4):
         assert_tracks_equal(got[(0, f)], want[f], (0, f))
     ctx.close()
+
+
+def test_single_shot_extract_frame(orc):
+    """movfe_extract_frame: MOVExtractor::operator() on host raster results (the shim's entry point), frame by frame."""
+    from movfe import lib
+    sp = synth.Spec(320, 240, n_frames=6, refs=3, seed=0x5EED0016)
+    r, o, fl = synth.make_records(sp)
+    grey = synth.make_grey(sp)
+    clip = orc.Clip(sp.W, sp.H, r, o, fl, 2)
+    ctx = lib.Context(1, sp.W, sp.H, max_records_per_frame=1200, max_ref=2, window_frames=1, max_tracks=2048)
+    prev_g, prev_w = np.zeros(0, T.TRACK), np.zeros(0, T.TRACK)
+    cid_g = cid_w = 0
+    for f in range(sp.n_frames):
+        args = (clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f))
+        got, cid_g = ctx.extract_frame(fl[f], grey[f], *args, prev_g, cid_g)
+        want, _, cid_w, _ = orc.extract_frame(sp.W, sp.H, fl[f], grey[f], *args, prev_w, cid_w, max_tracks=2048)
+        assert_tracks_equal(got, want, ("single", f))
+        assert cid_g == cid_w
+        prev_g, prev_w = got, want
+    ctx.close()

@@ -1,0 +1,98 @@
+"""The drop-in C++ shims (mov-slam_b200/shim): same class names and signatures as the reference's MOVExtractor,
+MOVMatcher and Optimizer::PoseOptimization, plus the RasterQueue that stands where VideoDecoder::NextImage's MV loop
+was. not gpu: they compile against the stand-in headers and link with libmovfe.so. gpu: a C++ driver runs them the way
+Tracking.cc drives the reference classes and every output is compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from movfe import synth, types as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "mov-slam_b200", "shim")
+
+
+def _build():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "mov-slam_b200")], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", SHIM], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_shims_compile_and_link():
+    _build()
+    assert os.path.exists(os.path.join(SHIM, "test_shim"))
+    # the reference's signatures are what the shim headers declare
+    h = open(os.path.join(SHIM, "MOVExtractor_movfe.h")).read()
+    assert "MOVExtractor(int threshold = 20, double coverageThreshold = 0.60, double relocalizationDistance = 0.25)" in h
+    assert "int operator()(const shared_ptr<MotionVectorImage> &_smv, std::vector<cv::KeyPoint> &_keypoints" in h
+    m = open(os.path.join(SHIM, "MOVMatcher_movfe.h")).read()
+    for sig in ("static int SearchByVideoFeature(Frame &F, const vector<MapPoint *> &vpMapPoints, const bool bFarPoints, const float thFarPoints)",
+                "static int SearchByVideoFeature(KeyFrame *pKF, Frame &F, vector<MapPoint *> &vpMapPointMatches)",
+                "static int SearchForInitialization(Frame &F1, Frame &F2, vector<cv::Point2f> &vbPrevMatched, vector<int> &vnMatches12, int windowSize)"):
+        assert sig in m
+
+
+@pytest.mark.gpu
+def test_shims_against_oracle(orc, tmp_path):
+    _build()
+    W, H, NF, K, thr = 320, 240, 7, 2, 25
+    sp = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0020, fx=160.0, fy=160.0)
+    recs, off, flags = synth.make_records(sp)
+    grey = synth.make_grey(sp)
+    clip = orc.Clip(W, H, recs, off, flags, 10)     # the shim's raster context accepts the reference's full ref range
+    # oracle chain: tracks per frame
+    prev, cid, tracks = np.zeros(0, T.TRACK), 0, []
+    for f in range(NF):
+        t, _, cid, _ = orc.extract_frame(W, H, flags[f], grey[f], clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f), prev, cid,
+                                         threshold=thr, coverage_threshold=0.20, max_tracks=8192)
+        tracks.append(t)
+        prev = t
+    mp = synth.map_from_tracks(sp, tracks[0], synth.pose_at(sp, 0))
+    mp["flags"][3] = T.MP_BAD
+    mp["flags"][5] = T.MP_NULL
+    n_kf = len(mp) - 7
+    pose0 = synth.pose_struct(synth.pose_at(sp, 0))
+    cam = sp.camera()
+    d = str(tmp_path)
+    np.array([W, H, NF, 10, thr, len(mp), n_kf], np.int32).tofile(d + "/meta.bin")
+    recs.tofile(d + "/recs.bin"); off.tofile(d + "/off.bin"); flags.tofile(d + "/flags.bin"); grey.tofile(d + "/grey.bin")
+    mp.tofile(d + "/map.bin")
+    np.concatenate([pose0["R"], pose0["t"]]).astype(np.float64).tofile(d + "/pose0.bin")
+    np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).tofile(d + "/cam.bin")
+    r = subprocess.run([os.path.join(SHIM, "test_shim"), d], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+    def f32(p):  # the Frame stores Sophus::SE3f: the pose is rounded to float between calls
+        q = p.copy()
+        q["R"] = q["R"].astype(np.float32)
+        q["t"] = q["t"].astype(np.float32)
+        return q
+
+    pp = T.pose_params()
+    last = f32(pose0)
+    for f in range(NF):
+        got_t = np.fromfile(d + "/out_tracks_%d.bin" % f, T.TRACK)
+        assert got_t.tobytes() == tracks[f].tobytes(), ("tracks", f)
+        want_m, n_m = orc.search_by_keyframe(tracks[f], mp[:n_kf])
+        got_m = np.fromfile(d + "/out_match_%d.bin" % f, np.int32)
+        assert np.array_equal(got_m, want_m), ("match", f)
+        got_p = np.fromfile(d + "/out_pose_%d.bin" % f, np.float64)
+        assert int(got_p[12]) == n_m
+        sel = np.nonzero(want_m >= 0)[0]
+        got_o = np.fromfile(d + "/out_outlier_%d.bin" % f, np.uint8)
+        if len(sel) < 4:
+            assert int(got_p[13]) == 0
+            continue
+        pts = mp["pos"][want_m[sel]]
+        obs = np.stack([tracks[f]["pt_x"][sel], tracks[f]["pt_y"][sel]], 1)
+        n, pose, outl, _ = orc.pose_optimize(cam, pp, pts, obs, last)
+        assert int(got_p[13]) == n, ("inliers", f, got_p[13], n)
+        want_o = np.ones(len(tracks[f]), np.uint8)
+        want_o[sel] = outl
+        assert np.array_equal(got_o, want_o), ("outlier", f)
+        ref = np.concatenate([pose["R"], pose["t"]])
+        assert np.max(np.abs(got_p[:12] - ref)) <= 1e-5 * max(1.0, float(np.max(np.abs(ref)))), ("pose", f)
+        if n > 0:
+            last = f32(pose)
