@@ -294,28 +294,55 @@ constexpr int CW_INFO = 4;   // need (4 bits) | mw << 8 | mh << 16
 constexpr int CW_OIDX = 5;   // index of the track in the previous table
 constexpr int CW_WORDS = 6;
 
+// Loads of one candidate patch for the propagation kernel (mask pixels at column offset 1). For the shapes whose four
+// centre pixels lie inside the loaded 1..COLS columns the centre costs four shuffles instead of four more loads.
+template <int ROWS, int COLS>
+struct CentreInPatch {
+    static constexpr bool value = COLS / 2 < ROWS;  // rows cols/2-1, cols/2 exist; columns rows/2-1, rows/2 are within 1..COLS
+};
+
+template <int ROWS, int COLS, int STRIDE>
+__device__ __forceinline__ void cand_issue(const uint8_t *__restrict__ img, unsigned origin, int stride_rt, int lane,
+                                           int (&vals)[ROWS * COLS / 32], int (&cen)[4]) {
+    const int stride = STRIDE ? STRIDE : stride_rt;
+    constexpr int LC = COLS == 16 ? 4 : 3;
+    const uint8_t *pc = img + origin;
+    const uint8_t *pq = pc + ((lane >> LC) * stride + (lane & (COLS - 1)) + 1);
+    const int step = (32 >> LC) * stride;
+#pragma unroll
+    for (int it = 0; it < ROWS * COLS / 32; it++) vals[it] = pq[it * step];
+    if (!CentreInPatch<ROWS, COLS>::value) {
+        constexpr int cr = ROWS / 2, cc = COLS / 2;
+        cen[0] = pc[cc * stride + cr];
+        cen[1] = pc[(cc - 1) * stride + (cr - 1)];
+        cen[2] = pc[cc * stride + (cr - 1)];
+        cen[3] = pc[(cc - 1) * stride + cr];
+    }
+}
+
+template <int ROWS, int COLS>
+__device__ __forceinline__ Band cand_band(const int (&vals)[ROWS * COLS / 32], const int (&cen)[4], int thr) {
+    if (!CentreInPatch<ROWS, COLS>::value) return band_of(cen, thr);
+    // pixel (r, c) of the block sits at raster index r*COLS + (c-1) of the loaded columns
+    constexpr int cr = ROWS / 2, cc = COLS / 2;
+    constexpr int p0 = cc * COLS + (cr - 1), p1 = (cc - 1) * COLS + (cr - 2), p2 = cc * COLS + (cr - 2), p3 = (cc - 1) * COLS + (cr - 1);
+    const int c4[4] = {__shfl_sync(0xffffffffu, vals[p0 >> 5], p0 & 31), __shfl_sync(0xffffffffu, vals[p1 >> 5], p1 & 31),
+                       __shfl_sync(0xffffffffu, vals[p2 >> 5], p2 & 31), __shfl_sync(0xffffffffu, vals[p3 >> 5], p3 & 31)};
+    return band_of(c4, thr);
+}
+
 template <int ROWS, int COLS, int STRIDE>
 __device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int stride_rt, int thr, const int (&mxy)[4], unsigned need,
                                          const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
     constexpr int IT = ROWS * COLS / 32;
     int vals[4][IT], cen[4][4];
     const int stride = STRIDE ? STRIDE : stride_rt;
+    // every needed candidate's loads are issued before any is consumed (the branches are warp-uniform)
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-        const bool on = (need >> j) & 1u;  // candidates that are not evaluated read the block at (0,0) (always valid)
-        patch_issue<ROWS, COLS, STRIDE>(img, on ? (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)) : 0u, stride_rt, 1, lane,
-                                        vals[j], cen[j]);
-    }
-    if (need >> 2) {  // warp-uniform
-#pragma unroll
-        for (int j = 2; j < 4; j++) {
-            const bool on = (need >> j) & 1u;
-            patch_issue<ROWS, COLS, STRIDE>(img, on ? (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)) : 0u, stride_rt, 1,
-                                            lane, vals[j], cen[j]);
-        }
-    } else {
-#pragma unroll
-        for (int j = 2; j < 4; j++) {
+    for (int j = 0; j < 4; j++) {
+        if ((need >> j) & 1u) {
+            cand_issue<ROWS, COLS, STRIDE>(img, (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)), stride_rt, lane, vals[j], cen[j]);
+        } else {
 #pragma unroll
             for (int it = 0; it < IT; it++) vals[j][it] = 0;
 #pragma unroll
@@ -328,7 +355,7 @@ __device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int st
     for (int j = 0; j < 4; j++) {
         if ((need >> j) & 1u) {  // warp-uniform
             uint32_t b[IT], d[8];
-            patch_words<IT>(vals[j], band_of(cen[j], thr), b);
+            patch_words<IT>(vals[j], cand_band<ROWS, COLS>(vals[j], cen[j], thr), b);
             desc_layout<ROWS, COLS>(b, d);
             const int dist = hamming256(pd, d);
             // :292-296 strict '<' from 256. Candidate 0 is also the default choice (:270), so taking it at dist == 256
@@ -758,6 +785,94 @@ __device__ void sort_keys(unsigned long long *keys, int n, uint16_t *__restrict_
     __syncthreads();
 }
 
+// The table finalize builds is already ordered by age (survivors keep the previous order with age + 1, births and
+// lattice entries have age 0 and come last), so the reference's (age desc, popcount desc) order only permutes entries
+// INSIDE runs of equal age. Each run is ordered by one warp with a stable counting sort on the 257 popcount values -
+// about a microsecond for a 4000-entry table where the full bitonic network takes tens. pk = 256 - popcount.
+// Returns false (nothing written) when the ages are not non-increasing; the caller then takes the general sort.
+constexpr int HIST_STRIDE = 264;
+
+__device__ bool sort_runs(const int *age, const uint16_t *pk, int n, uint16_t *run_start, int *hist, int *wsum,
+                          uint16_t *__restrict__ order_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    // run heads (ordered compaction) and the monotonicity check
+    int n_runs = 0;
+    bool bad = false;
+    for (int base = 0; base < n; base += FIN_THREADS * 8) {
+        const int i0 = base + threadIdx.x * 8;
+        unsigned hm = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int i = i0 + e;
+            if (i < n) {
+                const int a = age[i];
+                if (i == 0) hm |= 1u << e;
+                else {
+                    const int ap = age[i - 1];
+                    if (a != ap) hm |= 1u << e;
+                    if (a > ap) bad = true;
+                }
+            }
+        }
+        int tot;
+        int r = n_runs + block_excl_scan(__popc(hm), wsum, tot);
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            if ((hm >> e) & 1u) run_start[r++] = (uint16_t)(i0 + e);
+        n_runs += tot;
+    }
+    if (__syncthreads_or(bad)) return false;
+    int *h = hist + warp * HIST_STRIDE;
+    for (int r = warp; r < n_runs; r += FIN_WARPS) {
+        const int s = run_start[r], e = r + 1 < n_runs ? run_start[r + 1] : n, L = e - s;
+        if (L == 1) {
+            if (lane == 0) order_out[s] = (uint16_t)s;
+        } else if (L <= 32) {
+            const int p = lane < L ? pk[s + lane] : 0x7fff;
+            int cnt = 0;
+            for (int k = 0; k < L; k++) {
+                const int o = __shfl_sync(0xffffffffu, p, k);
+                cnt += (o < p) || (o == p && k < lane);
+            }
+            if (lane < L) order_out[s + cnt] = (uint16_t)(s + lane);
+        } else {
+            for (int b = lane; b < 257; b += 32) h[b] = 0;
+            __syncwarp();
+            for (int i = s + lane; i < e; i += 32) atomicAdd(&h[pk[i]], 1);
+            __syncwarp();
+            int carry = 0;
+            for (int b0 = 0; b0 < 257; b0 += 32) {  // exclusive prefix, ascending pk = descending popcount
+                const int b = b0 + lane;
+                const int v = b < 257 ? h[b] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (b < 257) h[b] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            __syncwarp();
+            for (int c0 = s; c0 < e; c0 += 32) {  // stable placement, 32 consecutive entries at a time
+                const int i = c0 + lane;
+                const bool valid = i < e;
+                const int p = valid ? pk[i] : 1000 + lane;
+                const unsigned peers = __match_any_sync(0xffffffffu, p);
+                const int rk = __popc(peers & lt);
+                const int bs = valid ? h[p] : 0;
+                __syncwarp();
+                if (valid && rk == 0) h[p] = bs + __popc(peers);
+                __syncwarp();
+                if (valid) order_out[s + bs + rk] = (uint16_t)i;
+            }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 // keys of entries [from, n) from the table in global memory (entries written outside the fused copy paths)
 __device__ void fill_keys(const movfe_track *__restrict__ tab, int from, int n, unsigned long long *keys) {
     for (int i = from + threadIdx.x; i < n; i += blockDim.x) {
@@ -823,10 +938,14 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                 const int32_t *__restrict__ nkps, const double *__restrict__ cov, const uint8_t *__restrict__ birth_flag,
                 const uint32_t *__restrict__ birth_desc, const int4 *__restrict__ grid,
                 const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags) {
-    extern __shared__ unsigned long long keys[];
+    extern __shared__ unsigned long long keys[];  // general sort: keys[N]; run sort: age[maxT] pk[maxT] run_start[maxT] hist[32][264]
     __shared__ int wsum[FIN_WARPS];
     __shared__ uint32_t scratch[FIN_WARPS][8];
     __shared__ int lat_flag[FIN_WARPS];
+    int *s_age = reinterpret_cast<int *>(keys);
+    uint16_t *s_pk = reinterpret_cast<uint16_t *>(s_age + p.maxT);
+    uint16_t *s_run = s_pk + p.maxT;
+    int *s_hist = reinterpret_cast<int *>(s_run + p.maxT);
     const int s = blockIdx.x;
     movfe_track *cur = tracks + ((size_t)s * p.TSLOTS + p.tslot_cur) * p.maxT;
     const movfe_track *st = stage + (size_t)s * p.maxT;
@@ -873,7 +992,8 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                         dst[3] = r3;
                         const int pc = __popc(r2.x) + __popc(r2.y) + __popc(r2.z) + __popc(r2.w) + __popc(r3.x) + __popc(r3.y) +
                                        __popc(r3.z) + __popc(r3.w);
-                        keys[pos] = sort_key((int)r1.y, pc, pos);
+                        s_age[pos] = max((int)r1.y, 0);
+                        s_pk[pos] = (uint16_t)(256 - pc);
                     }
                     pos++;
                 }
@@ -913,7 +1033,8 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                             dst[3] = d1;
                             const int pc = __popc(d0.x) + __popc(d0.y) + __popc(d0.z) + __popc(d0.w) + __popc(d1.x) + __popc(d1.y) +
                                            __popc(d1.z) + __popc(d1.w);
-                            keys[pos] = sort_key(0, pc, pos);
+                            s_age[pos] = 0;
+                            s_pk[pos] = (uint16_t)(256 - pc);
                         }
                         r++;
                     }
@@ -937,9 +1058,17 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
         ntracks[s * p.TSLOTS + p.tslot_cur] = n_new;
         cur_id[s * p.TSLOTS + p.tslot_cur] = id;
     }
-    __syncthreads();  // cur[] and keys[] writes visible to the whole CTA
-    fill_keys(cur, n_keyed, n_new, keys);
-    sort_keys(keys, n_new, order + (size_t)s * p.maxT);
+    __syncthreads();  // cur[] and the shared age / popcount arrays are visible to the whole CTA
+    for (int i = n_keyed + threadIdx.x; i < n_new; i += blockDim.x) {  // lattice entries were written outside the fused copies
+        const movfe_track &t = cur[i];
+        s_age[i] = max(t.age, 0);
+        s_pk[i] = (uint16_t)(256 - popc256(t.desc));
+    }
+    __syncthreads();
+    if (!sort_runs(s_age, s_pk, n_new, s_run, s_hist, wsum, order + (size_t)s * p.maxT)) {
+        fill_keys(cur, 0, n_new, keys);  // ages not ordered (cannot happen for tables this kernel built): general sort
+        sort_keys(keys, n_new, order + (size_t)s * p.maxT);
+    }
 }
 
 // Sorts a table that was installed from the host (movfe_set_tracks).
@@ -994,7 +1123,9 @@ ExtScratch carve(const movfe_ctx *ctx, size_t *total) {
 size_t sort_smem(int maxT) {
     int N = SORT_MIN_N;
     while (N < maxT) N <<= 1;
-    return (size_t)N * sizeof(unsigned long long);
+    const size_t general = (size_t)N * sizeof(unsigned long long);
+    const size_t runs = (size_t)maxT * 8 + (size_t)FIN_WARPS * HIST_STRIDE * sizeof(int);
+    return std::max(general, runs);
 }
 
 }  // namespace
@@ -1017,8 +1148,6 @@ int movfe_extract_init(movfe_ctx *ctx) {
     const size_t n = (size_t)c.n_streams * ctx->max_kps;
     fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(e.claim, n, 0x7fffffff);
     MOVFE_CUDA(ctx, cudaMemsetAsync(e.order, 0, (size_t)c.n_streams * c.max_tracks * sizeof(uint16_t), ctx->stream));
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(sort_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
@@ -1030,6 +1159,8 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
     for (const auto &pl : ctx->pose_launches)
         if (pl.first >= 0 && pl.first <= first_frame + n_frames - 1 - ctx->TSLOTS)
             MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl.done, 0));
+    // the attribute is per function, not per context: set it for THIS context's table size before launching
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
     ProfScope prof(ctx, MOVFE_STAGE_EXTRACT);
     for (int k = 0; k < n_frames; k++) {
         const int64_t a = first_frame + k;
@@ -1108,6 +1239,7 @@ extern "C" int movfe_set_tracks(movfe_ctx *ctx, int stream, const movfe_track *t
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cur_id + stream * T + ts, &current_id, 4, cudaMemcpyHostToDevice, ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nn / current_id live on this stack frame
     ExtScratch e = carve(ctx, nullptr);
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(sort_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
     sort_only_kernel<<<1, FIN_THREADS, sort_smem(c.max_tracks), ctx->stream>>>(c.max_tracks, T, ts, stream, ctx->d_tracks,
                                                                               ctx->d_ntracks, e.order);
     MOVFE_CUDA(ctx, cudaGetLastError());

@@ -75,7 +75,7 @@ def test_shims_against_oracle(orc, tmp_path):
     for f in range(NF):
         got_t = np.fromfile(d + "/out_tracks_%d.bin" % f, T.TRACK)
         assert got_t.tobytes() == tracks[f].tobytes(), ("tracks", f)
-        want_m, n_m = orc.search_by_keyframe(tracks[f], mp[:n_kf])
+        n_m, want_m = orc.search_by_keyframe(tracks[f], mp[:n_kf])
         got_m = np.fromfile(d + "/out_match_%d.bin" % f, np.int32)
         assert np.array_equal(got_m, want_m), ("match", f)
         got_p = np.fromfile(d + "/out_pose_%d.bin" % f, np.float64)
