@@ -37,6 +37,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     for (int b = 0; b < 2; b++) {
+        if (ctx->h_meta[b]) cudaFreeHost(ctx->h_meta[b]);
         if (ctx->ev_copied[b]) cudaEventDestroy(ctx->ev_copied[b]);
         if (ctx->ev_consumed[b]) cudaEventDestroy(ctx->ev_consumed[b]);
     }
@@ -285,8 +286,23 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
     cudaStream_t cs = ctx->copy_stream;
     if (n_records > 0)
         MOVFE_CUDA(ctx, cudaMemcpyAsync(base, recs, (size_t)n_records * sizeof(movfe_mv_record), cudaMemcpyHostToDevice, cs));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes, rec_off, (n_seg + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes + off_bytes, frame_flags, n_seg, cudaMemcpyHostToDevice, cs));
+    // offsets and flags are small and usually live on the caller's stack: they go through a pinned copy owned by the
+    // context (reused only after ev_consumed[b], like the device buffer). Records and grey planes are the caller's to keep.
+    if (ctx->h_meta_bytes[b] < off_bytes + flag_bytes) {
+        if (ctx->h_meta[b]) {
+            MOVFE_CUDA(ctx, cudaStreamSynchronize(cs));
+            cudaFreeHost(ctx->h_meta[b]);
+            ctx->h_meta[b] = nullptr;
+            ctx->h_meta_bytes[b] = 0;
+        }
+        MOVFE_CUDA(ctx, cudaMallocHost(&ctx->h_meta[b], 2 * (off_bytes + flag_bytes)));
+        ctx->h_meta_bytes[b] = 2 * (off_bytes + flag_bytes);
+    } else if (ctx->stage_used[b]) {
+        MOVFE_CUDA(ctx, cudaEventSynchronize(ctx->ev_consumed[b]));  // the previous copy out of h_meta[b] has completed
+    }
+    memcpy(ctx->h_meta[b], rec_off, (n_seg + 1) * sizeof(int64_t));
+    memcpy((uint8_t *)ctx->h_meta[b] + off_bytes, frame_flags, n_seg);
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes, ctx->h_meta[b], off_bytes + flag_bytes, cudaMemcpyHostToDevice, cs));
     uint8_t *d_grey = nullptr;
     if (with_grey) {
         d_grey = base + rec_bytes + off_bytes + flag_bytes;

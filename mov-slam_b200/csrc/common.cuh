@@ -71,6 +71,8 @@ struct movfe_ctx {
     cudaEvent_t ev_copied[2] = {nullptr, nullptr};    // recorded on copy_stream after the copies into d_stage[b]
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};  // recorded on stream after the ingest kernels read d_stage[b]
     bool    stage_used[2] = {false, false};
+    void   *h_meta[2] = {nullptr, nullptr};   // pinned copies of the offsets + flags of a push (callers pass stack arrays)
+    size_t  h_meta_bytes[2] = {0, 0};
     int     push_parity = 0;
     int     grey_pitch = 0;        // row pitch of the grey ring: power of two >= width (compile-time strides in extract.cu)
 

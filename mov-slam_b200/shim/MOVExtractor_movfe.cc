@@ -4,6 +4,8 @@
 // src/MOVExtractor.cc:81-120,161-243,337-377); coverage features are emitted with coverage = true and are dropped at the
 // next frame, exactly like the oracle with lk_status == NULL.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #ifdef MOVFE_IN_TREE
 #include "MOVExtractor.h"
@@ -52,6 +54,9 @@ int MOVExtractor::operator()(const shared_ptr<MotionVectorImage> &_smv, std::vec
     const int n = movfe_extract_frame(ctx, flags, grey.data(), reinterpret_cast<const int32_t *>(_smv->mvi.data), hops.data(), (int)hops.size(),
                                       kps.data(), (int)kps.size(), _smv->coverageArea, prev.data(), (int)prev.size(), &cid, out.data(),
                                       (int)out.size());
+    if (getenv("MOVFE_SHIM_DEBUG"))
+        fprintf(stderr, "shim extract: flags=%u prev=%zu hops=%zu kps=%zu cov=%.6f -> n=%d cid=%d\n", flags, prev.size(), hops.size(), kps.size(),
+                _smv->coverageArea, n, cid);
     if (n < 0) {
         movfe_shim::fail(ctx, "extract_frame");
         return -1;

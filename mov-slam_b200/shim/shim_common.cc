@@ -1,5 +1,6 @@
 // shim_common.cc — contexts and record conversions shared by the drop-in shims.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <tuple>
@@ -131,10 +132,18 @@ bool RasterQueue::push(const std::shared_ptr<MOV_SLAM::MotionVectorImage> &img, 
     if (!d->ctx) return false;
     const int64_t off[2] = {0, n_records};
     uint8_t flags = (img->ft == MOV_SLAM::P_FRAME ? MOVFE_FRAME_P : 0u) | (mv && n_records > 0 ? MOVFE_FRAME_MV : 0u);
+    if (getenv("MOVFE_SHIM_DEBUG") && n_records > 0) {
+        const movfe_mv_record *r = (const movfe_mv_record *)side_data;
+        fprintf(stderr, "shim push: n=%d flags=%u first rec: src=%d w=%d h=%d s=(%d,%d) d=(%d,%d) ref=%d\n", n_records, flags, r->source, r->w, r->h,
+                r->src_x, r->src_y, r->dst_x, r->dst_y, r->ref);
+    }
     if (movfe_push_frames(d->ctx, 1, (const movfe_mv_record *)side_data, off, &flags, nullptr) != MOVFE_OK) {
         fail(d->ctx, "push_frames");
         return false;
     }
+    // side_data belongs to the AVFrame and is gone after av_frame_unref: wait for the host->device copy before returning
+    // (one frame of one stream per call - the batched harness keeps its buffers pinned and never waits here)
+    movfe_synchronize(d->ctx);
     img->frame = (int)d->pushed;
     d->pending.push_back(img);
     d->pushed++;
@@ -154,7 +163,10 @@ std::shared_ptr<MOV_SLAM::MotionVectorImage> RasterQueue::pop(bool flush) {
     d->pending.pop_front();
     d->popped++;
     int32_t nh = 0, nk = 0;
-    movfe_raster_counts(d->ctx, 0, f, &nh, &nk, &img->coverageArea);
+    const int rc_counts = movfe_raster_counts(d->ctx, 0, f, &nh, &nk, &img->coverageArea);
+    if (getenv("MOVFE_SHIM_DEBUG"))
+        fprintf(stderr, "shim raster: frame %lld rc=%d hops=%d kps=%d cov=%f pushed=%lld rejected=%lld\n", (long long)f, rc_counts, nh, nk,
+                img->coverageArea, (long long)d->pushed, (long long)movfe_rejected_records(d->ctx));
     std::vector<movfe_hop> hops((size_t)std::max(nh, 1));
     std::vector<movfe_rect> kps((size_t)std::max(nk, 1));
     movfe_download_hops(d->ctx, 0, f, hops.data(), (int)hops.size());

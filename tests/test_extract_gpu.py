@@ -81,3 +81,31 @@ def test_single_shot_extract_frame(orc):
         assert cid_g == cid_w
         prev_g, prev_w = got, want
     ctx.close()
+
+
+def test_decoder_context_feeding_extractor_context(orc):
+    """The shims' arrangement: one context rasterises (whole ref range as look-ahead), another one extracts frame by frame
+    from the downloaded results, a third context exists beside them."""
+    from movfe import lib
+    W, H, NF = 320, 240, 7
+    sp = synth.Spec(W, H, n_frames=NF, refs=3, seed=0x5EED0020, fx=160.0, fy=160.0)
+    r, o, fl = synth.make_records(sp)
+    grey = synth.make_grey(sp)
+    clip = orc.Clip(W, H, r, o, fl, 10)
+    rctx = lib.Context(1, W, H, max_records_per_frame=1200, max_ref=10, window_frames=1, max_tracks=1, max_map_points=1, has_grey=False)
+    ectx = lib.Context(1, W, H, max_records_per_frame=1200, max_ref=10, window_frames=1, max_tracks=8192, max_map_points=1)
+    octx = lib.Context(1, 16, 16, max_records_per_frame=1, max_ref=0, window_frames=1, max_tracks=1, max_map_points=1, has_grey=False)
+    for f in range(NF):
+        rctx.push_frames(1, r[o[f]:o[f + 1]], np.array([0, o[f + 1] - o[f]], np.int64), fl[f:f + 1])
+    prev_g, prev_w = np.zeros(0, T.TRACK), np.zeros(0, T.TRACK)
+    cid_g = cid_w = 0
+    for f in range(NF):
+        rctx.raster(f, 1)
+        nh, nk, cov = rctx.raster_counts(0, f)
+        got, cid_g = ectx.extract_frame(fl[f], grey[f], rctx.grid(0, f), rctx.hops(0, f), rctx.kps(0, f), cov, prev_g, cid_g)
+        want, _, cid_w, _ = orc.extract_frame(W, H, fl[f], grey[f], clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f), prev_w,
+                                              cid_w, max_tracks=8192)
+        assert_tracks_equal(got, want, ("two-context", f))
+        prev_g, prev_w = got, want
+    for c in (rctx, ectx, octx):
+        c.close()

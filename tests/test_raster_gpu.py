@@ -130,3 +130,21 @@ def test_max_ref_10(orc):
         r["ref"] = rng.integers(0, min(10, f - 1) + 1, n)
         frames.append(list(r))
     _check(orc, [_clip(frames)], W, H, window=2, max_ref=10)
+
+
+def test_single_frame_pushes_full_ref_range(orc):
+    """The decoder shim's usage: one frame per push, window of one frame, the reference's whole ref range as look-ahead."""
+    from movfe import lib
+    W, H, NF = 320, 240, 9
+    sp = synth.Spec(W, H, n_frames=NF, refs=3, seed=0x5EED0031)
+    r, o, fl = synth.make_records(sp)
+    clip = orc.Clip(W, H, r, o, fl, 10)
+    ctx = lib.Context(1, W, H, max_records_per_frame=1200, max_ref=10, window_frames=1, has_grey=False)
+    for f in range(NF):
+        ctx.push_frames(1, r[o[f]:o[f + 1]], np.array([0, o[f + 1] - o[f]], np.int64), fl[f:f + 1])
+    got = {}
+    for f in range(NF):
+        ctx.raster(f, 1)
+        got[(0, f)] = dict(grid=ctx.grid(0, f), hops=ctx.hops(0, f), kps=ctx.kps(0, f), cov=ctx.raster_counts(0, f)[2])
+        assert_raster_equal(clip, got, 0, f)
+    ctx.close()

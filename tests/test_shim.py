@@ -57,11 +57,12 @@ def test_shims_against_oracle(orc, tmp_path):
     cam = sp.camera()
     d = str(tmp_path)
     np.array([W, H, NF, 10, thr, len(mp), n_kf], np.int32).tofile(d + "/meta.bin")
-    recs.tofile(d + "/recs.bin"); off.tofile(d + "/off.bin"); flags.tofile(d + "/flags.bin"); grey.tofile(d + "/grey.bin")
+    np.ascontiguousarray(recs, T.MV_RECORD).tofile(d + "/recs.bin")   # the 40-byte layout (numpy packs concatenated records)
+    off.tofile(d + "/off.bin"); flags.tofile(d + "/flags.bin"); grey.tofile(d + "/grey.bin")
     mp.tofile(d + "/map.bin")
     np.concatenate([pose0["R"], pose0["t"]]).astype(np.float64).tofile(d + "/pose0.bin")
     np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).tofile(d + "/cam.bin")
-    r = subprocess.run([os.path.join(SHIM, "test_shim"), d], capture_output=True, text=True)
+    r = subprocess.run([os.path.join(SHIM, "test_shim"), d], capture_output=True, text=True, )
     assert r.returncode == 0, r.stdout + r.stderr
 
     def f32(p):  # the Frame stores Sophus::SE3f: the pose is rounded to float between calls
@@ -74,7 +75,7 @@ def test_shims_against_oracle(orc, tmp_path):
     last = f32(pose0)
     for f in range(NF):
         got_t = np.fromfile(d + "/out_tracks_%d.bin" % f, T.TRACK)
-        assert got_t.tobytes() == tracks[f].tobytes(), ("tracks", f)
+        assert got_t.tobytes() == tracks[f].tobytes(), ("tracks", f, len(got_t), len(tracks[f]), r.stderr[-400:])
         n_m, want_m = orc.search_by_keyframe(tracks[f], mp[:n_kf])
         got_m = np.fromfile(d + "/out_match_%d.bin" % f, np.int32)
         assert np.array_equal(got_m, want_m), ("match", f)
