@@ -17,7 +17,8 @@ for vals in rows[2:]:
     def get(name):
         return float(d[name].replace(',', '')) * UNIT[units[hdr.index(name)]]
     rd, wr = get('dram__bytes_read.sum'), get('dram__bytes_write.sum')
-    us = float(d['gpu__time_duration.sum'].replace(',', ''))
+    tu = units[hdr.index('gpu__time_duration.sum')]
+    us = float(d['gpu__time_duration.sum'].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(tu, 1.0)
     res = {"kernel": "grid_kernel", "report": os.path.basename(rep), "streams": S, "frames_per_launch": F,
            "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes_per_launch": rd + wr,
            "dram_bytes_per_frame_stream": (rd + wr) / (S * F), "gpu_time_us_under_ncu": us,
