@@ -250,10 +250,10 @@ def run_product(args):
     log("[rank %d] generated %d clips x %d frames in %.1fs" % (rank, N_BASE, n_frames, time.time() - t0))
     cam = clips[0]["spec"].camera()
 
-    def new_context():
+    def new_context(serial_raster=False):
         """Context + untimed setup: window 0 seeds the tracks; map points are built from the frame-0 tables."""
         ctx = lib.Context(S, W, H, max_records_per_frame=MAX_RECORDS, max_ref=MAX_REF, window_frames=F, max_tracks=MAX_TRACKS,
-                          max_map_points=2048, has_grey=True, device=local)
+                          max_map_points=2048, has_grey=True, device=local, serial_raster=serial_raster)
         ctx.set_camera(cam, T.pose_params(), 0.5)
         win0 = pack_window(clips, S, 0, F + LA)
         ctx.push_frames(win0["n"], win0["recs"].numpy()[:win0["n_records"] * 40].view(T.MV_RECORD), win0["off"].numpy(),
@@ -332,25 +332,47 @@ def run_product(args):
         ctx.extract(first, F)
         ctx.track_poses(first, F)
 
-    dev_ms, _, stage_ms, launches, clocks = timed(ctx, ext, step_device, "device-resident")
+    dev_ms, _, stage_ovl, launches, clocks = timed(ctx, ext, step_device, "device-resident")
     frames_total = world * S * F * args.steps
     value = frames_total / (dev_ms / 1e3)
+    step_ms = dev_ms / args.steps
+    ctx.close()
+    if os.environ.get("BENCH_QUICK"):   # development sweeps: the device-resident headline region only
+        if rank == 0:
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": step_ms,
+                              "stage_ms_per_step": {k: v / args.steps for k, v in stage_ovl.items()}}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- the same steps once more with MOVFE_CFG_SERIAL_RASTER: the raster kernels of a window wait for the propagation of
+    # the previous one instead of running beside it, so the CUDA events around grid_kernel time that kernel ALONE (beside
+    # another kernel its event span measures the sharing, not the kernel). This pass feeds `roofline`; `value` does not use it.
+    ctx, ext = new_context(serial_raster=True)
+    serial_ms, _, stage_ms, _, _ = timed(ctx, ext, step_device, "device-resident, serial raster")
 
     grid_bytes = S * F * W * H * 16.0                       # algorithmic bytes of the dominant HBM kernel per launch
     grid_ms = stage_ms["grid"] / max(args.steps, 1)
+    grid_ms_ovl = stage_ovl["grid"] / max(args.steps, 1)
     peak, peak_src = peaks()
     achieved = grid_bytes / 1e9 / (grid_ms / 1e3)
-    step_ms = dev_ms / args.steps
+    serial_step_ms = serial_ms / args.steps
     # whole-step view: compulsory bytes of one step (records + grids + hops + grey planes) over the step time
     n_rec = host[args.warmup]["n_records"]
     step_bytes = 40.0 * n_rec + grid_bytes + 12.0 * 2.7 * n_rec + float(S * F * W * H)
     roofline = {"bound": "hbm", "kernel": "grid_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": grid_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": grid_bytes,
-                "launch_ms": grid_ms, "kernel_share_of_step": grid_ms / step_ms,
+                "launch_ms": grid_ms, "kernel_share_of_step": grid_ms / serial_step_ms,
+                "timed": "CUDA events on the raster stream around every grid_kernel launch of a second timed region (same steps, "
+                         "MOVFE_CFG_SERIAL_RASTER: the kernel runs alone, as under ncu); in the headline region it runs beside the "
+                         "previous window's propagation, see `overlapped`",
+                "serial_ms_per_step": serial_step_ms,
                 "stage_ms_per_step": {k: v / args.steps for k, v in stage_ms.items()},
+                "overlapped": {"launch_ms": grid_ms_ovl, "achieved": grid_bytes / 1e9 / (grid_ms_ovl / 1e3),
+                               "stage_ms_per_step": {k: v / args.steps for k, v in stage_ovl.items()}},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / 1e9 / (step_ms / 1e3),
                                "frac": step_bytes / 1e9 / (step_ms / 1e3) / peak,
-                               "note": "pose stage runs on its own stream beside raster/propagation of the next window"}}
+                               "note": "headline region: raster of window k+1 and the pose chain of window k run on their own streams beside the propagation of window k"}}
     ctx.close()
     del dev
     torch.cuda.empty_cache()

@@ -8,7 +8,7 @@
  *
  * Conventions
  *  - Every call returns MOVFE_OK (0) or a negative MOVFE_E_* code; movfe_last_error() gives the text.
- *  - A context owns one GPU, one CUDA stream and all device buffers. It is not thread-safe; use one context
+ *  - A context owns one GPU, its CUDA streams and all device buffers. It is not thread-safe; use one context
  *    per host thread / GPU (streams shard across GPUs with no collective).
  *  - Work is batched over the context's n_streams independent video streams. All batched arrays are
  *    stream-major: element (stream s, frame f) of a call with n frames lives at index s*n + f.
@@ -46,20 +46,28 @@ typedef struct movfe_config {
     double  coverage_threshold;     /* MOVExtractor::mCoverageThreshold */
     int32_t has_grey;               /* 1: grey planes are pushed (descriptor gating on); 0: MV-only mode ==
                                        the reference's behaviour on a flat image */
-    int32_t reserved;
+    int32_t flags;                  /* MOVFE_CFG_* bits, 0 by default */
 } movfe_config;
+
+/* By default the ingest + raster kernels of window k+1 run on their own low-priority CUDA stream beside the propagation
+ * of window k (raster results are double-buffered). With this flag every movfe_raster first waits for all propagation
+ * enqueued so far, so that the raster kernels run alone - bench.py uses it to time grid_kernel for the roofline. */
+#define MOVFE_CFG_SERIAL_RASTER 1
 
 /* -- lifetime -------------------------------------------------------------------------------------------- */
 int         movfe_create(const movfe_config *cfg, movfe_ctx **out);
 void        movfe_destroy(movfe_ctx *ctx);
 const char *movfe_last_error(const movfe_ctx *ctx);   /* ctx may be NULL: error of the last failed create */
 int         movfe_synchronize(movfe_ctx *ctx);        /* waits for all of the context's streams */
-void       *movfe_cuda_stream(movfe_ctx *ctx);        /* the primary cudaStream_t (ingest, raster, propagation) */
-/* The context also owns a copy stream (host->device staging of movfe_push_frames) and a pose stream (movfe_track_poses
- * runs beside raster/propagation of the next window). movfe_fence makes the primary stream wait, on the device, for
- * everything enqueued so far on the pose stream - call it before recording a timing event or enqueueing dependent work
- * on movfe_cuda_stream(). Host buffers handed to movfe_push_frames must stay unchanged until the next call that
- * synchronises (any download, movfe_synchronize) or until the second following push. */
+void       *movfe_cuda_stream(movfe_ctx *ctx);        /* the primary cudaStream_t (propagation, single-shot operators) */
+/* The context also owns a copy stream (host->device staging of movfe_push_frames), a raster stream (ingest + raster of
+ * window k+1 run beside the propagation of window k) and a pose stream (movfe_track_poses runs beside raster/propagation
+ * of the next window). movfe_fence makes the primary stream wait, on the device, for everything enqueued so far on the
+ * raster and pose streams - call it before recording a timing event or enqueueing dependent work on
+ * movfe_cuda_stream(). Host buffers handed to movfe_push_frames must stay unchanged until the next call that
+ * synchronises (any download, movfe_synchronize) or until the second following push. Device buffers handed to
+ * movfe_push_frames_device must be complete when the call is made and stay unchanged until the next movfe_fence /
+ * movfe_synchronize has completed. */
 int         movfe_fence(movfe_ctx *ctx);
 const char *movfe_version(void);
 
@@ -143,6 +151,19 @@ int movfe_frustum(movfe_ctx *ctx, int n_problems, const movfe_pose *poses, const
 int movfe_join(movfe_ctx *ctx, int n_problems, const int32_t *track_ids, const int32_t *track_off,
                const int32_t *probe_ids, const uint8_t *probe_valid, const int32_t *probe_off, int32_t *match,
                int32_t *n_matches);
+/* Frame::AssignFeaturesToGrid (src/Frame.cc:356-388; Frame::PosInGrid :670-680, which rounds) for n_problems keypoint
+ * sets of a width x height frame (mono, undistorted: mnMinX = mnMinY = 0). pts_xy: packed (x, y) pairs = mvKeysUn[i].pt,
+ * off: n_problems+1 offsets. cell_start: n_problems * (64*48+1) CSR offsets local to the set, cell = ix*48 + iy
+ * (mGrid[ix][iy]); cell_items: same length as the points, the set's keypoint indices cell by cell in insertion order
+ * (entries past cell_start[64*48] are -1: keypoints outside the grid). At most 16384 keypoints per set. */
+int movfe_assign_features_to_grid(movfe_ctx *ctx, int n_problems, const float *pts_xy, const int32_t *off,
+                                  int32_t *cell_start, int32_t *cell_items);
+/* Frame::GetFeaturesInArea (src/Frame.cc:602-668) for n_queries queries against the grids built above: out[q*capacity..]
+ * receives the indices in the reference's (ix, iy, insertion) order, counts[q] the full count (it may exceed capacity,
+ * in which case only the first `capacity` indices were written). */
+int movfe_features_in_area(movfe_ctx *ctx, int n_problems, const float *pts_xy, const int32_t *off,
+                           const int32_t *cell_start, const int32_t *cell_items, int n_queries,
+                           const movfe_area_query *queries, int capacity, int32_t *out, int32_t *counts);
 /* Optimizer::PoseOptimization for n_problems correspondence sets (pts xyz float, obs uv float, packed). */
 int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_camera *cam, const movfe_pose_params *pp,
                         const float *pts, const float *obs, const int32_t *off, movfe_pose *poses /* in/out */,

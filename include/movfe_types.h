@@ -82,6 +82,12 @@ typedef struct movfe_projection {
     int32_t  in_view;       /* mbTrackInView */
 } movfe_projection;
 
+/* One Frame::GetFeaturesInArea(x, y, r) call (src/Frame.cc:602; minLevel = 0, maxLevel = -1) against keypoint set `problem`. */
+typedef struct movfe_area_query {
+    int32_t problem;
+    float   x, y, r;
+} movfe_area_query;
+
 /* Camera: GeometricCamera::mvParameters = [fx,fy,cx,cy,(k1..k4)] (GeometricCamera.h:61-101). */
 #define MOVFE_CAM_PINHOLE 0
 #define MOVFE_CAM_FISHEYE 1   /* KannalaBrandt8: not in the reference tree; ORB-SLAM3 lineage formulae */

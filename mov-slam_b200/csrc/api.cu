@@ -2,6 +2,7 @@
 // There is no CPU fallback anywhere in this library: without a CUDA device movfe_create fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -26,14 +27,32 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->pose_stream) cudaStreamSynchronize(ctx->pose_stream);
+    if (ctx->raster_stream) cudaStreamSynchronize(ctx->raster_stream);
+    for (int g = 1; g < movfe_ctx::MAX_GROUPS; g++)
+        if (ctx->ext_stream[g]) cudaStreamSynchronize(ctx->ext_stream[g]);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *bufs[] = {ctx->d_stage[0], ctx->d_stage[1], ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected, ctx->d_cls_cnt,
-                    ctx->d_area, ctx->d_hop_base, ctx->d_kps_base, ctx->d_nhops, ctx->d_nkps, ctx->d_cov, ctx->d_hops,
-                    ctx->d_hop_rect, ctx->d_kps, ctx->d_chunk_bbox, ctx->d_grid, ctx->d_tracks, ctx->d_ntracks,
+    void *bufs[] = {ctx->d_stage[0], ctx->d_stage[1], ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected,
+                    ctx->d_tracks, ctx->d_ntracks,
                     ctx->d_cur_id, ctx->d_ext_scratch, ctx->d_map, ctx->d_nmap, ctx->d_nkf, ctx->d_pose_cur,
                     ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier, ctx->d_pose_scratch, ctx->d_op};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    for (RasterBuf &w : ctx->rb) {
+        void *wb[] = {w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
+                      w.d_chunk_bbox, w.d_grid};
+        for (void *b : wb)
+            if (b) cudaFree(b);
+        if (w.done) cudaEventDestroy(w.done);
+        if (w.consumed) cudaEventDestroy(w.consumed);
+    }
+    for (auto &el : ctx->ext_launches)
+        if (el.done) cudaEventDestroy(el.done);
+    if (ctx->ev_serial) cudaEventDestroy(ctx->ev_serial);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int g = 1; g < movfe_ctx::MAX_GROUPS; g++) {
+        if (ctx->ev_join[g]) cudaEventDestroy(ctx->ev_join[g]);
+        if (ctx->ext_stream[g]) cudaStreamDestroy(ctx->ext_stream[g]);
+    }
     for (auto &sp : ctx->prof_spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto e : ctx->prof_free) cudaEventDestroy(e);
     for (int b = 0; b < 2; b++) {
@@ -48,6 +67,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
         if (pl.done) cudaEventDestroy(pl.done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pose_stream) cudaStreamDestroy(ctx->pose_stream);
+    if (ctx->raster_stream) cudaStreamDestroy(ctx->raster_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -94,11 +114,40 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c.device));
     ctx->sm_count = prop.multiProcessorCount;
-    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ctx->pose_stream, cudaStreamNonBlocking));
+    // propagation is a serial chain of short launches (three per frame): it gets the high priority, so that its CTAs are
+    // placed as soon as they are ready and the long, throughput-bound raster kernels of the NEXT window fill what is left
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    ctx->serial_raster = (c.flags & MOVFE_CFG_SERIAL_RASTER) != 0;
+    CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&ctx->pose_stream, cudaStreamNonBlocking, prio_hi));
+    CK(cudaStreamCreateWithPriority(&ctx->raster_stream, cudaStreamNonBlocking, prio_lo));
+    CK(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming));
-    ctx->ev_frame.resize(c.window_frames, nullptr);
+    CK(cudaEventCreateWithFlags(&ctx->ev_serial, cudaEventDisableTiming));
+    for (RasterBuf &w : ctx->rb) {
+        CK(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&w.consumed, cudaEventDisableTiming));
+    }
+    for (auto &el : ctx->ext_launches) {
+        el.first = -1;
+        el.n = 0;
+        CK(cudaEventCreateWithFlags(&el.done, cudaEventDisableTiming));
+    }
+    {
+        // groups of independent propagation chains (MOVFE_EXTRACT_GROUPS, default 1: on B200 with 64 streams of C2 the
+        // launches already fill the chip, and 2..8 groups measured the same or slower - profiles/README.md)
+        int g = 1;
+        if (const char *e = getenv("MOVFE_EXTRACT_GROUPS")) g = atoi(e);
+        ctx->n_groups = std::max(1, std::min(std::min(g, c.n_streams), (int)movfe_ctx::MAX_GROUPS));
+    }
+    ctx->ext_stream[0] = ctx->stream;
+    for (int g = 1; g < ctx->n_groups; g++) {
+        CK(cudaStreamCreateWithPriority(&ctx->ext_stream[g], cudaStreamNonBlocking, prio_hi));
+        CK(cudaEventCreateWithFlags(&ctx->ev_join[g], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    ctx->ev_frame.resize((size_t)ctx->n_groups * c.window_frames, nullptr);
     for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &pl : ctx->pose_launches) {
         pl.first = -1;
@@ -115,7 +164,9 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->K = c.max_ref;
     ctx->LA = ctx->K + 1;
     ctx->NIN = c.window_frames + ctx->LA;
-    ctx->RING = ctx->NIN;
+    // two windows deep: the push + raster of window k+1 overwrite the slots of window k-1 while propagation still reads
+    // the grey planes of window k
+    ctx->RING = 2 * c.window_frames + ctx->LA;
     ctx->NB = (c.height + 7) / 8;
     ctx->NT = (c.width + 31) / 32;
     ctx->max_hops = c.max_records_per_frame * (ctx->K + 1);
@@ -135,18 +186,20 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(cudaMemset(ctx->d_rejected, 0, sizeof(unsigned long long)));
     CK(cudaMemset(ctx->d_rec_cnt, 0, S * RING * sizeof(int32_t)));
     CK(cudaMemset(ctx->d_fflags, 0, S * RING));
-    CK(dalloc(&ctx->d_cls_cnt, S * NIN * MOVFE_NCLS(MOVFE_MAX_K)));
-    CK(dalloc(&ctx->d_area, S * NIN));
-    CK(dalloc(&ctx->d_hop_base, S * NIN * (ctx->K + 2)));
-    CK(dalloc(&ctx->d_kps_base, S * NIN * (ctx->K + 2)));
-    CK(dalloc(&ctx->d_nhops, S * NIN));
-    CK(dalloc(&ctx->d_nkps, S * NIN));
-    CK(dalloc(&ctx->d_cov, S * NIN));
-    CK(dalloc(&ctx->d_hops, S * F * ctx->max_hops));
-    CK(dalloc(&ctx->d_hop_rect, S * F * ctx->max_hops));
-    CK(dalloc(&ctx->d_kps, S * F * ctx->max_kps));
-    CK(dalloc(&ctx->d_chunk_bbox, S * F * ctx->max_chunks));
-    CK(dalloc(&ctx->d_grid, S * F * plane));
+    for (RasterBuf &w : ctx->rb) {
+        CK(dalloc(&w.d_cls_cnt, S * NIN * MOVFE_NCLS(MOVFE_MAX_K)));
+        CK(dalloc(&w.d_area, S * NIN));
+        CK(dalloc(&w.d_hop_base, S * NIN * (ctx->K + 2)));
+        CK(dalloc(&w.d_kps_base, S * NIN * (ctx->K + 2)));
+        CK(dalloc(&w.d_nhops, S * NIN));
+        CK(dalloc(&w.d_nkps, S * NIN));
+        CK(dalloc(&w.d_cov, S * NIN));
+        CK(dalloc(&w.d_hops, S * F * ctx->max_hops));
+        CK(dalloc(&w.d_hop_rect, S * F * ctx->max_hops));
+        CK(dalloc(&w.d_kps, S * F * ctx->max_kps));
+        CK(dalloc(&w.d_chunk_bbox, S * F * ctx->max_chunks));
+        CK(dalloc(&w.d_grid, S * F * plane));
+    }
     // track tables
     ctx->TSLOTS = 2 * c.window_frames + 1;
     const size_t TS = ctx->TSLOTS;
@@ -196,6 +249,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
 
 extern "C" int movfe_synchronize(movfe_ctx *ctx) {
     if (!ctx) return MOVFE_E_INVALID;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     return MOVFE_OK;
@@ -207,6 +261,8 @@ extern "C" int movfe_fence(movfe_ctx *ctx) {
     // primary stream (an event record for timing, a dependent kernel)
     MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->pose_stream));
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tables, 0));
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->raster_stream));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tables, 0));
     return MOVFE_OK;
 }
 
@@ -216,6 +272,7 @@ extern "C" int64_t movfe_frames_pushed(const movfe_ctx *ctx) { return ctx ? ctx-
 static int ensure_stage(movfe_ctx *ctx, int b, size_t bytes) {
     if (bytes <= ctx->stage_bytes[b]) return MOVFE_OK;
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_stage[b]) cudaFree(ctx->d_stage[b]);
     ctx->d_stage[b] = nullptr;
@@ -239,10 +296,32 @@ static int ensure_op(movfe_ctx *ctx, size_t bytes) {
 }
 int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes) { return ensure_op(ctx, bytes); }
 
+// The ingest kernels of a push overwrite the ring slots of frames [pushed-RING, pushed+n-RING): propagation launches (on
+// the primary stream) that read the grey planes / frame flags of those frames must have finished. Launches are ordered on
+// one stream, so waiting for the newest launch that starts at or before the last overwritten frame covers all of them;
+// when that launch has already left the bookkeeping ring, its oldest entry (a later launch) stands in for it.
+static int wait_ring_readers(movfe_ctx *ctx, int n_frames) {
+    const int64_t last_overwritten = ctx->pushed + n_frames - 1 - ctx->RING;
+    if (last_overwritten < 0 || ctx->ext_launch_count == 0) return MOVFE_OK;
+    const int N = movfe_ctx::N_EXT_LAUNCHES;
+    const int live = (int)std::min<int64_t>(ctx->ext_launch_count, N);
+    const movfe_ctx::ExtLaunch *pick = nullptr;
+    for (int i = 0; i < live; i++) {  // newest first
+        const movfe_ctx::ExtLaunch &el = ctx->ext_launches[((ctx->ext_launch_head - 1 - i) % N + N) % N];
+        if (el.first <= last_overwritten) {
+            pick = &el;
+            break;
+        }
+    }
+    if (!pick && ctx->ext_launch_count > N) pick = &ctx->ext_launches[ctx->ext_launch_head];  // oldest entry
+    if (pick) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, pick->done, 0));
+    return MOVFE_OK;
+}
+
 static int check_push(movfe_ctx *ctx, int n_frames) {
     if (!ctx) return MOVFE_E_INVALID;
     if (n_frames < 1 || n_frames > ctx->RING)
-        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "push of %d frames exceeds the ring depth %d (window_frames + max_ref + 1)", n_frames, ctx->RING);
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "push of %d frames exceeds the ring depth %d (2*window_frames + max_ref + 1)", n_frames, ctx->RING);
     return MOVFE_OK;
 }
 
@@ -254,6 +333,8 @@ extern "C" int movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movf
     if (!d_rec_off || !d_frame_flags || (n_records > 0 && !d_recs)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: null pointer");
     if (((uintptr_t)d_recs & 15) != 0) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: device record array must be 16-byte aligned");
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    rc = wait_ring_readers(ctx, n_frames);
+    if (rc) return rc;
     rc = movfe_ingest_launch(ctx, n_frames, d_recs, d_rec_off, n_records, d_frame_flags, d_grey);
     if (rc) return rc;
     ctx->pushed += n_frames;
@@ -309,11 +390,13 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
         MOVFE_CUDA(ctx, cudaMemcpyAsync(d_grey, grey, grey_bytes, cudaMemcpyHostToDevice, cs));
     }
     MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
-    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[b], 0));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_copied[b], 0));
+    rc = wait_ring_readers(ctx, n_frames);
+    if (rc) return rc;
     rc = movfe_ingest_launch(ctx, n_frames, (const movfe_mv_record *)base, (const int64_t *)(base + rec_bytes), n_records,
                              base + rec_bytes + off_bytes, d_grey);
     if (rc) return rc;
-    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->stream));
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->raster_stream));
     ctx->stage_used[b] = true;
     ctx->push_parity ^= 1;
     ctx->pushed += n_frames;
@@ -332,20 +415,31 @@ extern "C" int movfe_raster(movfe_ctx *ctx, int64_t first_frame, int n_out) {
                    (long long)ctx->pushed, ctx->RING);
     const int n_in = (int)std::min<int64_t>(ctx->pushed - first_frame, (int64_t)n_out + ctx->LA);
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
-    int rc = movfe_raster_launch(ctx, first_frame, n_out, n_in);
+    // results go to the buffer that the propagation of the previous window is NOT reading
+    RasterBuf &w = ctx->rb[ctx->rb_cur ^ 1];
+    if (w.consumed_valid) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, w.consumed, 0));
+    if (ctx->serial_raster) {
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_serial, ctx->stream));
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_serial, 0));
+    }
+    int rc = movfe_raster_launch(ctx, w, first_frame, n_out, n_in);
     if (rc) return rc;
-    ctx->win_first = first_frame;
-    ctx->win_nout = n_out;
-    ctx->win_nin = n_in;
+    MOVFE_CUDA(ctx, cudaEventRecord(w.done, ctx->raster_stream));
+    w.first = first_frame;
+    w.nout = n_out;
+    w.nin = n_in;
+    w.consumed_valid = false;
+    ctx->rb_cur ^= 1;
     return MOVFE_OK;
 }
 
 static int win_index(movfe_ctx *ctx, int stream, int64_t frame, int *fi) {
     if (!ctx) return MOVFE_E_INVALID;
     if (stream < 0 || stream >= ctx->cfg.n_streams) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "stream %d out of range", stream);
-    if (ctx->win_first < 0 || frame < ctx->win_first || frame >= ctx->win_first + ctx->win_nout)
+    const RasterBuf &w = ctx->rb[ctx->rb_cur];
+    if (w.first < 0 || frame < w.first || frame >= w.first + w.nout)
         MOVFE_FAIL(ctx, MOVFE_E_STATE, "frame %lld is not in the last raster window", (long long)frame);
-    *fi = (int)(frame - ctx->win_first);
+    *fi = (int)(frame - w.first);
     return MOVFE_OK;
 }
 
@@ -354,11 +448,13 @@ extern "C" int movfe_raster_counts(movfe_ctx *ctx, int stream, int64_t frame, in
     int fi;
     int rc = win_index(ctx, stream, frame, &fi);
     if (rc) return rc;
-    const size_t sg = (size_t)stream * ctx->win_nin + fi;
-    if (n_hops) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_hops, ctx->d_nhops + sg, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n_kps) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_kps, ctx->d_nkps + sg, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (coverage_area) MOVFE_CUDA(ctx, cudaMemcpyAsync(coverage_area, ctx->d_cov + sg, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const RasterBuf &w = ctx->rb[ctx->rb_cur];
+    const size_t sg = (size_t)stream * w.nin + fi;
+    cudaStream_t st = ctx->raster_stream;  // the stream the results were produced on
+    if (n_hops) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_hops, w.d_nhops + sg, 4, cudaMemcpyDeviceToHost, st));
+    if (n_kps) MOVFE_CUDA(ctx, cudaMemcpyAsync(n_kps, w.d_nkps + sg, 4, cudaMemcpyDeviceToHost, st));
+    if (coverage_area) MOVFE_CUDA(ctx, cudaMemcpyAsync(coverage_area, w.d_cov + sg, 8, cudaMemcpyDeviceToHost, st));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
     return MOVFE_OK;
 }
 
@@ -367,9 +463,10 @@ extern "C" int movfe_download_grid(movfe_ctx *ctx, int stream, int64_t frame, in
     int rc = win_index(ctx, stream, frame, &fi);
     if (rc) return rc;
     const size_t plane = (size_t)ctx->cfg.width * ctx->cfg.height;
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_grid + ((size_t)stream * ctx->win_nout + fi) * plane, plane * sizeof(int4),
-                                    cudaMemcpyDeviceToHost, ctx->stream));
-    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const RasterBuf &w = ctx->rb[ctx->rb_cur];
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(out, w.d_grid + ((size_t)stream * w.nout + fi) * plane, plane * sizeof(int4),
+                                    cudaMemcpyDeviceToHost, ctx->raster_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     return MOVFE_OK;
 }
 
@@ -381,9 +478,10 @@ extern "C" int movfe_download_hops(movfe_ctx *ctx, int stream, int64_t frame, mo
     if (rc) return rc;
     if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_hops: %d hops, capacity %d", n, capacity);
     if (n > 0) {
-        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_hops + ((size_t)stream * ctx->win_nout + fi) * ctx->max_hops,
-                                        (size_t)n * sizeof(movfe_hop), cudaMemcpyDeviceToHost, ctx->stream));
-        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const RasterBuf &w = ctx->rb[ctx->rb_cur];
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, w.d_hops + ((size_t)stream * w.nout + fi) * ctx->max_hops,
+                                        (size_t)n * sizeof(movfe_hop), cudaMemcpyDeviceToHost, ctx->raster_stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     }
     return n;
 }
@@ -396,9 +494,10 @@ extern "C" int movfe_download_kps(movfe_ctx *ctx, int stream, int64_t frame, mov
     if (rc) return rc;
     if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_kps: %d kps, capacity %d", n, capacity);
     if (n > 0) {
-        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_kps + ((size_t)stream * ctx->win_nout + fi) * ctx->max_kps,
-                                        (size_t)n * sizeof(movfe_rect), cudaMemcpyDeviceToHost, ctx->stream));
-        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const RasterBuf &w = ctx->rb[ctx->rb_cur];
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, w.d_kps + ((size_t)stream * w.nout + fi) * ctx->max_kps,
+                                        (size_t)n * sizeof(movfe_rect), cudaMemcpyDeviceToHost, ctx->raster_stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     }
     return n;
 }
@@ -406,8 +505,8 @@ extern "C" int movfe_download_kps(movfe_ctx *ctx, int stream, int64_t frame, mov
 extern "C" int64_t movfe_rejected_records(movfe_ctx *ctx) {
     if (!ctx) return -1;
     unsigned long long v = 0;
-    if (cudaMemcpyAsync(&v, ctx->d_rejected, sizeof v, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    if (cudaMemcpyAsync(&v, ctx->d_rejected, sizeof v, cudaMemcpyDeviceToHost, ctx->raster_stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->raster_stream) != cudaSuccess) return -1;
     return (int64_t)v;
 }
 
@@ -419,6 +518,7 @@ extern "C" int movfe_profile_enable(movfe_ctx *ctx, int on) {
 
 extern "C" int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset) {
     if (!ctx) return MOVFE_E_INVALID;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
     for (auto &sp : ctx->prof_spans) {

@@ -1,0 +1,199 @@
+// bucket.cu — the frame's keypoint bucket grid: Frame::AssignFeaturesToGrid (src/Frame.cc:356-388), Frame::PosInGrid
+// (:670-680) and the radius query Frame::GetFeaturesInArea (:602-668), batched over independent keypoint sets.
+// The reference builds this 64x48 grid for every frame and never queries it on the MOV path; it is
+// provided as a single-shot operator so that a caller that does query it finds the same lists in the same order.
+//
+// Layout: CSR per problem, cell = ix*48 + iy (mGrid[ix][iy]); a cell's items are keypoint indices in insertion order,
+// which is what `mGrid[x][y].push_back(i)` for i = 0..N-1 produces. Built as one stable sort per keypoint set: the key is
+// (cell << 14 | index), so equal cells keep ascending index and no atomics are involved.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BG_COLS = 64, BG_ROWS = 48;  // FRAME_GRID_COLS / FRAME_GRID_ROWS (include/Frame.h:40-41)
+constexpr int BG_CELLS = BG_COLS * BG_ROWS;
+constexpr int BG_THREADS = 1024;
+constexpr int BG_MAX_N = 16384;            // keypoints per set (index field of the sort key: 14 bits)
+constexpr uint32_t BG_INVALID = 0xffffffffu;
+
+// Frame.cc:670-680 with mnMinX = mnMinY = 0 (undistorted mono frame, Frame.cc:739-745): round(), not floor()
+__device__ __forceinline__ bool pos_in_grid(float x, float y, float w_inv, float h_inv, int &px, int &py) {
+    px = (int)roundf(__fmul_rn(__fsub_rn(x, 0.0f), w_inv));
+    py = (int)roundf(__fmul_rn(__fsub_rn(y, 0.0f), h_inv));
+    return !(px < 0 || px >= BG_COLS || py < 0 || py >= BG_ROWS);
+}
+
+__global__ void __launch_bounds__(BG_THREADS)
+assign_kernel(const float2 *__restrict__ pts, const int32_t *__restrict__ off, float w_inv, float h_inv, int N2,
+              int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_items) {
+    extern __shared__ uint32_t keys[];  // [N2], N2 = power of two >= the largest set
+    const int pidx = blockIdx.x;
+    const int b = off[pidx], n = off[pidx + 1] - b;
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) {
+        uint32_t k = BG_INVALID;
+        if (i < n) {
+            const float2 q = pts[b + i];
+            int px, py;
+            if (pos_in_grid(q.x, q.y, w_inv, h_inv, px, py)) k = ((uint32_t)(px * BG_ROWS + py) << 14) | (uint32_t)i;
+        }
+        keys[i] = k;
+    }
+    __syncthreads();
+    // bitonic sort, ascending; keys are distinct (the index is part of the key), so the result is the stable order
+    for (int k = 2; k <= N2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (N2 >> 1); t += blockDim.x) {
+                const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+                const int hi = lo | j;
+                const uint32_t a = keys[lo], c = keys[hi];
+                const bool up = (lo & k) == 0;
+                if ((a > c) == up) {
+                    keys[lo] = c;
+                    keys[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    int32_t *cs = cell_start + (size_t)pidx * (BG_CELLS + 1);
+    for (int c = threadIdx.x; c <= BG_CELLS; c += blockDim.x) {  // lower bound of (c << 14): first item of cell c
+        const uint32_t want = (uint32_t)c << 14;
+        int lo = 0, hi = n;  // invalid keys sort last and are >= any (c << 14), c <= 3072
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (keys[mid] < want) lo = mid + 1;
+            else hi = mid;
+        }
+        cs[c] = lo;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (keys[i] != BG_INVALID) cell_items[b + i] = (int32_t)(keys[i] & 0x3fffu);
+}
+
+// Frame.cc:602-668 with minLevel = 0, maxLevel = -1 (every MOV keypoint is octave 0, Frame.cc:105-118): one thread per query
+__global__ void area_kernel(const float2 *__restrict__ pts, const int32_t *__restrict__ off, const int32_t *__restrict__ cell_start,
+                            const int32_t *__restrict__ cell_items, const movfe_area_query *__restrict__ queries, int n_queries,
+                            float w_inv, float h_inv, int capacity, int32_t *__restrict__ out, int32_t *__restrict__ counts) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_queries) return;
+    const movfe_area_query Q = queries[q];
+    const float x = Q.x, y = Q.y, r = Q.r;
+    const int b = off[Q.problem];
+    const int32_t *cs = cell_start + (size_t)Q.problem * (BG_CELLS + 1);
+    int cnt = 0;
+    const int min_cx = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, 0.0f), r), w_inv)));
+    const int max_cx = min(BG_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, 0.0f), r), w_inv)));
+    const int min_cy = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, 0.0f), r), h_inv)));
+    const int max_cy = min(BG_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, 0.0f), r), h_inv)));
+    if (min_cx < BG_COLS && max_cx >= 0 && min_cy < BG_ROWS && max_cy >= 0) {  // the four early returns of :611-625
+        for (int ix = min_cx; ix <= max_cx; ix++)
+            for (int iy = min_cy; iy <= max_cy; iy++) {
+                const int c = ix * BG_ROWS + iy;
+                for (int j = cs[c]; j < cs[c + 1]; j++) {
+                    const int item = cell_items[b + j];
+                    const float2 kp = pts[b + item];
+                    if (fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r) {
+                        if (cnt < capacity) out[(size_t)q * capacity + cnt] = item;
+                        cnt++;
+                    }
+                }
+            }
+    }
+    counts[q] = cnt;
+}
+
+}  // namespace
+
+int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes);  // api.cu
+
+static size_t a256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int movfe_assign_features_to_grid(movfe_ctx *ctx, int n_problems, const float *pts_xy, const int32_t *off,
+                                             int32_t *cell_start, int32_t *cell_items) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (n_problems < 1 || !off || !cell_start) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "assign_features_to_grid: bad argument");
+    const int n = off[n_problems];
+    int largest = 0;
+    for (int p = 0; p < n_problems; p++) {
+        if (off[p + 1] < off[p]) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "assign_features_to_grid: offsets must not decrease");
+        largest = std::max(largest, off[p + 1] - off[p]);
+    }
+    if (n < 0 || (n > 0 && (!pts_xy || !cell_items))) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "assign_features_to_grid: null array");
+    if (largest > BG_MAX_N) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "assign_features_to_grid: %d keypoints in one set, limit %d", largest, BG_MAX_N);
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int N2 = 64;
+    while (N2 < largest) N2 <<= 1;
+    const size_t b_pts = a256((size_t)std::max(n, 1) * sizeof(float2)), b_off = a256((size_t)(n_problems + 1) * 4);
+    const size_t b_cs = a256((size_t)n_problems * (BG_CELLS + 1) * 4), b_it = a256((size_t)std::max(n, 1) * 4);
+    int rc = movfe_ensure_op_scratch(ctx, b_pts + b_off + b_cs + b_it);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_op;
+    float2 *d_pts = (float2 *)base;
+    int32_t *d_off = (int32_t *)(base + b_pts), *d_cs = (int32_t *)(base + b_pts + b_off), *d_it = (int32_t *)(base + b_pts + b_off + b_cs);
+    cudaStream_t st = ctx->stream;
+    if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pts, pts_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_off, off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n) MOVFE_CUDA(ctx, cudaMemsetAsync(d_it, 0xff, (size_t)n * 4, st));  // entries past a set's valid count stay -1
+    const float w_inv = (float)BG_COLS / (float)ctx->cfg.width, h_inv = (float)BG_ROWS / (float)ctx->cfg.height;  // Frame.cc:147-148
+    const size_t smem = (size_t)N2 * sizeof(uint32_t);
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assign_kernel<<<n_problems, BG_THREADS, smem, st>>>(d_pts, d_off, w_inv, h_inv, N2, d_cs, d_it);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_start, d_cs, (size_t)n_problems * (BG_CELLS + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_items, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_features_in_area(movfe_ctx *ctx, int n_problems, const float *pts_xy, const int32_t *off,
+                                      const int32_t *cell_start, const int32_t *cell_items, int n_queries,
+                                      const movfe_area_query *queries, int capacity, int32_t *out, int32_t *counts) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (n_problems < 1 || !off || !cell_start || n_queries < 0 || capacity < 0 || (n_queries && (!queries || !counts)) ||
+        (n_queries && capacity && !out))
+        MOVFE_FAIL(ctx, MOVFE_E_INVALID, "features_in_area: bad argument");
+    const int n = off[n_problems];
+    if (n < 0 || (n > 0 && (!pts_xy || !cell_items))) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "features_in_area: null array");
+    for (int q = 0; q < n_queries; q++)
+        if (queries[q].problem < 0 || queries[q].problem >= n_problems)
+            MOVFE_FAIL(ctx, MOVFE_E_INVALID, "features_in_area: query %d names set %d of %d", q, queries[q].problem, n_problems);
+    if (n_queries == 0) return MOVFE_OK;
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    const size_t b_pts = a256((size_t)std::max(n, 1) * sizeof(float2)), b_off = a256((size_t)(n_problems + 1) * 4);
+    const size_t b_cs = a256((size_t)n_problems * (BG_CELLS + 1) * 4), b_it = a256((size_t)std::max(n, 1) * 4);
+    const size_t b_q = a256((size_t)n_queries * sizeof(movfe_area_query)), b_out = a256((size_t)n_queries * std::max(capacity, 1) * 4);
+    const size_t b_cnt = a256((size_t)n_queries * 4);
+    int rc = movfe_ensure_op_scratch(ctx, b_pts + b_off + b_cs + b_it + b_q + b_out + b_cnt);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_op;
+    float2 *d_pts = (float2 *)base;
+    base += b_pts;
+    int32_t *d_off = (int32_t *)base;
+    base += b_off;
+    int32_t *d_cs = (int32_t *)base;
+    base += b_cs;
+    int32_t *d_it = (int32_t *)base;
+    base += b_it;
+    movfe_area_query *d_q = (movfe_area_query *)base;
+    base += b_q;
+    int32_t *d_out = (int32_t *)base;
+    base += b_out;
+    int32_t *d_cnt = (int32_t *)base;
+    cudaStream_t st = ctx->stream;
+    if (n) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_pts, pts_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(d_it, cell_items, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_off, off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_cs, cell_start, (size_t)n_problems * (BG_CELLS + 1) * 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_q, queries, (size_t)n_queries * sizeof(movfe_area_query), cudaMemcpyHostToDevice, st));
+    const float w_inv = (float)BG_COLS / (float)ctx->cfg.width, h_inv = (float)BG_ROWS / (float)ctx->cfg.height;
+    area_kernel<<<(n_queries + 127) / 128, 128, 0, st>>>(d_pts, d_off, d_cs, d_it, d_q, n_queries, w_inv, h_inv, capacity, d_out, d_cnt);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    if (capacity) MOVFE_CUDA(ctx, cudaMemcpyAsync(out, d_out, (size_t)n_queries * capacity * 4, cudaMemcpyDeviceToHost, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+    return MOVFE_OK;
+}

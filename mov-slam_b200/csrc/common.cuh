@@ -37,6 +37,27 @@ struct __align__(8) HopRect {
 #define MOVFE_MAX_K 10
 #define MOVFE_NCLS(K) (2 * (K) + 2)
 
+// Results of one movfe_raster call for frames [first, first+nout) of every stream (window-local index fi = frame - first).
+struct RasterBuf {
+    int64_t first = -1;
+    int     nout = 0, nin = 0;
+    int32_t *d_cls_cnt = nullptr;   // [S][NIN][NCLS]
+    int64_t *d_area = nullptr;      // [S][NIN]
+    int32_t *d_hop_base = nullptr;  // [S][NIN][K+2]
+    int32_t *d_kps_base = nullptr;  // [S][NIN][K+2]
+    int32_t *d_nhops = nullptr;     // [S][NIN]
+    int32_t *d_nkps = nullptr;      // [S][NIN]
+    double  *d_cov = nullptr;       // [S][NIN]
+    movfe_hop  *d_hops = nullptr;   // [S][F][max_hops]
+    HopRect    *d_hop_rect = nullptr;
+    movfe_rect *d_kps = nullptr;    // [S][F][max_kps]
+    int32_t *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  (ymin | ymax<<16)
+    int4    *d_grid = nullptr;      // [S][F][H*W]
+    cudaEvent_t done = nullptr;      // recorded on raster_stream: the buffer is complete
+    cudaEvent_t consumed = nullptr;  // recorded on stream after the last propagation launch that read it
+    bool    consumed_valid = false;
+};
+
 struct movfe_ctx {
     movfe_config cfg;
     int K = 0, LA = 0, RING = 0, NIN = 0;  // max_ref, look-ahead frames, ring depth, max input frames per window
@@ -48,7 +69,14 @@ struct movfe_ctx {
     // window (the chains are independent once a window's track tables exist)
     cudaStream_t pose_stream = nullptr;
     cudaEvent_t ev_tables = nullptr;   // scratch event of movfe_fence
-    std::vector<cudaEvent_t> ev_frame; // [window_frames] recorded on `stream` after the finalize of frame f (index f % F)
+    // Propagation is a dependent chain of three short launches per frame, but the video streams are independent: they are
+    // split into n_groups groups, each walking its own chain on its own CUDA stream (group 0 on `stream`), so that one
+    // group's cand/birth CTAs fill the tail and the sparse finalize launch of another group.
+    static constexpr int MAX_GROUPS = 8;
+    int n_groups = 1;
+    cudaStream_t ext_stream[MAX_GROUPS] = {};   // [0] aliases `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
+    std::vector<cudaEvent_t> ev_frame; // [n_groups][window_frames] recorded on the group's stream after the finalize of frame f (index f % F)
     struct PoseLaunch { int64_t first; int n; cudaEvent_t done; };
     PoseLaunch pose_launches[4] = {};  // ring of the last pose launches (events created at movfe_create)
     int     pose_launch_head = 0;
@@ -56,8 +84,6 @@ struct movfe_ctx {
     std::string err;
 
     int64_t pushed = 0;            // frames pushed per stream so far
-    int64_t win_first = -1;        // last raster window
-    int     win_nout = 0, win_nin = 0;
     int64_t ext_first = -1;        // last extract window
     int     ext_n = 0;
     int64_t pose_first = -1;
@@ -83,19 +109,18 @@ struct movfe_ctx {
     uint8_t *d_grey = nullptr;     // [S][RING][H*grey_pitch]   (has_grey)
     unsigned long long *d_rejected = nullptr;
 
-    // raster window (window-local frame index fi = frame - win_first)
-    int32_t *d_cls_cnt = nullptr;   // [S][NIN][NCLS]
-    int64_t *d_area = nullptr;      // [S][NIN]
-    int32_t *d_hop_base = nullptr;  // [S][NIN][K+2]
-    int32_t *d_kps_base = nullptr;  // [S][NIN][K+2]
-    int32_t *d_nhops = nullptr;     // [S][NIN]
-    int32_t *d_nkps = nullptr;      // [S][NIN]
-    double  *d_cov = nullptr;       // [S][NIN]
-    movfe_hop  *d_hops = nullptr;   // [S][F][max_hops]
-    HopRect    *d_hop_rect = nullptr;
-    movfe_rect *d_kps = nullptr;    // [S][F][max_kps]
-    int32_t *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  (ymin | ymax<<16)
-    int4    *d_grid = nullptr;      // [S][F][H*W]
+    // raster results: two buffers, so that the raster of window k+1 (on raster_stream) runs beside the propagation of
+    // window k (on stream); rb_cur is the buffer of the last movfe_raster call
+    RasterBuf rb[2];
+    int rb_cur = 0;
+    cudaStream_t raster_stream = nullptr;  // ingest kernels + raster kernels (low priority: they fill what propagation leaves)
+    bool serial_raster = false;            // MOVFE_CFG_SERIAL_RASTER: raster waits for all earlier propagation (timing a kernel alone)
+    cudaEvent_t ev_serial = nullptr;
+    struct ExtLaunch { int64_t first; int n; cudaEvent_t done; };
+    static constexpr int N_EXT_LAUNCHES = 8;
+    ExtLaunch ext_launches[N_EXT_LAUNCHES] = {};  // ring of the last extract launches (ring-slot reuse by later pushes waits on them)
+    int ext_launch_head = 0;               // next entry to overwrite == oldest entry once the ring has wrapped
+    int64_t ext_launch_count = 0;
 
     // track tables: [S][TSLOTS][max_tracks], slot = frame % TSLOTS; two windows are resident so that the pose stream can
     // still read window k while propagation writes window k+1
@@ -186,9 +211,9 @@ struct WinParams {
 };
 
 // grid.cu
-int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p);
+int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w);
 // raster.cu
-int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in);
+int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n_out, int n_in);
 int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs, const int64_t *d_rec_off,
                         int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey);
 // extract.cu

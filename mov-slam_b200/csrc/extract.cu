@@ -34,6 +34,7 @@ constexpr int MAX_TRACKS_CAP = 8192;
 
 struct ExtParams {
     int S, W, H, maxT, max_kps, max_hops, maxM, n_out, n_in, RING, TSLOTS;
+    int s0;          // first video stream of this launch (the streams of a context are propagated in independent groups)
     int P;           // row pitch of the grey ring (power of two >= W)
     int fi;          // raster-window slot of this frame
     int gslot;       // ring slot of this frame (grey, flags)
@@ -291,8 +292,8 @@ __device__ __forceinline__ void desc_layout(const uint32_t (&b)[ROWS * COLS / 32
 constexpr int CAND_THREADS = CAND_WARPS * 32;
 constexpr int CW_MXY = 0;    // [4] candidate rectangle origin, mx | my << 16
 constexpr int CW_INFO = 4;   // need (4 bits) | mw << 8 | mh << 16
-constexpr int CW_OIDX = 5;   // index of the track in the previous table
-constexpr int CW_WORDS = 6;
+constexpr int CW_DESC = 5;   // [8] the track's previous descriptor (fetched at thread level, 32 tracks at once)
+constexpr int CW_WORDS = 13;
 
 // Loads of one candidate patch for the propagation kernel (mask pixels at column offset 1). For the shapes whose four
 // centre pixels lie inside the loaded 1..COLS columns the centre costs four shuffles instead of four more loads.
@@ -399,7 +400,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
             int2 *__restrict__ cinfo, int32_t *__restrict__ claim) {
     __shared__ int sm[CAND_WARPS][CW_WORDS][32];
-    const int s = blockIdx.y;
+    const int s = p.s0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_prev = ntracks[s * p.TSLOTS + p.tslot_prev];
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;  // I frame: nothing is propagated
@@ -417,12 +418,16 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         // ---- thread level: the track's own chain ------------------------------------------------------------------
         const bool act = i < n_prev;
         int oidx = 0;
-        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0);
+        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0), d0 = a0, d1 = a0;
         if (act) {
             oidx = ord[i];
             const uint4 *tp = reinterpret_cast<const uint4 *>(prev + oidx);
             a0 = __ldg(tp);      // pt_x, pt_y, mb.x | mb.y << 16, mb.w | mb.h << 16
             a1 = __ldg(tp + 1);  // track_id, age, q_indx, flags
+            if (img) {           // previous descriptor: one more dependent latency if it were fetched per track below
+                d0 = __ldg(tp + 2);
+                d1 = __ldg(tp + 3);
+            }
         }
         const float ptx = __uint_as_float(a0.x), pty = __uint_as_float(a0.y);
         const int mw = (int16_t)(a0.w & 0xffffu), mh = (int16_t)(a0.w >> 16);
@@ -462,7 +467,14 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
 #pragma unroll
             for (int j = 0; j < 4; j++) sm[warp][CW_MXY + j][lane] = mxy[j];
             sm[warp][CW_INFO][lane] = (int)need | (mw << 8) | (mh << 16);
-            sm[warp][CW_OIDX][lane] = oidx;
+            sm[warp][CW_DESC + 0][lane] = (int)d0.x;
+            sm[warp][CW_DESC + 1][lane] = (int)d0.y;
+            sm[warp][CW_DESC + 2][lane] = (int)d0.z;
+            sm[warp][CW_DESC + 3][lane] = (int)d0.w;
+            sm[warp][CW_DESC + 4][lane] = (int)d1.x;
+            sm[warp][CW_DESC + 5][lane] = (int)d1.y;
+            sm[warp][CW_DESC + 6][lane] = (int)d1.z;
+            sm[warp][CW_DESC + 7][lane] = (int)d1.w;
         }
         __syncwarp();
         // ---- warp level: descriptors of the candidate patches -------------------------------------------------------
@@ -478,9 +490,9 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             const int info = sm[warp][CW_INFO][t];
             const unsigned nd = info & 0xf;
             const int tw = (info >> 8) & 0xff, th = info >> 16;
-            const uint4 *dp = reinterpret_cast<const uint4 *>(prev + sm[warp][CW_OIDX][t]) + 2;
-            const uint4 p0 = __ldg(dp), p1 = __ldg(dp + 1);
-            const uint32_t pd[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            uint32_t pd[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) pd[k] = (uint32_t)sm[warp][CW_DESC + k][t];
             uint32_t bd[8];
             int best, ch;
             if (tw == 16 && th == 16) ch = cand_eval<16, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
@@ -608,7 +620,7 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
              uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
     __shared__ uint32_t scratch[CAND_WARPS][8];
     __shared__ int sm[CAND_WARPS][2][32];
-    const int s = blockIdx.y;
+    const int s = p.s0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = nkps[s * p.n_in + p.fi];
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;
@@ -946,7 +958,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     uint16_t *s_pk = reinterpret_cast<uint16_t *>(s_age + p.maxT);
     uint16_t *s_run = s_pk + p.maxT;
     int *s_hist = reinterpret_cast<int *>(s_run + p.maxT);
-    const int s = blockIdx.x;
+    const int s = p.s0 + blockIdx.x;
     movfe_track *cur = tracks + ((size_t)s * p.TSLOTS + p.tslot_cur) * p.maxT;
     const movfe_track *st = stage + (size_t)s * p.maxT;
     const int2 *ci = cinfo + (size_t)s * p.maxT;
@@ -1161,7 +1173,17 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
             MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl.done, 0));
     // the attribute is per function, not per context: set it for THIS context's table size before launching
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
+    // the raster results of this window were produced on the raster stream
+    RasterBuf &w = ctx->rb[ctx->rb_cur];
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, w.done, 0));
+    {
     ProfScope prof(ctx, MOVFE_STAGE_EXTRACT);
+    // fork: the other groups' streams start after everything enqueued so far on the primary stream
+    const int G = ctx->n_groups;
+    if (G > 1) {
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int g = 1; g < G; g++) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->ext_stream[g], ctx->ev_fork, 0));
+    }
     for (int k = 0; k < n_frames; k++) {
         const int64_t a = first_frame + k;
         ExtParams p;
@@ -1172,11 +1194,11 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.max_kps = ctx->max_kps;
         p.max_hops = ctx->max_hops;
         p.maxM = c.max_records_per_frame;
-        p.n_out = ctx->win_nout;
-        p.n_in = ctx->win_nin;
+        p.n_out = w.nout;
+        p.n_in = w.nin;
         p.RING = ctx->RING;
         p.TSLOTS = ctx->TSLOTS;
-        p.fi = (int)(a - ctx->win_first);
+        p.fi = (int)(a - w.first);
         p.gslot = (int)(a % ctx->RING);
         p.tslot_prev = tslot_of(ctx, a - 1);
         p.tslot_cur = tslot_of(ctx, a);
@@ -1184,12 +1206,16 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.has_grey = c.has_grey;
         p.P = ctx->grey_pitch;
         p.cov_thr = c.coverage_threshold;
+        for (int g = 0; g < G; g++) {
+        const int s_lo = (int)((int64_t)c.n_streams * g / G), ns = (int)((int64_t)c.n_streams * (g + 1) / G) - s_lo;
+        cudaStream_t gs = ctx->ext_stream[g];
+        p.s0 = s_lo;
         // grid-stride over tracks / kps: enough CTAs to fill the chip, never one CTA per (mostly empty) capacity slot
         const int bps = std::max(4, (8 * ctx->sm_count + c.n_streams - 1) / c.n_streams);
-        dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), c.n_streams);  // a warp takes 32 tracks
+        dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
 #define MOVFE_CAND(PITCH)                                                                                              \
-    cand_kernel<PITCH><<<gc, CAND_THREADS, 0, ctx->stream>>>(p, ctx->d_tracks, ctx->d_ntracks, e.order, ctx->d_grid, ctx->d_hops, \
-                                                             ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim)
+    cand_kernel<PITCH><<<gc, CAND_THREADS, 0, gs>>>(p, ctx->d_tracks, ctx->d_ntracks, e.order, w.d_grid, w.d_hops, \
+                                                    ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim)
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
             case 2048: MOVFE_CAND(2048); break;
@@ -1198,10 +1224,10 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
 #undef MOVFE_CAND
         int nl = 2;
         if (c.has_grey) {
-            dim3 gb(std::min((ctx->max_kps + CAND_THREADS - 1) / CAND_THREADS, bps), c.n_streams);
+            dim3 gb(std::min((ctx->max_kps + CAND_THREADS - 1) / CAND_THREADS, bps), ns);
 #define MOVFE_BIRTH(PITCH)                                                                                             \
-    birth_kernel<PITCH><<<gb, CAND_THREADS, 0, ctx->stream>>>(p, ctx->d_kps, ctx->d_nkps, ctx->d_grey, ctx->d_fflags, e.claim,    \
-                                                              e.birth_flag, e.birth_desc)
+    birth_kernel<PITCH><<<gb, CAND_THREADS, 0, gs>>>(p, w.d_kps, w.d_nkps, ctx->d_grey, ctx->d_fflags, e.claim,    \
+                                                     e.birth_flag, e.birth_desc)
             switch (ctx->grey_pitch) {
                 case 1024: MOVFE_BIRTH(1024); break;
                 case 2048: MOVFE_BIRTH(2048); break;
@@ -1210,14 +1236,30 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
 #undef MOVFE_BIRTH
             nl = 3;
         }
-        finalize_kernel<<<c.n_streams, FIN_THREADS, sort_smem(c.max_tracks), ctx->stream>>>(
-            p, ctx->d_tracks, ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, ctx->d_kps, ctx->d_nkps, ctx->d_cov,
-            e.birth_flag, e.birth_desc, ctx->d_grid, ctx->d_grey, ctx->d_fflags);
+        finalize_kernel<<<ns, FIN_THREADS, sort_smem(c.max_tracks), gs>>>(
+            p, ctx->d_tracks, ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, w.d_kps, w.d_nkps, w.d_cov,
+            e.birth_flag, e.birth_desc, w.d_grid, ctx->d_grey, ctx->d_fflags);
         prof.launches(nl);
-        // frame a's table is complete: the pose stream may start on it while propagation goes on with frame a+1
-        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_frame[a % c.window_frames], ctx->stream));
+        // frame a's table is complete for this group: the pose stream may start on it while propagation goes on with frame a+1
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_frame[(size_t)g * c.window_frames + a % c.window_frames], gs));
+        }
+    }
+    // join: whatever follows on the primary stream sees every group's tables
+    for (int g = 1; g < G; g++) {
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_join[g], ctx->ext_stream[g]));
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
+    }
     }
     MOVFE_CUDA(ctx, cudaGetLastError());
+    // the next raster into this buffer and later pushes into the ring slots of these frames wait for this launch
+    MOVFE_CUDA(ctx, cudaEventRecord(w.consumed, ctx->stream));
+    w.consumed_valid = true;
+    movfe_ctx::ExtLaunch &el = ctx->ext_launches[ctx->ext_launch_head];
+    el.first = first_frame;
+    el.n = n_frames;
+    MOVFE_CUDA(ctx, cudaEventRecord(el.done, ctx->stream));
+    ctx->ext_launch_head = (ctx->ext_launch_head + 1) % movfe_ctx::N_EXT_LAUNCHES;
+    ctx->ext_launch_count++;
     return MOVFE_OK;
 }
 
@@ -1251,7 +1293,8 @@ extern "C" int movfe_extract(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
     if (first_frame != next)
         MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract: frames must be consumed in order (expected %lld, got %lld)", (long long)next, (long long)first_frame);
-    if (n_frames < 1 || ctx->win_first < 0 || first_frame < ctx->win_first || first_frame + n_frames > ctx->win_first + ctx->win_nout)
+    const RasterBuf &w = ctx->rb[ctx->rb_cur];
+    if (n_frames < 1 || w.first < 0 || first_frame < w.first || first_frame + n_frames > w.first + w.nout)
         MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract: frames [%lld,%lld) are not inside the last raster window", (long long)first_frame,
                    (long long)(first_frame + n_frames));
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
@@ -1325,14 +1368,15 @@ extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const u
     const int slot = (int)(a % ctx->RING);
     const size_t plane = (size_t)c.width * c.height;
     cudaStream_t st = ctx->stream;
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_grid, grid, plane * sizeof(int4), cudaMemcpyHostToDevice, st));
-    if (n_hops) MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_hops, hops, (size_t)n_hops * sizeof(movfe_hop), cudaMemcpyHostToDevice, st));
-    if (n_kps) MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_kps, kps, (size_t)n_kps * sizeof(movfe_rect), cudaMemcpyHostToDevice, st));
+    RasterBuf &w = ctx->rb[ctx->rb_cur];  // the caller's raster results stand in for a movfe_raster call
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(w.d_grid, grid, plane * sizeof(int4), cudaMemcpyHostToDevice, st));
+    if (n_hops) MOVFE_CUDA(ctx, cudaMemcpyAsync(w.d_hops, hops, (size_t)n_hops * sizeof(movfe_hop), cudaMemcpyHostToDevice, st));
+    if (n_kps) MOVFE_CUDA(ctx, cudaMemcpyAsync(w.d_kps, kps, (size_t)n_kps * sizeof(movfe_rect), cudaMemcpyHostToDevice, st));
     const int32_t nh = n_hops, nk = n_kps;
     const uint8_t ff = (uint8_t)frame_flags;
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nhops, &nh, 4, cudaMemcpyHostToDevice, st));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkps, &nk, 4, cudaMemcpyHostToDevice, st));
-    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cov, &coverage_area, 8, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(w.d_nhops, &nh, 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(w.d_nkps, &nk, 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(w.d_cov, &coverage_area, 8, cudaMemcpyHostToDevice, st));
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_fflags + slot, &ff, 1, cudaMemcpyHostToDevice, st));
     if (grey) {
         if (ctx->stage_bytes[0] < plane + 16) {
@@ -1349,9 +1393,9 @@ extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const u
     }
     MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // nh / nk / ff live on this stack frame
     ctx->pushed = a + 1;
-    ctx->win_first = a;
-    ctx->win_nout = 1;
-    ctx->win_nin = 1;
+    w.first = a;
+    w.nout = 1;
+    w.nin = 1;
     rc = movfe_extract(ctx, a, 1);
     if (rc) return rc;
     int32_t n = 0;

@@ -4,17 +4,19 @@
 // hop when four or more cover it; untouched slots are -1.
 //
 // This is the HBM-bound kernel of the front-end: 16 bytes are written per pixel, nothing is read back.
-// Design (DESIGN.md §K2):
-//  * per-block ownership, no atomics: a CTA owns an 8-row band of one frame, a warp owns 32x8-pixel tiles of it,
+// Design (DESIGN.md §3):
+//  * per-block ownership, no atomics: a CTA owns a 32-row band of one frame, a warp owns 32x32-pixel tiles of it,
 //    a lane owns one pixel column; every pixel is written exactly once with one 128-bit streaming store, so a warp
 //    store covers 512 contiguous bytes and the -1 fill is implicit.
 //  * the band's hops are gathered once, in list order, into shared memory (ordered ballot compaction, 32-hop chunks
 //    skipped by their y-extent); chunks of the staged list carry an x-extent so a tile only scans chunks near it.
-//  * a tile's candidates are processed 31 at a time, candidate i of a chunk sitting in lane 30-i: one 32x32 bit
-//    transpose gives every lane the candidates covering its column, one ballot per row gives the candidates covering
-//    that row, and the slots fall out of bit scans — highest bit = first hop, lowest bit = last hop. Lane 31 holds
-//    the index -1, so "no such hop" shuffles -1 out without a select.
-//  * rows are independent, so the running state is four slot registers and a count, not a tile of registers.
+//  * hops are rectangles, so the set of hops covering pixel (x, y) is (hops covering column x) AND (hops covering row
+//    y), and both change only at block edges. A tile's columns fall into a few runs with the same column set, its
+//    rows into a few runs with the same row set; the slots are computed ONCE per (column run, row run) cell - a lane
+//    per cell - into a small shared-memory table, and a pixel's 16 bytes are one table read away.
+//  * candidates sit 31 to a chunk, candidate i in lane 30-i: one 32x32 bit transpose turns per-candidate column (row)
+//    masks into per-column (per-row) candidate sets, and the slots fall out of bit scans - highest bit = first hop,
+//    lowest bit = last hop. Lane 31 holds the index -1, so "no such hop" shuffles -1 out without a select.
 #include <cstdio>
 
 #include "common.cuh"
@@ -24,7 +26,18 @@ namespace {
 constexpr int GRID_MAX_WARPS = 16;
 constexpr int GRID_LIST_CAP = 2048;    // band-list entries staged in shared memory (2 words each = 16 KB); multiple of 32
 constexpr int GRID_CHUNK_CAP = 1024;   // surviving 32-hop chunk ids per band
-constexpr int TILE_Q = 124;            // a tile's candidate queue: 4 chunks of 31
+constexpr int TILE_CHUNKS = 6;         // a tile's candidates: up to 6 chunks of 31
+constexpr int TILE_Q = 31 * TILE_CHUNKS;
+constexpr int CELL_CAP = 128;          // (column run, row run) cells resolved per batch
+constexpr int SB_ROWS = 32;            // rows a CTA owns = rows of a tile
+
+// per-warp scratch in shared memory
+struct __align__(16) WarpScratch {
+    int4 tab[CELL_CAP];                // slots of the cells of the current batch, index (row run - first run) * ncp + column run
+    uint32_t qx[TILE_Q + 6];           // the tile's candidate queue: x0 | x1 << 16
+    uint32_t qi[TILE_Q + 6];           //                             hop index | r0 << 22 | r1 << 27
+    uint8_t repc[32], repr[32];        // first column / row of every run
+};
 
 __device__ __forceinline__ int bfind(unsigned x) {  // position of the highest set bit, -1 when x == 0
     int r;
@@ -110,28 +123,24 @@ __device__ __forceinline__ void warp_counts_prefix(const int *wcnt, int nwarps, 
     before = __shfl_sync(0xffffffffu, incl - v, warp);
 }
 
-constexpr int SB_ROWS = 32;  // rows a CTA owns: four 8-row bands share one staged hop list
-
 // list_i word: hop index (22 bits) | first row (5 bits) << 22 | last row (5 bits) << 27, rows relative to the CTA's band
-__device__ __forceinline__ unsigned row_mask8(uint32_t wi, int sub) {
-    const int r0 = (int)((wi >> 22) & 31u) - 8 * sub, r1 = (int)(wi >> 27) - 8 * sub;
-    const int a = max(r0, 0), b = min(r1, 7);
-    return b >= a ? ((2u << (b - a)) - 1u) << a : 0u;
+__device__ __forceinline__ unsigned row_mask32(uint32_t wi) {
+    const int r0 = (int)((wi >> 22) & 31u), r1 = (int)(wi >> 27);
+    return ((2u << (r1 - r0)) - 1u) << r0;  // r1 >= r0; 2u << 31 wraps to 0 -> all ones
 }
 
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
 grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
             const int32_t *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
-    extern __shared__ uint32_t smem[];
-    uint32_t *list_x = smem;                                   // [CAP] x0 | x1<<16
-    uint32_t *list_i = smem + GRID_LIST_CAP;                   // [CAP] hop index | r0<<22 | r1<<27
-    int32_t  *clist = (int32_t *)(smem + 2 * GRID_LIST_CAP);   // [CHUNK_CAP] surviving chunk ids; reused as x-extents
-    __shared__ int32_t wcnt[GRID_MAX_WARPS];
-    __shared__ uint32_t cext[GRID_LIST_CAP / 32];              // per list chunk: rows touched, bit r = some entry covers row r
-    __shared__ uint32_t cand[GRID_MAX_WARPS][2][TILE_Q + 36];  // per-warp candidate queue (x word, i word)
-
+    extern __shared__ __align__(16) uint32_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem)[warp];
+    uint32_t *list_x = smem + nwarps * (sizeof(WarpScratch) / 4);  // [CAP] x0 | x1<<16
+    uint32_t *list_i = list_x + GRID_LIST_CAP;                     // [CAP] hop index | r0<<22 | r1<<27
+    int32_t  *clist = (int32_t *)(list_i + GRID_LIST_CAP);         // [CHUNK_CAP] surviving chunk ids; reused as x-extents
+    __shared__ int32_t wcnt[GRID_MAX_WARPS];
+
     const unsigned lt = lanemask_lt();
     const int band = blockIdx.x % NSB;
     const int sg = blockIdx.x / NSB;  // s*n_out + g
@@ -196,53 +205,43 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
     }
     const bool direct = chunk_overflow || n_list > GRID_LIST_CAP;  // pathological input: tiles scan global memory
 
-    // ---- phase 1c: x-extent and touched rows of every 32-entry chunk of the staged list (reuses clist) --------
+    // ---- phase 1c: x-extent of every 32-entry chunk of the staged list (reuses clist) ---------------------------
     const int n_lc = direct ? 0 : (n_list + 31) >> 5;
     for (int c = warp; c < n_lc; c += nwarps) {
         const int e = c * 32 + lane;
         int xmin = 65535, xmax = -1;
-        unsigned rows = 0;
         if (e < n_list) {
-            const uint32_t wx = list_x[e], wi = list_i[e];
+            const uint32_t wx = list_x[e];
             xmin = (int)(wx & 0xffffu);
             xmax = (int)(wx >> 16);
-            const int r0 = (wi >> 22) & 31u, r1 = wi >> 27;
-            rows = ((2u << (r1 - r0)) - 1u) << r0;
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
             xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
             xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-            rows |= __shfl_xor_sync(0xffffffffu, rows, o);
         }
-        if (lane == 0) {
-            clist[c] = xmin | (xmax << 16);
-            cext[c] = rows;
-        }
+        if (lane == 0) clist[c] = xmin | (xmax << 16);
     }
     __syncthreads();
 
-    // ---- phase 2: a warp takes (8-row band, 64-px strip) items; no barrier from here on ------------------------
-    uint32_t *qx = cand[warp][0], *qi = cand[warp][1];
-    const int n_strips = (NT + 1) >> 1;  // a warp gathers once for a 64-px strip = two adjacent tiles
-    const int n_sub = (yhi - ylo + 8) >> 3;
-    for (int item = warp; item < n_sub * n_strips; item += nwarps) {
-        const int sub = item / n_strips, strip = item - sub * n_strips;
-        const int sx = strip * 64;
-        const int by = ylo + 8 * sub;  // first row of this 8-row band
-        const unsigned submask = 0xffu << (8 * sub);
-        // gather the strip's candidates (ascending hop order) into the queue
+    // ---- phase 2: a warp takes 32x32-pixel tiles of the band; no block barrier from here on -----------------------
+    const int nrows = yhi - ylo + 1;
+    for (int t = warp; t < NT; t += nwarps) {
+        const int tx = t * 32;
+        const int x = tx + lane;
+        const bool xin = x < p.W;
+        int4 *out = grid + ((size_t)sg * p.H + ylo) * p.W + x;
+        // gather the tile's candidates (ascending hop order) into the queue
         int nq = 0;
         bool overflow = direct;
         if (!direct) {
-            // list chunks that can matter to this item (x-extent meets the strip, some entry covers one of its rows): 32
-            // chunks are tested per ballot, only the survivors are visited, in ascending order
+            // list chunks whose x-extent meets the tile: 32 chunks are tested per ballot, only the survivors are visited
             for (int cb = 0; cb < n_lc && !overflow; cb += 32) {
                 const int cc = cb + lane;
                 bool rel = false;
                 if (cc < n_lc) {
                     const int ext = clist[cc];
-                    rel = (ext >> 16) >= sx && (ext & 0xffff) <= sx + 63 && (cext[cc] & submask);
+                    rel = (ext >> 16) >= tx && (ext & 0xffff) <= tx + 31;
                 }
                 unsigned todo = __ballot_sync(0xffffffffu, rel);
                 while (todo) {
@@ -254,7 +253,7 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                     if (e < n_list) {
                         wx = list_x[e];
                         wi = list_i[e];
-                        pred = (int)(wx >> 16) >= sx && (int)(wx & 0xffffu) <= sx + 63 && row_mask8(wi, sub) != 0;
+                        pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31;
                     }
                     const unsigned b = __ballot_sync(0xffffffffu, pred);
                     if (nq + __popc(b) > TILE_Q) {
@@ -263,100 +262,105 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                     }
                     if (pred) {
                         const int pos = nq + __popc(b & lt);
-                        qx[pos] = wx;
-                        qi[pos] = wi;
+                        ws.qx[pos] = wx;
+                        ws.qi[pos] = wi;
                     }
                     nq += __popc(b);
                 }
             }
         }
         __syncwarp();
-        const int nchk = (nq + 30) / 31;
-        // per-chunk lane data shared by both tiles of the strip: candidate i of chunk c sits in lane 30-i
-        uint32_t cwx[4];
-        int idx[4];
-        unsigned rm[4];
-        if (!overflow) {
+        if (!overflow && nq == 0) {
+            // no hop touches the tile (I frames, intra blocks): the implicit fill
+            const int4 v = make_int4(-1, -1, -1, -1);
+            if (xin)
+                for (int y = 0; y < nrows; y++) st_cs_v4(out + (size_t)y * p.W, v);
+        } else if (!overflow) {
+            // ---- fast path -------------------------------------------------------------------------------------
+            const int nchk = (nq + 30) / 31;
+            unsigned col[TILE_CHUNKS], row[TILE_CHUNKS];  // lane = column (row): candidates of the chunk covering it
+            int idx[TILE_CHUNKS];                         // lane 30-i: hop index of candidate i of the chunk; lane 31: -1
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                cwx[c] = 0x0000ffffu;  // x0 = 65535 > x1 = 0: covers no column
+            for (int c = 0; c < TILE_CHUNKS; c++) {
+                col[c] = row[c] = 0;
                 idx[c] = -1;
-                rm[c] = 0;
-                const int e = c * 31 + (30 - lane);
-                if (c < nchk && lane < 31 && e < nq) {
-                    const uint32_t wi = qi[e];
-                    cwx[c] = qx[e];
-                    idx[c] = (int)(wi & 0x3fffffu);
-                    rm[c] = row_mask8(wi, sub);
+                if (c < nchk) {  // warp-uniform
+                    const int e = c * 31 + (30 - lane);
+                    unsigned cm = 0, rmk = 0;
+                    if (lane < 31 && e < nq) {
+                        const uint32_t wi = ws.qi[e];
+                        idx[c] = (int)(wi & 0x3fffffu);
+                        cm = col_mask(ws.qx[e], tx);  // queue entries meet the tile in x
+                        rmk = row_mask32(wi);
+                    }
+                    col[c] = transpose32(cm, lane);
+                    row[c] = transpose32(rmk, lane);
                 }
             }
-        }
-        for (int tsub = 0; tsub < 2; tsub++) {
-        const int tx = sx + 32 * tsub;
-        if (tx >= p.W) break;
-        const int x = tx + lane;
-        int4 *out = grid + ((size_t)sg * p.H + by) * p.W + x;
-        if (!overflow) {
-            // fast path: <= 4 chunks of 31 candidates, column masks in registers. Rows are folded independently, and a
-            // row whose covering set equals the previous row's (block edges are sparse) reuses its slots.
-            const bool full = tx + 31 < p.W && by + 7 < p.H;  // warp-uniform: no per-store bounds test needed
-            const size_t rstride = (size_t)p.W;
-            if (nchk <= 1) {
-                const unsigned cm = (lane < 31 && (int)(cwx[0] >> 16) >= tx && (int)(cwx[0] & 0xffffu) <= tx + 31) ? col_mask(cwx[0], tx) : 0u;
-                const unsigned col0 = transpose32(cm, lane);
-                Slots st = {-1, -1, -1, -1, 0};
-                unsigned prev0 = 0;
+            // runs of columns (rows) with the same covering set
+            bool dcol = lane == 0, drow = lane == 0;
 #pragma unroll
-                for (int y = 0; y < 8; y++) {
-                    const unsigned rowm0 = __ballot_sync(0xffffffffu, (rm[0] >> y) & 1u);
-                    if (y == 0 || rowm0 != prev0) {  // warp-uniform
-                        fold<true, false>(st, col0 & rowm0, idx[0]);
-                        prev0 = rowm0;
-                    }
-                    if (full || (x < p.W && by + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
-                    out += rstride;
-                }
-            } else {
-                unsigned col[4];
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    col[c] = 0;
-                    if (c < nchk) {  // warp-uniform
-                        const unsigned cm = (lane < 31 && (int)(cwx[c] >> 16) >= tx && (int)(cwx[c] & 0xffffu) <= tx + 31) ? col_mask(cwx[c], tx) : 0u;
-                        col[c] = transpose32(cm, lane);
+            for (int c = 0; c < TILE_CHUNKS; c++)
+                if (c < nchk) {
+                    const unsigned pc = __shfl_up_sync(0xffffffffu, col[c], 1), pr = __shfl_up_sync(0xffffffffu, row[c], 1);
+                    if (lane > 0) {
+                        dcol = dcol || pc != col[c];
+                        drow = drow || pr != row[c];
                     }
                 }
-                Slots st = {-1, -1, -1, -1, 0};
-                unsigned prev[4] = {0, 0, 0, 0};
+            const unsigned cb = __ballot_sync(0xffffffffu, dcol), rb = __ballot_sync(0xffffffffu, drow);
+            const int ncc = __popc(cb), nrc = __popc(rb);
+            const unsigned le = lt | (1u << lane);
+            const int mycc = __popc(cb & le) - 1;  // run of column `lane`
+            if (dcol) ws.repc[mycc] = (uint8_t)lane;
+            if (drow) ws.repr[__popc(rb & le) - 1] = (uint8_t)lane;
+            __syncwarp();
+            int lg = 0;
+            while ((1 << lg) < ncc) lg++;
+            const int ncp = 1 << lg;          // column runs padded to a power of two: a lane's cell is (lane >> lg, lane & (ncp-1))
+            const int per_pass = 32 >> lg;    // row runs resolved per fold pass
+            const int per_batch = CELL_CAP >> lg;
+            const int kc = lane & (ncp - 1), krl = lane >> lg;
+            const int sc = kc < ncc ? ws.repc[kc] : 0;
+            for (int kr0 = 0; kr0 < nrc; kr0 += per_batch) {
+                const int kr1 = min(kr0 + per_batch, nrc);
+                for (int krb = kr0; krb < kr1; krb += per_pass) {
+                    const int kr = krb + krl;
+                    const bool valid = kc < ncc && kr < kr1;
+                    const int sr = valid ? ws.repr[kr] : 0;
+                    Slots st = {-1, -1, -1, -1, 0};
 #pragma unroll
-                for (int y = 0; y < 8; y++) {
-                    unsigned rowm[4];
-                    bool same = y != 0;
-#pragma unroll
-                    for (int c = 0; c < 4; c++) {
-                        rowm[c] = c < nchk ? __ballot_sync(0xffffffffu, (rm[c] >> y) & 1u) : 0u;
-                        same = same && rowm[c] == prev[c];
-                    }
-                    if (!same) {  // warp-uniform
-                        fold<true, true>(st, col[0] & rowm[0], idx[0]);
-#pragma unroll
-                        for (int c = 1; c < 4; c++)
-                            if (c < nchk) fold<false, true>(st, col[c] & rowm[c], idx[c]);
-#pragma unroll
-                        for (int c = 0; c < 4; c++) prev[c] = rowm[c];
-                    }
-                    if (full || (x < p.W && by + y < p.H)) st_cs_v4(out, make_int4(st.s0, st.s1, st.s2, st.s3));
-                    out += rstride;
+                    for (int c = 0; c < TILE_CHUNKS; c++)
+                        if (c < nchk) {  // warp-uniform
+                            const unsigned m = __shfl_sync(0xffffffffu, col[c], sc) & __shfl_sync(0xffffffffu, row[c], sr);
+                            if (c == 0) fold<true, true>(st, m, idx[0]);
+                            else fold<false, true>(st, m, idx[c]);
+                        }
+                    if (valid) ws.tab[((kr - kr0) << lg) + kc] = make_int4(st.s0, st.s1, st.s2, st.s3);
                 }
+                __syncwarp();
+                // the rows of these runs: one table read per run and column, one 128-bit store per pixel
+                const int y0 = ws.repr[kr0], y1 = min(kr1 < nrc ? (int)ws.repr[kr1] : 32, nrows);
+                int cell = mycc - ncp;
+                int4 v = make_int4(-1, -1, -1, -1);
+                int4 *o = out + (size_t)y0 * p.W;
+                for (int y = y0; y < y1; y++) {
+                    if ((rb >> y) & 1u) {  // warp-uniform: a new row run starts
+                        cell += ncp;
+                        v = ws.tab[cell];
+                    }
+                    if (xin) st_cs_v4(o, v);
+                    o += p.W;
+                }
+                __syncwarp();
             }
         } else {
-            // slow path (more than 124 candidates in one tile, or the band list did not fit): one row at a time,
+            // slow path (more than 186 candidates in one tile, or the band list did not fit): one row at a time,
             // streaming every source entry again and folding 31 candidates per step.
             const int n_src = direct ? n_h : n_list;
-            for (int y = 0; y < 8; y++) {
-                if (by + y >= p.H) break;
+            for (int y = 0; y < nrows; y++) {
                 Slots st = {-1, -1, -1, -1, 0};
-                int nq = 0;
+                int nq2 = 0;
                 for (int base = 0; base <= n_src; base += 32) {  // one extra, empty pass flushes the queue
                     const int e = base + lane;
                     bool pred = false;
@@ -365,80 +369,77 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                         if (!direct) {
                             wx = list_x[e];
                             wi = list_i[e];
-                            pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31 && ((row_mask8(wi, sub) >> y) & 1u);
+                            pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31 && ((row_mask32(wi) >> y) & 1u);
                             wi &= 0x3fffffu;
                         } else {
                             const HopRect r = rects[e];
-                            pred = r.y1 >= by + y && r.y0 <= by + y && r.x1 >= tx && r.x0 <= tx + 31;
+                            pred = r.y1 >= ylo + y && r.y0 <= ylo + y && r.x1 >= tx && r.x0 <= tx + 31;
                             wx = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
                             wi = (uint32_t)e;
                         }
                     }
                     const unsigned b = __ballot_sync(0xffffffffu, pred);
                     if (pred) {
-                        const int pos = nq + __popc(b & lt);
-                        qx[pos] = wx;
-                        qi[pos] = wi;
+                        const int pos = nq2 + __popc(b & lt);
+                        ws.qx[pos] = wx;
+                        ws.qi[pos] = wi;
                     }
-                    nq += __popc(b);
+                    nq2 += __popc(b);
                     __syncwarp();
                     const bool last = base + 32 > n_src;
-                    while (nq >= 31 || (last && nq > 0)) {
-                        const int take = min(nq, 31);
+                    while (nq2 >= 31 || (last && nq2 > 0)) {
+                        const int take = min(nq2, 31);
                         const int e2 = 30 - lane;
                         unsigned cm = 0;
                         int id = -1;
                         if (lane < 31 && e2 < take) {
-                            cm = col_mask(qx[e2], tx);
-                            id = (int)qi[e2];
+                            cm = col_mask(ws.qx[e2], tx);
+                            id = (int)ws.qi[e2];
                         }
                         const unsigned colm = transpose32(cm, lane);
                         fold<false, true>(st, colm, id);
                         __syncwarp();
-                        // move the remainder to the front (reads 31.., writes 0..: disjoint for nq-take <= 32)
+                        // move the remainder to the front (reads 31.., writes 0..: disjoint for nq2-take <= 32)
                         uint32_t a = 0, c2 = 0;
-                        const bool mv = lane < nq - take;
+                        const bool mv = lane < nq2 - take;
                         if (mv) {
-                            a = qx[take + lane];
-                            c2 = qi[take + lane];
+                            a = ws.qx[take + lane];
+                            c2 = ws.qi[take + lane];
                         }
                         __syncwarp();
                         if (mv) {
-                            qx[lane] = a;
-                            qi[lane] = c2;
+                            ws.qx[lane] = a;
+                            ws.qi[lane] = c2;
                         }
-                        nq -= take;
+                        nq2 -= take;
                         __syncwarp();
                     }
                 }
-                if (x < p.W) st_cs_v4(out + (size_t)y * p.W, make_int4(st.s0, st.s1, st.s2, st.s3));
+                if (xin) st_cs_v4(out + (size_t)y * p.W, make_int4(st.s0, st.s1, st.s2, st.s3));
             }
         }
         __syncwarp();
-        }  // tiles of the strip
     }
 }
 
 }  // namespace
 
-int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p) {
-    ProfScope prof(ctx, MOVFE_STAGE_GRID);
+int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w) {
+    ProfScope prof(ctx, MOVFE_STAGE_GRID, ctx->raster_stream);
     prof.launches(1);
-    // a CTA owns a 32-row band = 4 x n_strips (8-row band, 64-px strip) items; warps per CTA: the largest divisor of the
-    // item count that is <= 16 keeps every warp equally loaded
-    const int n_strips = (ctx->NT + 1) / 2;
+    // a CTA owns a 32-row band = NT tiles of 32x32 pixels; warps per CTA: the largest divisor of the tile count that is
+    // <= 16 keeps every warp equally loaded
     const int nsb = (p.H + SB_ROWS - 1) / SB_ROWS;
     int nw = 8;
-    for (int w = GRID_MAX_WARPS; w >= 4; w--)
-        if ((4 * n_strips) % w == 0) {
-            nw = w;
+    for (int k = GRID_MAX_WARPS; k >= 4; k--)
+        if (ctx->NT % k == 0) {
+            nw = k;
             break;
         }
-    const size_t smem = (2 * GRID_LIST_CAP + GRID_CHUNK_CAP) * sizeof(uint32_t);
+    const size_t smem = (size_t)nw * sizeof(WarpScratch) + (2 * GRID_LIST_CAP + GRID_CHUNK_CAP) * sizeof(uint32_t);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = p.S * p.n_out * nsb;
-    grid_kernel<<<blocks, nw * 32, smem, ctx->stream>>>(p, nsb, ctx->NT, ctx->d_hop_rect, ctx->d_nhops, ctx->d_chunk_bbox,
-                                                       ctx->d_grid);
+    grid_kernel<<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nsb, ctx->NT, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid);
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }

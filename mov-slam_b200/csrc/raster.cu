@@ -402,23 +402,23 @@ int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_r
                         int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey) {
     const movfe_config &c = ctx->cfg;
     const int n_seg = c.n_streams * n_frames;
-    ProfScope prof(ctx, MOVFE_STAGE_INGEST);
+    ProfScope prof(ctx, MOVFE_STAGE_INGEST, ctx->raster_stream);
     prof.launches(n_records > 0 ? 2 : 1);
     if (n_records > 0) {
         const int64_t warps = (n_records + INGEST_REC_PER_WARP - 1) / INGEST_REC_PER_WARP;
         const int blocks = (int)((warps + INGEST_WARPS - 1) / INGEST_WARPS);
-        ingest_kernel<<<blocks, INGEST_WARPS * 32, 0, ctx->stream>>>(
+        ingest_kernel<<<blocks, INGEST_WARPS * 32, 0, ctx->raster_stream>>>(
             reinterpret_cast<const uint4 *>(d_recs), n_records, d_rec_off, n_seg, n_frames, ctx->pushed, ctx->RING,
             c.max_records_per_frame, ctx->d_rec, ctx->d_rejected);
     }
-    ingest_meta_kernel<<<(n_seg + 255) / 256, 256, 0, ctx->stream>>>(d_rec_off, d_flags, n_seg, n_frames, ctx->pushed,
+    ingest_meta_kernel<<<(n_seg + 255) / 256, 256, 0, ctx->raster_stream>>>(d_rec_off, d_flags, n_seg, n_frames, ctx->pushed,
                                                                      ctx->RING, c.max_records_per_frame,
                                                                      ctx->d_rec_cnt, ctx->d_fflags);
     if (c.has_grey && d_grey) {
         const int vec = (c.width % 16 == 0 && ((uintptr_t)d_grey & 15) == 0) ? 16 : 1;
         const int64_t total = (int64_t)n_seg * c.height * (c.width / vec);
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-        grey_ingest_kernel<<<blocks, 256, 0, ctx->stream>>>(d_grey, n_seg, n_frames, c.width, c.height, ctx->grey_pitch, vec, ctx->pushed,
+        grey_ingest_kernel<<<blocks, 256, 0, ctx->raster_stream>>>(d_grey, n_seg, n_frames, c.width, c.height, ctx->grey_pitch, vec, ctx->pushed,
                                                           ctx->RING, ctx->d_grey);
         prof.launches(1);
     }
@@ -437,7 +437,7 @@ int movfe_grey_upload(movfe_ctx *ctx, const uint8_t *d_src, int slot) {
     return MOVFE_OK;
 }
 
-int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in) {
+int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n_out, int n_in) {
     const movfe_config &c = ctx->cfg;
     WinParams p;
     p.S = c.n_streams;
@@ -454,20 +454,20 @@ int movfe_raster_launch(movfe_ctx *ctx, int64_t first_frame, int n_out, int n_in
     p.max_chunks = ctx->max_chunks;
     const int SF = p.S * n_in;
     {
-    ProfScope prof(ctx, MOVFE_STAGE_HOPS);
+    ProfScope prof(ctx, MOVFE_STAGE_HOPS, ctx->raster_stream);
     prof.launches(4);
-    count_kernel<<<SF, CNT_THREADS, 0, ctx->stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_cls_cnt,
-                                                      ctx->d_area, ctx->d_rejected);
-    bases_kernel<<<(SF + 127) / 128, 128, 0, ctx->stream>>>(p, ctx->d_cls_cnt, ctx->d_area, ctx->d_hop_base,
-                                                            ctx->d_kps_base, ctx->d_nhops, ctx->d_nkps, ctx->d_cov);
-    emit_kernel<<<SF, CNT_THREADS, 0, ctx->stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_hop_base,
-                                                     ctx->d_kps_base, ctx->d_hops, ctx->d_hop_rect, ctx->d_kps);
+    count_kernel<<<SF, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_cls_cnt,
+                                                      w.d_area, ctx->d_rejected);
+    bases_kernel<<<(SF + 127) / 128, 128, 0, ctx->raster_stream>>>(p, w.d_cls_cnt, w.d_area, w.d_hop_base,
+                                                            w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov);
+    emit_kernel<<<SF, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_hop_base,
+                                                     w.d_kps_base, w.d_hops, w.d_hop_rect, w.d_kps);
     {
         dim3 g((ctx->max_chunks * 32 + 255) / 256, p.S * n_out);
-        bbox_kernel<<<g, 256, 0, ctx->stream>>>(p, ctx->d_hop_rect, ctx->d_nhops, ctx->d_chunk_bbox);
+        bbox_kernel<<<g, 256, 0, ctx->raster_stream>>>(p, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox);
     }
     }
-    if (int rc = movfe_grid_launch(ctx, p)) return rc;
+    if (int rc = movfe_grid_launch(ctx, p, w)) return rc;
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }

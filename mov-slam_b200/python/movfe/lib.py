@@ -23,7 +23,7 @@ class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_streams", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("max_records_per_frame", C.c_int32), ("max_ref", C.c_int32), ("window_frames", C.c_int32),
                 ("max_tracks", C.c_int32), ("max_map_points", C.c_int32), ("express_threshold", C.c_int32),
-                ("coverage_threshold", C.c_double), ("has_grey", C.c_int32), ("reserved", C.c_int32)]
+                ("coverage_threshold", C.c_double), ("has_grey", C.c_int32), ("flags", C.c_int32)]
 
 
 def load():
@@ -68,6 +68,8 @@ def load():
     L.movfe_download_matches.argtypes = [vp, i32, i64, vp, vp, i32]
     L.movfe_frustum.argtypes = [vp, i32, vp, vp, vp, vp]
     L.movfe_join.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.movfe_assign_features_to_grid.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.movfe_features_in_area.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp]
     L.movfe_pose_optimize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.movfe_profile_enable.argtypes = [vp, i32]
     L.movfe_profile_read.argtypes = [vp, vp, vp, i32]
@@ -81,6 +83,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
+           "movfe_assign_features_to_grid", "movfe_features_in_area",
            "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read"]
 
 
@@ -92,13 +95,16 @@ def _p(a):
     return C.c_void_p(int(a))        # raw device pointer
 
 
+CFG_SERIAL_RASTER = 1   # MOVFE_CFG_SERIAL_RASTER
+
+
 class Context:
     def __init__(self, n_streams, width, height, max_records_per_frame=4800, max_ref=3, window_frames=16,
                  max_tracks=4096, max_map_points=4096, express_threshold=25, coverage_threshold=0.20, has_grey=True,
-                 device=0):
+                 device=0, serial_raster=False):
         self.L = load()
         self.cfg = Config(device, n_streams, width, height, max_records_per_frame, max_ref, window_frames, max_tracks,
-                          max_map_points, express_threshold, coverage_threshold, int(bool(has_grey)), 0)
+                          max_map_points, express_threshold, coverage_threshold, int(bool(has_grey)), CFG_SERIAL_RASTER if serial_raster else 0)
         h = C.c_void_p()
         rc = self.L.movfe_create(C.byref(self.cfg), C.byref(h))
         if rc != 0:
@@ -272,6 +278,27 @@ class Context:
         self._ck(self.L.movfe_join(self.h, len(track_off) - 1, _p(track_ids), _p(track_off), _p(probe_ids),
                                    _p(probe_valid), _p(probe_off), _p(match), _p(n)))
         return match, n
+
+    def assign_features_to_grid(self, pts_xy, off):
+        """Frame::AssignFeaturesToGrid for packed keypoint sets -> (cell_start [n_sets, 64*48+1], cell_items [n])."""
+        pts_xy = np.ascontiguousarray(pts_xy, np.float32).reshape(-1, 2)
+        off = np.ascontiguousarray(off, np.int32)
+        start = np.zeros((len(off) - 1, 64 * 48 + 1), np.int32)
+        items = np.full(max(len(pts_xy), 1), -1, np.int32)
+        self._ck(self.L.movfe_assign_features_to_grid(self.h, len(off) - 1, _p(pts_xy), _p(off), _p(start), _p(items)))
+        return start, items[:len(pts_xy)]
+
+    def features_in_area(self, pts_xy, off, start, items, queries, capacity):
+        """Frame::GetFeaturesInArea for a batch of (set, x, y, r) queries -> (indices [n_queries, capacity], counts)."""
+        pts_xy = np.ascontiguousarray(pts_xy, np.float32).reshape(-1, 2)
+        off = np.ascontiguousarray(off, np.int32)
+        queries = np.ascontiguousarray(queries, T.AREA_QUERY)
+        out = np.full((len(queries), max(capacity, 1)), -1, np.int32)
+        counts = np.zeros(max(len(queries), 1), np.int32)
+        self._ck(self.L.movfe_features_in_area(self.h, len(off) - 1, _p(pts_xy), _p(off), _p(np.ascontiguousarray(start, np.int32)),
+                                               _p(np.ascontiguousarray(items, np.int32)), len(queries), _p(queries), capacity,
+                                               _p(out), _p(counts)))
+        return out[:, :capacity], counts[:len(queries)]
 
     def pose_optimize(self, cam, pp, pts, obs, off, poses):
         cam = np.ascontiguousarray(cam, T.CAMERA)

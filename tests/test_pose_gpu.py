@@ -165,3 +165,46 @@ def test_pipeline_mv_only_seeded(orc):
     specs = [synth.Spec(640, 480, n_frames=8, refs=2, seed=0x5EED0051, start_p=True)]
     seeds = [synth.seed_tracks_lattice(sp) for sp in specs]
     _pipeline_case(orc, specs, window=8, max_ref=1, with_grey=False, seeds=seeds)
+
+
+def test_bucket_grid_parity(orc, ctx):
+    """Frame::AssignFeaturesToGrid / GetFeaturesInArea (Frame.cc:356-388, 602-680): same CSR lists, same query results in
+    the same order. Sets: empty, one point, clustered (many per cell), points on / outside the frame border, 9000 points."""
+    rng = np.random.Generator(np.random.PCG64(0x5EED0031))
+    sets = [np.zeros((0, 2), np.float32), np.array([[639.9, 479.9]], np.float32),
+            rng.normal([320, 240], [30, 20], (700, 2)).astype(np.float32),
+            np.concatenate([rng.uniform([-20, -20], [660, 500], (500, 2)), [[0, 0], [640, 480], [635.1, 475.1], [634.9, 474.9], [-0.4, -0.4]]]).astype(np.float32),
+            rng.uniform([0, 0], [640, 480], (9000, 2)).astype(np.float32)]
+    off = np.cumsum([0] + [len(s) for s in sets]).astype(np.int32)
+    pts = np.concatenate(sets)
+    start, items = ctx.assign_features_to_grid(pts, off)
+    want = []
+    for i, s in enumerate(sets):
+        tr = np.zeros(len(s), T.TRACK)
+        tr["pt_x"], tr["pt_y"] = s[:, 0], s[:, 1]
+        ws, wi = orc.assign_features_to_grid(tr, 640, 480)
+        want.append((tr, ws, wi))
+        assert np.array_equal(start[i], ws), i
+        nv = int(ws[-1])
+        assert np.array_equal(items[off[i]:off[i] + nv], wi[:nv]), i
+        assert (items[off[i] + nv:off[i + 1]] == -1).all()
+    assert 0 < want[3][1][-1] < len(sets[3])          # some points of set 3 fall outside the grid
+    q = []
+    for i in (0, 1, 2, 3, 4):
+        for _ in range(40):
+            q.append((i, rng.uniform(-30, 670), rng.uniform(-30, 510), rng.choice([0.5, 5.0, 15.0, 60.0, 400.0])))
+    q += [(4, 320.0, 240.0, 1000.0), (2, 320.0, 240.0, 0.0), (1, 639.0, 479.0, 2.0)]
+    q = np.array(q, T.AREA_QUERY)
+    cap = 9000
+    out, counts = ctx.features_in_area(pts, off, start, items, q, cap)
+    hit = 0
+    for k, (i, x, y, r) in enumerate(q.tolist()):
+        tr, ws, wi = want[i]
+        w = orc.get_features_in_area(tr, 640, 480, ws, wi, np.float32(x), np.float32(y), np.float32(r))
+        assert counts[k] == len(w), (k, counts[k], len(w))
+        assert np.array_equal(out[k, :len(w)], w), k
+        hit += len(w)
+    assert hit > 1000
+    # truncation: the full count is still reported
+    out2, counts2 = ctx.features_in_area(pts, off, start, items, q[-3:], 10)
+    assert counts2[0] == counts[-3] and np.array_equal(out2[0], out[-3, :10])
