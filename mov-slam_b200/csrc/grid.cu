@@ -24,19 +24,21 @@
 namespace {
 
 constexpr int GRID_MAX_WARPS = 16;
-constexpr int GRID_LIST_CAP = 2048;    // band-list entries staged in shared memory (2 words each = 16 KB); multiple of 32
 constexpr int GRID_CHUNK_CAP = 1024;   // surviving 32-hop chunk ids per band
 constexpr int TILE_CHUNKS = 6;         // a tile's candidates: up to 6 chunks of 31
 constexpr int TILE_Q = 31 * TILE_CHUNKS;
+constexpr int TQ_STRIDE = TILE_Q + 6;  // queue words per tile
 constexpr int CELL_CAP = 128;          // (column run, row run) cells resolved per batch
 constexpr int SB_ROWS = 32;            // rows a CTA owns = rows of a tile
+constexpr int MAX_TILES = 32;          // tiles a CTA owns (wider frames are split in x): "lane = tile" bookkeeping
 
 // per-warp scratch in shared memory
 struct __align__(16) WarpScratch {
     int4 tab[CELL_CAP];                // slots of the cells of the current batch, index (row run - first run) * ncp + column run
-    uint32_t qx[TILE_Q + 6];           // the tile's candidate queue: x0 | x1 << 16
-    uint32_t qi[TILE_Q + 6];           //                             hop index | r0 << 22 | r1 << 27
-    uint8_t repc[32], repr[32];        // first column / row of every run
+    uint32_t amask[MAX_TILES];         // phase 1: lanes of this warp's chunk whose first tile is t ...
+    uint32_t cmask[MAX_TILES];         //          ... and whose second tile is t
+    int32_t cnt[MAX_TILES];            //          entries this warp's chunk adds to tile t
+    uint8_t repc[32], repr[32];        // phase 2: first column / row of every run
 };
 
 __device__ __forceinline__ int bfind(unsigned x) {  // position of the highest set bit, -1 when x == 0
@@ -123,29 +125,35 @@ __device__ __forceinline__ void warp_counts_prefix(const int *wcnt, int nwarps, 
     before = __shfl_sync(0xffffffffu, incl - v, warp);
 }
 
-// list_i word: hop index (22 bits) | first row (5 bits) << 22 | last row (5 bits) << 27, rows relative to the CTA's band
+// queue word i: hop index (22 bits) | first row (5 bits) << 22 | last row (5 bits) << 27, rows relative to the CTA's band
 __device__ __forceinline__ unsigned row_mask32(uint32_t wi) {
     const int r0 = (int)((wi >> 22) & 31u), r1 = (int)(wi >> 27);
     return ((2u << (r1 - r0)) - 1u) << r0;  // r1 >= r0; 2u << 31 wraps to 0 -> all ones
 }
 
+// grid = (32-row bands, frames of the window x x-splits, streams)
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
-grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
+grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
             const int32_t *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpScratch &ws = reinterpret_cast<WarpScratch *>(smem)[warp];
-    uint32_t *list_x = smem + nwarps * (sizeof(WarpScratch) / 4);  // [CAP] x0 | x1<<16
-    uint32_t *list_i = list_x + GRID_LIST_CAP;                     // [CAP] hop index | r0<<22 | r1<<27
-    int32_t  *clist = (int32_t *)(list_i + GRID_LIST_CAP);         // [CHUNK_CAP] surviving chunk ids; reused as x-extents
+    WarpScratch *wsa = reinterpret_cast<WarpScratch *>(smem);
+    WarpScratch &ws = wsa[warp];
+    uint32_t *tq_x = smem + nwarps * (sizeof(WarpScratch) / 4);  // [NTC][TQ_STRIDE] per-tile candidate queues: x0 | x1<<16
+    uint32_t *tq_i = tq_x + NTC * TQ_STRIDE;                     // [NTC][TQ_STRIDE]                             hop | r0<<22 | r1<<27
+    int32_t  *clist = (int32_t *)(tq_i + NTC * TQ_STRIDE);       // [CHUNK_CAP] surviving chunk ids
     __shared__ int32_t wcnt[GRID_MAX_WARPS];
 
     const unsigned lt = lanemask_lt();
-    const int band = blockIdx.x % NSB;
-    const int sg = blockIdx.x / NSB;  // s*n_out + g
-    const int s = sg / p.n_out, g = sg - s * p.n_out;
+    const int band = blockIdx.x;
+    const int g = nxs == 1 ? blockIdx.y : blockIdx.y / nxs;
+    const int xs = blockIdx.y - g * nxs;
+    const int s = blockIdx.z;
+    const int sg = s * p.n_out + g;
     const int ylo = band * SB_ROWS, yhi = min(ylo + SB_ROWS - 1, p.H - 1);
+    const int X0 = xs * NTC * 32, X1 = min(X0 + NTC * 32, p.W) - 1;   // pixel columns of this CTA
+    const int ntl = (X1 - X0 + 32) >> 5;                              // its tiles (the last split may own fewer than NTC)
     const int n_h = nhops[s * p.n_in + g];
     const HopRect *rects = hop_rects + (size_t)sg * p.max_hops;
     const int32_t *bbox = chunk_bbox + (size_t)sg * p.max_chunks;
@@ -171,105 +179,108 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
         n_cl += tot;
         __syncthreads();
     }
-    const bool chunk_overflow = n_cl > GRID_CHUNK_CAP;
+    const bool direct = n_cl > GRID_CHUNK_CAP;  // pathological input: every tile streams the whole hop list
 
-    // ---- phase 1b: ordered list of the hops touching the band, staged in shared memory -----------------------
-    int n_list = 0;
-    if (!chunk_overflow) {
+    // ---- phase 1b: the band's hops go straight into per-tile queues, in list order ---------------------------------
+    // A warp takes one surviving chunk per round (lower warp = earlier chunk). A hop meets one or two tiles (blocks are
+    // narrower than a tile): match.any groups the lanes by tile, so a lane knows its rank inside the chunk for each of its
+    // tiles and lane t knows the chunk's count for tile t; counts are prefixed across the warps of the round.
+    int run_total = 0;  // lane t: entries queued so far in tile t (the same in every warp)
+    if (!direct) {
         for (int base = 0; base < n_cl; base += nwarps) {
             const int ci = base + warp;
             bool pred = false;
-            HopRect r = {0, 32767, -1, -32768};
-            int h = 0;
+            uint32_t wx = 0, wi = 0;
+            int t0 = 0, t1 = 0;
             if (ci < n_cl) {
-                h = clist[ci] * 32 + lane;
+                const int h = clist[ci] * 32 + lane;
                 if (h < n_h) {
-                    r = rects[h];
-                    pred = r.y1 >= ylo && r.y0 <= yhi;
+                    const HopRect r = rects[h];
+                    pred = r.y1 >= ylo && r.y0 <= yhi && r.x1 >= X0 && r.x0 <= X1;
+                    if (pred) {
+                        const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
+                        wx = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
+                        wi = (uint32_t)h | ((uint32_t)r0 << 22) | ((uint32_t)r1 << 27);
+                        t0 = (max((int)r.x0, X0) - X0) >> 5;
+                        t1 = (min((int)r.x1, X1) - X0) >> 5;
+                    }
                 }
             }
-            const unsigned b = __ballot_sync(0xffffffffu, pred);
-            if (lane == 0) wcnt[warp] = __popc(b);
-            __syncthreads();
-            int before, tot;
-            warp_counts_prefix(wcnt, nwarps, warp, lane, before, tot);
-            const int pos = n_list + before + __popc(b & lt);
-            if (pred && pos < GRID_LIST_CAP) {
-                const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
-                list_x[pos] = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
-                list_i[pos] = (uint32_t)h | ((uint32_t)r0 << 22) | ((uint32_t)r1 << 27);
+            const bool two = pred && t1 != t0;
+            const bool wide = __any_sync(0xffffffffu, pred && t1 - t0 > 1);  // blocks wider than a tile: generic ballots
+            int rank0 = 0, rank1 = 0, mycnt = 0, tmin = 0, tmax = -1;
+            if (!wide) {
+                ws.amask[lane] = 0;
+                ws.cmask[lane] = 0;
+                __syncwarp();
+                const unsigned p0 = __match_any_sync(0xffffffffu, pred ? t0 : 64 + lane);
+                const unsigned p1 = __match_any_sync(0xffffffffu, two ? t1 : 64 + lane);
+                if (pred && (p0 & lt) == 0) ws.amask[t0] = p0;
+                if (two && (p1 & lt) == 0) ws.cmask[t1] = p1;
+                __syncwarp();
+                if (pred) rank0 = __popc((ws.amask[t0] | ws.cmask[t0]) & lt);
+                if (two) rank1 = __popc((ws.amask[t1] | ws.cmask[t1]) & lt);
+                mycnt = __popc(ws.amask[lane] | ws.cmask[lane]);
+            } else {
+                tmin = __reduce_min_sync(0xffffffffu, pred ? t0 : MAX_TILES);
+                tmax = __reduce_max_sync(0xffffffffu, pred ? t1 : -1);
+                for (int t = tmin; t <= tmax; t++) {
+                    const unsigned b = __ballot_sync(0xffffffffu, pred && t0 <= t && t <= t1);
+                    if (lane == t) mycnt = __popc(b);
+                }
             }
-            n_list += tot;
+            ws.cnt[lane] = mycnt;
+            __syncthreads();
+            int before = 0, tot = 0;
+            for (int w2 = 0; w2 < nwarps; w2++) {
+                const int c = wsa[w2].cnt[lane];
+                tot += c;
+                if (w2 < warp) before += c;
+            }
+            const int basepos = run_total + before;
+            run_total += tot;
+            if (!wide) {
+                const int b0 = __shfl_sync(0xffffffffu, basepos, t0), b1 = __shfl_sync(0xffffffffu, basepos, t1);
+                if (pred) {
+                    const int pos = b0 + rank0;
+                    if (pos < TILE_Q) {
+                        tq_x[t0 * TQ_STRIDE + pos] = wx;
+                        tq_i[t0 * TQ_STRIDE + pos] = wi;
+                    }
+                }
+                if (two) {
+                    const int pos = b1 + rank1;
+                    if (pos < TILE_Q) {
+                        tq_x[t1 * TQ_STRIDE + pos] = wx;
+                        tq_i[t1 * TQ_STRIDE + pos] = wi;
+                    }
+                }
+            } else {
+                for (int t = tmin; t <= tmax; t++) {
+                    const bool in = pred && t0 <= t && t <= t1;
+                    const unsigned b = __ballot_sync(0xffffffffu, in);
+                    const int pos = __shfl_sync(0xffffffffu, basepos, t) + __popc(b & lt);
+                    if (in && pos < TILE_Q) {
+                        tq_x[t * TQ_STRIDE + pos] = wx;
+                        tq_i[t * TQ_STRIDE + pos] = wi;
+                    }
+                }
+            }
             __syncthreads();
         }
-    }
-    const bool direct = chunk_overflow || n_list > GRID_LIST_CAP;  // pathological input: tiles scan global memory
-
-    // ---- phase 1c: x-extent of every 32-entry chunk of the staged list (reuses clist) ---------------------------
-    const int n_lc = direct ? 0 : (n_list + 31) >> 5;
-    for (int c = warp; c < n_lc; c += nwarps) {
-        const int e = c * 32 + lane;
-        int xmin = 65535, xmax = -1;
-        if (e < n_list) {
-            const uint32_t wx = list_x[e];
-            xmin = (int)(wx & 0xffffu);
-            xmax = (int)(wx >> 16);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
-            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
-        }
-        if (lane == 0) clist[c] = xmin | (xmax << 16);
     }
     __syncthreads();
 
     // ---- phase 2: a warp takes 32x32-pixel tiles of the band; no block barrier from here on -----------------------
     const int nrows = yhi - ylo + 1;
-    for (int t = warp; t < NT; t += nwarps) {
-        const int tx = t * 32;
+    for (int t = warp; t < ntl; t += nwarps) {
+        const int tx = X0 + t * 32;
         const int x = tx + lane;
         const bool xin = x < p.W;
         int4 *out = grid + ((size_t)sg * p.H + ylo) * p.W + x;
-        // gather the tile's candidates (ascending hop order) into the queue
-        int nq = 0;
-        bool overflow = direct;
-        if (!direct) {
-            // list chunks whose x-extent meets the tile: 32 chunks are tested per ballot, only the survivors are visited
-            for (int cb = 0; cb < n_lc && !overflow; cb += 32) {
-                const int cc = cb + lane;
-                bool rel = false;
-                if (cc < n_lc) {
-                    const int ext = clist[cc];
-                    rel = (ext >> 16) >= tx && (ext & 0xffff) <= tx + 31;
-                }
-                unsigned todo = __ballot_sync(0xffffffffu, rel);
-                while (todo) {
-                    const int c = cb + __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int e = c * 32 + lane;
-                    bool pred = false;
-                    uint32_t wx = 0, wi = 0;
-                    if (e < n_list) {
-                        wx = list_x[e];
-                        wi = list_i[e];
-                        pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31;
-                    }
-                    const unsigned b = __ballot_sync(0xffffffffu, pred);
-                    if (nq + __popc(b) > TILE_Q) {
-                        overflow = true;
-                        break;
-                    }
-                    if (pred) {
-                        const int pos = nq + __popc(b & lt);
-                        ws.qx[pos] = wx;
-                        ws.qi[pos] = wi;
-                    }
-                    nq += __popc(b);
-                }
-            }
-        }
-        __syncwarp();
+        uint32_t *qx = tq_x + t * TQ_STRIDE, *qi = tq_i + t * TQ_STRIDE;
+        const int nq = __shfl_sync(0xffffffffu, run_total, t);
+        const bool overflow = direct || nq > TILE_Q;
         if (!overflow && nq == 0) {
             // no hop touches the tile (I frames, intra blocks): the implicit fill
             const int4 v = make_int4(-1, -1, -1, -1);
@@ -288,9 +299,9 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                     const int e = c * 31 + (30 - lane);
                     unsigned cm = 0, rmk = 0;
                     if (lane < 31 && e < nq) {
-                        const uint32_t wi = ws.qi[e];
+                        const uint32_t wi = qi[e];
                         idx[c] = (int)(wi & 0x3fffffu);
-                        cm = col_mask(ws.qx[e], tx);  // queue entries meet the tile in x
+                        cm = col_mask(qx[e], tx);  // queue entries meet the tile in x
                         rmk = row_mask32(wi);
                     }
                     col[c] = transpose32(cm, lane);
@@ -315,8 +326,7 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
             if (dcol) ws.repc[mycc] = (uint8_t)lane;
             if (drow) ws.repr[__popc(rb & le) - 1] = (uint8_t)lane;
             __syncwarp();
-            int lg = 0;
-            while ((1 << lg) < ncc) lg++;
+            const int lg = ncc > 1 ? 32 - __clz(ncc - 1) : 0;
             const int ncp = 1 << lg;          // column runs padded to a power of two: a lane's cell is (lane >> lg, lane & (ncp-1))
             const int per_pass = 32 >> lg;    // row runs resolved per fold pass
             const int per_batch = CELL_CAP >> lg;
@@ -355,23 +365,18 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                 __syncwarp();
             }
         } else {
-            // slow path (more than 186 candidates in one tile, or the band list did not fit): one row at a time,
-            // streaming every source entry again and folding 31 candidates per step.
-            const int n_src = direct ? n_h : n_list;
+            // slow path (more than 186 candidates in one tile, or the chunk list did not fit): one row at a time,
+            // streaming the band's chunks again from global memory and folding 31 candidates per step.
+            const int n_src = direct ? nchunks : n_cl;
             for (int y = 0; y < nrows; y++) {
                 Slots st = {-1, -1, -1, -1, 0};
                 int nq2 = 0;
-                for (int base = 0; base <= n_src; base += 32) {  // one extra, empty pass flushes the queue
-                    const int e = base + lane;
+                for (int k = 0; k <= n_src; k++) {  // one extra, empty pass flushes the queue
                     bool pred = false;
                     uint32_t wx = 0, wi = 0;
-                    if (e < n_src) {
-                        if (!direct) {
-                            wx = list_x[e];
-                            wi = list_i[e];
-                            pred = (int)(wx >> 16) >= tx && (int)(wx & 0xffffu) <= tx + 31 && ((row_mask32(wi) >> y) & 1u);
-                            wi &= 0x3fffffu;
-                        } else {
+                    if (k < n_src) {
+                        const int e = (direct ? k : clist[k]) * 32 + lane;
+                        if (e < n_h) {
                             const HopRect r = rects[e];
                             pred = r.y1 >= ylo + y && r.y0 <= ylo + y && r.x1 >= tx && r.x0 <= tx + 31;
                             wx = (uint32_t)(uint16_t)r.x0 | ((uint32_t)(uint16_t)r.x1 << 16);
@@ -381,20 +386,20 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                     const unsigned b = __ballot_sync(0xffffffffu, pred);
                     if (pred) {
                         const int pos = nq2 + __popc(b & lt);
-                        ws.qx[pos] = wx;
-                        ws.qi[pos] = wi;
+                        qx[pos] = wx;
+                        qi[pos] = wi;
                     }
                     nq2 += __popc(b);
                     __syncwarp();
-                    const bool last = base + 32 > n_src;
+                    const bool last = k == n_src;
                     while (nq2 >= 31 || (last && nq2 > 0)) {
                         const int take = min(nq2, 31);
                         const int e2 = 30 - lane;
                         unsigned cm = 0;
                         int id = -1;
                         if (lane < 31 && e2 < take) {
-                            cm = col_mask(ws.qx[e2], tx);
-                            id = (int)ws.qi[e2];
+                            cm = col_mask(qx[e2], tx);
+                            id = (int)qi[e2];
                         }
                         const unsigned colm = transpose32(cm, lane);
                         fold<false, true>(st, colm, id);
@@ -403,13 +408,13 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
                         uint32_t a = 0, c2 = 0;
                         const bool mv = lane < nq2 - take;
                         if (mv) {
-                            a = ws.qx[take + lane];
-                            c2 = ws.qi[take + lane];
+                            a = qx[take + lane];
+                            c2 = qi[take + lane];
                         }
                         __syncwarp();
                         if (mv) {
-                            ws.qx[lane] = a;
-                            ws.qi[lane] = c2;
+                            qx[lane] = a;
+                            qi[lane] = c2;
                         }
                         nq2 -= take;
                         __syncwarp();
@@ -427,19 +432,23 @@ grid_kernel(WinParams p, int NSB, int NT, const HopRect *__restrict__ hop_rects,
 int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w) {
     ProfScope prof(ctx, MOVFE_STAGE_GRID, ctx->raster_stream);
     prof.launches(1);
-    // a CTA owns a 32-row band = NT tiles of 32x32 pixels; warps per CTA: the largest divisor of the tile count that is
-    // <= 16 keeps every warp equally loaded
+    // a CTA owns a 32-row band (of an x-split of at most 32 tiles when the frame is wider than 1024 px) = NTC tiles of
+    // 32x32 pixels; warps per CTA: the largest divisor of the tile count that is <= 16 keeps every warp equally loaded
     const int nsb = (p.H + SB_ROWS - 1) / SB_ROWS;
-    int nw = 8;
+    const int nxs = (ctx->NT + MAX_TILES - 1) / MAX_TILES;
+    const int ntc = (ctx->NT + nxs - 1) / nxs;
+    int nw = 4;
     for (int k = GRID_MAX_WARPS; k >= 4; k--)
-        if (ctx->NT % k == 0) {
+        if (ntc % k == 0) {
             nw = k;
             break;
         }
-    const size_t smem = (size_t)nw * sizeof(WarpScratch) + (2 * GRID_LIST_CAP + GRID_CHUNK_CAP) * sizeof(uint32_t);
+    if (nw == 4 && ntc % 4 != 0 && ntc > 4) nw = 8;
+    const size_t smem = (size_t)nw * sizeof(WarpScratch) + ((size_t)2 * ntc * TQ_STRIDE + GRID_CHUNK_CAP) * sizeof(uint32_t);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = p.S * p.n_out * nsb;
-    grid_kernel<<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nsb, ctx->NT, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid);
+    if ((size_t)p.n_out * nxs > 65535 || p.S > 65535) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "grid: launch grid out of range");
+    dim3 blocks(nsb, p.n_out * nxs, p.S);
+    grid_kernel<<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid);
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
