@@ -34,7 +34,7 @@ constexpr int MAX_TILES = 32;          // tiles a CTA owns (wider frames are spl
 
 // per-warp scratch in shared memory
 struct __align__(16) WarpScratch {
-    int4 tab[CELL_CAP];                // slots of the cells of the current batch, index (row run - first run) * ncp + column run
+    int4 tab[CELL_CAP];                // slots of the cells of the current batch, index (row run - first run) * ncc + column run
     uint32_t amask[MAX_TILES];         // phase 1: lanes of this warp's chunk whose first tile is t ...
     uint32_t cmask[MAX_TILES];         //          ... and whose second tile is t
     int32_t cnt[MAX_TILES];            //          entries this warp's chunk adds to tile t
@@ -131,6 +131,91 @@ __device__ __forceinline__ unsigned row_mask32(uint32_t wi) {
     return ((2u << (r1 - r0)) - 1u) << r0;  // r1 >= r0; 2u << 31 wraps to 0 -> all ones
 }
 
+// 65535 / n + 1 for n = 1..32: (j * magic) >> 16 == j / n for j < 2048
+__constant__ uint32_t c_magic[33] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
+
+// Fast path of one 32x32 tile whose candidates (at most NCH chunks of 31) are queued in shared memory.
+template <int NCH>
+__device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, const uint32_t *qi, int nq, int tx, int lane, unsigned lt,
+                                          int4 *out, int W, int nrows, bool xin) {
+    const int nchk = (nq + 30) / 31;
+    unsigned col[NCH], row[NCH];  // lane = column (row): candidates of the chunk covering it
+    int idx[NCH];                         // lane 30-i: hop index of candidate i of the chunk; lane 31: -1
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        col[c] = row[c] = 0;
+        idx[c] = -1;
+        if (c < nchk) {  // warp-uniform
+            const int e = c * 31 + (30 - lane);
+            unsigned cm = 0, rmk = 0;
+            if (lane < 31 && e < nq) {
+                const uint32_t wi = qi[e];
+                idx[c] = (int)(wi & 0x3fffffu);
+                cm = col_mask(qx[e], tx);  // queue entries meet the tile in x
+                rmk = row_mask32(wi);
+            }
+            col[c] = transpose32(cm, lane);
+            row[c] = transpose32(rmk, lane);
+        }
+    }
+    // runs of columns (rows) with the same covering set
+    bool dcol = lane == 0, drow = lane == 0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++)
+        if (c < nchk) {
+            const unsigned pc = __shfl_up_sync(0xffffffffu, col[c], 1), pr = __shfl_up_sync(0xffffffffu, row[c], 1);
+            if (lane > 0) {
+                dcol = dcol || pc != col[c];
+                drow = drow || pr != row[c];
+            }
+        }
+    const unsigned cb = __ballot_sync(0xffffffffu, dcol), rb = __ballot_sync(0xffffffffu, drow);
+    const int ncc = __popc(cb), nrc = __popc(rb);
+    const unsigned le = lt | (1u << lane);
+    const int mycc = __popc(cb & le) - 1;  // run of column `lane`
+    if (dcol) ws.repc[mycc] = (uint8_t)lane;
+    if (drow) ws.repr[__popc(rb & le) - 1] = (uint8_t)lane;
+    __syncwarp();
+    // cells are numbered densely, cell j = (row run j / ncc, column run j % ncc); 32 cells are resolved per fold pass,
+    // up to CELL_CAP per batch. j / ncc by a multiply: exact for j < 2048 (ncc <= 32).
+    const unsigned magic = c_magic[ncc];
+    const int per_batch = (int)((CELL_CAP * magic) >> 16);  // row runs per batch: CELL_CAP / ncc >= 4
+    for (int kr0 = 0; kr0 < nrc; kr0 += per_batch) {
+        const int kr1 = min(kr0 + per_batch, nrc);
+        const int ncell = (kr1 - kr0) * ncc;
+        for (int j0 = 0; j0 < ncell; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = j < ncell;
+            const int q = (int)(((unsigned)j * magic) >> 16);
+            const int sc = valid ? ws.repc[j - q * ncc] : 0, sr = valid ? ws.repr[kr0 + q] : 0;
+            Slots st = {-1, -1, -1, -1, 0};
+#pragma unroll
+            for (int c = 0; c < NCH; c++)
+                if (c < nchk) {  // warp-uniform
+                    const unsigned m = __shfl_sync(0xffffffffu, col[c], sc) & __shfl_sync(0xffffffffu, row[c], sr);
+                    if (c == 0) fold<true, true>(st, m, idx[0]);
+                    else fold<false, true>(st, m, idx[c]);
+                }
+            if (valid) ws.tab[j] = make_int4(st.s0, st.s1, st.s2, st.s3);
+        }
+        __syncwarp();
+        // the rows of these runs: one table read per run and column, one 128-bit store per pixel
+        const int y0 = ws.repr[kr0], y1 = min(kr1 < nrc ? (int)ws.repr[kr1] : 32, nrows);
+        int cell = mycc - ncc;
+        int4 v = make_int4(-1, -1, -1, -1);
+        int4 *o = out + (size_t)y0 * W;
+        for (int y = y0; y < y1; y++) {
+            if ((rb >> y) & 1u) {  // warp-uniform: a new row run starts
+                cell += ncc;
+                v = ws.tab[cell];
+            }
+            if (xin) st_cs_v4(o, v);
+            o += W;
+        }
+        __syncwarp();
+    }
+}
+
 // grid = (32-row bands, frames of the window x x-splits, streams)
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
 grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
@@ -187,15 +272,27 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
     // tiles and lane t knows the chunk's count for tile t; counts are prefixed across the warps of the round.
     int run_total = 0;  // lane t: entries queued so far in tile t (the same in every warp)
     if (!direct) {
+        const HopRect none = {0, 32767, -1, -32768};  // overlaps nothing
+        HopRect r_next = none;
+        int h_next = 0;
+        if (warp < n_cl) {
+            h_next = clist[warp] * 32 + lane;
+            if (h_next < n_h) r_next = rects[h_next];
+        }
         for (int base = 0; base < n_cl; base += nwarps) {
             const int ci = base + warp;
             bool pred = false;
             uint32_t wx = 0, wi = 0;
             int t0 = 0, t1 = 0;
-            if (ci < n_cl) {
-                const int h = clist[ci] * 32 + lane;
-                if (h < n_h) {
-                    const HopRect r = rects[h];
+            const HopRect r = r_next;
+            const int h = h_next;
+            r_next = none;
+            if (ci + nwarps < n_cl) {  // the next round's rectangle is in flight across this round's barriers
+                h_next = clist[ci + nwarps] * 32 + lane;
+                if (h_next < n_h) r_next = rects[h_next];
+            }
+            {
+                {
                     pred = r.y1 >= ylo && r.y0 <= yhi && r.x1 >= X0 && r.x0 <= X1;
                     if (pred) {
                         const int r0 = max((int)r.y0, ylo) - ylo, r1 = min((int)r.y1, yhi) - ylo;
@@ -287,83 +384,9 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
             if (xin)
                 for (int y = 0; y < nrows; y++) st_cs_v4(out + (size_t)y * p.W, v);
         } else if (!overflow) {
-            // ---- fast path -------------------------------------------------------------------------------------
-            const int nchk = (nq + 30) / 31;
-            unsigned col[TILE_CHUNKS], row[TILE_CHUNKS];  // lane = column (row): candidates of the chunk covering it
-            int idx[TILE_CHUNKS];                         // lane 30-i: hop index of candidate i of the chunk; lane 31: -1
-#pragma unroll
-            for (int c = 0; c < TILE_CHUNKS; c++) {
-                col[c] = row[c] = 0;
-                idx[c] = -1;
-                if (c < nchk) {  // warp-uniform
-                    const int e = c * 31 + (30 - lane);
-                    unsigned cm = 0, rmk = 0;
-                    if (lane < 31 && e < nq) {
-                        const uint32_t wi = qi[e];
-                        idx[c] = (int)(wi & 0x3fffffu);
-                        cm = col_mask(qx[e], tx);  // queue entries meet the tile in x
-                        rmk = row_mask32(wi);
-                    }
-                    col[c] = transpose32(cm, lane);
-                    row[c] = transpose32(rmk, lane);
-                }
-            }
-            // runs of columns (rows) with the same covering set
-            bool dcol = lane == 0, drow = lane == 0;
-#pragma unroll
-            for (int c = 0; c < TILE_CHUNKS; c++)
-                if (c < nchk) {
-                    const unsigned pc = __shfl_up_sync(0xffffffffu, col[c], 1), pr = __shfl_up_sync(0xffffffffu, row[c], 1);
-                    if (lane > 0) {
-                        dcol = dcol || pc != col[c];
-                        drow = drow || pr != row[c];
-                    }
-                }
-            const unsigned cb = __ballot_sync(0xffffffffu, dcol), rb = __ballot_sync(0xffffffffu, drow);
-            const int ncc = __popc(cb), nrc = __popc(rb);
-            const unsigned le = lt | (1u << lane);
-            const int mycc = __popc(cb & le) - 1;  // run of column `lane`
-            if (dcol) ws.repc[mycc] = (uint8_t)lane;
-            if (drow) ws.repr[__popc(rb & le) - 1] = (uint8_t)lane;
-            __syncwarp();
-            const int lg = ncc > 1 ? 32 - __clz(ncc - 1) : 0;
-            const int ncp = 1 << lg;          // column runs padded to a power of two: a lane's cell is (lane >> lg, lane & (ncp-1))
-            const int per_pass = 32 >> lg;    // row runs resolved per fold pass
-            const int per_batch = CELL_CAP >> lg;
-            const int kc = lane & (ncp - 1), krl = lane >> lg;
-            const int sc = kc < ncc ? ws.repc[kc] : 0;
-            for (int kr0 = 0; kr0 < nrc; kr0 += per_batch) {
-                const int kr1 = min(kr0 + per_batch, nrc);
-                for (int krb = kr0; krb < kr1; krb += per_pass) {
-                    const int kr = krb + krl;
-                    const bool valid = kc < ncc && kr < kr1;
-                    const int sr = valid ? ws.repr[kr] : 0;
-                    Slots st = {-1, -1, -1, -1, 0};
-#pragma unroll
-                    for (int c = 0; c < TILE_CHUNKS; c++)
-                        if (c < nchk) {  // warp-uniform
-                            const unsigned m = __shfl_sync(0xffffffffu, col[c], sc) & __shfl_sync(0xffffffffu, row[c], sr);
-                            if (c == 0) fold<true, true>(st, m, idx[0]);
-                            else fold<false, true>(st, m, idx[c]);
-                        }
-                    if (valid) ws.tab[((kr - kr0) << lg) + kc] = make_int4(st.s0, st.s1, st.s2, st.s3);
-                }
-                __syncwarp();
-                // the rows of these runs: one table read per run and column, one 128-bit store per pixel
-                const int y0 = ws.repr[kr0], y1 = min(kr1 < nrc ? (int)ws.repr[kr1] : 32, nrows);
-                int cell = mycc - ncp;
-                int4 v = make_int4(-1, -1, -1, -1);
-                int4 *o = out + (size_t)y0 * p.W;
-                for (int y = y0; y < y1; y++) {
-                    if ((rb >> y) & 1u) {  // warp-uniform: a new row run starts
-                        cell += ncp;
-                        v = ws.tab[cell];
-                    }
-                    if (xin) st_cs_v4(o, v);
-                    o += p.W;
-                }
-                __syncwarp();
-            }
+            // ---- fast path: specialised for the usual one or two chunks of candidates ------------------------------
+            if (nq <= 62) fast_tile<2>(ws, qx, qi, nq, tx, lane, lt, out, p.W, nrows, xin);
+            else fast_tile<TILE_CHUNKS>(ws, qx, qi, nq, tx, lane, lt, out, p.W, nrows, xin);
         } else {
             // slow path (more than 186 candidates in one tile, or the chunk list did not fit): one row at a time,
             // streaming the band's chunks again from global memory and folding 31 candidates per step.
