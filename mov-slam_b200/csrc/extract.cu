@@ -393,8 +393,11 @@ __device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, i
     return chosen;
 }
 
+#ifndef CAND_MINB
+#define CAND_MINB 2
+#endif
 template <int PITCH>
-__global__ void __launch_bounds__(CAND_THREADS)
+__global__ void __launch_bounds__(CAND_THREADS, CAND_MINB)
 cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
             const uint16_t *__restrict__ order, const int4 *__restrict__ grid, const movfe_hop *__restrict__ hops,
             const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
@@ -481,15 +484,21 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         uint32_t my_d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int my_best = 0;
         unsigned todo = __ballot_sync(0xffffffffu, warp_job);
+        unsigned odd = 0;  // tracks whose block is none of the four H.264 shapes: second loop (its arrays live in local memory)
         while (todo) {
             const int t = __ffs(todo) - 1;
             todo &= todo - 1;
-            int cm[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) cm[j] = sm[warp][CW_MXY + j][t];
             const int info = sm[warp][CW_INFO][t];
             const unsigned nd = info & 0xf;
             const int tw = (info >> 8) & 0xff, th = info >> 16;
+            const bool std_shape = (tw == 16 || tw == 8) && (th == 16 || th == 8);
+            if (!std_shape) {  // warp-uniform
+                odd |= 1u << t;
+                continue;
+            }
+            int cm[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cm[j] = sm[warp][CW_MXY + j][t];
             uint32_t pd[8];
 #pragma unroll
             for (int k = 0; k < 8; k++) pd[k] = (uint32_t)sm[warp][CW_DESC + k][t];
@@ -498,10 +507,29 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             if (tw == 16 && th == 16) ch = cand_eval<16, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
             else if (tw == 8 && th == 8) ch = cand_eval<8, 8, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
             else if (tw == 8 && th == 16) ch = cand_eval<16, 8, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
-            else if (tw == 16 && th == 8) ch = cand_eval<8, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
-            else ch = cand_eval_generic(img, p.P, p.thr, tw, th, cm, nd, pd, lane, bd, best);
+            else ch = cand_eval<8, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
             if (lane == t) {
                 // single-candidate pixels never compare (:272): slot 0 stays chosen; its descriptor is the one evaluated
+                if (sl.y >= 0 && ch >= 0) chosen = ch;
+                my_best = best;
+#pragma unroll
+                for (int k = 0; k < 8; k++) my_d[k] = bd[k];
+            }
+        }
+        while (odd) {
+            const int t = __ffs(odd) - 1;
+            odd &= odd - 1;
+            int cm[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cm[j] = sm[warp][CW_MXY + j][t];
+            const int info = sm[warp][CW_INFO][t];
+            uint32_t pd[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) pd[k] = (uint32_t)sm[warp][CW_DESC + k][t];
+            uint32_t bd[8];
+            int best;
+            const int ch = cand_eval_generic(img, p.P, p.thr, (info >> 8) & 0xff, info >> 16, cm, info & 0xf, pd, lane, bd, best);
+            if (lane == t) {
                 if (sl.y >= 0 && ch >= 0) chosen = ch;
                 my_best = best;
 #pragma unroll
@@ -614,7 +642,7 @@ __device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ img, u
 }
 
 template <int PITCH>
-__global__ void __launch_bounds__(CAND_THREADS)
+__global__ void __launch_bounds__(CAND_THREADS, 4)
 birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
              const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
              uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
@@ -642,27 +670,45 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
         sm[warp][1][lane] = r.y;
         __syncwarp();
         unsigned todo = __ballot_sync(0xffffffffu, job);
+        unsigned odd = 0;  // blocks of none of the four H.264 shapes: second loop (the generic mask indexes its array dynamically)
         while (todo) {
             const int t = __ffs(todo) - 1;
             todo &= todo - 1;
             const int rx = sm[warp][0][t], ry = sm[warp][1][t];
             const int x = (int16_t)(rx & 0xffff), y = rx >> 16, w = (int16_t)(ry & 0xffff), h = ry >> 16;
+            if (!((w == 16 || w == 8) && (h == 16 || h == 8))) {  // warp-uniform
+                odd |= 1u << t;
+                continue;
+            }
             const int stride = PITCH ? PITCH : p.P;
             const unsigned origin = (unsigned)(y * stride + x);
-            const uint8_t *roi = img + origin;
             uint32_t d[8];
             bool pass;
             if (w == 16 && h == 16) pass = express_birth<16, 16, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
             else if (w == 8 && h == 8) pass = express_birth<8, 8, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
             else if (w == 8 && h == 16) pass = express_birth<16, 8, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
-            else if (w == 16 && h == 8) pass = express_birth<8, 16, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
-            else {
-                pass = express_test(roi, stride, h, w, p.thr, scratch[warp], lane);  // :391
-                if (pass) express_mask(roi, stride, h, w, express_band(roi, stride, h, w, p.thr), 1, false, d, lane);
-            }
-            if (pass) {
+            else pass = express_birth<8, 16, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
+            if (pass && lane == 0) {
                 const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
+                birth_flag[o] = 1;
+                uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
+                bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
+                bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
+            }
+        }
+        while (odd) {
+            const int t = __ffs(odd) - 1;
+            odd &= odd - 1;
+            const int rx = sm[warp][0][t], ry = sm[warp][1][t];
+            const int x = (int16_t)(rx & 0xffff), y = rx >> 16, w = (int16_t)(ry & 0xffff), h = ry >> 16;
+            const int stride = PITCH ? PITCH : p.P;
+            const uint8_t *roi = img + (unsigned)(y * stride + x);
+            uint32_t d[8];
+            const bool pass = express_test(roi, stride, h, w, p.thr, scratch[warp], lane);  // :391
+            if (pass) {
+                express_mask(roi, stride, h, w, express_band(roi, stride, h, w, p.thr), 1, false, d, lane);
                 if (lane == 0) {
+                    const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
                     birth_flag[o] = 1;
                     uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
                     bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);

@@ -11,7 +11,7 @@ import numpy as np
 from . import types as T
 
 _PKG = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # mov-slam_b200/
-SO_PATH = os.path.join(_PKG, "lib", "libmovfe.so")
+SO_PATH = os.environ.get("MOVFE_LIB") or os.path.join(_PKG, "lib", "libmovfe.so")   # MOVFE_LIB: development builds
 _LIB = None
 
 
