@@ -330,7 +330,8 @@ def run_product(args):
         ctx.push_frames_device(F, d["recs"].data_ptr(), d["off"].data_ptr(), d["n_records"], d["flags"].data_ptr(), d["grey"].data_ptr())
         ctx.raster(first, F)
         ctx.extract(first, F)
-        ctx.track_poses(first, F)
+        if not os.environ.get("BENCH_NO_POSE"):     # development only: how much the pose chain costs the other streams
+            ctx.track_poses(first, F)
 
     dev_ms, _, stage_ovl, launches, clocks = timed(ctx, ext, step_device, "device-resident")
     frames_total = world * S * F * args.steps

@@ -467,9 +467,17 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         int chosen = (!img && sl.y >= 0 && need) ? __ffs(need) - 1 : 0;
         const bool warp_job = alive && need != 0 && img != nullptr;
         if (warp_job) {
+            // a later candidate whose block lands on the same pixels as an earlier in-bounds one has the same descriptor and
+            // distance, and the strict '<' of :292 never prefers it: it is not evaluated
+            unsigned need_eval = need;
+#pragma unroll
+            for (int j = 1; j < 4; j++)
+#pragma unroll
+                for (int k = 0; k < j; k++)
+                    if (((need >> k) & 1u) && mxy[j] == mxy[k]) need_eval &= ~(1u << j);
 #pragma unroll
             for (int j = 0; j < 4; j++) sm[warp][CW_MXY + j][lane] = mxy[j];
-            sm[warp][CW_INFO][lane] = (int)need | (mw << 8) | (mh << 16);
+            sm[warp][CW_INFO][lane] = (int)need_eval | (mw << 8) | (mh << 16);
             sm[warp][CW_DESC + 0][lane] = (int)d0.x;
             sm[warp][CW_DESC + 1][lane] = (int)d0.y;
             sm[warp][CW_DESC + 2][lane] = (int)d0.z;
