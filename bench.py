@@ -352,15 +352,37 @@ def run_product(args):
     ctx, ext = new_context(serial_raster=True)
     serial_ms, _, stage_ms, _, _ = timed(ctx, ext, step_device, "device-resident, serial raster")
 
+    # workload statistics for the whole-step byte count, sampled on stream 0 of the last window: T tracks per
+    # frame, c = candidate hops per track (non-empty slots of the slot-grid cell under the track), hops per frame
+    last_first = F * n_steps
+    t_cnt, c_sum, c_n, hop_cnt = [], 0, 0, []
+    for f in range(last_first + 1, last_first + F, 5):
+        prev = ctx.tracks(0, f - 1)
+        g = ctx.grid(0, f).reshape(H, W, 4)
+        xs, ys = prev["pt_x"].astype(np.int64), prev["pt_y"].astype(np.int64)
+        ok = (xs >= 0) & (ys >= 0) & (xs < W) & (ys < H) & ((prev["flags"] & T.TRACK_COVERAGE) == 0)
+        c_sum += int((g[ys[ok], xs[ok]] >= 0).sum())
+        c_n += int(ok.sum())
+        t_cnt.append(len(prev))
+        hop_cnt.append(int(ctx.raster_counts(0, f)[0]))
+    T_mean, c_bar, hops_mean = float(np.mean(t_cnt)), c_sum / max(c_n, 1), float(np.mean(hop_cnt))
+
     grid_bytes = S * F * W * H * 16.0                       # algorithmic bytes of the dominant HBM kernel per launch
     grid_ms = stage_ms["grid"] / max(args.steps, 1)
     grid_ms_ovl = stage_ovl["grid"] / max(args.steps, 1)
     peak, peak_src = peaks()
     achieved = grid_bytes / 1e9 / (grid_ms / 1e3)
     serial_step_ms = serial_ms / args.steps
-    # whole-step view: compulsory bytes of one step (records + grids + hops + grey planes) over the step time
+    # whole-step view: algorithmic bytes of one step by SURVEY.md 8d's per-frame formulas, over the step time.
+    #   B_raster = 40 M + 16 W H + 12 Hops;  B_prop = T (64 + 16 + 12 c + 64) + T (1 + c) 272 (descriptor gating on);
+    #   B_match = 36 L + 8 L + 4 T + 4 T;    B_pose = I 20 P + P / 8 + 64, twice per frame
     n_rec = host[args.warmup]["n_records"]
-    step_bytes = 40.0 * n_rec + grid_bytes + 12.0 * 2.7 * n_rec + float(S * F * W * H)
+    L_pts, P_corr, I_pose = 450.0, 450.0, float(T.pose_params()["iteration_count"])
+    b_raster = 40.0 * n_rec + grid_bytes + 12.0 * hops_mean * S * F
+    b_prop = S * F * (T_mean * (64 + 16 + 12 * c_bar + 64) + T_mean * (1 + c_bar) * 272)
+    b_match = S * F * (44 * L_pts + 8 * T_mean)
+    b_pose = S * F * 2 * (I_pose * 20 * P_corr + P_corr / 8 + 64)
+    step_bytes = b_raster + b_prop + b_match + b_pose
     roofline = {"bound": "hbm", "kernel": "grid_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": grid_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": grid_bytes,
                 "launch_ms": grid_ms, "kernel_share_of_step": grid_ms / serial_step_ms,
@@ -373,6 +395,9 @@ def run_product(args):
                                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ovl.items()}},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / 1e9 / (step_ms / 1e3),
                                "frac": step_bytes / 1e9 / (step_ms / 1e3) / peak,
+                               "bytes": {"raster": b_raster, "propagation": b_prop, "match": b_match, "pose_upper_bound": b_pose},
+                               "workload": {"tracks_per_frame": T_mean, "candidates_per_track": c_bar, "hops_per_frame": hops_mean,
+                                            "records_per_frame": n_rec / float(S * F)},
                                "note": "headline region: raster of window k+1 and the pose chain of window k run on their own streams beside the propagation of window k"}}
     ctx.close()
     del dev
@@ -417,6 +442,8 @@ def run_product(args):
                            "samples": clocks["samples"]},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_wall_ms / args.steps, "median_inliers_last_step": med_inl,
+                        "h2d_gbs": h2d / 1e9 / (e2e_wall_ms / args.steps / 1e3),
+                        "bound": "host->device copy of the step's inputs (records + full grey planes) over PCIe",
                         "pipelining": "push of window k+1 overlaps compute of window k; poses of window k read back every step"},
                 "gpu_launches": int(sum(launches.values())), "roofline": roofline,
                 "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",

@@ -22,7 +22,7 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 1 > $OUT/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
   for K in ${NCU_KERNELS:-grid_kernel cand_kernel finalize_kernel track_poses_kernel}; do
-    STEPS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip ${NCU_SKIP:-20} -c 1 \
+    STEPS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip ${NCU_SKIP:-1} -c 1 \
         -o $OUT/${K}_$TAG -f python scripts/bench_probe.py > $OUT/ncu_${K}_$TAG.log 2>&1; echo "ncu $K rc=$?"
   done
 fi
