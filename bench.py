@@ -366,6 +366,7 @@ def run_product(args):
         t_cnt.append(len(prev))
         hop_cnt.append(int(ctx.raster_counts(0, f)[0]))
     T_mean, c_bar, hops_mean = float(np.mean(t_cnt)), c_sum / max(c_n, 1), float(np.mean(hop_cnt))
+    P_corr = float(np.mean(ctx.poses(last_first, F)[1]))    # inliers of the last window (<= correspondences per solve)
 
     grid_bytes = S * F * W * H * 16.0                       # algorithmic bytes of the dominant HBM kernel per launch
     grid_ms = stage_ms["grid"] / max(args.steps, 1)
@@ -377,7 +378,7 @@ def run_product(args):
     #   B_raster = 40 M + 16 W H + 12 Hops;  B_prop = T (64 + 16 + 12 c + 64) + T (1 + c) 272 (descriptor gating on);
     #   B_match = 36 L + 8 L + 4 T + 4 T;    B_pose = I 20 P + P / 8 + 64, twice per frame
     n_rec = host[args.warmup]["n_records"]
-    L_pts, P_corr, I_pose = 450.0, 450.0, float(T.pose_params()["iteration_count"])
+    L_pts, I_pose = 450.0, float(T.pose_params()["iteration_count"])   # I: the iteration budget (an upper bound of the passes run)
     b_raster = 40.0 * n_rec + grid_bytes + 12.0 * hops_mean * S * F
     b_prop = S * F * (T_mean * (64 + 16 + 12 * c_bar + 64) + T_mean * (1 + c_bar) * 272)
     b_match = S * F * (44 * L_pts + 8 * T_mean)
@@ -395,9 +396,9 @@ def run_product(args):
                                "stage_ms_per_step": {k: v / args.steps for k, v in stage_ovl.items()}},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / 1e9 / (step_ms / 1e3),
                                "frac": step_bytes / 1e9 / (step_ms / 1e3) / peak,
-                               "bytes": {"raster": b_raster, "propagation": b_prop, "match": b_match, "pose_upper_bound": b_pose},
+                               "bytes": {"raster": b_raster, "propagation": b_prop, "match": b_match, "pose": b_pose},
                                "workload": {"tracks_per_frame": T_mean, "candidates_per_track": c_bar, "hops_per_frame": hops_mean,
-                                            "records_per_frame": n_rec / float(S * F)},
+                                            "pose_correspondences": P_corr, "records_per_frame": n_rec / float(S * F)},
                                "note": "headline region: raster of window k+1 and the pose chain of window k run on their own streams beside the propagation of window k"}}
     ctx.close()
     del dev

@@ -147,6 +147,9 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
         CK(cudaEventCreateWithFlags(&ctx->ev_join[g], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    ctx->ev_of_frame.assign(c.window_frames, 0);
+    if (const char *e = getenv("MOVFE_EVENT_BATCH")) ctx->ev_batch = std::max(1, atoi(e));
+    if (const char *e = getenv("MOVFE_PDL")) ctx->pdl_mode = atoi(e);
     ctx->ev_frame.resize((size_t)ctx->n_groups * c.window_frames, nullptr);
     for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &pl : ctx->pose_launches) {

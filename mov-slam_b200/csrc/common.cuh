@@ -77,6 +77,12 @@ struct movfe_ctx {
     cudaStream_t ext_stream[MAX_GROUPS] = {};   // [0] aliases `stream`
     cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
     std::vector<cudaEvent_t> ev_frame; // [n_groups][window_frames] recorded on the group's stream after the finalize of frame f (index f % F)
+    // The propagation launches of consecutive frames are chained with programmatic dependent launch, which an event record
+    // between two kernels would break, so a frame's table is announced in batches: ev_of_frame[f % F] is the frame whose
+    // event (recorded after a later finalize of the same extract call) covers frame f.
+    std::vector<int> ev_of_frame;      // [window_frames]
+    int ev_batch = 4;                  // frames per event (MOVFE_EVENT_BATCH)
+    int pdl_mode = 0;                  // MOVFE_PDL: 0 off (default, see profiles/README.md), 1 every edge of the chain, 2 all but finalize -> next frame's cand
     struct PoseLaunch { int64_t first; int n; cudaEvent_t done; };
     PoseLaunch pose_launches[4] = {};  // ring of the last pose launches (events created at movfe_create)
     int     pose_launch_head = 0;
@@ -180,6 +186,27 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
+}
+
+// Programmatic dependent launch (sm_90+): a kernel launched with launch_pdl() may be scheduled while the previous kernel
+// of its stream is still running; it must execute pdl_wait() before it touches anything that kernel wrote. pdl_trigger()
+// lets the NEXT kernel of the stream be scheduled early in the same way. Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // RAII span: records an event pair around a stage when profiling is on, and always counts kernel launches.

@@ -403,6 +403,8 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
             int2 *__restrict__ cinfo, int32_t *__restrict__ claim) {
     __shared__ int sm[CAND_WARPS][CW_WORDS][32];
+    pdl_wait();     // the previous frame's finalize_kernel wrote the tables read below
+    pdl_trigger();  // after the wait: at most one dependent grid is resident and waiting
     const int s = p.s0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_prev = ntracks[s * p.TSLOTS + p.tslot_prev];
@@ -656,6 +658,8 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
              uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
     __shared__ uint32_t scratch[CAND_WARPS][8];
     __shared__ int sm[CAND_WARPS][2][32];
+    pdl_wait();  // cand_kernel wrote the claims
+    pdl_trigger();
     const int s = p.s0 + blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = nkps[s * p.n_in + p.fi];
@@ -1012,6 +1016,8 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     uint16_t *s_pk = reinterpret_cast<uint16_t *>(s_age + p.maxT);
     uint16_t *s_run = s_pk + p.maxT;
     int *s_hist = reinterpret_cast<int *>(s_run + p.maxT);
+    pdl_wait();  // cand_kernel / birth_kernel wrote the staging tables
+    pdl_trigger();
     const int s = p.s0 + blockIdx.x;
     movfe_track *cur = tracks + ((size_t)s * p.TSLOTS + p.tslot_cur) * p.maxT;
     const movfe_track *st = stage + (size_t)s * p.maxT;
@@ -1238,6 +1244,12 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
         for (int g = 1; g < G; g++) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->ext_stream[g], ctx->ev_fork, 0));
     }
+    const bool pdl = ctx->pdl_mode != 0;       // cand -> birth -> finalize edges
+    const bool pdl_cand = ctx->pdl_mode == 1;  // finalize -> next frame's cand edge as well
+    for (int k = 0; k < n_frames; k++) {  // which event announces frame k's table
+        const int kend = pdl_cand ? std::min((k / ctx->ev_batch + 1) * ctx->ev_batch - 1, n_frames - 1) : k;
+        ctx->ev_of_frame[(first_frame + k) % c.window_frames] = (int)((first_frame + kend) % c.window_frames);
+    }
     for (int k = 0; k < n_frames; k++) {
         const int64_t a = first_frame + k;
         ExtParams p;
@@ -1260,6 +1272,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.has_grey = c.has_grey;
         p.P = ctx->grey_pitch;
         p.cov_thr = c.coverage_threshold;
+        const bool batch_end = !pdl_cand || (k + 1) % ctx->ev_batch == 0 || k == n_frames - 1;
         for (int g = 0; g < G; g++) {
         const int s_lo = (int)((int64_t)c.n_streams * g / G), ns = (int)((int64_t)c.n_streams * (g + 1) / G) - s_lo;
         cudaStream_t gs = ctx->ext_stream[g];
@@ -1268,8 +1281,8 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         const int bps = std::max(4, (8 * ctx->sm_count + c.n_streams - 1) / c.n_streams);
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
 #define MOVFE_CAND(PITCH)                                                                                              \
-    cand_kernel<PITCH><<<gc, CAND_THREADS, 0, gs>>>(p, ctx->d_tracks, ctx->d_ntracks, e.order, w.d_grid, w.d_hops, \
-                                                    ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim)
+    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, cand_kernel<PITCH>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
+                               w.d_grid, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim))
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
             case 2048: MOVFE_CAND(2048); break;
@@ -1280,8 +1293,8 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         if (c.has_grey) {
             dim3 gb(std::min((ctx->max_kps + CAND_THREADS - 1) / CAND_THREADS, bps), ns);
 #define MOVFE_BIRTH(PITCH)                                                                                             \
-    birth_kernel<PITCH><<<gb, CAND_THREADS, 0, gs>>>(p, w.d_kps, w.d_nkps, ctx->d_grey, ctx->d_fflags, e.claim,    \
-                                                     e.birth_flag, e.birth_desc)
+    MOVFE_CUDA(ctx, launch_pdl(pdl, birth_kernel<PITCH>, gb, dim3(CAND_THREADS), 0, gs, p, w.d_kps, w.d_nkps, ctx->d_grey,  \
+                               ctx->d_fflags, e.claim, e.birth_flag, e.birth_desc))
             switch (ctx->grey_pitch) {
                 case 1024: MOVFE_BIRTH(1024); break;
                 case 2048: MOVFE_BIRTH(2048); break;
@@ -1290,12 +1303,14 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
 #undef MOVFE_BIRTH
             nl = 3;
         }
-        finalize_kernel<<<ns, FIN_THREADS, sort_smem(c.max_tracks), gs>>>(
-            p, ctx->d_tracks, ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, w.d_kps, w.d_nkps, w.d_cov,
-            e.birth_flag, e.birth_desc, w.d_grid, ctx->d_grey, ctx->d_fflags);
+        MOVFE_CUDA(ctx, launch_pdl(pdl, finalize_kernel, dim3(ns), dim3(FIN_THREADS), sort_smem(c.max_tracks), gs, p, ctx->d_tracks,
+                                   ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, w.d_kps, w.d_nkps, w.d_cov,
+                                   e.birth_flag, e.birth_desc, w.d_grid, ctx->d_grey, ctx->d_fflags));
         prof.launches(nl);
-        // frame a's table is complete for this group: the pose stream may start on it while propagation goes on with frame a+1
-        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_frame[(size_t)g * c.window_frames + a % c.window_frames], gs));
+        // the tables up to frame a are complete for this group: the pose stream may start on them while propagation goes on.
+        // One event per ev_batch frames (and at the end of the call): an event record between two kernels breaks their
+        // programmatic dependency.
+        if (batch_end) MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_frame[(size_t)g * c.window_frames + a % c.window_frames], gs));
         }
     }
     // join: whatever follows on the primary stream sees every group's tables

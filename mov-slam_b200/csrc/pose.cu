@@ -803,7 +803,7 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     // runs beside the propagation of frame f+1 instead of after the window
     for (int k = 0; k < n_frames; k++) {
         for (int g = 0; g < ctx->n_groups; g++)  // every group of streams has finished this frame's table
-            MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(size_t)g * c.window_frames + (first_frame + k) % c.window_frames], 0));
+            MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(size_t)g * c.window_frames + ctx->ev_of_frame[(first_frame + k) % c.window_frames]], 0));
         p.n_frames = 1;
         p.tslot0 = (int)((first_frame + k) % p.TSLOTS);
         p.out0 = k;
