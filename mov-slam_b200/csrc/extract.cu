@@ -27,7 +27,10 @@
 
 namespace {
 
-constexpr int CAND_WARPS = 8;
+#ifndef MOVFE_CAND_WARPS
+#define MOVFE_CAND_WARPS 4   // 128-thread CTAs pack better around the pose / finalize / raster CTAs they share SMs with
+#endif
+constexpr int CAND_WARPS = MOVFE_CAND_WARPS;
 constexpr int FIN_THREADS = 1024;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int MAX_TRACKS_CAP = 8192;
@@ -394,7 +397,7 @@ __device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, i
 }
 
 #ifndef CAND_MINB
-#define CAND_MINB 2
+#define CAND_MINB (16 / MOVFE_CAND_WARPS)  // 128 registers per thread
 #endif
 template <int PITCH>
 __global__ void __launch_bounds__(CAND_THREADS, CAND_MINB)
@@ -652,7 +655,7 @@ __device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ img, u
 }
 
 template <int PITCH>
-__global__ void __launch_bounds__(CAND_THREADS, 4)
+__global__ void __launch_bounds__(CAND_THREADS, 32 / MOVFE_CAND_WARPS)  // 64 registers per thread
 birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
              const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
              uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
@@ -1278,7 +1281,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         cudaStream_t gs = ctx->ext_stream[g];
         p.s0 = s_lo;
         // grid-stride over tracks / kps: enough CTAs to fill the chip, never one CTA per (mostly empty) capacity slot
-        const int bps = std::max(4, (8 * ctx->sm_count + c.n_streams - 1) / c.n_streams);
+        const int bps = std::max(4, (64 * ctx->sm_count + c.n_streams * CAND_WARPS - 1) / (c.n_streams * CAND_WARPS));
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
 #define MOVFE_CAND(PITCH)                                                                                              \
     MOVFE_CUDA(ctx, launch_pdl(pdl_cand, cand_kernel<PITCH>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \

@@ -17,7 +17,10 @@
 
 namespace {
 
-constexpr int TP_THREADS = 256;  // 256 x 128 registers: half an SM's register file, so propagation CTAs co-reside
+#ifndef MOVFE_TP_THREADS
+#define MOVFE_TP_THREADS 256
+#endif
+constexpr int TP_THREADS = MOVFE_TP_THREADS;  // 256 x 128 registers: half an SM's register file, so propagation CTAs co-reside
 constexpr int TP_WARPS = TP_THREADS / 32;
 constexpr int HASH_EMPTY = (int)0x80000000;
 
@@ -628,7 +631,10 @@ __device__ void join_frame(const movfe_track *__restrict__ tr, int n, const movf
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 2)
+#ifndef MOVFE_TP_MINB
+#define MOVFE_TP_MINB (512 / MOVFE_TP_THREADS)  // 128 registers per thread
+#endif
+__global__ void __launch_bounds__(TP_THREADS, MOVFE_TP_MINB)
 track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
                    const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
                    movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses, int32_t *__restrict__ ninl,

@@ -115,6 +115,42 @@ def test_deep_stacks_and_band_overflow(orc):
     _check(orc, [_clip([[], many, more, huge, []])], 256, 64, window=5, max_ref=0)
 
 
+def test_wide_blocks_span_many_tiles(orc):
+    """Blocks wider than a 32-px tile (synthetic: H.264 stops at 16): a hop meets three or more tiles, which takes the
+    slot-grid kernel's generic per-tile ballots instead of the match.any ranks. Mixed with ordinary blocks, several streams."""
+    rng = np.random.Generator(np.random.PCG64(0x5EED0007))
+    W, H, NF = 328, 136, 6
+    streams = []
+    for s in range(3):
+        frames = [[]]
+        for f in range(1, NF):
+            n = int(rng.integers(50, 400))
+            r = np.zeros(n, T.MV_RECORD)
+            r["source"] = -1
+            r["w"] = rng.choice([8, 16, 40, 64, 100, 200], n, p=[.3, .3, .1, .1, .1, .1])
+            r["h"] = rng.choice([8, 16, 48, 90], n, p=[.4, .4, .1, .1])
+            r["dst_x"], r["dst_y"] = rng.integers(0, W, n), rng.integers(0, H, n)
+            r["src_x"] = r["dst_x"] + rng.integers(-20, 20, n)
+            r["src_y"] = r["dst_y"] + rng.integers(-20, 20, n)
+            r["ref"] = rng.integers(0, min(2, f - 1) + 1, n)
+            frames.append(list(r))
+        streams.append(_clip(frames))
+    _check(orc, streams, W, H, window=3, max_ref=2)
+
+
+def test_more_chunks_in_a_band_than_the_chunk_list_holds(orc):
+    """> 1024 32-hop chunks meet one 32-row band: the slot-grid kernel streams the whole hop list per row (its last resort)."""
+    rng = np.random.Generator(np.random.PCG64(0x5EED0008))
+    W, H, n = 160, 40, 34000
+    r = np.zeros(n, T.MV_RECORD)
+    r["source"] = -1
+    r["w"] = r["h"] = 4
+    r["dst_x"], r["dst_y"] = rng.integers(4, W - 5, n), rng.integers(4, H - 5, n)
+    r["src_x"] = r["dst_x"] + rng.integers(-2, 3, n)
+    r["src_y"] = r["dst_y"] + rng.integers(-2, 3, n)
+    _check(orc, [_clip([[], list(r), []])], W, H, window=3, max_ref=0, max_records=n)
+
+
 def test_max_ref_10(orc):
     rng = np.random.Generator(np.random.PCG64(0x5EED0006))
     W, H, NF = 128, 96, 16
