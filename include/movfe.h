@@ -158,6 +158,11 @@ int movfe_join(movfe_ctx *ctx, int n_problems, const int32_t *track_ids, const i
  * (entries past cell_start[64*48] are -1: keypoints outside the grid). At most 16384 keypoints per set. */
 int movfe_assign_features_to_grid(movfe_ctx *ctx, int n_problems, const float *pts_xy, const int32_t *off,
                                   int32_t *cell_start, int32_t *cell_items);
+/* The same grid for the RESIDENT track table of (stream, frame) after movfe_extract - what the Frame constructors build
+ * (src/Frame.cc:118,216) - without the keypoints leaving the device. Returns the number of keypoints (<= capacity);
+ * cell_start has 64*48+1 entries, cell_items `capacity`. */
+int movfe_track_feature_grid(movfe_ctx *ctx, int stream, int64_t frame, int32_t *cell_start, int32_t *cell_items,
+                             int capacity);
 /* Frame::GetFeaturesInArea (src/Frame.cc:602-668) for n_queries queries against the grids built above: out[q*capacity..]
  * receives the indices in the reference's (ix, iy, insertion) order, counts[q] the full count (it may exceed capacity,
  * in which case only the first `capacity` indices were written). */

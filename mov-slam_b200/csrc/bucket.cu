@@ -26,15 +26,15 @@ __device__ __forceinline__ bool pos_in_grid(float x, float y, float w_inv, float
 }
 
 __global__ void __launch_bounds__(BG_THREADS)
-assign_kernel(const float2 *__restrict__ pts, const int32_t *__restrict__ off, float w_inv, float h_inv, int N2,
-              int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_items) {
+assign_kernel(const float *__restrict__ pts, int stride, const int32_t *__restrict__ off, float w_inv, float h_inv, int N2,
+              int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_items) {  // point i = pts[i*stride], pts[i*stride + 1]
     extern __shared__ uint32_t keys[];  // [N2], N2 = power of two >= the largest set
     const int pidx = blockIdx.x;
     const int b = off[pidx], n = off[pidx + 1] - b;
     for (int i = threadIdx.x; i < N2; i += blockDim.x) {
         uint32_t k = BG_INVALID;
         if (i < n) {
-            const float2 q = pts[b + i];
+            const float2 q = *reinterpret_cast<const float2 *>(pts + (size_t)(b + i) * stride);
             int px, py;
             if (pos_in_grid(q.x, q.y, w_inv, h_inv, px, py)) k = ((uint32_t)(px * BG_ROWS + py) << 14) | (uint32_t)i;
         }
@@ -139,7 +139,7 @@ extern "C" int movfe_assign_features_to_grid(movfe_ctx *ctx, int n_problems, con
     const float w_inv = (float)BG_COLS / (float)ctx->cfg.width, h_inv = (float)BG_ROWS / (float)ctx->cfg.height;  // Frame.cc:147-148
     const size_t smem = (size_t)N2 * sizeof(uint32_t);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assign_kernel<<<n_problems, BG_THREADS, smem, st>>>(d_pts, d_off, w_inv, h_inv, N2, d_cs, d_it);
+    assign_kernel<<<n_problems, BG_THREADS, smem, st>>>(reinterpret_cast<const float *>(d_pts), 2, d_off, w_inv, h_inv, N2, d_cs, d_it);
     MOVFE_CUDA(ctx, cudaGetLastError());
     MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_start, d_cs, (size_t)n_problems * (BG_CELLS + 1) * 4, cudaMemcpyDeviceToHost, st));
     if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_items, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -196,4 +196,47 @@ extern "C" int movfe_features_in_area(movfe_ctx *ctx, int n_problems, const floa
     MOVFE_CUDA(ctx, cudaMemcpyAsync(counts, d_cnt, (size_t)n_queries * 4, cudaMemcpyDeviceToHost, st));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
     return MOVFE_OK;
+}
+
+// The bucket grid of a RESIDENT track table (the frame's keypoints never leave the device): Frame::AssignFeaturesToGrid as
+// the Frame constructors call it (src/Frame.cc:118,216), for frame `frame` of stream `stream` after movfe_extract.
+extern "C" int movfe_track_feature_grid(movfe_ctx *ctx, int stream, int64_t frame, int32_t *cell_start, int32_t *cell_items,
+                                        int capacity) {
+    if (!ctx) return MOVFE_E_INVALID;
+    const movfe_config &c = ctx->cfg;
+    if (stream < 0 || stream >= c.n_streams || !cell_start || capacity < 0 || (capacity && !cell_items))
+        MOVFE_FAIL(ctx, MOVFE_E_INVALID, "track_feature_grid: bad argument");
+    const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
+    if (frame >= next || frame < next - 1 - c.window_frames)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "track table of frame %lld is not resident", (long long)frame);
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    const int T = ctx->TSLOTS;
+    const int ts = (int)(((frame % T) + T) % T);
+    int32_t n = 0;
+    cudaStream_t st = ctx->stream;
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(&n, ctx->d_ntracks + stream * T + ts, 4, cudaMemcpyDeviceToHost, st));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_feature_grid: %d keypoints, capacity %d", n, capacity);
+    if (n > BG_MAX_N) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_feature_grid: %d keypoints, limit %d", n, BG_MAX_N);
+    const size_t b_off = a256(8), b_cs = a256((size_t)(BG_CELLS + 1) * 4), b_it = a256((size_t)std::max(n, 1) * 4);
+    int rc = movfe_ensure_op_scratch(ctx, b_off + b_cs + b_it);
+    if (rc) return rc;
+    uint8_t *base = (uint8_t *)ctx->d_op;
+    int32_t *d_off = (int32_t *)base, *d_cs = (int32_t *)(base + b_off), *d_it = (int32_t *)(base + b_off + b_cs);
+    const int32_t off[2] = {0, n};
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(d_off, off, 8, cudaMemcpyHostToDevice, st));
+    if (n) MOVFE_CUDA(ctx, cudaMemsetAsync(d_it, 0xff, (size_t)n * 4, st));
+    int N2 = 64;
+    while (N2 < n) N2 <<= 1;
+    const float w_inv = (float)BG_COLS / (float)c.width, h_inv = (float)BG_ROWS / (float)c.height;
+    const size_t smem = (size_t)N2 * sizeof(uint32_t);
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const movfe_track *tab = ctx->d_tracks + ((size_t)stream * T + ts) * c.max_tracks;  // pt_x, pt_y lead the 64-byte record
+    assign_kernel<<<1, BG_THREADS, smem, st>>>(reinterpret_cast<const float *>(tab), (int)(sizeof(movfe_track) / 4), d_off, w_inv, h_inv,
+                                               N2, d_cs, d_it);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_start, d_cs, (size_t)(BG_CELLS + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_items, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // `off` and `n` live on this stack frame
+    return n;
 }

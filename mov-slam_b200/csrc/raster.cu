@@ -12,11 +12,11 @@
 //   emit_kernel     per record: hop j = ref+1..1 written at its final index in frame f-(j-1)'s list, kps rectangle
 //                   written at its final index; order = the reference's push_back order (ballot ranks).
 //   bbox_kernel     y-extent of every 32-hop chunk (lets the grid kernel skip chunks without reading them).
-//   grid_kernel     one CTA owns an 8-row band of one frame's grid: ordered compaction of the hops touching
-//                   the band into shared memory, then one warp per 32x8 tile: column masks by a 32x32 bit
-//                   transpose, row masks by ballots, slots 0..2 = three lowest set bits, slot 3 = highest of the
-//                   rest. Every pixel is written exactly once with one 128-bit streaming store (no atomics,
-//                   no read-modify-write, the -1 fill is implicit).
+//   grid_kernel     (grid.cu) one CTA owns a 32-row band of one frame's grid: the hops touching the band go into
+//                   per-tile queues in shared memory in list order, then one warp per 32x32 tile resolves the slots
+//                   once per (column run, row run) cell. Every pixel is written exactly once with one 128-bit
+//                   streaming store (no atomics, no read-modify-write, the -1 fill is implicit).
+// All of these run on the context's raster stream, beside the propagation of the previous window.
 #include <algorithm>
 #include <cstdio>
 

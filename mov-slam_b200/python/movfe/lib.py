@@ -69,6 +69,7 @@ def load():
     L.movfe_frustum.argtypes = [vp, i32, vp, vp, vp, vp]
     L.movfe_join.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.movfe_assign_features_to_grid.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.movfe_track_feature_grid.argtypes = [vp, i32, i64, vp, vp, i32]
     L.movfe_features_in_area.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp]
     L.movfe_pose_optimize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.movfe_profile_enable.argtypes = [vp, i32]
@@ -83,7 +84,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
-           "movfe_assign_features_to_grid", "movfe_features_in_area",
+           "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
            "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read"]
 
 
@@ -287,6 +288,13 @@ class Context:
         items = np.full(max(len(pts_xy), 1), -1, np.int32)
         self._ck(self.L.movfe_assign_features_to_grid(self.h, len(off) - 1, _p(pts_xy), _p(off), _p(start), _p(items)))
         return start, items[:len(pts_xy)]
+
+    def track_feature_grid(self, stream, frame):
+        """Bucket grid of a resident track table -> (cell_start [64*48+1], cell_items [n_tracks])."""
+        start = np.zeros(64 * 48 + 1, np.int32)
+        items = np.full(self.cfg.max_tracks, -1, np.int32)
+        n = self._ck(self.L.movfe_track_feature_grid(self.h, stream, frame, _p(start), _p(items), len(items)))
+        return start, items[:n]
 
     def features_in_area(self, pts_xy, off, start, items, queries, capacity):
         """Frame::GetFeaturesInArea for a batch of (set, x, y, r) queries -> (indices [n_queries, capacity], counts)."""

@@ -67,3 +67,27 @@ def test_pipelined_windows_match_oracle(orc, serial_raster):
                     worst = max(worst, float(np.max(np.abs(a - w)) / max(1.0, float(np.max(np.abs(w))))))
     assert worst <= 1e-5, worst
     ctx.close()
+
+
+def test_feature_grid_of_resident_tables(orc):
+    """Frame::AssignFeaturesToGrid (Frame.cc:356-388) on the device-resident track table of a frame == the oracle's grid of
+    the same keypoints; a radius query through it returns the oracle's list."""
+    from gpu_util import run_frontend_clip
+    W, H, NF, K = 640, 480, 7, 2
+    spec = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0051)
+    stream, grey = synth.make_records(spec), synth.make_grey(spec)
+    tracks, _, ctx = run_frontend_clip([stream], W, H, NF, 4, K, grey=[grey])
+    for f in (NF - 1, NF - 3):
+        tr = tracks[(0, f)]
+        assert len(tr) > 300
+        start, items = ctx.track_feature_grid(0, f)
+        ws, wi = orc.assign_features_to_grid(tr, W, H)
+        assert np.array_equal(start, ws)
+        assert np.array_equal(items[:ws[-1]], wi[:ws[-1]]) and (items[ws[-1]:] == -1).all()
+        pts = np.stack([tr["pt_x"], tr["pt_y"]], 1)
+        q = np.array([(0, 320.0, 240.0, 50.0), (0, 10.0, 470.0, 30.0)], T.AREA_QUERY)
+        out, cnt = ctx.features_in_area(pts, [0, len(tr)], start[None], items, q, 2048)
+        for k in range(2):
+            w = orc.get_features_in_area(tr, W, H, ws, wi, q[k]["x"], q[k]["y"], q[k]["r"])
+            assert cnt[k] == len(w) and np.array_equal(out[k, :len(w)], w)
+    ctx.close()
