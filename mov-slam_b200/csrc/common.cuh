@@ -149,6 +149,12 @@ struct movfe_ctx {
     uint8_t *d_outlier = nullptr;      // [S][F][max_tracks]
     void    *d_pose_scratch = nullptr;
     size_t   pose_scratch_bytes = 0;
+    // split pose chain (join kernels + small solver kernels, pose.cu): correspondences of one frame per stream
+    float   *d_pairs = nullptr;        // [S][6][max_map_points]: x y z u v idx
+    int32_t *d_npairs = nullptr;       // [S]
+    int      h_nmap_max = 0;           // largest local map installed so far (sizes the solver CTAs)
+    bool     pose_split = false;       // MOVFE_POSE_SPLIT=1: join kernels + small solver kernels instead of the fused
+                                       // one-kernel-per-frame chain (measured slower under load)
 
     // instrumentation
     bool prof_on = false;

@@ -706,6 +706,121 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
     }
 }
 
+// ---- the same per-frame chain as four launches (movfe_track_poses_launch, split mode) ------------------------------
+// The fused kernel above keeps 256 threads x 128 registers resident per stream for the whole frame, although the two
+// solves - most of its time - are a one-warp job between barriers; those registers are what the propagation CTAs on the
+// same SM are waiting for. Split: the joins run wide and short, the solves run in small CTAs (a quarter or less of the
+// registers), and the correspondences travel between them through a per-stream buffer in global memory.
+struct PairBuf {
+    float *x, *y, *z, *u, *v;
+    int *idx;
+};
+__device__ __forceinline__ PairBuf pair_buf(float *base, int s, int maxMap) {
+    float *b = base + (size_t)s * 6 * maxMap;
+    return PairBuf{b, b + maxMap, b + 2 * maxMap, b + 3 * maxMap, b + 4 * maxMap, reinterpret_cast<int *>(b + 5 * maxMap)};
+}
+
+// phase 0: TrackReferenceKeyFrame's SearchByVideoFeature(KF, F, matches) + the gather of Optimizer.cc:404-413
+// phase 1: SearchLocalPoints (tags, isInFrustum, SearchByVideoFeature(F, local points)) + gather; mvbOutlier prefilled
+__global__ void __launch_bounds__(TP_THREADS)
+tp_join_kernel(TrackPoseParams p, int phase, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
+               const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
+               const movfe_pose *__restrict__ pose_cur, int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out,
+               int32_t *__restrict__ skip_tag, float *__restrict__ pairs, int32_t *__restrict__ npairs) {
+    extern __shared__ int hsm[];  // keys[cap] vals[cap] first[maxMap] elig[maxMap bytes]
+    __shared__ int wsum[TP_WARPS];
+    int *keys = hsm, *vals = hsm + p.hash_cap, *first = hsm + 2 * p.hash_cap;
+    uint8_t *elig = reinterpret_cast<uint8_t *>(first + p.maxMap);
+    const int s = blockIdx.x;
+    const movfe_map_point *mp = map + (size_t)s * p.maxMap;
+    const int n_map = nmap[s], n_kf = min(nkf[s], n_map);
+    int32_t *tag = skip_tag + (size_t)s * p.maxMap;
+    const PairBuf pb = pair_buf(pairs, s, p.maxMap);
+    int cap = 2;
+    while (cap < 2 * n_map) cap <<= 1;
+    const int ts = p.tslot0 % p.TSLOTS;
+    const movfe_track *tr = tracks + ((size_t)s * p.TSLOTS + ts) * p.maxT;
+    const int n = ntracks[s * p.TSLOTS + ts];
+    int32_t *match = match_out + ((size_t)s * p.F + p.out0) * p.maxT;
+    uint8_t *outl = outlier_out + ((size_t)s * p.F + p.out0) * p.maxT;
+    if (!(n > 0 && n_map > 0)) {
+        if (phase == 0) {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) {
+                match[t] = -1;
+                outl[t] = 1;
+            }
+            if (threadIdx.x == 0) npairs[s] = 0;
+        }
+        return;
+    }
+    if (phase == 0) {
+        join_frame(tr, n, mp, n_kf, [&](int i) { return !(mp[i].flags & (MOVFE_MP_NULL | MOVFE_MP_BAD)); }, true, keys, vals, cap, first, match);
+    } else {
+        const int np0 = npairs[s];
+        for (int i = threadIdx.x; i < np0; i += blockDim.x) tag[match[pb.idx[i]]] = 1;  // mnLastFrameSeen = current frame
+        for (int t = threadIdx.x; t < n; t += blockDim.x) outl[t] = 1;                  // Optimizer.cc:452: true everywhere ...
+        __syncthreads();
+        const FrustumPose fp = frustum_pose(pose_cur[s]);
+        for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
+            const movfe_map_point m = mp[i];
+            const movfe_projection pr = frustum_point(fp, p.cam, p.W, p.H, p.view_cos, m, tag[i] == 1);
+            elig[i] = pr.in_view && !(m.flags & MOVFE_MP_BAD);
+        }
+        __syncthreads();
+        join_frame(tr, n, mp, n_map, [&](int i) { return elig[i] != 0; }, false, keys, vals, cap, first, match);
+    }
+    const int np = gather_pairs(tr, n, match, mp, pb.x, pb.y, pb.z, pb.u, pb.v, pb.idx, p.maxMap, wsum);
+    if (threadIdx.x == 0) npairs[s] = np;
+}
+
+// Optimizer::PoseOptimization on the gathered pairs of one stream; phase 1 also writes the frame's results.
+// At most 128 threads x 128 registers = a quarter of an SM's register file: a CTA fits wherever one propagation CTA left.
+constexpr int TP_SOLVE_THREADS = 128;
+__global__ void __launch_bounds__(TP_SOLVE_THREADS, 4)
+tp_solve_kernel(TrackPoseParams p, int phase, int np_lo, int np_hi, const int32_t *__restrict__ ntracks, const int32_t *__restrict__ nmap,
+                movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses, int32_t *__restrict__ ninl,
+                uint8_t *__restrict__ outlier_out, int32_t *__restrict__ skip_tag, float *__restrict__ pairs,
+                const int32_t *__restrict__ npairs) {
+    extern __shared__ int hsm[];  // x y z u v [maxMap] out[maxMap bytes]
+    __shared__ SolverShared sh;
+    float *cx = reinterpret_cast<float *>(hsm), *cy = cx + p.maxMap, *cz = cy + p.maxMap, *cu = cz + p.maxMap, *cv = cu + p.maxMap;
+    uint8_t *cout = reinterpret_cast<uint8_t *>(cv + p.maxMap);
+    const int s = blockIdx.x;
+    const int n_map = nmap[s];
+    const int ts = p.tslot0 % p.TSLOTS;
+    const int n = ntracks[s * p.TSLOTS + ts];
+    const bool active = n > 0 && n_map > 0;
+    const int np = active ? npairs[s] : 0;
+    // the launch is repeated with CTA sizes fitted to the correspondence count; a CTA of the wrong size leaves at once
+    if (np < np_lo || np > np_hi) return;
+    movfe_pose *pc = pose_cur + s;
+    int n_inl = 0;
+    if (active) {
+        const PairBuf pb = pair_buf(pairs, s, p.maxMap);
+        for (int i = threadIdx.x; i < np; i += blockDim.x) {
+            cx[i] = pb.x[i];
+            cy[i] = pb.y[i];
+            cz[i] = pb.z[i];
+            cu[i] = pb.u[i];
+            cv[i] = pb.v[i];
+        }
+        __syncthreads();
+        const CompactSrc src{cx, cy, cz, cu, cv};
+        n_inl = pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);
+        if (phase == 1) {
+            uint8_t *outl = outlier_out + ((size_t)s * p.F + p.out0) * p.maxT;
+            // Frame::mvbOutlier (Optimizer.cc:452-456): ... false for the inliers; <4 pairs: the frame is left untouched
+            for (int i = threadIdx.x; i < np; i += blockDim.x) outl[pb.idx[i]] = np >= 4 ? cout[i] : 0;
+            int32_t *tag = skip_tag + (size_t)s * p.maxMap;
+            for (int i = threadIdx.x; i < n_map; i += blockDim.x) tag[i] = 0;  // leave the tags clean for the next frame
+        }
+    }
+    if (phase == 1 && threadIdx.x == 0) {
+        poses[(size_t)s * p.F + p.out0] = *pc;
+        ninl[(size_t)s * p.F + p.out0] = n_inl;
+    }
+}
+
 // ------------------------------------------------------------------------------------ single-shot kernels ----
 __global__ void frustum_kernel(const movfe_pose *__restrict__ poses, const movfe_map_point *__restrict__ pts,
                                const int32_t *__restrict__ off, movfe_camera cam, int W, int H, float cosLimit,
@@ -805,8 +920,18 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
         MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_poses: max_tracks=%d / max_map_points=%d need %zu bytes of shared memory per stream (limit %zu)",
                    c.max_tracks, c.max_map_points, smem, (size_t)optin - fa.sharedSizeBytes);
     MOVFE_CUDA(ctx, cudaFuncSetAttribute(track_poses_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // one launch per frame, each released by the event recorded after that frame's finalize: the pose chain of frame f
+    // one chain per frame, each released by the event recorded after that frame's finalize: the pose chain of frame f
     // runs beside the propagation of frame f+1 instead of after the window
+    const bool split = ctx->pose_split && ctx->d_pairs != nullptr && ctx->h_nmap_max <= 4096;  // larger maps: wide fused CTAs
+    const size_t smem_join = ((size_t)2 * p.hash_cap + p.maxMap) * sizeof(int) + (size_t)p.maxMap;
+    const size_t smem_solve = (size_t)p.maxMap * 21;
+    // solver CTAs are sized by the correspondence count, which only the device knows: one launch per size class, the CTAs
+    // of the other class leave at once (the classes a context can need follow from the largest local map installed)
+    const int n_cls = ctx->h_nmap_max <= 64 ? 1 : 2;
+    if (split) {
+        MOVFE_CUDA(ctx, cudaFuncSetAttribute(tp_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_join));
+        MOVFE_CUDA(ctx, cudaFuncSetAttribute(tp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
+    }
     for (int k = 0; k < n_frames; k++) {
         for (int g = 0; g < ctx->n_groups; g++)  // every group of streams has finished this frame's table
             MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(size_t)g * c.window_frames + ctx->ev_of_frame[(first_frame + k) % c.window_frames]], 0));
@@ -814,10 +939,24 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
         p.tslot0 = (int)((first_frame + k) % p.TSLOTS);
         p.out0 = k;
         ProfScope prof(ctx, MOVFE_STAGE_POSE, ctx->pose_stream);
-        prof.launches(1);
-        track_poses_kernel<<<c.n_streams, TP_THREADS, smem, ctx->pose_stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap,
-                                                                                ctx->d_nkf, ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl,
-                                                                                ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch);
+        if (!split) {
+            prof.launches(1);
+            track_poses_kernel<<<c.n_streams, TP_THREADS, smem, ctx->pose_stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap,
+                                                                                    ctx->d_nkf, ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl,
+                                                                                    ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch);
+        } else {
+            prof.launches(2 + 2 * n_cls);
+            int32_t *tags = (int32_t *)ctx->d_pose_scratch;
+            for (int phase = 0; phase < 2; phase++) {
+                tp_join_kernel<<<c.n_streams, TP_THREADS, smem_join, ctx->pose_stream>>>(p, phase, ctx->d_tracks, ctx->d_ntracks, ctx->d_map,
+                                                                                         ctx->d_nmap, ctx->d_nkf, ctx->d_pose_cur, ctx->d_match,
+                                                                                         ctx->d_outlier, tags, ctx->d_pairs, ctx->d_npairs);
+                for (int cls = 0; cls < n_cls; cls++)
+                    tp_solve_kernel<<<c.n_streams, cls == 0 ? 64 : TP_SOLVE_THREADS, smem_solve, ctx->pose_stream>>>(
+                        p, phase, cls == 0 ? 0 : 65, cls == 0 ? 64 : 0x7fffffff, ctx->d_ntracks, ctx->d_nmap, ctx->d_pose_cur, ctx->d_poses,
+                        ctx->d_ninl, ctx->d_outlier, tags, ctx->d_pairs, ctx->d_npairs);
+            }
+        }
     }
     movfe_ctx::PoseLaunch &pl = ctx->pose_launches[ctx->pose_launch_head];
     ctx->pose_launch_head = (ctx->pose_launch_head + 1) % 4;
@@ -849,6 +988,7 @@ extern "C" int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_
         MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_map + (size_t)stream * std::max(c.max_map_points, 1), pts, (size_t)n * sizeof(movfe_map_point),
                                         cudaMemcpyHostToDevice, ctx->pose_stream));
     const int32_t nn = n, nk = std::min(n_keyframe_points, n);
+    ctx->h_nmap_max = std::max(ctx->h_nmap_max, n);
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nmap + stream, &nn, 4, cudaMemcpyHostToDevice, ctx->pose_stream));
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkf + stream, &nk, 4, cudaMemcpyHostToDevice, ctx->pose_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));

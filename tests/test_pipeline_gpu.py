@@ -13,8 +13,11 @@ from gpu_util import assert_tracks_equal, oracle_tracks, pack_streams
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("serial_raster", [False, True])
-def test_pipelined_windows_match_oracle(orc, serial_raster):
+@pytest.mark.parametrize("serial_raster,env", [(False, {}), (True, {}), (False, {"MOVFE_POSE_SPLIT": "1"}),
+                                               (False, {"MOVFE_PDL": "1"}), (False, {"MOVFE_EXTRACT_GROUPS": "3"})])
+def test_pipelined_windows_match_oracle(orc, serial_raster, env, monkeypatch):
+    for k, v in env.items():      # development switches of the library, read at movfe_create: every path stays parity-tested
+        monkeypatch.setenv(k, v)
     W, H, F, K, NW, S, NB = 640, 480, 8, 3, 6, 12, 3
     LA = K + 1
     n_frames = F * NW + LA
