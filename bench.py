@@ -44,6 +44,27 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries (NCCL's version banner) write to fd 1 as well, so fd 1 is pointed at
+    stderr for the whole run and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -209,7 +230,7 @@ def run_reference(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "i32/f32 raster+tracks, f64 pose", "data": "synthetic",
             "config": config_dict(1, cores), "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def grid_traffic():
@@ -239,7 +260,6 @@ def run_product(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines must not share stdout with the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     S = S_PER_GPU
@@ -341,8 +361,8 @@ def run_product(args):
     ctx.close()
     if os.environ.get("BENCH_QUICK"):   # development sweeps: the device-resident headline region only
         if rank == 0:
-            print(json.dumps({"quick": True, "value": value, "ms_per_step": step_ms,
-                              "stage_ms_per_step": {k: v / args.steps for k, v in stage_ovl.items()}}), flush=True)
+            emit({"quick": True, "value": value, "ms_per_step": step_ms,
+                              "stage_ms_per_step": {k: v / args.steps for k, v in stage_ovl.items()}})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -451,7 +471,7 @@ def run_product(args):
                 "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": "%d streams (one per host thread) x %d frames x %d repeats of the same C2 clips, %.1fs" %
                                            (cores, REF_FRAMES, CPU_REPEATS, cpu_dt)}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -464,6 +484,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
