@@ -1,0 +1,121 @@
+"""The C++ oracle against a second, independently written restatement of the reference (oracle/literal.py: plain Python,
+one float32 rounding per operation, literal containers) on random inputs. The reference ships no test vectors and cannot
+be built here, so agreement of two separate transcriptions is what pins the oracle beyond the hand-derived KATs."""
+import numpy as np
+import pytest
+
+from movfe import synth, types as T
+from oracle import literal as lit
+
+
+def _records(rng, W, H, n, max_ref, sizes, frame_index):
+    r = np.zeros(n, T.MV_RECORD)
+    r["source"] = rng.choice([-1, -1, -1, -1, 0, 1], n)
+    r["w"], r["h"] = rng.choice(sizes, n), rng.choice(sizes, n)
+    r["dst_x"], r["dst_y"] = rng.integers(-6, W + 6, n), rng.integers(-6, H + 6, n)
+    r["src_x"] = r["dst_x"] + rng.integers(-40, 41, n)
+    r["src_y"] = r["dst_y"] + rng.integers(-40, 41, n)
+    r["ref"] = rng.integers(0, min(max_ref, max(frame_index - 1, 0)) + 1, n)
+    return r
+
+
+@pytest.mark.parametrize("seed,W,H,max_ref", [(1, 64, 48, 3), (2, 97, 61, 2), (3, 40, 40, 0), (4, 128, 72, 5)])
+def test_raster_matches_literal_transcription(orc, seed, W, H, max_ref):
+    rng = np.random.Generator(np.random.PCG64(0x11E0 + seed))
+    NF = 8
+    frames, flags = [], []
+    for f in range(NF):
+        mv_on = f > 0 and rng.random() > 0.15
+        n = int(rng.integers(0, 70)) if f > 0 else 0
+        frames.append(_records(rng, W, H, n, max_ref, [4, 8, 16], f))
+        flags.append((T.FRAME_P if f > 0 else 0) | (T.FRAME_MV if mv_on else 0))
+    off = np.cumsum([0] + [len(fr) for fr in frames]).astype(np.int64)
+    recs = np.concatenate(frames) if off[-1] else np.zeros(0, T.MV_RECORD)
+    clip = orc.Clip(W, H, recs, off, np.array(flags, np.uint8), max_ref)
+    vqueue = []
+    for f in range(NF):
+        rl = [dict(source=int(r["source"]), w=int(r["w"]), h=int(r["h"]), src_x=int(r["src_x"]), src_y=int(r["src_y"]),
+                   dst_x=int(r["dst_x"]), dst_y=int(r["dst_y"]), ref=int(r["ref"])) for r in frames[f]]
+        lit.next_image_mv_loop(W, H, vqueue, rl, mv_enabled=bool(flags[f] & T.FRAME_MV))
+    for f in range(NF):
+        want = vqueue[f]
+        hops, kps = clip.hops(f), clip.kps(f)
+        assert len(hops) == len(want.mvs) and len(kps) == len(want.kps), (f, len(hops), len(want.mvs), len(kps), len(want.kps))
+        for i, (mx, my, d) in enumerate(want.mvs):
+            assert (hops["mv_x"][i], hops["mv_y"][i], hops["d_indx"][i]) == (mx, my, d), (f, i)
+        for i, k in enumerate(want.kps):
+            assert (kps["x"][i], kps["y"][i], kps["w"][i], kps["h"][i]) == k, (f, i)
+        assert np.array_equal(clip.grid(f), want.mvi), f
+        assert clip.coverage(f) == want.coverageArea, (f, clip.coverage(f), want.coverageArea)
+    assert sum(len(v.mvs) for v in vqueue) > 100
+
+
+@pytest.mark.parametrize("shape", [(16, 16), (8, 8), (16, 8), (8, 16)])
+def test_express_matches_literal_transcription(orc, shape):
+    rows, cols = shape
+    rng = np.random.Generator(np.random.PCG64(0x11F0 + rows * 3 + cols))
+    spec = synth.Spec(160, 120, n_frames=2, refs=1, seed=0x5EED0061)
+    textured = synth.make_grey(spec)[1]
+    noisy = rng.integers(0, 256, (120, 160)).astype(np.uint8)
+    steps = (np.add.outer(np.arange(120) // 9, np.arange(160) // 7) % 2 * 180 + 20).astype(np.uint8)
+    smooth = (np.add.outer(np.arange(120), np.arange(160)) % 256).astype(np.uint8)   # exercises the uint8 wrap of the band
+    n_true = 0
+    for img in (textured, noisy, steps, smooth):
+        for _ in range(60):
+            x0, y0 = int(rng.integers(0, 160 - cols - 1)), int(rng.integers(0, 120 - rows))
+            thr = int(rng.choice([5, 25, 60, 140]))
+            m = lit.Roi(img, x0, y0, cols, rows)
+            assert orc.express_center(img, x0, y0, cols, rows) == lit.compute_center(m)
+            d = orc.express_descriptor(img, x0, y0, cols, rows, thr)
+            want = lit.compute_descriptor(m, thr)
+            got = sum(int(w) << (32 * i) for i, w in enumerate(d))
+            assert got == want, (x0, y0, thr)
+            e = bool(orc.express_test(img, x0, y0, cols, rows, thr))
+            assert e == lit.compute_express(m, thr), (x0, y0, thr)
+            n_true += e
+    assert 0 < n_true < 240
+
+
+def _tracks_of(vfs):
+    t = np.zeros(len(vfs), T.TRACK)
+    for i, v in enumerate(vfs):
+        t[i]["pt_x"], t[i]["pt_y"] = v.pt
+        t[i]["mb"] = v.mb
+        t[i]["track_id"], t[i]["age"], t[i]["q_indx"] = v.trackId, v.age, v.qIndx
+        t[i]["flags"] = T.TRACK_COVERAGE if v.coverage else 0
+        t[i]["desc"] = [(v.desc >> (32 * k)) & 0xffffffff for k in range(8)]
+    return t
+
+
+@pytest.mark.parametrize("seed,cov_thr", [(0, 0.20), (1, 0.95)])
+def test_extractor_matches_literal_transcription(orc, seed, cov_thr):
+    """MOVExtractor::operator() frame after frame (I-frame seeding, propagation with candidate choice, claims, descriptor
+    gate, births, lattice back-fill), both restatements fed their own previous table."""
+    W, H, NF, K = 160, 112, 6, 2
+    spec = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0070 + seed, fx=80.0, fy=80.0)
+    recs, off, flags = synth.make_records(spec)
+    grey = synth.make_grey(spec)
+    clip = orc.Clip(W, H, recs, off, flags, K)
+    vqueue = []
+    for f in range(NF):
+        rl = [dict(source=int(r["source"]), w=int(r["w"]), h=int(r["h"]), src_x=int(r["src_x"]), src_y=int(r["src_y"]),
+                   dst_x=int(r["dst_x"]), dst_y=int(r["dst_y"]), ref=int(r["ref"])) for r in recs[off[f]:off[f + 1]]]
+        lit.next_image_mv_loop(W, H, vqueue, rl, mv_enabled=bool(flags[f] & T.FRAME_MV))
+    prev_o, cid_o = np.zeros(0, T.TRACK), 0
+    prev_l, cid_l = [], 0
+    seen_multi = births = 0
+    for f in range(NF):
+        got, _, cid_o, _ = orc.extract_frame(W, H, flags[f], grey[f], clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f),
+                                             prev_o, cid_o, threshold=25, coverage_threshold=cov_thr, max_tracks=4096)
+        want_vf, cid_l = lit.extractor(vqueue[f], grey[f], bool(flags[f] & T.FRAME_P), prev_l, cid_l, 25, cov_thr)
+        want = _tracks_of(want_vf)
+        assert cid_o == cid_l, (f, cid_o, cid_l)
+        assert len(got) == len(want), (f, len(got), len(want))
+        for name in got.dtype.names:
+            assert got[name].tobytes() == want[name].tobytes(), (f, name)
+        births += int((got["q_indx"] < 0).sum()) if f > 0 else 0
+        prev_o, prev_l = got, want_vf
+        if f > 0:
+            g = clip.grid(f).reshape(H, W, 4)
+            seen_multi += int(sum(g[int(v.pt[1]), int(v.pt[0]), 1] >= 0 for v in want_vf if v.qIndx >= 0))
+    assert len(prev_o) > 20 and births > 0 and seen_multi >= 0
