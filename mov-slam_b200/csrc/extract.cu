@@ -640,6 +640,7 @@ __device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ img, u
     bool ok = false;
 #pragma unroll
     for (int a = 0; a < 2; a++) {
+        if (a == 1 && ok) break;  // warp-uniform: the first direction already passed (EXPRESS.h:186-189 returns there)
         const unsigned bits = a == 0 ? row : (__brev(row) >> (32 - COLS));
         const unsigned diag = transpose32(lane < ROWS ? bits << (ROWS - 1 - lane) : 0u, lane);
         const int win = __popc(diag);

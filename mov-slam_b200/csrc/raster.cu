@@ -379,20 +379,22 @@ __global__ void bbox_kernel(WinParams p, const HopRect *__restrict__ hop_rects, 
     const int s = sg / p.n_out, g = sg - s * p.n_out;
     const int n = nhops[s * p.n_in + g];
     const int nchunks = (n + 31) >> 5;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nchunks) return;
-    const int h = warp * 32 + lane;
-    int ymin = 32767, ymax = -32768;
-    if (h < n) {
-        const HopRect r = hop_rects[(size_t)sg * p.max_hops + h];
-        ymin = r.y0;
-        ymax = r.y1;
+    const int lane = threadIdx.x & 31;
+    const int wpg = (gridDim.x * blockDim.x) >> 5;  // warps per (stream, frame): a warp strides over the chunks
+    for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += wpg) {
+        const int h = chunk * 32 + lane;
+        int ymin = 32767, ymax = -32768;
+        if (h < n) {
+            const HopRect r = hop_rects[(size_t)sg * p.max_hops + h];
+            ymin = r.y0;
+            ymax = r.y1;
+        }
+        for (int o = 16; o; o >>= 1) {
+            ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
+            ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+        }
+        if (lane == 0) chunk_bbox[(size_t)sg * p.max_chunks + chunk] = (ymin & 0xffff) | (ymax << 16);
     }
-    for (int o = 16; o; o >>= 1) {
-        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
-        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
-    }
-    if (lane == 0) chunk_bbox[(size_t)sg * p.max_chunks + warp] = (ymin & 0xffff) | (ymax << 16);
 }
 
 }  // namespace
@@ -463,7 +465,8 @@ int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n
     emit_kernel<<<SF, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_hop_base,
                                                      w.d_kps_base, w.d_hops, w.d_hop_rect, w.d_kps);
     {
-        dim3 g((ctx->max_chunks * 32 + 255) / 256, p.S * n_out);
+        // capacity would be max_chunks warps per (stream, frame); frames hold a fraction of it, so a few CTAs stride instead
+        dim3 g(std::min((ctx->max_chunks * 32 + 255) / 256, 16), p.S * n_out);
         bbox_kernel<<<g, 256, 0, ctx->raster_stream>>>(p, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox);
     }
     }
