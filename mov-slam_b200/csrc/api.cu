@@ -38,7 +38,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     for (void *b : bufs)
         if (b) cudaFree(b);
     for (RasterBuf &w : ctx->rb) {
-        void *wb[] = {w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
+        void *wb[] = {w.d_seg_cnt, w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
                       w.d_chunk_bbox, w.d_grid};
         for (void *b : wb)
             if (b) cudaFree(b);
@@ -178,6 +178,9 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->max_hops = c.max_records_per_frame * (ctx->K + 1);
     ctx->max_kps = c.max_records_per_frame * (ctx->K + 1);
     ctx->max_chunks = (ctx->max_hops + 31) / 32;
+    // count / emit: one CTA per frame up to 8192 records, segments of 4096 records beyond (dense 4x4 fields)
+    ctx->rseg = c.max_records_per_frame <= 8192 ? ((c.max_records_per_frame + 511) / 512) * 512 : 4096;
+    ctx->n_rseg = (c.max_records_per_frame + ctx->rseg - 1) / ctx->rseg;
     if (ctx->max_hops >= (1 << 22)) {
         ctx->err = "movfe_create: max_records_per_frame*(max_ref+1) must stay below 2^22";
         return fail(MOVFE_E_INVALID);
@@ -193,6 +196,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(cudaMemset(ctx->d_rec_cnt, 0, S * RING * sizeof(int32_t)));
     CK(cudaMemset(ctx->d_fflags, 0, S * RING));
     for (RasterBuf &w : ctx->rb) {
+        CK(dalloc(&w.d_seg_cnt, S * NIN * ctx->n_rseg * (MOVFE_NCLS(MOVFE_MAX_K) + 2)));
         CK(dalloc(&w.d_cls_cnt, S * NIN * MOVFE_NCLS(MOVFE_MAX_K)));
         CK(dalloc(&w.d_area, S * NIN));
         CK(dalloc(&w.d_hop_base, S * NIN * (ctx->K + 2)));

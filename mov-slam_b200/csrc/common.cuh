@@ -41,6 +41,7 @@ struct __align__(8) HopRect {
 struct RasterBuf {
     int64_t first = -1;
     int     nout = 0, nin = 0;
+    int32_t *d_seg_cnt = nullptr;   // [S][NIN][n_rseg][NCLS+2] per-segment class counts, area, rejects (raster.cu)
     int32_t *d_cls_cnt = nullptr;   // [S][NIN][NCLS]
     int64_t *d_area = nullptr;      // [S][NIN]
     int32_t *d_hop_base = nullptr;  // [S][NIN][K+2]
@@ -51,7 +52,7 @@ struct RasterBuf {
     movfe_hop  *d_hops = nullptr;   // [S][F][max_hops]
     HopRect    *d_hop_rect = nullptr;
     movfe_rect *d_kps = nullptr;    // [S][F][max_kps]
-    int32_t *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  (ymin | ymax<<16)
+    int2    *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  extent of every 32-hop chunk: (ymin | ymax<<16, xmin | xmax<<16)
     int4    *d_grid = nullptr;      // [S][F][H*W]
     cudaEvent_t done = nullptr;      // recorded on raster_stream: the buffer is complete
     cudaEvent_t consumed = nullptr;  // recorded on stream after the last propagation launch that read it
@@ -63,6 +64,7 @@ struct movfe_ctx {
     int K = 0, LA = 0, RING = 0, NIN = 0;  // max_ref, look-ahead frames, ring depth, max input frames per window
     int NB = 0, NT = 0;                    // 8-row bands per frame, 32-px tiles per band
     int max_hops = 0, max_kps = 0, max_chunks = 0;
+    int rseg = 0, n_rseg = 1;              // records per count/emit segment (multiple of 512), segments per frame
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     // join / frustum / pose of a window run on their own stream, concurrently with raster + propagation of the next

@@ -193,8 +193,13 @@ __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, c
             for (int c = 0; c < NCH; c++)
                 if (c < nchk) {  // warp-uniform
                     const unsigned m = __shfl_sync(0xffffffffu, col[c], sc) & __shfl_sync(0xffffffffu, row[c], sr);
-                    if (c == 0) fold<true, true>(st, m, idx[0]);
-                    else fold<false, true>(st, m, idx[c]);
+                    if (c == 0) {
+                        fold<true, true>(st, m, idx[0]);
+                    } else if (NCH <= 2 || __any_sync(0xffffffffu, m != 0)) {
+                        // many chunks (dense small blocks): a pass's cells lie in one or two row runs, and hops arrive in
+                        // raster order, so most chunks cover none of them and are skipped for the whole warp
+                        fold<false, true>(st, m, idx[c]);
+                    }
                 }
             if (valid) ws.tab[j] = make_int4(st.s0, st.s1, st.s2, st.s3);
         }
@@ -219,7 +224,7 @@ __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, c
 // grid = (32-row bands, frames of the window x x-splits, streams)
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
 grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
-            const int32_t *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
+            const int2 *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -241,18 +246,18 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
     const int ntl = (X1 - X0 + 32) >> 5;                              // its tiles (the last split may own fewer than NTC)
     const int n_h = nhops[s * p.n_in + g];
     const HopRect *rects = hop_rects + (size_t)sg * p.max_hops;
-    const int32_t *bbox = chunk_bbox + (size_t)sg * p.max_chunks;
+    const int2 *bbox = chunk_bbox + (size_t)sg * p.max_chunks;
     const int nchunks = (n_h + 31) >> 5;
 
-    // ---- phase 1a: ordered list of the 32-hop chunks whose y-extent touches the band --------------------------
+    // ---- phase 1a: ordered list of the 32-hop chunks whose extent touches the band (and this x-split) ---------
     int n_cl = 0;  // identical in every thread
     for (int base = 0; base < nchunks; base += blockDim.x) {
         const int c = base + threadIdx.x;
         bool pred = false;
         if (c < nchunks) {
-            const int bb = __ldg(&bbox[c]);
-            const int ymin = (int16_t)(bb & 0xffff), ymax = bb >> 16;
-            pred = ymax >= ylo && ymin <= yhi;
+            const int2 bb = __ldg(&bbox[c]);
+            const int ymin = (int16_t)(bb.x & 0xffff), ymax = bb.x >> 16, xmin = (int16_t)(bb.y & 0xffff), xmax = bb.y >> 16;
+            pred = ymax >= ylo && ymin <= yhi && xmax >= X0 && xmin <= X1;  // the x test matters for x-split frames
         }
         const unsigned b = __ballot_sync(0xffffffffu, pred);
         if (lane == 0) wcnt[warp] = __popc(b);

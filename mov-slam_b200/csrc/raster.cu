@@ -11,7 +11,7 @@
 //                   look-ahead frames) -> every output index is known without atomics.
 //   emit_kernel     per record: hop j = ref+1..1 written at its final index in frame f-(j-1)'s list, kps rectangle
 //                   written at its final index; order = the reference's push_back order (ballot ranks).
-//   bbox_kernel     y-extent of every 32-hop chunk (lets the grid kernel skip chunks without reading them).
+//   bbox_kernel     y- and x-extent of every 32-hop chunk (lets the grid kernel skip chunks without reading them).
 //   grid_kernel     (grid.cu) one CTA owns a 32-row band of one frame's grid: the hops touching the band go into
 //                   per-tile queues in shared memory in list order, then one warp per 32x32 tile resolves the slots
 //                   once per (column run, row run) cell. Every pixel is written exactly once with one 128-bit
@@ -183,12 +183,17 @@ constexpr int MAXCLS = MOVFE_NCLS(MOVFE_MAX_K);
 
 
 
+// A frame's records are cut into segments of `rseg` records (a multiple of CNT_THREADS); count and emit run one CTA per
+// (stream, frame, segment), so a dense frame (129 600 records at 1920x1080 / 4x4) is spread over many CTAs. seg_cnt holds
+// the per-segment class counts [S][n_in][n_rseg][SEG_WORDS]: classes, then area, then rejected records.
+constexpr int SEG_WORDS = MAXCLS + 2;
+
 __global__ void __launch_bounds__(CNT_THREADS)
-count_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
-             const uint8_t *__restrict__ fflags, int32_t *__restrict__ cls_cnt, int64_t *__restrict__ area,
-             unsigned long long *__restrict__ rejected) {
+count_kernel(WinParams p, int rseg, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
+             const uint8_t *__restrict__ fflags, int32_t *__restrict__ seg_cnt) {
     __shared__ int32_t part[CNT_WARPS][MAXCLS + 2];
     const int sf = blockIdx.x;  // s*n_in + fi
+    const int seg = blockIdx.y, n_rseg = gridDim.y;
     const int s = sf / p.n_in, fi = sf - s * p.n_in;
     const int slot = (int)((p.first + fi) % p.RING);
     const int ncls = MOVFE_NCLS(p.K);
@@ -200,7 +205,8 @@ count_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__rest
 #pragma unroll
     for (int c = 0; c < MAXCLS; c++) cnt[c] = 0;
     int ar = 0, bad = 0;
-    for (int i = threadIdx.x; i < M; i += CNT_THREADS) {
+    const int i_end = min(M, (seg + 1) * rseg);
+    for (int i = seg * rseg + threadIdx.x; i < i_end; i += CNT_THREADS) {
         const Rec16 r = recs[i];
         const RecInfo c = classify(r, p.W, p.H, p.K);
         bad += c.bad;
@@ -230,14 +236,26 @@ count_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__rest
         part[warp][MAXCLS + 1] = bad;
     }
     __syncthreads();
-    if (threadIdx.x < MAXCLS + 2) {
-        long long v = 0;
+    if (threadIdx.x < SEG_WORDS) {
+        int v = 0;  // a segment's area is at most rseg * 255 * 255 < 2^31
         for (int w = 0; w < CNT_WARPS; w++) v += part[w][threadIdx.x];
-        if (threadIdx.x < ncls) cls_cnt[(size_t)sf * MAXCLS + threadIdx.x] = (int32_t)v;
-        if (threadIdx.x == MAXCLS) area[sf] = v;
-        // a look-ahead frame is counted again when it becomes an output frame: charge rejects once
-        if (threadIdx.x == MAXCLS + 1 && v && fi < p.n_out) atomicAdd(rejected, (unsigned long long)v);
+        seg_cnt[((size_t)sf * n_rseg + seg) * SEG_WORDS + threadIdx.x] = v;
     }
+    (void)ncls;
+    (void)fi;
+}
+
+// per-frame totals of the segment counts
+__global__ void seg_sum_kernel(WinParams p, int n_rseg, const int32_t *__restrict__ seg_cnt, int32_t *__restrict__ cls_cnt,
+                               int64_t *__restrict__ area, unsigned long long *__restrict__ rejected) {
+    const int sf = blockIdx.x, c = threadIdx.x;
+    if (c >= SEG_WORDS) return;
+    long long v = 0;
+    for (int seg = 0; seg < n_rseg; seg++) v += seg_cnt[((size_t)sf * n_rseg + seg) * SEG_WORDS + c];
+    if (c < MAXCLS) cls_cnt[(size_t)sf * MAXCLS + c] = (int32_t)v;
+    if (c == MAXCLS) area[sf] = v;
+    // a look-ahead frame is counted again when it becomes an output frame: charge rejects once
+    if (c == MAXCLS + 1 && v && sf % p.n_in < p.n_out) atomicAdd(rejected, (unsigned long long)v);
 }
 
 // ------------------------------------------------------------------------------------------------- bases -----
@@ -270,13 +288,14 @@ __global__ void bases_kernel(WinParams p, const int32_t *__restrict__ cls_cnt, c
 
 // -------------------------------------------------------------------------------------------------- emit -----
 __global__ void __launch_bounds__(CNT_THREADS)
-emit_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
+emit_kernel(WinParams p, int rseg, const int32_t *__restrict__ seg_cnt, const Rec16 *__restrict__ d_rec, const int32_t *__restrict__ rec_cnt,
             const uint8_t *__restrict__ fflags, const int32_t *__restrict__ hop_base,
             const int32_t *__restrict__ kps_base, movfe_hop *__restrict__ hops, HopRect *__restrict__ hop_rects,
             movfe_rect *__restrict__ kps) {
     __shared__ int32_t wtot[MAXCLS][CNT_WARPS];  // per-chunk: exclusive prefix over warps (after the scan step)
-    __shared__ int32_t cbase[MAXCLS];            // records of each class seen in earlier chunks
+    __shared__ int32_t cbase[MAXCLS];            // records of each class seen in earlier chunks (and earlier segments)
     const int sf = blockIdx.x;
+    const int seg = blockIdx.y, n_rseg = gridDim.y;
     const int s = sf / p.n_in, fi = sf - s * p.n_in;
     const int slot = (int)((p.first + fi) % p.RING);
     const int K = p.K, ncls = MOVFE_NCLS(K);
@@ -285,14 +304,19 @@ emit_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restr
     const Rec16 *recs = d_rec + ((size_t)s * p.RING + slot) * p.maxM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
-    if (threadIdx.x < MAXCLS) cbase[threadIdx.x] = 0;
+    if (threadIdx.x < MAXCLS) {
+        int v = 0;
+        for (int q = 0; q < seg; q++) v += seg_cnt[((size_t)sf * n_rseg + q) * SEG_WORDS + threadIdx.x];
+        cbase[threadIdx.x] = v;
+    }
     __syncthreads();
 
-    for (int base = 0; base < M; base += CNT_THREADS) {
+    const int i_end = min(M, (seg + 1) * rseg);
+    for (int base = seg * rseg; base < i_end; base += CNT_THREADS) {
         const int i = base + threadIdx.x;
         Rec16 r = {};
         RecInfo c = {};
-        if (i < M) {
+        if (i < i_end) {
             r = recs[i];
             c = classify(r, p.W, p.H, K);
         }
@@ -374,7 +398,7 @@ emit_kernel(WinParams p, const Rec16 *__restrict__ d_rec, const int32_t *__restr
 
 // -------------------------------------------------------------------------------------------------- bbox -----
 __global__ void bbox_kernel(WinParams p, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
-                            int32_t *__restrict__ chunk_bbox) {
+                            int2 *__restrict__ chunk_bbox) {
     const int sg = blockIdx.y;  // s*n_out + g
     const int s = sg / p.n_out, g = sg - s * p.n_out;
     const int n = nhops[s * p.n_in + g];
@@ -383,17 +407,23 @@ __global__ void bbox_kernel(WinParams p, const HopRect *__restrict__ hop_rects, 
     const int wpg = (gridDim.x * blockDim.x) >> 5;  // warps per (stream, frame): a warp strides over the chunks
     for (int chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < nchunks; chunk += wpg) {
         const int h = chunk * 32 + lane;
-        int ymin = 32767, ymax = -32768;
+        int ymin = 32767, ymax = -32768, xmin = 32767, xmax = -32768;
         if (h < n) {
             const HopRect r = hop_rects[(size_t)sg * p.max_hops + h];
             ymin = r.y0;
             ymax = r.y1;
+            if (r.y1 >= r.y0) {  // empty rectangles carry an inverted extent
+                xmin = r.x0;
+                xmax = r.x1;
+            }
         }
         for (int o = 16; o; o >>= 1) {
             ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, o));
             ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
+            xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+            xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
         }
-        if (lane == 0) chunk_bbox[(size_t)sg * p.max_chunks + chunk] = (ymin & 0xffff) | (ymax << 16);
+        if (lane == 0) chunk_bbox[(size_t)sg * p.max_chunks + chunk] = make_int2((ymin & 0xffff) | (ymax << 16), (xmin & 0xffff) | (xmax << 16));
     }
 }
 
@@ -457,13 +487,14 @@ int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n
     const int SF = p.S * n_in;
     {
     ProfScope prof(ctx, MOVFE_STAGE_HOPS, ctx->raster_stream);
-    prof.launches(4);
-    count_kernel<<<SF, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_cls_cnt,
-                                                      w.d_area, ctx->d_rejected);
+    prof.launches(5);
+    const dim3 gseg(SF, ctx->n_rseg);
+    count_kernel<<<gseg, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->rseg, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_seg_cnt);
+    seg_sum_kernel<<<SF, 32, 0, ctx->raster_stream>>>(p, ctx->n_rseg, w.d_seg_cnt, w.d_cls_cnt, w.d_area, ctx->d_rejected);
     bases_kernel<<<(SF + 127) / 128, 128, 0, ctx->raster_stream>>>(p, w.d_cls_cnt, w.d_area, w.d_hop_base,
                                                             w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov);
-    emit_kernel<<<SF, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_hop_base,
-                                                     w.d_kps_base, w.d_hops, w.d_hop_rect, w.d_kps);
+    emit_kernel<<<gseg, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->rseg, w.d_seg_cnt, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags,
+                                                       w.d_hop_base, w.d_kps_base, w.d_hops, w.d_hop_rect, w.d_kps);
     {
         // capacity would be max_chunks warps per (stream, frame); frames hold a fraction of it, so a few CTAs stride instead
         dim3 g(std::min((ctx->max_chunks * 32 + 255) / 256, 16), p.S * n_out);
