@@ -51,7 +51,7 @@ typedef struct movfe_config {
 
 /* By default the ingest + raster kernels of window k+1 run on their own low-priority CUDA stream beside the propagation
  * of window k (raster results are double-buffered). With this flag every movfe_raster first waits for all propagation
- * enqueued so far, so that the raster kernels run alone - bench.py uses it to time grid_kernel for the roofline. */
+ * and pose work enqueued so far, so that the raster kernels run alone - bench.py uses it to time grid_kernel for the roofline. */
 #define MOVFE_CFG_SERIAL_RASTER 1
 
 /* -- lifetime -------------------------------------------------------------------------------------------- */

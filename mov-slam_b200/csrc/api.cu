@@ -432,8 +432,10 @@ extern "C" int movfe_raster(movfe_ctx *ctx, int64_t first_frame, int n_out) {
     // results go to the buffer that the propagation of the previous window is NOT reading
     RasterBuf &w = ctx->rb[ctx->rb_cur ^ 1];
     if (w.consumed_valid) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, w.consumed, 0));
-    if (ctx->serial_raster) {
+    if (ctx->serial_raster) {  // alone: after all propagation AND all pose work enqueued so far
         MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_serial, ctx->stream));
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_serial, 0));
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_serial, ctx->pose_stream));
         MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_serial, 0));
     }
     int rc = movfe_raster_launch(ctx, w, first_frame, n_out, n_in);

@@ -12,7 +12,7 @@ STEPS = int(os.environ.get("STEPS", 3))
 LA = bench.MAX_REF + 1
 clips = bench.make_clips(F * (STEPS + 1) + LA, n_base=4)
 ctx = lib.Context(S, bench.W, bench.H, max_records_per_frame=bench.MAX_RECORDS, max_ref=bench.MAX_REF, window_frames=F,
-                  max_tracks=bench.MAX_TRACKS, max_map_points=2048, has_grey=True)
+                  max_tracks=bench.MAX_TRACKS, max_map_points=2048, has_grey=True, serial_raster=bool(os.environ.get("SERIAL_RASTER")))
 ctx.set_camera(clips[0]["spec"].camera(), T.pose_params(), 0.5)
 w = bench.pack_window(clips, S, 0, F + LA, pinned=False)
 ctx.push_frames(w["n"], w["recs"].numpy()[:w["n_records"] * 40].view(T.MV_RECORD), w["off"].numpy(), w["flags"].numpy(), w["grey"].numpy())
