@@ -208,3 +208,32 @@ def test_bucket_grid_parity(orc, ctx):
     # truncation: the full count is still reported
     out2, counts2 = ctx.features_in_area(pts, off, start, items, q[-3:], 10)
     assert counts2[0] == counts[-3] and np.array_equal(out2[0], out[-3, :10])
+
+
+def test_keyframe_join_and_initialization_search_parity(orc, ctx):
+    """MOVMatcher::SearchByVideoFeature(KeyFrame*, Frame&, out) (MOVMatcher.h:70-103: output starts all-NULL, null / bad
+    entries of the keyframe's list are skipped) and SearchForInitialization (:105-137) as calls of movfe_join, the way the
+    shim makes them."""
+    rng = np.random.Generator(np.random.PCG64(0x5EED0023))
+    tr = np.zeros(2500, T.TRACK)
+    tr["track_id"] = rng.integers(1, 1800, len(tr))
+    kf = np.zeros(900, T.MAP_POINT)
+    kf["track_id"] = rng.integers(1, 2200, len(kf))
+    kf["flags"] = rng.choice([0, 0, 0, T.MP_BAD, T.MP_NULL], len(kf))
+    valid = ((kf["flags"] & (T.MP_BAD | T.MP_NULL)) == 0).astype(np.uint8)
+    match, n = ctx.join(tr["track_id"], [0, len(tr)], kf["track_id"], valid, [0, len(kf)], np.full(len(tr), -1, np.int32))
+    wn, wm = orc.search_by_keyframe(tr, kf)
+    assert n[0] == wn and np.array_equal(match, wm) and 0 < wn < len(tr)
+    # initialisation: F1's tracks probed with F2's ids -> vnMatches12[i1] = i2; vbPrevMatched from F2's keypoints
+    f1, f2 = np.zeros(1200, T.TRACK), np.zeros(1500, T.TRACK)
+    f1["track_id"], f2["track_id"] = rng.integers(1, 1400, len(f1)), rng.integers(1, 1400, len(f2))
+    f2["pt_x"], f2["pt_y"] = rng.uniform(0, 640, len(f2)), rng.uniform(0, 480, len(f2))
+    m12, n12 = ctx.join(f1["track_id"], [0, len(f1)], f2["track_id"], np.ones(len(f2), np.uint8), [0, len(f2)],
+                        np.full(len(f1), -1, np.int32))
+    prev = np.full((len(f1), 2), -9, np.float32)
+    wn, wm12, wprev = orc.search_for_initialization(f1, f2, prev)
+    assert n12[0] == wn and np.array_equal(m12, wm12)
+    got_prev = prev.copy()
+    hit = m12 >= 0
+    got_prev[hit, 0], got_prev[hit, 1] = f2["pt_x"][m12[hit]], f2["pt_y"][m12[hit]]      # MOVMatcher.h:131-134, host side
+    assert np.array_equal(got_prev, wprev)
