@@ -251,6 +251,30 @@ def config_dict(n_gpus, cores=None):
             "map_points_per_stream": "one per frame-0 track (~450), half of them as the reference keyframe's list"}
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run on (and therefore allocate pinned host buffers from) the NUMA node the GPU hangs off, so that
+    the host->device copies of N ranks do not all read one socket's memory. Best effort: returns the node or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        dev = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % dev).read())
+        nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+        if node < 0 or len(nodes) < 2:
+            return "gpu %s node %d of %s: nothing to bind" % (dev, node, nodes)
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "gpu %s node %d: no allowed cpu there" % (dev, node)
+        os.sched_setaffinity(0, cpus)
+        return "gpu %s -> node %d (%d cpus)" % (dev, node, len(cpus))
+    except Exception as e:      # containers without sysfs topology, older torch: run unbound
+        return "unbound (%s)" % (e,)
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm ------
 def run_product(args):
     import torch
@@ -262,6 +286,8 @@ def run_product(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    all_cpus = os.sched_getaffinity(0)
+    log("[rank %d] numa: %s" % (rank, bind_to_gpu_numa_node(local)))
     S = S_PER_GPU
     n_steps = args.warmup + args.steps
     LA = MAX_REF + 1
@@ -454,6 +480,7 @@ def run_product(args):
 
     if rank == 0:
         cores = os.cpu_count() or 1
+        os.sched_setaffinity(0, all_cpus)        # the CPU baseline uses every host core again
         cpu_fps, cpu_dt = cpu_frontend_sample(clips, REF_FRAMES, cores, repeats=CPU_REPEATS)
         cfg = config_dict(world)
         cfg["tracks_in_last_table"] = int(max_tracks_seen)
