@@ -37,7 +37,6 @@ struct __align__(16) WarpScratch {
     int4 tab[CELL_CAP];                // slots of the cells of the current batch, index (row run - first run) * ncc + column run
     uint32_t amask[MAX_TILES];         // phase 1: lanes of this warp's chunk whose first tile is t ...
     uint32_t cmask[MAX_TILES];         //          ... and whose second tile is t
-    int32_t cnt[MAX_TILES];            //          entries this warp's chunk adds to tile t
     uint8_t repc[32], repr[32];        // phase 2: first column / row of every run
 };
 
@@ -234,6 +233,8 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
     uint32_t *tq_i = tq_x + NTC * TQ_STRIDE;                     // [NTC][TQ_STRIDE]                             hop | r0<<22 | r1<<27
     int32_t  *clist = (int32_t *)(tq_i + NTC * TQ_STRIDE);       // [CHUNK_CAP] surviving chunk ids
     __shared__ int32_t wcnt[GRID_MAX_WARPS];
+    // phase 1b: entries warp w's chunk adds to tile t, one byte each (<= 32), a tile's 16 warps in one 128-bit word
+    __shared__ __align__(16) uint8_t tcnt[MAX_TILES][GRID_MAX_WARPS];
 
     const unsigned lt = lanemask_lt();
     const int band = blockIdx.x;
@@ -276,6 +277,15 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
     // narrower than a tile): match.any groups the lanes by tile, so a lane knows its rank inside the chunk for each of its
     // tiles and lane t knows the chunk's count for tile t; counts are prefixed across the warps of the round.
     int run_total = 0;  // lane t: entries queued so far in tile t (the same in every warp)
+    uint4 all_m, before_m;  // byte j = 1 for warps j < nwarps / j < warp
+    {
+        auto ones_below = [](int n, int word) {  // bytes 4*word .. 4*word+3: 1 where the byte index is < n
+            const int k = min(max(n - 4 * word, 0), 4);
+            return k == 0 ? 0u : (0x01010101u >> (8 * (4 - k)));
+        };
+        all_m = make_uint4(ones_below(nwarps, 0), ones_below(nwarps, 1), ones_below(nwarps, 2), ones_below(nwarps, 3));
+        before_m = make_uint4(ones_below(warp, 0), ones_below(warp, 1), ones_below(warp, 2), ones_below(warp, 3));
+    }
     if (!direct) {
         const HopRect none = {0, 32767, -1, -32768};  // overlaps nothing
         HopRect r_next = none;
@@ -331,14 +341,12 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
                     if (lane == t) mycnt = __popc(b);
                 }
             }
-            ws.cnt[lane] = mycnt;
+            tcnt[lane][warp] = (uint8_t)mycnt;
             __syncthreads();
-            int before = 0, tot = 0;
-            for (int w2 = 0; w2 < nwarps; w2++) {
-                const int c = wsa[w2].cnt[lane];
-                tot += c;
-                if (w2 < warp) before += c;
-            }
+            // lane t: sum of the tile's counts over all warps and over the warps before this one (byte-wise dot products)
+            const uint4 cw = *reinterpret_cast<const uint4 *>(tcnt[lane]);
+            const int tot = __dp4a(cw.x, all_m.x, __dp4a(cw.y, all_m.y, __dp4a(cw.z, all_m.z, __dp4a(cw.w, all_m.w, 0u))));
+            const int before = __dp4a(cw.x, before_m.x, __dp4a(cw.y, before_m.y, __dp4a(cw.z, before_m.z, __dp4a(cw.w, before_m.w, 0u))));
             const int basepos = run_total + before;
             run_total += tot;
             if (!wide) {
