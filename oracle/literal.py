@@ -322,3 +322,94 @@ def extractor(smv, img, is_p_frame, prev_vf, current_id, threshold, coverage_thr
                 current_id += 1
                 vf_out.append(VideoFeature(current_id, -1, pt, mb, 0, desc, coverage=True))
     return vf_out, current_id
+
+
+# ---- pose-only Gauss-Newton / Huber, second restatement -------------------------------------
+# Independent of oracle/pose.cc in its building blocks: the SE3 exponential is scipy's matrix exponential of the 4x4 twist,
+# the Jacobian of the residual is taken by central differences of the projection (no analytic formula), the normal
+# equations are solved by numpy's LU solver, Huber is restated from its definition.
+def _project(cam, Xc):
+    x, y, z = Xc
+    if cam["model"] == 0:                                    # Pinhole.cpp:45-52
+        return np.array([cam["fx"] * x / z + cam["cx"], cam["fy"] * y / z + cam["cy"]])
+    r = np.hypot(x, y)                                       # KannalaBrandt8 (App. A.6)
+    if r < 1e-12:
+        return np.array([float(cam["cx"]), float(cam["cy"])])
+    th = np.arctan2(r, z)
+    k = [float(v) for v in cam["k"]]
+    thd = th * (1 + k[0] * th ** 2 + k[1] * th ** 4 + k[2] * th ** 6 + k[3] * th ** 8)
+    return np.array([cam["fx"] * thd * x / r + cam["cx"], cam["fy"] * thd * y / r + cam["cy"]])
+
+
+def se3_exp_expm(dx):
+    """exp of the twist [omega, upsilon] (rotation first, g2o SE3Quat::exp) through scipy.linalg.expm."""
+    from scipy.linalg import expm
+    w, v = dx[:3], dx[3:]
+    M = np.zeros((4, 4))
+    M[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]
+    M[:3, 3] = v
+    E = expm(M)
+    return E[:3, :3], E[:3, 3]
+
+
+def residual_jacobian_fd(cam, Xc, h=1e-6):
+    """d e / d dx at dx = 0 for e = obs - pi(exp(dx) * Xc), by central differences: 2 x 6."""
+    J = np.zeros((2, 6))
+    for k in range(6):
+        d = np.zeros(6)
+        d[k] = h
+        Rp, tp = se3_exp_expm(d)
+        Rm, tm = se3_exp_expm(-d)
+        J[:, k] = -(_project(cam, Rp @ Xc + tp) - _project(cam, Rm @ Xc + tm)) / (2 * h)
+    return J
+
+
+def pose_optimize_ref(cam, pts, obs, R, t, rep_error, iteration_count, jac):
+    """The schedule of App. A.5: 4 rounds of iteration_count/4 Gauss-Newton steps, Huber (delta = rep_error) in the first
+    three, re-classification (chi2 > rep_error^2 -> outlier, excluded from the next round) after every round, early exit
+    at |dx|_inf < 1e-10 and below 3 inliers. `jac(cam, Xc)` supplies the 2x6 residual Jacobian. Returns (R, t, outlier)."""
+    pts, obs = np.asarray(pts, np.float64), np.asarray(obs, np.float64)
+    n = len(pts)
+    outlier = np.zeros(n, bool)
+    if n < 4:
+        return R, t, outlier, 0
+    delta = float(np.float32(rep_error))
+    its = max(iteration_count // 4, 1)
+    for rnd in range(4):
+        robust = rnd < 3
+        for _ in range(its):
+            H, b = np.zeros((6, 6)), np.zeros(6)
+            for i in range(n):
+                if outlier[i]:
+                    continue
+                Xc = R @ pts[i] + t
+                if not Xc[2] > 0:
+                    continue
+                e = obs[i] - _project(cam, Xc)
+                chi2 = float(e @ e)
+                w = 1.0
+                if robust and chi2 > delta * delta:           # Huber: rho'(chi2) = delta / sqrt(chi2) beyond delta^2
+                    w = delta / np.sqrt(chi2)
+                J = jac(cam, Xc)
+                H += w * J.T @ J
+                b -= w * J.T @ e
+            try:
+                dx = np.linalg.solve(H, b)
+            except np.linalg.LinAlgError:
+                break
+            dR, dt = se3_exp_expm(dx)
+            R, t = dR @ R, dR @ t + dt
+            if np.max(np.abs(dx)) < 1e-10:
+                break
+        bad = 0
+        for i in range(n):
+            Xc = R @ pts[i] + t
+            o = True
+            if Xc[2] > 0:
+                e = obs[i] - _project(cam, Xc)
+                o = float(e @ e) > delta * delta
+            outlier[i] = o
+            bad += o
+        if n - bad < 3:
+            break
+    return R, t, outlier, n - int(outlier.sum())
