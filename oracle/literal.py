@@ -413,3 +413,67 @@ def pose_optimize_ref(cam, pts, obs, R, t, rep_error, iteration_count, jac):
         if n - bad < 3:
             break
     return R, t, outlier, n - int(outlier.sum())
+
+
+# ---- Frame::isInFrustum, mono branch (src/Frame.cc:456-519) + the joins (include/MOVMatcher.h:35-137) -------------------
+def _dot3(a, b):
+    # float32, no contraction, Eigen 3.4's unrolled 3-term reduction order c0 + (c1 + c2) (see oracle/match.cc's header)
+    return f32(f32(a[0] * b[0]) + f32(f32(a[1] * b[1]) + f32(a[2] * b[2])))
+
+
+def is_in_frustum(Rcw, tcw, cam, width, height, cos_limit, pos, normal, min_dist, max_dist):
+    """Pinhole only. Returns (in_view, u, v, depth, view_cos) as the reference leaves them in the MapPoint."""
+    R = [[f32(Rcw[i][j]) for j in range(3)] for i in range(3)]
+    t = [f32(v) for v in tcw]
+    Ow = [f32(-(Rcw[0][i] * tcw[0] + Rcw[1][i] * tcw[1] + Rcw[2][i] * tcw[2])) for i in range(3)]   # -R^T t in double
+    P = [f32(v) for v in pos]
+    out = [0, f32(-1), f32(-1), f32(0), f32(0)]                           # :460-462
+    Pc = [f32(_dot3(R[i], P) + t[i]) for i in range(3)]                   # :468
+    Pc_dist = f32(np.sqrt(_dot3(Pc, Pc)))                                 # :469
+    if Pc[2] < f32(0):                                                    # :474
+        return out
+    u = f32(f32(f32(f32(cam["fx"]) * Pc[0]) / Pc[2]) + f32(cam["cx"]))    # Pinhole.cpp:48-49
+    v = f32(f32(f32(f32(cam["fy"]) * Pc[1]) / Pc[2]) + f32(cam["cy"]))
+    if u < f32(0) or u > f32(width) or v < f32(0) or v > f32(height):     # :479-482 with mnMin/Max of an undistorted frame
+        return out
+    out[1], out[2] = u, v                                                 # :484-485
+    maxD, minD = f32(f32(1.2) * f32(max_dist)), f32(f32(0.8) * f32(min_dist))   # MapPoint.cc:443-453
+    PO = [f32(P[i] - Ow[i]) for i in range(3)]                            # :490
+    dist = f32(np.sqrt(_dot3(PO, PO)))
+    if dist < minD or dist > maxD:                                        # :493
+        return out
+    view_cos = f32(_dot3(PO, [f32(x) for x in normal]) / dist)            # :499
+    if view_cos < f32(cos_limit):                                         # :501
+        return out
+    out[0], out[3], out[4] = 1, Pc_dist, view_cos                         # :508-516
+    return out
+
+
+def search_by_video_feature(track_ids, mp_track_ids, mp_ok, match):
+    """MOVMatcher.h:35-68: vfmap = first index per id (std::map::insert never overwrites); every eligible map point, in
+    order, overwrites the match of its track (last wins). Returns nmatches; `match` is updated in place."""
+    vfmap = {}
+    for i, tid in enumerate(track_ids):
+        vfmap.setdefault(int(tid), i)
+    n = 0
+    for k, tid in enumerate(mp_track_ids):
+        if not mp_ok[k]:
+            continue
+        if int(tid) in vfmap:
+            match[vfmap[int(tid)]] = k
+            n += 1
+    return n
+
+
+def assign_features_to_grid(xs, ys, width, height):
+    """Frame.cc:356-388 with PosInGrid (:670-680, round()) -> {(ix, iy): [indices in insertion order]}."""
+    w_inv, h_inv = f32(f32(64) / f32(width)), f32(f32(48) / f32(height))
+    grid = {}
+    for i, (x, y) in enumerate(zip(xs, ys)):
+        fx, fy = f32(f32(f32(x) - f32(0)) * w_inv), f32(f32(f32(y) - f32(0)) * h_inv)
+        px = int(np.floor(abs(fx) + f32(0.5))) * (1 if fx >= 0 else -1)   # C round(): half away from zero
+        py = int(np.floor(abs(fy) + f32(0.5))) * (1 if fy >= 0 else -1)
+        if px < 0 or px >= 64 or py < 0 or py >= 48:
+            continue
+        grid.setdefault((px, py), []).append(i)
+    return grid

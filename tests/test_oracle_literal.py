@@ -159,3 +159,43 @@ def test_pose_solver_matches_second_restatement(orc, model, n, seed):
         assert ninl == wn and np.array_equal(outl.astype(np.uint8), woutl), (ninl, wn)
         assert np.abs(R - np.asarray(wpose["R"]).reshape(3, 3)).max() < tol and np.abs(t - np.asarray(wpose["t"])).max() < tol * 10
     assert 0.7 * n < wn < n                                               # the gross outliers were rejected, the rest kept
+
+
+def test_frustum_joins_and_bucket_grid_match_literal(orc):
+    rng = np.random.Generator(np.random.PCG64(0x11B0))
+    spec = synth.Spec(640, 480, n_frames=2, refs=1, seed=1)
+    Rcw, tcw = synth.pose_at(spec, 7)
+    pose, cam = synth.pose_struct((Rcw, tcw)), T.camera(320, 320, 320, 240)
+    n = 400
+    mp = np.zeros(n, T.MAP_POINT)
+    mp["pos"] = rng.uniform([-8, -6, -2], [8, 6, 25], (n, 3))
+    Ow = -np.asarray(Rcw).T @ np.asarray(tcw)
+    d = mp["pos"].astype(np.float64) - Ow
+    dist = np.linalg.norm(d, axis=1)
+    nrm = d / dist[:, None] + rng.normal(0, 0.5, (n, 3))
+    mp["normal"] = nrm / np.linalg.norm(nrm, axis=1)[:, None]
+    mp["min_dist"], mp["max_dist"] = dist * rng.uniform(0.5, 1.3, n), dist * rng.uniform(0.8, 2.0, n)
+    got = orc.frustum(pose, cam, 640, 480, 0.5, mp)
+    for k in range(n):
+        w = lit.is_in_frustum(np.asarray(Rcw), np.asarray(tcw), cam, 640, 480, 0.5, mp["pos"][k], mp["normal"][k],
+                              mp["min_dist"][k], mp["max_dist"][k])
+        g = got[k]
+        assert (int(g["in_view"]), g["u"], g["v"], g["depth"], g["view_cos"]) == tuple(w), (k, g, w)
+    assert 20 < got["in_view"].sum() < n
+    # joins
+    tr = np.zeros(300, T.TRACK)
+    tr["track_id"] = rng.integers(1, 200, len(tr))
+    mp["track_id"] = rng.integers(1, 260, n)
+    proj = got
+    init = np.where(rng.random(len(tr)) < 0.2, 7, -1).astype(np.int32)
+    wn, wm = orc.search_by_video_feature(tr, mp, proj, init)
+    m = init.copy()
+    assert lit.search_by_video_feature(tr["track_id"], mp["track_id"], proj["in_view"] != 0, m) == wn and np.array_equal(m, wm)
+    # bucket grid
+    tr["pt_x"], tr["pt_y"] = rng.uniform(-10, 650, len(tr)), rng.uniform(-10, 490, len(tr))
+    start, items = orc.assign_features_to_grid(tr, 640, 480)
+    want = lit.assign_features_to_grid(tr["pt_x"], tr["pt_y"], 640, 480)
+    for ix in range(64):
+        for iy in range(48):
+            c = ix * 48 + iy
+            assert list(items[start[c]:start[c + 1]]) == want.get((ix, iy), []), (ix, iy)
