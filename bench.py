@@ -30,7 +30,7 @@ from movfe import synth, types as T  # noqa: E402
 
 W, H = 640, 480
 S_PER_GPU = 64
-F = 16              # frames per stream per step
+F = int(os.environ.get("BENCH_F", 16))   # frames per stream per step (window length)
 MAX_REF = 3         # ref=4 chaining -> reference indices 0..3
 CPU_REPEATS = 4     # repeats of the cpu_baseline sample (about 10-20 s of CPU work)
 REF_FRAMES = 100    # frames per stream of one CPU sample (reference arm / cpu_baseline)
