@@ -94,3 +94,48 @@ def test_feature_grid_of_resident_tables(orc):
             w = orc.get_features_in_area(tr, W, H, ws, wi, q[k]["x"], q[k]["y"], q[k]["r"])
             assert cnt[k] == len(w) and np.array_equal(out[k, :len(w)], w)
     ctx.close()
+
+
+def test_device_resident_push_and_two_contexts(orc):
+    """movfe_push_frames_device (inputs already in HBM, what bench.py's `value` region uses) gives the same tables as the
+    host push, and two contexts alive on one GPU (the bench creates them back to back) do not disturb each other."""
+    import torch
+    W, H, F, K, NW, S = 320, 240, 4, 2, 3, 2
+    LA = K + 1
+    n_frames = F * NW + LA
+    specs = [synth.Spec(W, H, n_frames=n_frames, refs=K + 1, seed=0x5EED0055 + s, fx=160.0, fy=160.0, phase=0.3 * s) for s in range(S)]
+    clips = [synth.make_records(sp) for sp in specs]
+    greys = [synth.make_grey(sp) for sp in specs]
+    want = [oracle_tracks(orc, clips[s], W, H, K, grey=greys[s], max_tracks=2048) for s in range(S)]
+    ctx_a = lib.Context(S, W, H, max_records_per_frame=1300, max_ref=K, window_frames=F, max_tracks=2048, has_grey=True)
+    ctx_b = lib.Context(S, W, H, max_records_per_frame=1300, max_ref=K, window_frames=F, max_tracks=2048, has_grey=True)
+    keep = []
+
+    def push(ctx, f0, f1, device):
+        r, o, fl = pack_streams(clips, n_frames, f0, f1)
+        g = np.stack([greys[s][f0:f1] for s in range(S)])
+        if not device:
+            ctx.push_frames(f1 - f0, r, o, fl, g)
+            return
+        r = np.ascontiguousarray(r, T.MV_RECORD)              # np.concatenate may hand back a packed (36-byte) dtype
+        pad = np.zeros(len(r) * 40 + 16, np.uint8)
+        pad[:len(r) * 40] = r.view(np.uint8)
+        d = [torch.from_numpy(a).cuda() for a in (pad, o, fl, g)]
+        torch.cuda.synchronize()
+        keep.append(d)                                         # device inputs stay alive until the run is read back
+        ctx.push_frames_device(f1 - f0, d[0].data_ptr(), d[1].data_ptr(), len(r), d[2].data_ptr(), d[3].data_ptr())
+
+    push(ctx_a, 0, F + LA, True)
+    push(ctx_b, 0, F + LA, False)
+    for k in range(NW):
+        for ctx, device in ((ctx_a, True), (ctx_b, False)):
+            ctx.raster(F * k, F)
+            ctx.extract(F * k, F)
+            if k + 1 < NW:
+                push(ctx, F * (k + 1) + LA, F * (k + 2) + LA, device)
+    for ctx in (ctx_a, ctx_b):
+        for s in range(S):
+            for f in range(F * (NW - 1), F * NW):
+                assert_tracks_equal(ctx.tracks(s, f), want[s][f], (s, f))
+        assert ctx.rejected_records() == 0
+        ctx.close()
