@@ -22,7 +22,7 @@ def _build():
 
 def test_shims_compile_and_link():
     _build()
-    assert os.path.exists(os.path.join(SHIM, "test_shim"))
+    assert os.path.exists(os.path.join(SHIM, "test_shim")) and os.path.exists(os.path.join(SHIM, "batched_frontend"))
     # the reference's signatures are what the shim headers declare
     h = open(os.path.join(SHIM, "MOVExtractor_movfe.h")).read()
     assert "MOVExtractor(int threshold = 20, double coverageThreshold = 0.60, double relocalizationDistance = 0.25)" in h
@@ -97,3 +97,42 @@ def test_shims_against_oracle(orc, tmp_path):
         assert np.max(np.abs(got_p[:12] - ref)) <= 1e-5 * max(1.0, float(np.max(np.abs(ref)))), ("pose", f)
         if n > 0:
             last = f32(pose)
+
+
+@pytest.mark.gpu
+def test_batched_cpp_driver(orc, tmp_path):
+    """The batched front-end driven from C++ through the C ABI alone (shim/batched_frontend.cc, the loop of INTEGRATION.md
+    section 3, nothing but movfe_download_poses waits for the GPU): last window's track tables bit-exact, poses within 1e-5."""
+    from gpu_util import oracle_tracks
+    _build()
+    W, H, F, K, NW, S, thr = 320, 240, 4, 2, 4, 5, 25
+    NF = F * NW + K + 1
+    sp = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0027, fx=160.0, fy=160.0)
+    recs, off, flags = synth.make_records(sp)
+    grey = synth.make_grey(sp)
+    want = oracle_tracks(orc, (recs, off, flags), W, H, K, grey=grey, max_tracks=8192)
+    mp = synth.map_from_tracks(sp, want[0], synth.pose_at(sp, 0))
+    pose0, cam, pp = synth.pose_struct(synth.pose_at(sp, 0)), sp.camera(), T.pose_params()
+    d = str(tmp_path)
+    np.array([W, H, NF, K, thr, len(mp), len(mp) // 2, S, F], np.int32).tofile(d + "/meta.bin")
+    np.ascontiguousarray(recs, T.MV_RECORD).tofile(d + "/recs.bin")
+    off.tofile(d + "/off.bin"); flags.tofile(d + "/flags.bin"); grey.tofile(d + "/grey.bin"); mp.tofile(d + "/map.bin")
+    np.concatenate([pose0["R"], pose0["t"]]).astype(np.float64).tofile(d + "/pose0.bin")
+    np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).tofile(d + "/cam.bin")
+    r = subprocess.run([os.path.join(SHIM, "batched_frontend"), d], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rejected records 0" in r.stdout
+    last = F * (NW - 1)
+    for s in (0, S - 1):
+        for f in range(last, last + F):
+            got = np.fromfile(d + "/b_tracks_%d_%d.bin" % (s, f), T.TRACK)
+            assert got.tobytes() == want[f].tobytes(), (s, f, len(got), len(want[f]))
+    ref = orc.frontend_run(W, H, recs, off, flags, grey, None, mp, pose0, cam, pp, max_ref=K, max_tracks=8192, n_kf_points=len(mp) // 2)
+    poses = np.fromfile(d + "/b_poses.bin", T.POSE).reshape(S, F)
+    ninl = np.fromfile(d + "/b_ninl.bin", np.int32).reshape(S, F)
+    for s in range(S):
+        for k in range(F):
+            assert ninl[s, k] == ref["n_inliers"][last + k], (s, k)
+            for name in ("R", "t"):
+                w = ref["poses"][last + k][name]
+                assert np.max(np.abs(poses[s, k][name] - w)) <= 1e-5 * max(1.0, float(np.max(np.abs(w)))), (s, k, name)
