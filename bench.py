@@ -33,7 +33,7 @@ S_PER_GPU = 64
 F = int(os.environ.get("BENCH_F", 16))   # frames per stream per step (window length)
 MAX_REF = 3         # ref=4 chaining -> reference indices 0..3
 CPU_REPEATS = 4     # repeats of the cpu_baseline sample (about 10-20 s of CPU work)
-REF_FRAMES = 100    # frames per stream of one CPU sample (reference arm / cpu_baseline)
+REF_FRAMES = int(os.environ.get("BENCH_REF_FRAMES", 100))    # frames per stream of one CPU sample (reference arm / cpu_baseline)
 N_BASE = 8          # distinct synthetic clips; stream s replays clip s % N_BASE (every stream is processed separately)
 MAX_RECORDS = 4800
 MAX_TRACKS = 8192   # the reference's tables are unbounded; the C2 tables plateau near 4000 entries
