@@ -6,11 +6,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * liboracle.so. Nothing under mov-slam_b200/ links, imports or calls it.
  *
- * Parity pinning: the reference ships no tests, golden vectors or fixtures and cannot be
- * built here (OpenCV C++/Eigen/Sophus/g2o/FFmpeg absent). The oracle is pinned against the
- * hand-derived known-answer vectors of SURVEY.md Appendix B (tests/test_oracle_kat.py). For arithmetic that
- * lives in un-vendored third-party code (cv::solvePnPRansac, Eigen evaluation order, KannalaBrandt8) the
- * status is "parity unpinned" — see DESIGN.md §Oracle.
+ * Parity pinning: the reference ships no tests, golden vectors or fixtures. The raster, EXPRESS,
+ * extractor and matcher functions below are pinned against THE REFERENCE'S OWN SOURCES, compiled unmodified
+ * into oracle/_ref (Makefile target `ref`; stand-in headers in ref_standin/) and compared on random inputs by
+ * tests/test_ref_parity.py, plus the hand-derived known-answer vectors of SURVEY.md Appendix B
+ * (tests/test_oracle_kat.py). For arithmetic that lives in un-vendored third-party code (cv::solvePnPRansac,
+ * Eigen evaluation order inside Frame::isInFrustum, KannalaBrandt8) the status is "parity unpinned" — see
+ * DESIGN.md §Oracle.
  *
  * Float semantics: non-contracted IEEE-754 binary32 (-ffp-contract=off), see SURVEY.md §7 "hard parts".
  */
