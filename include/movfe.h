@@ -102,8 +102,26 @@ int64_t movfe_rejected_records(movfe_ctx *ctx);   /* records dropped for ref > m
 /* -- propagation: replaces MOVExtractor::operator() (include/MOVExtractor.h:36-37, src/MOVExtractor.cc:63-455)
  *    for frames [first_frame, first_frame+n_frames) of every stream, in frame order, on the raster results of
  *    the last movfe_raster call. Track tables persist per stream across calls (prev frame = Frame::mpPrevFrame).
- *    LK-carried features (cv::calcOpticalFlowPyrLK, :91,:196,:347) are host work and are dropped here. */
+ *
+ *    LK hand-over. cv::calcOpticalFlowPyrLK (:91,:196,:347) is OpenCV arithmetic and stays on the host; its RESULTS enter
+ *    through movfe_set_lk_results and are merged on the device exactly where the reference merges them. They apply to the
+ *    NEXT frame propagated on `stream` (the first frame of the next movfe_extract / the frame of movfe_extract_frame) and
+ *    are cleared after it, so a caller that needs LK propagates one frame per call (the carried set of frame f+1 depends on
+ *    the table of frame f, which the host needs to run LK). Which features the reference hands to LK:
+ *      I frame with a non-empty previous table (:81-120): every previous track, in TABLE order: n = n_prev;
+ *      P frame (:337-377): the previous table's coverage tracks (MOVFE_TRACK_COVERAGE) in SORTED order (stable, age
+ *        descending then descriptor popcount descending, :249-252): n = their count;
+ *      status[i] / pts_xy[2i..2i+1] = LK status and position of the i-th such feature; the bounds test (:98,:354) is applied
+ *        on the device. n = -1: nothing installed (carried tracks are dropped and counted, see below).
+ *      reloc / n_reloc: lost relocalisation (prev->mLost, :161-243): keyframe points the host carried with LK that passed
+ *        status, image bounds and the distance test (:207-215); the device adds block, bounds test and descriptor
+ *        (:218-238) and emits them ahead of the propagated tracks. Needs grey planes.
+ *    Without results every carried track of a frame is dropped - what the reference does when LK loses them all - and
+ *    movfe_dropped_lk_tracks() counts them since create, so a drop-in can tell. */
 int movfe_set_tracks(movfe_ctx *ctx, int stream, const movfe_track *tracks, int n, int32_t current_id);
+int movfe_set_lk_results(movfe_ctx *ctx, int stream, const uint8_t *status, const float *pts_xy, int n,
+                         const movfe_reloc_seed *reloc, int n_reloc);
+int64_t movfe_dropped_lk_tracks(movfe_ctx *ctx);
 int movfe_extract(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 int movfe_track_count(movfe_ctx *ctx, int stream, int64_t frame, int32_t *n_tracks, int32_t *current_id);
 int movfe_download_tracks(movfe_ctx *ctx, int stream, int64_t frame, movfe_track *out, int capacity);
@@ -135,13 +153,16 @@ int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset)
 /* -- single-shot operators (batch of independent problems; used by the drop-in shims and the parity tests) --- */
 /* MOVExtractor::operator() (include/MOVExtractor.h:36-37) for ONE frame whose raster results the caller holds on the
  * host: grid = VideoImage::mvi (height*width*4 int32), hops = mvs, kps, coverage_area, frame_flags = MOVFE_FRAME_*,
- * grey = imGray (height*width, or NULL for a context created with has_grey = 0); prev/n_prev = prev->mvVF (any order:
- * the reference's stable sort is applied); *current_id = MOVExtractor::mCurrentId, read and updated. Writes the new
- * frame's table to out and returns its size. The context must have n_streams == 1 and must not be mixed with the
- * batched push/raster/extract calls. */
-int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const uint8_t *grey, const int32_t *grid,
+ * grey = imGray with rows of grey_stride bytes (cv::Mat::step / AVFrame::linesize[0]; 0 = width; NULL for a context
+ * created with has_grey = 0); prev/n_prev = prev->mvVF (any order: the reference's stable sort is applied);
+ * lk_status / lk_pts / n_lk / reloc / n_reloc = host LK results for this frame as in movfe_set_lk_results (n_lk = -1 and
+ * n_reloc = 0: none); *current_id = MOVExtractor::mCurrentId, read and updated. Writes the new frame's table to out and
+ * returns its size (which may exceed `capacity`: MOVFE_E_CAPACITY). The context must have n_streams == 1 and must not be
+ * mixed with the batched push/raster/extract calls. */
+int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const uint8_t *grey, int grey_stride, const int32_t *grid,
                         const movfe_hop *hops, int n_hops, const movfe_rect *kps, int n_kps, double coverage_area,
-                        const movfe_track *prev, int n_prev, int32_t *current_id, movfe_track *out, int capacity);
+                        const movfe_track *prev, int n_prev, const uint8_t *lk_status, const float *lk_pts, int n_lk,
+                        const movfe_reloc_seed *reloc, int n_reloc, int32_t *current_id, movfe_track *out, int capacity);
 /* Frame::isInFrustum for n_problems point sets. pts/out are packed; off has n_problems+1 entries. */
 int movfe_frustum(movfe_ctx *ctx, int n_problems, const movfe_pose *poses, const movfe_map_point *pts,
                   const int32_t *off, movfe_projection *out);

@@ -61,6 +61,15 @@ typedef struct movfe_track {
 } movfe_track;
 #define MOVFE_TRACK_COVERAGE 0x1u
 
+/* One lost-relocalisation seed (src/MOVExtractor.cc:199-241): a reference-keyframe map point that the host carried into
+ * the current image with cv::calcOpticalFlowPyrLK and that passed the status / image-bounds / distance tests (:207-215).
+ * The device adds the 16x16 block around it, its bounds test and its descriptor (:218-238). 16 bytes. */
+typedef struct movfe_reloc_seed {
+    int32_t track_id;       /* MapPoint::mTrackId (:191) */
+    int32_t q_indx;         /* index in the point list handed to LK (:230) */
+    float   x, y;           /* ptR (:205) */
+} movfe_reloc_seed;
+
 /* A local map point as the front-end reads it (MapPoint::GetWorldPos/GetNormal/mfMin/MaxDistance/
  * mTrackId/isBad; Frame.cc:456-519, MOVMatcher.h:35-68). 40 bytes. */
 typedef struct movfe_map_point {

@@ -137,6 +137,7 @@ struct movfe_ctx {
     int32_t *d_cur_id = nullptr;    // [S][TSLOTS]  mCurrentId after each frame
     void    *d_ext_scratch = nullptr;
     size_t   ext_scratch_bytes = 0;
+    bool     lk_pending = false;    // movfe_set_lk_results installed host LK results for the next frame to be propagated
 
     // map / pose
     movfe_camera cam;

@@ -18,8 +18,11 @@
 //                    back-fill / I-frame seeding on the 16-px lattice, then the stable (age desc, popcount desc)
 //                    order of the new table for the next frame: bitonic sort of unique 64-bit keys, register- and
 //                    shuffle-resident for all but the widest steps.
-// LK-carried features (cv::calcOpticalFlowPyrLK; MOVExtractor.cc:81-120,161-243,337-377) are host work: coverage
-// tracks and I-frame carry-over are dropped here, exactly like the oracle with lk_status == NULL.
+// LK-carried features (cv::calcOpticalFlowPyrLK; MOVExtractor.cc:81-120,161-243,337-377): the LK arithmetic is OpenCV's
+// and stays on the host, its RESULTS are handed in with movfe_set_lk_results and merged by finalize_kernel exactly where
+// the reference merges them (I-frame carry-over of every track, coverage tracks after the propagated ones, lost-
+// relocalisation seeds first). A frame that gets no results drops its carried tracks - the oracle's lk_status == NULL
+// mode - and counts them (movfe_dropped_lk_tracks).
 #include <algorithm>
 #include <cstdio>
 
@@ -44,7 +47,18 @@ struct ExtParams {
     int tslot_prev, tslot_cur;
     int thr;         // EXPRESS threshold
     int has_grey;
+    int use_lk;      // this frame consumes the host LK results installed with movfe_set_lk_results
     double cov_thr;
+};
+
+// Host LK hand-over (movfe_set_lk_results), per stream. n < 0: nothing installed for this frame.
+struct LkBuf {
+    int32_t *n;               // [S]
+    uint8_t *status;          // [S][maxT]
+    float2  *pts;             // [S][maxT]
+    int32_t *n_reloc;         // [S]
+    movfe_reloc_seed *reloc;  // [S][maxT]
+    unsigned long long *dropped;
 };
 
 // ------------------------------------------------------------------------------------------------ EXPRESS -----
@@ -575,6 +589,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
                 o[3] = make_uint4(my_d[4], my_d[5], my_d[6], my_d[7]);
                 if (cd >= 0 && cd < p.max_kps) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
             }
+            if (a1.w & MOVFE_TRACK_COVERAGE) fl = 4;  // carried by the host LK step (:258-262), merged in finalize
             ci[i] = make_int2(alive ? cd : -1, fl);
         }
     }
@@ -1011,7 +1026,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                 const int2 *__restrict__ cinfo, int32_t *__restrict__ claim, const movfe_rect *__restrict__ kps,
                 const int32_t *__restrict__ nkps, const double *__restrict__ cov, const uint8_t *__restrict__ birth_flag,
                 const uint32_t *__restrict__ birth_desc, const int4 *__restrict__ grid,
-                const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags) {
+                const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, LkBuf lk) {
     extern __shared__ unsigned long long keys[];  // general sort: keys[N]; run sort: age[maxT] pk[maxT] run_start[maxT] hist[32][264]
     __shared__ int wsum[FIN_WARPS];
     __shared__ uint32_t scratch[FIN_WARPS][8];
@@ -1036,8 +1051,60 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     int n_keyed = 0;  // entries whose sort key is already in shared memory
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
+    const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
+    const int lk_n = p.use_lk ? lk.n[s] : -1;
+    const uint8_t *lk_st = lk.status + (size_t)s * p.maxT;
+    const float2 *lk_pt = lk.pts + (size_t)s * p.maxT;
+    bool rekey_all = false;  // entries were written outside the fused copy paths ahead of keyed ones
+    int n_dropped = 0;       // carried tracks that got no LK result
 
     if (is_p) {
+        // lost relocalisation (:161-243): seeds that passed the host-side tests (:207-215) come first
+        const int n_reloc = (p.use_lk && img) ? lk.n_reloc[s] : 0;
+        if (n_reloc > 0) {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const movfe_reloc_seed *rs = lk.reloc + (size_t)s * p.maxT;
+            for (int base = 0; base < n_reloc; base += FIN_WARPS) {
+                const int i = base + warp;
+                bool pass = false;
+                uint32_t d[8];
+                movfe_reloc_seed sd = {0, 0, 0.f, 0.f};
+                int mx = 0, my = 0;
+                if (i < n_reloc) {
+                    sd = rs[i];
+                    mx = (int)__fsub_rn(sd.x, 8.f);  // :218 cv::Rect(float, ...) truncates
+                    my = (int)__fsub_rn(sd.y, 8.f);
+                    if (rect_in_bounds(mx, my, 16, 16, p.W, p.H)) {  // :219
+                        const uint8_t *roi = img + (size_t)my * p.P + mx;
+                        express_mask(roi, p.P, 16, 16, express_band(roi, p.P, 16, 16, p.thr), 1, false, d, lane);  // :221-223
+                        pass = true;
+                    }
+                }
+                if (lane == 0) lat_flag[warp] = pass;
+                __syncthreads();
+                int before = 0, tot = 0;
+                for (int w = 0; w < FIN_WARPS; w++) {
+                    before += w < warp ? lat_flag[w] : 0;
+                    tot += lat_flag[w];
+                }
+                if (pass && n_out + before < p.maxT && lane == 0) {
+                    movfe_track t;
+                    t.pt_x = sd.x;
+                    t.pt_y = sd.y;
+                    t.mb = {(int16_t)mx, (int16_t)my, 16, 16};
+                    t.track_id = sd.track_id;
+                    t.age = 0;
+                    t.q_indx = sd.q_indx;
+                    t.flags = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) t.desc[k] = d[k];
+                    cur[n_out + before] = t;
+                }
+                n_out += tot;
+                __syncthreads();
+            }
+            rekey_all = true;
+        }
         // survivors in sorted order (:254-334): a thread owns FIN_IPT consecutive ranks, so one block scan orders a round
         for (int base = 0; base < n_prev; base += FIN_THREADS * FIN_IPT) {
             const int i0 = base + threadIdx.x * FIN_IPT;
@@ -1075,6 +1142,57 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                 }
             }
             n_out += tot;
+        }
+        // coverage tracks (:337-377): the i-th coverage track in sorted order owns LK result i; carried ones follow the
+        // propagated survivors, keep block and descriptor, age + 1, coverage flag, qIndx = i
+        {
+            const uint16_t *ord = order + (size_t)s * p.maxT;
+            int cov_seen = 0;
+            for (int base = 0; base < n_prev; base += FIN_THREADS * FIN_IPT) {
+                const int i0 = base + threadIdx.x * FIN_IPT;
+                unsigned covm = 0;
+#pragma unroll
+                for (int e = 0; e < FIN_IPT; e++)
+                    if (i0 + e < n_prev && (ci[i0 + e].y & 4)) covm |= 1u << e;
+                if (!__syncthreads_or(covm != 0)) continue;  // block-uniform: no coverage track in this round
+                int tot;
+                const int k0 = cov_seen + block_excl_scan(__popc(covm), wsum, tot);
+                cov_seen += tot;
+                if (lk_n < 0) continue;  // block-uniform: nothing installed, the tracks are dropped (counted below)
+                unsigned okm = 0;
+#pragma unroll
+                for (int e = 0; e < FIN_IPT; e++) {
+                    if ((covm >> e) & 1u) {
+                        const int k = k0 + __popc(covm & ((1u << e) - 1u));
+                        if (k < lk_n && lk_st[k]) {
+                            const float2 q = lk_pt[k];
+                            if (!(q.x < 0.f || q.y < 0.f || q.x >= (float)p.W || q.y >= (float)p.H)) okm |= 1u << e;  // :354
+                        }
+                    }
+                }
+                int tot2;
+                int pos = n_out + block_excl_scan(__popc(okm), wsum, tot2);
+#pragma unroll
+                for (int e = 0; e < FIN_IPT; e++) {
+                    if ((okm >> e) & 1u) {
+                        if (pos < p.maxT) {
+                            const int k = k0 + __popc(covm & ((1u << e) - 1u));
+                            const uint4 *src = reinterpret_cast<const uint4 *>(prev + ord[i0 + e]);
+                            const uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3];
+                            const float2 q = lk_pt[k];
+                            uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
+                            dst[0] = make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), r0.z, r0.w);
+                            dst[1] = make_uint4(r1.x, r1.y + 1, (uint32_t)k, MOVFE_TRACK_COVERAGE);
+                            dst[2] = r2;
+                            dst[3] = r3;
+                        }
+                        pos++;
+                    }
+                }
+                if (tot2) rekey_all = true;
+                n_out += tot2;
+            }
+            if (lk_n < 0) n_dropped += cov_seen;
         }
         // births in kps order (:379-416)
         int mov_cnt = 0;
@@ -1125,14 +1243,55 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
         if (img && (cov[s * p.n_in + p.fi] < p.cov_thr || mov_cnt < 60))
             lattice_pass(p, img, g, true, MOVFE_TRACK_COVERAGE, cur, n_out, id, scratch, lat_flag);
     } else if (n_prev == 0 && img) {
-        // I frame without previous features: seeding on the 16-px lattice (:123-157). With previous features the
-        // reference carries them by LK (:81-120) — host work, dropped here.
+        // I frame without previous features: seeding on the 16-px lattice (:123-157)
         lattice_pass(p, img, g, false, 0u, cur, n_out, id, scratch, lat_flag);
+    } else if (n_prev > 0) {
+        // I frame with previous features (:81-120): every track of the previous table, in TABLE order, is carried to its LK
+        // position with block and descriptor kept, age + 1, qIndx = its index; no seeding happens
+        if (lk_n >= 0) {
+            for (int base = 0; base < n_prev; base += FIN_THREADS * FIN_IPT) {
+                const int i0 = base + threadIdx.x * FIN_IPT;
+                unsigned okm = 0;
+#pragma unroll
+                for (int e = 0; e < FIN_IPT; e++) {
+                    const int i = i0 + e;
+                    if (i < n_prev && i < lk_n && lk_st[i]) {
+                        const float2 q = lk_pt[i];
+                        if (!(q.x < 0.f || q.y < 0.f || q.x >= (float)p.W || q.y >= (float)p.H)) okm |= 1u << e;  // :98
+                    }
+                }
+                int tot;
+                int pos = n_out + block_excl_scan(__popc(okm), wsum, tot);
+#pragma unroll
+                for (int e = 0; e < FIN_IPT; e++) {
+                    if ((okm >> e) & 1u) {
+                        if (pos < p.maxT) {
+                            const int i = i0 + e;
+                            const uint4 *src = reinterpret_cast<const uint4 *>(prev + i);
+                            const uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3];
+                            const float2 q = lk_pt[i];
+                            uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
+                            dst[0] = make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), r0.z, r0.w);
+                            dst[1] = make_uint4(r1.x, r1.y + 1, (uint32_t)i, 0u);
+                            dst[2] = r2;
+                            dst[3] = r3;
+                        }
+                        pos++;
+                    }
+                }
+                n_out += tot;
+            }
+            rekey_all = true;
+        } else {
+            n_dropped += n_prev;
+        }
     }
+    if (rekey_all) n_keyed = 0;
     const int n_new = min(n_out, p.maxT);
     if (threadIdx.x == 0) {
         ntracks[s * p.TSLOTS + p.tslot_cur] = n_new;
         cur_id[s * p.TSLOTS + p.tslot_cur] = id;
+        if (n_dropped) atomicAdd(lk.dropped, (unsigned long long)n_dropped);  // diagnostic counter, not on the data path
     }
     __syncthreads();  // cur[] and the shared age / popcount arrays are visible to the whole CTA
     for (int i = n_keyed + threadIdx.x; i < n_new; i += blockDim.x) {  // lattice entries were written outside the fused copies
@@ -1170,6 +1329,7 @@ struct ExtScratch {
     uint8_t *birth_flag;
     uint32_t *birth_desc;
     uint16_t *order;
+    LkBuf lk;
 };
 
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -1192,6 +1352,18 @@ ExtScratch carve(const movfe_ctx *ctx, size_t *total) {
     off += align256(S * (size_t)ctx->max_kps * 32);
     e.order = (uint16_t *)(base + off);
     off += align256(S * c.max_tracks * sizeof(uint16_t));
+    e.lk.n = (int32_t *)(base + off);
+    off += align256(S * sizeof(int32_t));
+    e.lk.n_reloc = (int32_t *)(base + off);
+    off += align256(S * sizeof(int32_t));
+    e.lk.dropped = (unsigned long long *)(base + off);
+    off += 256;
+    e.lk.status = (uint8_t *)(base + off);
+    off += align256(S * (size_t)c.max_tracks);
+    e.lk.pts = (float2 *)(base + off);
+    off += align256(S * (size_t)c.max_tracks * sizeof(float2));
+    e.lk.reloc = (movfe_reloc_seed *)(base + off);
+    off += align256(S * (size_t)c.max_tracks * sizeof(movfe_reloc_seed));
     if (total) *total = off;
     return e;
 }
@@ -1224,6 +1396,17 @@ int movfe_extract_init(movfe_ctx *ctx) {
     const size_t n = (size_t)c.n_streams * ctx->max_kps;
     fill_i32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(e.claim, n, 0x7fffffff);
     MOVFE_CUDA(ctx, cudaMemsetAsync(e.order, 0, (size_t)c.n_streams * c.max_tracks * sizeof(uint16_t), ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemsetAsync(e.lk.n, 0xff, (size_t)c.n_streams * sizeof(int32_t), ctx->stream));  // -1: nothing installed
+    MOVFE_CUDA(ctx, cudaMemsetAsync(e.lk.n_reloc, 0, (size_t)c.n_streams * sizeof(int32_t), ctx->stream));
+    MOVFE_CUDA(ctx, cudaMemsetAsync(e.lk.dropped, 0, sizeof(unsigned long long), ctx->stream));
+    // the attributes are per function and process-wide: set once to the device limit, never per launch (contexts on other
+    // host threads launch the same kernels)
+    int dev = 0, optin = 0;
+    MOVFE_CUDA(ctx, cudaGetDevice(&dev));
+    MOVFE_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if ((int)sort_smem(c.max_tracks) > optin) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "max_tracks=%d needs %zu bytes of shared memory, the device has %d", c.max_tracks, sort_smem(c.max_tracks), optin);
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    MOVFE_CUDA(ctx, cudaFuncSetAttribute(sort_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
@@ -1235,8 +1418,6 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
     for (const auto &pl : ctx->pose_launches)
         if (pl.first >= 0 && pl.first <= first_frame + n_frames - 1 - ctx->TSLOTS)
             MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl.done, 0));
-    // the attribute is per function, not per context: set it for THIS context's table size before launching
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
     // the raster results of this window were produced on the raster stream
     RasterBuf &w = ctx->rb[ctx->rb_cur];
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, w.done, 0));
@@ -1274,6 +1455,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.tslot_cur = tslot_of(ctx, a);
         p.thr = c.express_threshold;
         p.has_grey = c.has_grey;
+        p.use_lk = (k == 0 && ctx->lk_pending) ? 1 : 0;
         p.P = ctx->grey_pitch;
         p.cov_thr = c.coverage_threshold;
         const bool batch_end = !pdl_cand || (k + 1) % ctx->ev_batch == 0 || k == n_frames - 1;
@@ -1309,12 +1491,21 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         }
         MOVFE_CUDA(ctx, launch_pdl(pdl, finalize_kernel, dim3(ns), dim3(FIN_THREADS), sort_smem(c.max_tracks), gs, p, ctx->d_tracks,
                                    ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, w.d_kps, w.d_nkps, w.d_cov,
-                                   e.birth_flag, e.birth_desc, w.d_grid, ctx->d_grey, ctx->d_fflags));
+                                   e.birth_flag, e.birth_desc, w.d_grid, ctx->d_grey, ctx->d_fflags, e.lk));
         prof.launches(nl);
         // the tables up to frame a are complete for this group: the pose stream may start on them while propagation goes on.
         // One event per ev_batch frames (and at the end of the call): an event record between two kernels breaks their
         // programmatic dependency.
         if (batch_end) MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_frame[(size_t)g * c.window_frames + a % c.window_frames], gs));
+        }
+        if (p.use_lk) {  // the results belonged to this frame only (every group has consumed them once the groups join)
+            for (int g = 1; g < G; g++) {
+                MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_join[g], ctx->ext_stream[g]));
+                MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[g], 0));
+            }
+            MOVFE_CUDA(ctx, cudaMemsetAsync(e.lk.n, 0xff, (size_t)c.n_streams * sizeof(int32_t), ctx->stream));
+            MOVFE_CUDA(ctx, cudaMemsetAsync(e.lk.n_reloc, 0, (size_t)c.n_streams * sizeof(int32_t), ctx->stream));
+            ctx->lk_pending = false;
         }
     }
     // join: whatever follows on the primary stream sees every group's tables
@@ -1346,6 +1537,11 @@ extern "C" int movfe_set_tracks(movfe_ctx *ctx, int stream, const movfe_track *t
     const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
     const int ts = tslot_of(ctx, next - 1);
     const int T = ctx->TSLOTS;
+    // a pose chain still running on the pose stream may be reading the table of frame next-1 (or the frame that shares
+    // its slot): the copy below waits for every pose launch covering either
+    for (const auto &pl : ctx->pose_launches)
+        if (pl.first >= 0 && ((pl.first <= next - 1 && next - 1 < pl.first + pl.n) || (pl.first <= next - 1 - T && next - 1 - T < pl.first + pl.n)))
+            MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl.done, 0));
     if (n > 0)
         MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_tracks + ((size_t)stream * T + ts) * c.max_tracks, tracks, (size_t)n * sizeof(movfe_track),
                                         cudaMemcpyHostToDevice, ctx->stream));
@@ -1354,7 +1550,6 @@ extern "C" int movfe_set_tracks(movfe_ctx *ctx, int stream, const movfe_track *t
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_cur_id + stream * T + ts, &current_id, 4, cudaMemcpyHostToDevice, ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // nn / current_id live on this stack frame
     ExtScratch e = carve(ctx, nullptr);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(sort_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(c.max_tracks)));
     sort_only_kernel<<<1, FIN_THREADS, sort_smem(c.max_tracks), ctx->stream>>>(c.max_tracks, T, ts, stream, ctx->d_tracks,
                                                                               ctx->d_ntracks, e.order);
     MOVFE_CUDA(ctx, cudaGetLastError());
@@ -1370,6 +1565,11 @@ extern "C" int movfe_extract(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     if (n_frames < 1 || w.first < 0 || first_frame < w.first || first_frame + n_frames > w.first + w.nout)
         MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract: frames [%lld,%lld) are not inside the last raster window", (long long)first_frame,
                    (long long)(first_frame + n_frames));
+    // the grey planes and frame flags of these frames must still be in the ring (a later push may have overwritten them:
+    // push(k), raster(k), push(k+1), push(k+2), extract(k) passes every other check)
+    if (ctx->pushed - first_frame > ctx->RING)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract: frame %lld has left the ring (pushed=%lld, ring=%d)", (long long)first_frame,
+                   (long long)ctx->pushed, ctx->RING);
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     int rc = movfe_extract_launch(ctx, first_frame, n_frames);
     if (rc) return rc;
@@ -1382,7 +1582,7 @@ static int track_slot(movfe_ctx *ctx, int stream, int64_t frame, int *ts) {
     if (!ctx) return MOVFE_E_INVALID;
     if (stream < 0 || stream >= ctx->cfg.n_streams) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "stream %d out of range", stream);
     const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
-    if (frame >= next || frame < next - 1 - ctx->cfg.window_frames)
+    if (frame >= next || frame < next - ctx->TSLOTS)  // TSLOTS = 2F+1 tables per stream are resident (two windows + the seed)
         MOVFE_FAIL(ctx, MOVFE_E_STATE, "track table of frame %lld is not resident", (long long)frame);
     *ts = tslot_of(ctx, frame);
     return MOVFE_OK;
@@ -1415,16 +1615,54 @@ extern "C" int movfe_download_tracks(movfe_ctx *ctx, int stream, int64_t frame, 
     return n;
 }
 
+extern "C" int movfe_set_lk_results(movfe_ctx *ctx, int stream, const uint8_t *status, const float *pts_xy, int n,
+                                    const movfe_reloc_seed *reloc, int n_reloc) {
+    if (!ctx) return MOVFE_E_INVALID;
+    const movfe_config &c = ctx->cfg;
+    if (stream < 0 || stream >= c.n_streams || n < -1 || n_reloc < 0 || (n > 0 && (!status || !pts_xy)) || (n_reloc > 0 && !reloc))
+        MOVFE_FAIL(ctx, MOVFE_E_INVALID, "set_lk_results: bad argument");
+    if (n > c.max_tracks || n_reloc > c.max_tracks)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "set_lk_results: %d results / %d seeds, capacity %d", n, n_reloc, c.max_tracks);
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    ExtScratch e = carve(ctx, nullptr);
+    cudaStream_t st = ctx->stream;
+    if (n > 0) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(e.lk.status + (size_t)stream * c.max_tracks, status, (size_t)n, cudaMemcpyHostToDevice, st));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(e.lk.pts + (size_t)stream * c.max_tracks, pts_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+    }
+    if (n_reloc > 0)
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(e.lk.reloc + (size_t)stream * c.max_tracks, reloc, (size_t)n_reloc * sizeof(movfe_reloc_seed),
+                                        cudaMemcpyHostToDevice, st));
+    const int32_t nn = n, nr = n_reloc;
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(e.lk.n + stream, &nn, 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(e.lk.n_reloc + stream, &nr, 4, cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // the arrays are the caller's, nn / nr live on this stack frame
+    ctx->lk_pending = true;
+    return MOVFE_OK;
+}
+
+extern "C" int64_t movfe_dropped_lk_tracks(movfe_ctx *ctx) {
+    if (!ctx) return -1;
+    ExtScratch e = carve(ctx, nullptr);
+    unsigned long long v = 0;
+    if (cudaMemcpyAsync(&v, e.lk.dropped, sizeof v, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    return (int64_t)v;
+}
+
 // Single-shot MOVExtractor::operator() for callers that hold one frame's raster results on the host (the drop-in shim
 // when only MOVExtractor is replaced; the parity tests of propagation in isolation). One-stream contexts only; every call
 // is one new frame, so it must not be mixed with the batched push / raster / extract calls on the same context.
 int movfe_grey_upload(movfe_ctx *ctx, const uint8_t *d_src, int slot);  // raster.cu
 
-extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const uint8_t *grey, const int32_t *grid,
+extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const uint8_t *grey, int grey_stride, const int32_t *grid,
                                    const movfe_hop *hops, int n_hops, const movfe_rect *kps, int n_kps, double coverage_area,
-                                   const movfe_track *prev, int n_prev, int32_t *current_id, movfe_track *out, int capacity) {
+                                   const movfe_track *prev, int n_prev, const uint8_t *lk_status, const float *lk_pts, int n_lk,
+                                   const movfe_reloc_seed *reloc, int n_reloc, int32_t *current_id, movfe_track *out, int capacity) {
     if (!ctx) return MOVFE_E_INVALID;
     const movfe_config &c = ctx->cfg;
+    if (grey && grey_stride == 0) grey_stride = c.width;
+    if (grey && grey_stride < c.width) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "extract_frame: grey_stride %d below the frame width %d", grey_stride, c.width);
     if (c.n_streams != 1) MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract_frame: the context must have exactly one stream");
     if (!grid || !current_id || !out || n_hops < 0 || n_kps < 0 || n_prev < 0 || (n_hops && !hops) || (n_kps && !kps) || (n_prev && !prev))
         MOVFE_FAIL(ctx, MOVFE_E_INVALID, "extract_frame: bad argument");
@@ -1437,6 +1675,10 @@ extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const u
     MOVFE_CUDA(ctx, cudaSetDevice(c.device));
     int rc = movfe_set_tracks(ctx, 0, prev, n_prev, *current_id);
     if (rc) return rc;
+    if (n_lk >= 0 || n_reloc > 0) {
+        rc = movfe_set_lk_results(ctx, 0, lk_status, lk_pts, n_lk, reloc, n_reloc);
+        if (rc) return rc;
+    }
     const int64_t a = ctx->pushed;
     const int slot = (int)(a % ctx->RING);
     const size_t plane = (size_t)c.width * c.height;
@@ -1460,7 +1702,9 @@ extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const u
             MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_stage[0], plane + 4096));
             ctx->stage_bytes[0] = plane + 4096;
         }
-        MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage[0], grey, plane, cudaMemcpyHostToDevice, st));
+        // rows of `grey_stride` bytes (cv::Mat::step / AVFrame::linesize) are packed by the copy itself
+        MOVFE_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_stage[0], (size_t)c.width, grey, (size_t)grey_stride, (size_t)c.width, (size_t)c.height,
+                                          cudaMemcpyHostToDevice, st));
         rc = movfe_grey_upload(ctx, (const uint8_t *)ctx->d_stage[0], slot);
         if (rc) return rc;
     }

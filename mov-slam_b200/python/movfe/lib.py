@@ -57,7 +57,10 @@ def load():
     L.movfe_rejected_records.argtypes = [vp]
     L.movfe_set_tracks.argtypes = [vp, i32, vp, i32, i32]
     L.movfe_extract.argtypes = [vp, i64, i32]
-    L.movfe_extract_frame.argtypes = [vp, C.c_uint32, vp, vp, vp, i32, vp, i32, C.c_double, vp, i32, vp, vp, i32]
+    L.movfe_extract_frame.argtypes = [vp, C.c_uint32, vp, i32, vp, vp, i32, vp, i32, C.c_double, vp, i32, vp, vp, i32, vp, i32, vp, vp, i32]
+    L.movfe_set_lk_results.argtypes = [vp, i32, vp, vp, i32, vp, i32]
+    L.movfe_dropped_lk_tracks.restype = i64
+    L.movfe_dropped_lk_tracks.argtypes = [vp]
     L.movfe_track_count.argtypes = [vp, i32, i64, vp, vp]
     L.movfe_download_tracks.argtypes = [vp, i32, i64, vp, i32]
     L.movfe_set_camera.argtypes = [vp, vp, vp, C.c_float]
@@ -81,7 +84,7 @@ def load():
 EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchronize", "movfe_fence", "movfe_cuda_stream",
            "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_frames_pushed", "movfe_raster",
            "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
-           "movfe_rejected_records", "movfe_set_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
+           "movfe_rejected_records", "movfe_set_tracks", "movfe_set_lk_results", "movfe_dropped_lk_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
@@ -204,18 +207,44 @@ class Context:
     def extract(self, first_frame, n_frames):
         self._ck(self.L.movfe_extract(self.h, first_frame, n_frames))
 
-    def extract_frame(self, frame_flags, grey, grid, hops, kps, coverage_area, prev, current_id):
-        """Single-shot MOVExtractor::operator() on host raster results -> (tracks, current_id)."""
+    def set_lk_results(self, stream, status=None, pts_xy=None, reloc=None):
+        """Host LK results for the next frame propagated on `stream` (see movfe.h). status None: n = -1 (none)."""
+        n = -1
+        if status is not None:
+            status = np.ascontiguousarray(status, np.uint8)
+            pts_xy = np.ascontiguousarray(pts_xy, np.float32).reshape(-1, 2)
+            n = len(status)
+        reloc = None if reloc is None else np.ascontiguousarray(reloc, T.RELOC_SEED)
+        self._ck(self.L.movfe_set_lk_results(self.h, stream, _p(status), _p(pts_xy), n, _p(reloc), 0 if reloc is None else len(reloc)))
+
+    def dropped_lk_tracks(self):
+        return self.L.movfe_dropped_lk_tracks(self.h)
+
+    def extract_frame(self, frame_flags, grey, grid, hops, kps, coverage_area, prev, current_id, lk_status=None, lk_pts=None,
+                      reloc=None):
+        """Single-shot MOVExtractor::operator() on host raster results -> (tracks, current_id). grey may be a strided view
+        (rows of grey.strides[0] bytes, as a cv::Mat ROI / AVFrame plane)."""
         grid = np.ascontiguousarray(grid, np.int32)
         hops = np.ascontiguousarray(hops, T.HOP)
         kps = np.ascontiguousarray(kps, T.RECT)
         prev = np.ascontiguousarray(prev, T.TRACK)
+        stride = 0
         if grey is not None:
-            grey = np.ascontiguousarray(grey, np.uint8)
+            grey = np.asarray(grey, np.uint8)
+            if grey.ndim != 2 or grey.strides[1] != 1:
+                grey = np.ascontiguousarray(grey)
+            stride = grey.strides[0] if grey.ndim == 2 else 0
+        n_lk = -1
+        if lk_status is not None:
+            lk_status = np.ascontiguousarray(lk_status, np.uint8)
+            lk_pts = np.ascontiguousarray(lk_pts, np.float32).reshape(-1, 2)
+            n_lk = len(lk_status)
+        reloc = None if reloc is None else np.ascontiguousarray(reloc, T.RELOC_SEED)
         cid = C.c_int32(current_id)
         out = np.zeros(self.cfg.max_tracks, T.TRACK)
-        n = self._ck(self.L.movfe_extract_frame(self.h, int(frame_flags), _p(grey), _p(grid), _p(hops), len(hops), _p(kps), len(kps),
-                                                float(coverage_area), _p(prev), len(prev), C.byref(cid), _p(out), len(out)))
+        n = self._ck(self.L.movfe_extract_frame(self.h, int(frame_flags), _p(grey), stride, _p(grid), _p(hops), len(hops), _p(kps), len(kps),
+                                                float(coverage_area), _p(prev), len(prev), _p(lk_status), _p(lk_pts), n_lk, _p(reloc),
+                                                0 if reloc is None else len(reloc), C.byref(cid), _p(out), len(out)))
         return out[:n], cid.value
 
     def track_count(self, stream, frame):

@@ -22,6 +22,8 @@ POSE_PARAMS = np.dtype([("is_lost", "<i4"), ("iteration_count", "<i4"), ("reproj
                         ("reprojection_error_lost", "<f8"), ("confidence", "<f8"), ("algorithm", "<i4"),
                         ("_pad", "<i4")])
 
+RELOC_SEED = np.dtype([("track_id", "<i4"), ("q_indx", "<i4"), ("x", "<f4"), ("y", "<f4")])
+assert RELOC_SEED.itemsize == 16
 assert MV_RECORD.itemsize == 40 and HOP.itemsize == 16 and RECT.itemsize == 8 and TRACK.itemsize == 64
 assert MAP_POINT.itemsize == 40 and PROJECTION.itemsize == 20 and CAMERA.itemsize == 36
 assert POSE.itemsize == 96 and POSE_PARAMS.itemsize == 40

@@ -21,6 +21,12 @@ movfe_ctx *extractor_context(int width, int height, int threshold, double covera
 movfe_ctx *operator_context();  // joins / frustum / pose: geometry-only, no frame buffers
 void fail(movfe_ctx *ctx, const char *what);  // prints movfe_last_error to stderr like the reference's cerr paths
 
+// Test hook: when set, replaces cv::calcOpticalFlowPyrLK at the three call sites of MOVExtractor::operator() (outside the
+// MoV-SLAM tree there is no OpenCV; without a hook every carried point counts as lost).
+typedef void (*lk_fn)(const cv::Mat &prev_img, const cv::Mat &next_img, const std::vector<cv::Point2f> &pts,
+                      std::vector<cv::Point2f> &out, std::vector<unsigned char> &status);
+extern lk_fn lk_override;
+
 movfe_track pack(const MOV_SLAM::VideoFeature &vf);
 MOV_SLAM::VideoFeature unpack(const movfe_track &t, int index);
 movfe_camera pack(MOV_SLAM::GeometricCamera *cam);
@@ -37,6 +43,7 @@ public:
     bool push(const std::shared_ptr<MOV_SLAM::MotionVectorImage> &img, const void *side_data, int n_records, bool mv);
     // next frame whose raster is final, or nullptr; flush = true at end of stream (no more look-ahead will come)
     std::shared_ptr<MOV_SLAM::MotionVectorImage> pop(bool flush = false);
+    int pending() const;  // frames pushed and not yet popped
 private:
     struct Impl;
     Impl *d;

@@ -131,7 +131,7 @@ RasterQueue::~RasterQueue() {
 bool RasterQueue::push(const std::shared_ptr<MOV_SLAM::MotionVectorImage> &img, const void *side_data, int n_records, bool mv) {
     if (!d->ctx) return false;
     const int64_t off[2] = {0, n_records};
-    uint8_t flags = (img->ft == MOV_SLAM::P_FRAME ? MOVFE_FRAME_P : 0u) | (mv && n_records > 0 ? MOVFE_FRAME_MV : 0u);
+    uint8_t flags = (img->ft == MOV_SLAM::FrameType::P_FRAME ? MOVFE_FRAME_P : 0u) | (mv && n_records > 0 ? MOVFE_FRAME_MV : 0u);
     if (getenv("MOVFE_SHIM_DEBUG") && n_records > 0) {
         const movfe_mv_record *r = (const movfe_mv_record *)side_data;
         fprintf(stderr, "shim push: n=%d flags=%u first rec: src=%d w=%d h=%d s=(%d,%d) d=(%d,%d) ref=%d\n", n_records, flags, r->source, r->w, r->h,
@@ -149,6 +149,8 @@ bool RasterQueue::push(const std::shared_ptr<MOV_SLAM::MotionVectorImage> &img, 
     d->pushed++;
     return true;
 }
+
+int RasterQueue::pending() const { return (int)d->pending.size(); }
 
 std::shared_ptr<MOV_SLAM::MotionVectorImage> RasterQueue::pop(bool flush) {
     if (!d->ctx || d->pending.empty()) return nullptr;

@@ -11,6 +11,11 @@
 #include <memory>
 #include <vector>
 
+// OpenCV's type codes for the three element types the front-end uses
+#define CV_8UC1 0
+#define CV_8UC3 16
+#define CV_32SC4 28
+
 namespace cv {
 struct Point2f {
     float x = 0, y = 0;
@@ -35,7 +40,10 @@ public:
     size_t step = 0;  // bytes per row
     unsigned char *data = nullptr;
     Mat() {}
-    Mat(int r, int c, int elem_bytes) : rows(r), cols(c), step((size_t)c * elem_bytes), buf(new std::vector<unsigned char>((size_t)r * c * elem_bytes)) {
+    Mat(int r, int c, int type) : rows(r), cols(c) {
+        const size_t elem_bytes = type == CV_32SC4 ? 16 : type == CV_8UC3 ? 3 : 1;
+        step = (size_t)c * elem_bytes;
+        buf.reset(new std::vector<unsigned char>((size_t)r * step));
         data = buf->data();
     }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
@@ -81,7 +89,7 @@ using std::map;
 using std::shared_ptr;
 using std::vector;
 
-enum FrameType { I_FRAME, P_FRAME };  // include/Frame.h:49-53
+enum class FrameType { I_FRAME, P_FRAME };  // include/Frame.h:49-53
 
 struct MotionVector {  // include/Frame.h:55-77
     int indx = -1;
@@ -106,10 +114,10 @@ struct VideoImage {  // include/Frame.h:109-156
     cv::Mat imGray, imRGB, mvi;
     vector<cv::Rect> kps;
     vector<MotionVector> mvs;
-    FrameType ft = I_FRAME;
+    FrameType ft = FrameType::I_FRAME;
     double coverageArea = 0.0;
     int frame = 0;
-    VideoImage(int width, int height) : mvi(height, width, 16) { std::memset(mvi.data, 0xff, (size_t)width * height * 16); }
+    VideoImage(int width, int height) : mvi(height, width, CV_32SC4) { std::memset(mvi.data, 0xff, (size_t)width * height * 16); }
 };
 typedef VideoImage MotionVectorImage;
 
@@ -132,6 +140,7 @@ public:
     bool isBad() { return mbBad; }
     int mTrackId = -1;
     bool mbTrackInView = false;
+    float mTrackProjX = 0.f, mTrackProjY = 0.f;
     float mTrackDepth = 0.f;
     Eigen::Vector3f mWorldPos;
     bool mbBad = false;
@@ -141,6 +150,7 @@ class KeyFrame {
 public:
     vector<MapPoint *> GetMapPointMatches() { return mvpMapPoints; }
     vector<MapPoint *> mvpMapPoints;
+    cv::Mat mImage;
 };
 
 class Frame {  // include/Frame.h:158-466 (members the shims touch)
@@ -154,6 +164,9 @@ public:
     vector<bool> mvbOutlier;
     GeometricCamera *mpCamera = nullptr;
     bool mLost = false;
+    KeyFrame *mpReferenceKF = nullptr;
+    cv::Mat imgLeft;
+    int imageCols = 0, imageRows = 0;
     void SetPose(const Sophus::SE3<float> &Tcw) { mTcw = Tcw; }
     Sophus::SE3<float> GetPose() const { return mTcw; }
 private:

@@ -1,7 +1,10 @@
 // test_shim.cc — drives the drop-in shims the way Tracking.cc / the example mains drive the reference classes
 // (mono_video_tartan.cc:74 NextImage -> Frame.cc:390-393 MOVExtractor -> Tracking.cc:804-811 SearchByVideoFeature +
 // PoseOptimization) on inputs written by tests/test_shim.py, and dumps the results for comparison with the oracle.
-// Built against the stand-in headers; links libmovfe.so. usage: test_shim <dir>
+// The frames come out of the VideoDecoder shim (VideoDecoder_movfe.cc) running on the fake libav back-end
+// (standin/fake_libav.cc): demux / decode are faked, the side data takes the GPU raster path. cv::calcOpticalFlowPyrLK is
+// replaced by a deterministic hook that tests/test_shim.py mirrors, so the LK hand-over (I-frame carry-over, coverage
+// tracks) is exercised end to end. Built against the stand-in headers; links libmovfe.so. usage: test_shim <dir>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -9,7 +12,19 @@
 
 #include "MOVExtractor_movfe.h"
 #include "MOVMatcher_movfe.h"
+#include "VideoDecoder_movfe.h"
 #include "movfe_shim.h"
+
+// deterministic stand-in for cv::calcOpticalFlowPyrLK (mirrored by tests/test_shim.py::pseudo_lk)
+static void pseudo_lk(const cv::Mat &, const cv::Mat &, const std::vector<cv::Point2f> &pts, std::vector<cv::Point2f> &out,
+                      std::vector<unsigned char> &status) {
+    out.resize(pts.size());
+    status.resize(pts.size());
+    for (size_t i = 0; i < pts.size(); i++) {
+        out[i] = cv::Point2f(pts[i].x + 0.5f, pts[i].y - 0.25f);
+        status[i] = (((int)pts[i].x * 7 + (int)pts[i].y * 3) % 5) != 0;
+    }
+}
 
 namespace MOV_SLAM {
 class Optimizer {
@@ -43,8 +58,10 @@ static void dump(const std::string &path, const std::vector<T> &v) {
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
     const std::string dir = argv[1];
-    const std::vector<int32_t> meta = slurp<int32_t>(dir + "/meta.bin");  // W H NF max_ref threshold n_map n_kf
+    const std::vector<int32_t> meta = slurp<int32_t>(dir + "/meta.bin");  // W H NF max_ref threshold n_map n_kf [cov_thr permille]
     const int W = meta[0], H = meta[1], NF = meta[2], K = meta[3], thr = meta[4], n_map = meta[5], n_kf = meta[6];
+    const double cov_thr = meta.size() > 7 ? meta[7] / 1000.0 : 0.20;
+    movfe_shim::lk_override = pseudo_lk;
     const std::vector<movfe_mv_record> recs = slurp<movfe_mv_record>(dir + "/recs.bin");
     const std::vector<int64_t> off = slurp<int64_t>(dir + "/off.bin");
     const std::vector<uint8_t> flags = slurp<uint8_t>(dir + "/flags.bin");
@@ -53,9 +70,23 @@ int main(int argc, char **argv) {
     const std::vector<double> pose0 = slurp<double>(dir + "/pose0.bin");  // R(9) t(3)
     const std::vector<float> camp = slurp<float>(dir + "/cam.bin");       // fx fy cx cy
 
-    // --- decoder side: RasterQueue stands where VideoDecoder::NextImage's MV loop was ---------------------------------
-    movfe_shim::RasterQueue rq(W, H, K);
-    MOVExtractor extractor(thr, 0.20, 0.25);
+    // --- decoder side: the VideoDecoder shim on the fake libav back-end (qlen = K + 2: the reference's 12 for K = 10) -------
+    std::vector<uint8_t> is_p(NF);
+    std::vector<const uint8_t *> luma(NF), side(NF, nullptr);
+    std::vector<int> side_bytes(NF, 0);
+    for (int f = 0; f < NF; f++) {
+        is_p[f] = (flags[f] & MOVFE_FRAME_P) ? 1 : 0;
+        luma[f] = &grey[(size_t)f * W * H];
+        if ((flags[f] & MOVFE_FRAME_MV) && off[f + 1] > off[f]) {
+            side[f] = reinterpret_cast<const uint8_t *>(&recs[off[f]]);
+            side_bytes[f] = (int)((off[f + 1] - off[f]) * (int64_t)sizeof(movfe_mv_record));
+        }
+    }
+    fake_av_clip fc = {W, H, NF, is_p.data(), luma.data(), side.data(), side_bytes.data()};
+    fake_av_install(&fc);
+    VideoDecoder decoder("fake://clip", K + 2);
+    if (!decoder.Init() || decoder.GetWidth() != W || decoder.GetHeight() != H) return 3;
+    MOVExtractor extractor(thr, cov_thr, 0.25);
     GeometricCamera cam(std::vector<float>(camp.begin(), camp.end()), GeometricCamera::CAM_PINHOLE);
     std::vector<MapPoint> points(n_map);
     std::vector<MapPoint *> local;
@@ -82,8 +113,25 @@ int main(int argc, char **argv) {
         // Frame ctor -> ExtractMOV (Frame.cc:390-393)
         auto F = std::make_shared<Frame>();
         F->mpCamera = &cam;
+        F->imgLeft = img->imGray;  // Frame.cc:121
+        F->imageCols = W;
+        F->imageRows = H;
+        {   // what the decoder shim delivered: hop list, kps, slot grid, coverage
+            std::vector<movfe_hop> hv;
+            for (const auto &m : img->mvs) hv.push_back({m.pt.x, m.pt.y, m.dIndx, 0});
+            std::vector<movfe_rect> kv;
+            for (const auto &r : img->kps) kv.push_back({(int16_t)r.x, (int16_t)r.y, (int16_t)r.width, (int16_t)r.height});
+            dump(dir + "/out_hops_" + std::to_string(produced) + ".bin", hv);
+            dump(dir + "/out_kps_" + std::to_string(produced) + ".bin", kv);
+            std::vector<int32_t> gv(reinterpret_cast<const int32_t *>(img->mvi.data), reinterpret_cast<const int32_t *>(img->mvi.data) + (size_t)W * H * 4);
+            dump(dir + "/out_grid_" + std::to_string(produced) + ".bin", gv);
+            dump(dir + "/out_cov_" + std::to_string(produced) + ".bin", std::vector<double>{img->coverageArea, (double)img->frame,
+                                                                                            (double)(img->ft == FrameType::P_FRAME)});
+            dump(dir + "/out_ndesc_" + std::to_string(produced) + ".bin", std::vector<int32_t>{0});
+        }
         const int n = extractor(img, F->mvKeys, F->mvVF, F->mvVFMap, F->mDescriptors, prev);
         F->N = n < 0 ? 0 : n;
+        dump(dir + "/out_ndesc_" + std::to_string(produced) + ".bin", std::vector<int32_t>{(int32_t)F->mDescriptors.size()});
         F->mvKeysUn = F->mvKeys;
         F->mvpMapPoints.assign(F->N, nullptr);
         F->mvbOutlier.assign(F->N, false);
@@ -117,16 +165,8 @@ int main(int argc, char **argv) {
         prev = F.get();
         produced++;
     };
-    for (int f = 0; f < NF; f++) {
-        auto img = std::make_shared<MotionVectorImage>(W, H);
-        img->imGray = cv::Mat(H, W, 1);
-        memcpy(img->imGray.data, &grey[(size_t)f * W * H], (size_t)W * H);
-        img->ft = (flags[f] & MOVFE_FRAME_P) ? P_FRAME : I_FRAME;
-        const int n = (int)(off[f + 1] - off[f]);
-        if (!rq.push(img, n ? &recs[off[f]] : nullptr, n, (flags[f] & MOVFE_FRAME_MV) != 0)) return 3;
-        while (auto done = rq.pop(false)) consume(done);
-    }
-    while (auto done = rq.pop(true)) consume(done);
-    printf("test_shim: %d frames\n", produced);
+    while (auto img = decoder.NextImage(true)) consume(img);
+    printf("test_shim: %d frames, %lld carried tracks dropped for want of LK results\n", produced,
+           (long long)movfe_dropped_lk_tracks(movfe_shim::extractor_context(W, H, thr, cov_thr, true)));
     return produced == NF ? 0 : 4;
 }

@@ -2,7 +2,8 @@
 // CPU restatement of MOVExtractor::operator(), src/MOVExtractor.cc:63-455, for one frame of one stream.
 // cv::calcOpticalFlowPyrLK (:91,:196,:347) is third-party arithmetic that stays on the host: its results
 // enter through lk_status/lk_pts; with NULL every carried feature is dropped. The lost-relocalisation
-// branch (:161-243) only prepends LK-derived features and is not part of the GPU scope.
+// branch (:161-243) prepends features at LK-carried keyframe points: the LK call and the status / bounds /
+// distance tests on its output (:194-215) are the host's, the block + descriptor part (:218-238) is restated here.
 #include "oracle.h"
 
 #include <algorithm>
@@ -39,6 +40,16 @@ extern "C" int orc_extract_frame(int width, int height, uint32_t frame_flags, co
                                  double coverage_area, movfe_track *prev, int n_prev, const uint8_t *lk_status,
                                  const float *lk_pts, const orc_extract_params *params, int32_t *current_id,
                                  movfe_track *out_tracks, int32_t *n_births) {
+    return orc_extract_frame_lost(width, height, frame_flags, grey, grid, hops, kps, n_kps, coverage_area, prev, n_prev, lk_status,
+                                  lk_pts, nullptr, 0, params, current_id, out_tracks, n_births);
+}
+
+extern "C" int orc_extract_frame_lost(int width, int height, uint32_t frame_flags, const uint8_t *grey,
+                                      const int32_t *grid, const movfe_hop *hops, const movfe_rect *kps, int n_kps,
+                                      double coverage_area, movfe_track *prev, int n_prev, const uint8_t *lk_status,
+                                      const float *lk_pts, const movfe_reloc_seed *reloc, int n_reloc,
+                                      const orc_extract_params *params, int32_t *current_id,
+                                      movfe_track *out_tracks, int32_t *n_births) {
     if (!grey) return -1;  // :71-72 imGray.empty()
     const int cols = width, rows = height;
     const int thr = params->threshold;
@@ -92,6 +103,23 @@ extern "C" int orc_extract_frame(int width, int height, uint32_t frame_flags, co
             }
         }
     } else {
+        // Lost relocalisation (:161-243): the seeds already passed status / bounds / distance on the host (:207-215)
+        for (int i = 0; i < n_reloc; i++) {
+            const float x = reloc[i].x, y = reloc[i].y;
+            const int mx = (int)(x - 8), my = (int)(y - 8);  // :218 cv::Rect(float...) truncates
+            if (in_bounds(mx, my, 16, 16, cols, rows)) {      // :219
+                movfe_track vf;
+                orc_express_descriptor(grey, cols, mx, my, 16, 16, thr, vf.desc);  // :221-223
+                vf.pt_x = x;
+                vf.pt_y = y;
+                vf.mb = {(int16_t)mx, (int16_t)my, 16, 16};
+                vf.track_id = reloc[i].track_id;
+                vf.age = 0;
+                vf.q_indx = reloc[i].q_indx;
+                vf.flags = 0;
+                out.push(vf);
+            }
+        }
         // Project forward the previous frame keypoints (:246-335)
         std::vector<int> covFeat;  // indices (in sorted order) of coverage features
         if (n_prev > 0) {

@@ -62,9 +62,11 @@ typedef struct orc_extract_params {
 /* prev: previous frame's table, n_prev entries; it is stably sorted in place exactly as the reference
  * sorts prev->mvVF (MOVExtractor.cc:249-252, canonicalised to a stable sort).
  * grid/hops/kps/n_kps/coverage_area: this frame's raster outputs. grey: H*W uint8 (stride = width).
- * lk_status/lk_pts: optional results of the host LK step for the carried ("coverage" / I-frame) features,
- *   one entry per carried feature in sorted order; NULL means every carried feature is dropped
- *   (cv::calcOpticalFlowPyrLK stays on the host).
+ * lk_status/lk_pts: optional results of the host LK step for the carried features: on a P frame one entry per
+ *   coverage feature of prev in sorted order (:337-377), on an I frame one entry per feature of prev in table order
+ *   (:81-120); NULL means every carried feature is dropped (cv::calcOpticalFlowPyrLK stays on the host, SURVEY.md §8a
+ *   row a8). reloc/n_reloc (orc_extract_frame_lost only): seeds of the lost-relocalisation branch (:161-243) that passed
+ *   the host-side tests (:207-215); they are emitted first.
  * current_id: MOVExtractor::mCurrentId, read and updated. Returns the number of tracks written to out. */
 int orc_extract_frame(int width, int height, uint32_t frame_flags, const uint8_t *grey,
                       const int32_t *grid, const movfe_hop *hops, const movfe_rect *kps, int n_kps,
@@ -72,6 +74,13 @@ int orc_extract_frame(int width, int height, uint32_t frame_flags, const uint8_t
                       const uint8_t *lk_status, const float *lk_pts,
                       const orc_extract_params *params, int32_t *current_id, movfe_track *out,
                       int32_t *n_births /* mov_cnt, may be NULL */);
+int orc_extract_frame_lost(int width, int height, uint32_t frame_flags, const uint8_t *grey,
+                           const int32_t *grid, const movfe_hop *hops, const movfe_rect *kps, int n_kps,
+                           double coverage_area, movfe_track *prev, int n_prev,
+                           const uint8_t *lk_status, const float *lk_pts,
+                           const movfe_reloc_seed *reloc, int n_reloc,
+                           const orc_extract_params *params, int32_t *current_id, movfe_track *out,
+                           int32_t *n_births);
 
 /* ---- frustum + joins (src/Frame.cc:456-519, include/MOVMatcher.h:35-137) --------------------------------- */
 /* isInFrustum (mono branch) for n points; bounds are [0,width]x[0,height] (Frame.cc:739-745). */

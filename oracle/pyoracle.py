@@ -50,6 +50,8 @@ def lib():
         L.orc_express_distance.argtypes = [vp, vp]
         L.orc_extract_frame.restype = i32
         L.orc_extract_frame.argtypes = [i32, i32, C.c_uint32, vp, vp, vp, vp, i32, f64, vp, i32, vp, vp, vp, vp, vp, vp]
+        L.orc_extract_frame_lost.restype = i32
+        L.orc_extract_frame_lost.argtypes = [i32, i32, C.c_uint32, vp, vp, vp, vp, i32, f64, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         L.orc_frustum.argtypes = [vp, vp, i32, i32, f32, vp, i32, vp]
         L.orc_search_by_video_feature.restype = i32
         L.orc_search_by_video_feature.argtypes = [vp, i32, vp, vp, i32, i32, f32, vp]
@@ -152,8 +154,8 @@ assert EXTRACT_PARAMS.itemsize == 24
 
 
 def extract_frame(width, height, frame_flags, grey, grid, hops, kps, coverage_area, prev, current_id,
-                  threshold=25, coverage_threshold=0.20, max_tracks=4096, lk_status=None, lk_pts=None):
-    """Returns (tracks, sorted_prev, new_current_id, n_births)."""
+                  threshold=25, coverage_threshold=0.20, max_tracks=4096, lk_status=None, lk_pts=None, reloc=None):
+    """Returns (tracks, sorted_prev, new_current_id, n_births). reloc: RELOC_SEED array (lost relocalisation)."""
     grey = None if grey is None else np.ascontiguousarray(grey, np.uint8)
     grid = np.ascontiguousarray(grid, np.int32)
     hops = np.ascontiguousarray(hops, T.HOP)
@@ -167,9 +169,10 @@ def extract_frame(width, height, frame_flags, grey, grid, hops, kps, coverage_ar
     if lk_status is not None:
         lk_status = np.ascontiguousarray(lk_status, np.uint8)
         lk_pts = np.ascontiguousarray(lk_pts, np.float32)
-    n = lib().orc_extract_frame(width, height, int(frame_flags), _p(grey), _p(grid), _p(hops), _p(kps), len(kps),
-                                float(coverage_area), _p(prev), len(prev), _p(lk_status), _p(lk_pts), _p(ep),
-                                _p(cid), _p(out), _p(nb))
+    reloc = None if reloc is None else np.ascontiguousarray(reloc, T.RELOC_SEED)
+    n = lib().orc_extract_frame_lost(width, height, int(frame_flags), _p(grey), _p(grid), _p(hops), _p(kps), len(kps),
+                                     float(coverage_area), _p(prev), len(prev), _p(lk_status), _p(lk_pts), _p(reloc),
+                                     0 if reloc is None else len(reloc), _p(ep), _p(cid), _p(out), _p(nb))
     return out[:max(n, 0)].copy(), prev, int(cid[0]), int(nb[0])
 
 

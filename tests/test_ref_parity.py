@@ -233,6 +233,62 @@ def test_extractor_oracle_equals_unmodified_reference_on_tie_free_tables(orc, re
     assert checked > 100
 
 
+def reloc_seeds_host_side(pts_kf, track_ids, status, pts_out, W, H, reloc_distance):
+    """The host half of the lost-relocalisation branch (src/MOVExtractor.cc:199-215): status, image bounds and the distance
+    test on the LK output, in the reference's types (cv::norm in double). -> RELOC_SEED array for the device half."""
+    th = reloc_distance * np.sqrt(float(H * H + W * W))
+    seeds = []
+    for i in range(len(pts_kf)):
+        x, y = np.float32(pts_out[i][0]), np.float32(pts_out[i][1])
+        if status[i] == 0 or x < 0 or y < 0 or x >= W or y >= H:
+            continue
+        dx, dy = np.float32(x - np.float32(pts_kf[i][0])), np.float32(y - np.float32(pts_kf[i][1]))
+        if np.sqrt(float(dx) * float(dx) + float(dy) * float(dy)) < th:
+            seeds.append((int(track_ids[i]), i, x, y))
+    return np.array(seeds, T.RELOC_SEED) if seeds else np.zeros(0, T.RELOC_SEED)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_lost_relocalisation_oracle_equals_reference(orc, ref, seed):
+    """prev->mLost (MOVExtractor.cc:161-243): keyframe map points carried by LK seed tracks ahead of the propagated ones.
+    The reference runs the whole branch; the oracle gets the seeds that passed the host-side tests."""
+    W, H, NF, K = 160, 112, 4, 2
+    spec = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0590 + seed, fx=80.0, fy=80.0)
+    recs, off, flags = synth.make_records(spec)
+    grey = synth.make_grey(spec)
+    rclip = ref.Clip(W, H, recs, off, flags, grey=grey)
+    oclip = orc.Clip(W, H, recs, off, flags, K)
+    rng = np.random.Generator(np.random.PCG64(0x2E90 + seed))
+    prev, cid = np.zeros(0, T.TRACK), 0
+    for f in range(NF - 1):
+        prev, _, cid, _ = orc.extract_frame(W, H, flags[f], grey[f], oclip.grid(f), oclip.hops(f), oclip.kps(f), oclip.coverage(f),
+                                            prev, cid, threshold=25, coverage_threshold=0.95, max_tracks=8192)
+    f = NF - 1
+    n_kf = 120
+    in_view = (rng.random(n_kf) < 0.8).astype(np.uint8)
+    proj = np.stack([rng.uniform(0, W, n_kf), rng.uniform(0, H, n_kf)], 1).astype(np.float32)
+    ids = rng.integers(1, 400, n_kf).astype(np.int32)
+    sel = np.nonzero(in_view)[0]                       # the points the reference hands to LK, in order (:171-192)
+    st = (rng.random(len(sel)) > 0.2).astype(np.uint8)
+    out = proj[sel] + rng.normal(0, 12.0, (len(sel), 2)).astype(np.float32)
+    order = _sorted_order(prev)
+    cov = [i for i in order if prev["flags"][i] & T.TRACK_COVERAGE]
+    lk_cov = _lk_for(rng, np.stack([prev["pt_x"][cov], prev["pt_y"][cov]], 1), W, H) if cov else None
+    r = ref.extract_frame(W, H, flags[f], grey[f], rclip.grid(f), rclip.hops(f), rclip.kps(f), rclip.coverage(f), prev, cid,
+                          threshold=25, coverage_threshold=0.95, relocalization_distance=0.1, lost=True, kf_points=(in_view, proj, ids),
+                          lk_calls=[(st, out)] + ([lk_cov] if cov else []), variant="canon")
+    assert r["consistent"] and r["lk_calls"] == (2 if cov else 1)
+    seeds = reloc_seeds_host_side(proj[sel], ids[sel], st, out, W, H, 0.1)
+    assert 0 < len(seeds) < len(sel)                   # the distance test rejected some
+    got, _, cid_o, _ = orc.extract_frame(W, H, flags[f], grey[f], oclip.grid(f), oclip.hops(f), oclip.kps(f), oclip.coverage(f), prev, cid,
+                                         threshold=25, coverage_threshold=0.95, max_tracks=8192, lk_status=lk_cov[0] if cov else None,
+                                         lk_pts=lk_cov[1] if cov else None, reloc=seeds)
+    assert cid_o == r["current_id"]
+    _assert_tables_equal(got, r["tracks"], "lost")
+    n_seeded = int(((got["age"] == 0) & (got["q_indx"] >= 0)).sum())
+    assert 0 < n_seeded <= len(seeds)
+
+
 def test_plain_and_canon_reference_builds_differ_only_by_tie_order(ref):
     """Documents what the canonicalisation changes: on a table WITH ties both builds keep the same multiset of tracks in
     sorted_prev; the order of ties is std::sort's business in the plain build."""

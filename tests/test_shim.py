@@ -34,21 +34,52 @@ def test_shims_compile_and_link():
         assert sig in m
 
 
+def pseudo_lk(pts_xy):
+    """mirror of test_shim.cc::pseudo_lk, the deterministic stand-in for cv::calcOpticalFlowPyrLK"""
+    pts = np.asarray(pts_xy, np.float32).reshape(-1, 2)
+    out = (pts + np.array([0.5, -0.25], np.float32)).astype(np.float32)
+    status = (((pts[:, 0].astype(np.int32) * 7 + pts[:, 1].astype(np.int32) * 3) % 5) != 0).astype(np.uint8)
+    return status, out
+
+
+def _stable_order(tr):
+    pc = np.array([sum(bin(int(w)).count("1") for w in t["desc"]) for t in tr], np.int64)
+    return sorted(range(len(tr)), key=lambda i: (-int(tr["age"][i]), -int(pc[i])))
+
+
 @pytest.mark.gpu
-def test_shims_against_oracle(orc, tmp_path):
+@pytest.mark.parametrize("cov_thr,iframe_at", [(0.20, None), (0.95, 4)])
+def test_shims_against_oracle(orc, tmp_path, cov_thr, iframe_at):
+    """VideoDecoder shim (GPU raster behind the reference's class, fake libav in front) -> MOVExtractor shim (host LK hook,
+    GPU merge) -> MOVMatcher / PoseOptimization shims, against the oracle frame by frame. The second case turns on the
+    coverage back-fill (coverage tracks carried by LK from then on) and puts an intra picture in mid-stream (every track
+    carried by LK): the drop-in keeps its track ids where round 1 silently lost them."""
     _build()
     W, H, NF, K, thr = 320, 240, 7, 2, 25
     sp = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0020, fx=160.0, fy=160.0)
     recs, off, flags = synth.make_records(sp)
+    flags = flags.copy()
+    if iframe_at is not None:
+        flags[iframe_at] &= ~np.uint8(T.FRAME_P)
     grey = synth.make_grey(sp)
     clip = orc.Clip(W, H, recs, off, flags, 10)     # the shim's raster context accepts the reference's full ref range
-    # oracle chain: tracks per frame
-    prev, cid, tracks = np.zeros(0, T.TRACK), 0, []
+    # oracle chain: tracks per frame, LK results from the same deterministic hook
+    prev, cid, tracks, n_carried = np.zeros(0, T.TRACK), 0, [], 0
     for f in range(NF):
+        lk = None
+        if len(prev) and not (flags[f] & T.FRAME_P):
+            lk = pseudo_lk(np.stack([prev["pt_x"], prev["pt_y"]], 1))
+        elif len(prev):
+            cov = [i for i in _stable_order(prev) if prev["flags"][i] & T.TRACK_COVERAGE]
+            if cov:
+                lk = pseudo_lk(np.stack([prev["pt_x"][cov], prev["pt_y"][cov]], 1))
         t, _, cid, _ = orc.extract_frame(W, H, flags[f], grey[f], clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f), prev, cid,
-                                         threshold=thr, coverage_threshold=0.20, max_tracks=8192)
+                                         threshold=thr, coverage_threshold=cov_thr, max_tracks=8192,
+                                         lk_status=None if lk is None else lk[0], lk_pts=None if lk is None else lk[1])
+        n_carried += int(((t["q_indx"] >= 0) & (((t["flags"] & T.TRACK_COVERAGE) != 0) | (not (flags[f] & T.FRAME_P)))).sum())
         tracks.append(t)
         prev = t
+    assert n_carried > 0 or iframe_at is None
     mp = synth.map_from_tracks(sp, tracks[0], synth.pose_at(sp, 0))
     mp["flags"][3] = T.MP_BAD
     mp["flags"][5] = T.MP_NULL
@@ -56,7 +87,7 @@ def test_shims_against_oracle(orc, tmp_path):
     pose0 = synth.pose_struct(synth.pose_at(sp, 0))
     cam = sp.camera()
     d = str(tmp_path)
-    np.array([W, H, NF, 10, thr, len(mp), n_kf], np.int32).tofile(d + "/meta.bin")
+    np.array([W, H, NF, 10, thr, len(mp), n_kf, int(round(cov_thr * 1000))], np.int32).tofile(d + "/meta.bin")
     np.ascontiguousarray(recs, T.MV_RECORD).tofile(d + "/recs.bin")   # the 40-byte layout (numpy packs concatenated records)
     off.tofile(d + "/off.bin"); flags.tofile(d + "/flags.bin"); grey.tofile(d + "/grey.bin")
     mp.tofile(d + "/map.bin")
@@ -64,6 +95,7 @@ def test_shims_against_oracle(orc, tmp_path):
     np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).tofile(d + "/cam.bin")
     r = subprocess.run([os.path.join(SHIM, "test_shim"), d], capture_output=True, text=True, )
     assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 carried tracks dropped" in r.stdout, r.stdout        # every carried track got its LK result
 
     def f32(p):  # the Frame stores Sophus::SE3f: the pose is rounded to float between calls
         q = p.copy()
@@ -74,8 +106,17 @@ def test_shims_against_oracle(orc, tmp_path):
     pp = T.pose_params()
     last = f32(pose0)
     for f in range(NF):
+        # the VideoDecoder shim: what VideoDecoder::NextImage's MV loop would have left in the VideoImage
+        assert np.fromfile(d + "/out_hops_%d.bin" % f, T.HOP).tobytes() == clip.hops(f).tobytes(), ("hops", f)
+        assert np.fromfile(d + "/out_kps_%d.bin" % f, T.RECT).tobytes() == clip.kps(f).tobytes(), ("kps", f)
+        assert np.array_equal(np.fromfile(d + "/out_grid_%d.bin" % f, np.int32).reshape(H, W, 4), clip.grid(f)), ("grid", f)
+        cov, frame_no, is_p = np.fromfile(d + "/out_cov_%d.bin" % f, np.float64)
+        assert cov == clip.coverage(f) and int(is_p) == int(bool(flags[f] & T.FRAME_P)), ("coverage / type", f)
         got_t = np.fromfile(d + "/out_tracks_%d.bin" % f, T.TRACK)
         assert got_t.tobytes() == tracks[f].tobytes(), ("tracks", f, len(got_t), len(tracks[f]), r.stderr[-400:])
+        # mDescriptors: the reference pushes none for back-fill features (MOVExtractor.cc:421 shadows the argument)
+        n_backfill = int((((tracks[f]["flags"] & T.TRACK_COVERAGE) != 0) & (tracks[f]["q_indx"] < 0)).sum())
+        assert int(np.fromfile(d + "/out_ndesc_%d.bin" % f, np.int32)[0]) == len(tracks[f]) - n_backfill, ("descriptors", f)
         n_m, want_m = orc.search_by_keyframe(tracks[f], mp[:n_kf])
         got_m = np.fromfile(d + "/out_match_%d.bin" % f, np.int32)
         assert np.array_equal(got_m, want_m), ("match", f)
