@@ -132,6 +132,15 @@ int movfe_download_tracks(movfe_ctx *ctx, int stream, int64_t frame, movfe_track
  *    Tracking.cc drives them (TrackReferenceKeyFrame :796-811, TrackLocalMap :890-905). */
 int movfe_set_camera(movfe_ctx *ctx, const movfe_camera *cam, const movfe_pose_params *pp, float viewing_cos_limit);
 int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_point *pts, int n, int n_keyframe_points);
+/* The local maps of ALL streams in one call - what the mapping side hands the tracker after a keyframe insertion
+ * (Tracking::UpdateLocalPoints, src/Tracking.cc:1171-1198: the list building stays with the mapping code; its result arrives
+ * here). pts: packed points, stream-major; off: n_streams+1 offsets; n_keyframe_points: per stream, how many of its leading
+ * points are the reference keyframe's list (TrackReferenceKeyFrame's join); max_points_per_stream: upper bound of any
+ * stream's count (<= max_map_points). on_device = 1: all three arrays are device memory, complete when the call is made (a
+ * device-side mapper / a map kept resident); 0: host memory, unchanged until the next call that synchronises. Ordered with
+ * movfe_track_poses: frames tracked after the call see the new maps. */
+int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point *pts, const int64_t *off, const int32_t *n_keyframe_points,
+                               int max_points_per_stream, int on_device);
 int movfe_set_pose(movfe_ctx *ctx, int stream, const movfe_pose *pose);
 int movfe_track_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 int movfe_download_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames, movfe_pose *poses /* S*n */,

@@ -9,7 +9,7 @@
 
 #include "common.cuh"
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;  // per host thread: contexts are created from their own threads
 
 extern "C" const char *movfe_version(void) { return "movfe 0.1 (sm_100a)"; }
 
@@ -37,6 +37,8 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
                     ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier, ctx->d_pose_scratch, ctx->d_op, ctx->d_pairs, ctx->d_npairs};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (ctx->d_map_stage) cudaFree(ctx->d_map_stage);
+    if (ctx->h_map_meta) cudaFreeHost(ctx->h_map_meta);
     for (RasterBuf &w : ctx->rb) {
         void *wb[] = {w.d_seg_cnt, w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
                       w.d_chunk_bbox, w.d_grid};
@@ -114,6 +116,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c.device));
     ctx->sm_count = prop.multiProcessorCount;
+    CK(cudaDeviceGetAttribute(&ctx->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device));
     // propagation is a serial chain of short launches (three per frame): it gets the high priority, so that its CTAs are
     // placed as soon as they are ready and the long, throughput-bound raster kernels of the NEXT window fill what is left
     int prio_lo = 0, prio_hi = 0;
@@ -221,6 +224,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->ext_scratch_bytes = movfe_extract_scratch_bytes(ctx);
     CK(cudaMalloc(&ctx->d_ext_scratch, std::max<size_t>(ctx->ext_scratch_bytes, 16)));
     if (int rc = movfe_extract_init(ctx)) return fail(rc);
+    if (int rc = movfe_pose_init(ctx)) return fail(rc);
+    if (int rc = movfe_bucket_init(ctx)) return fail(rc);
     // map / pose
     CK(dalloc(&ctx->d_map, S * (size_t)std::max(c.max_map_points, 1)));
     CK(dalloc(&ctx->d_nmap, S));

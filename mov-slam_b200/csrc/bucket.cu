@@ -138,7 +138,6 @@ extern "C" int movfe_assign_features_to_grid(movfe_ctx *ctx, int n_problems, con
     if (n) MOVFE_CUDA(ctx, cudaMemsetAsync(d_it, 0xff, (size_t)n * 4, st));  // entries past a set's valid count stay -1
     const float w_inv = (float)BG_COLS / (float)ctx->cfg.width, h_inv = (float)BG_ROWS / (float)ctx->cfg.height;  // Frame.cc:147-148
     const size_t smem = (size_t)N2 * sizeof(uint32_t);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     assign_kernel<<<n_problems, BG_THREADS, smem, st>>>(reinterpret_cast<const float *>(d_pts), 2, d_off, w_inv, h_inv, N2, d_cs, d_it);
     MOVFE_CUDA(ctx, cudaGetLastError());
     MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_start, d_cs, (size_t)n_problems * (BG_CELLS + 1) * 4, cudaMemcpyDeviceToHost, st));
@@ -230,7 +229,6 @@ extern "C" int movfe_track_feature_grid(movfe_ctx *ctx, int stream, int64_t fram
     while (N2 < n) N2 <<= 1;
     const float w_inv = (float)BG_COLS / (float)c.width, h_inv = (float)BG_ROWS / (float)c.height;
     const size_t smem = (size_t)N2 * sizeof(uint32_t);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const movfe_track *tab = ctx->d_tracks + ((size_t)stream * T + ts) * c.max_tracks;  // pt_x, pt_y lead the 64-byte record
     assign_kernel<<<1, BG_THREADS, smem, st>>>(reinterpret_cast<const float *>(tab), (int)(sizeof(movfe_track) / 4), d_off, w_inv, h_inv,
                                                N2, d_cs, d_it);
@@ -239,4 +237,9 @@ extern "C" int movfe_track_feature_grid(movfe_ctx *ctx, int stream, int64_t fram
     if (n) MOVFE_CUDA(ctx, cudaMemcpyAsync(cell_items, d_it, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // `off` and `n` live on this stack frame
     return n;
+}
+
+int movfe_bucket_init(movfe_ctx *ctx) {
+    MOVFE_CUDA(ctx, optin_dynamic_smem(assign_kernel, ctx->smem_optin));
+    return MOVFE_OK;
 }

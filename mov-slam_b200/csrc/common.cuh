@@ -66,6 +66,7 @@ struct movfe_ctx {
     int max_hops = 0, max_kps = 0, max_chunks = 0;
     int rseg = 0, n_rseg = 1;              // records per count/emit segment (multiple of 512), segments per frame
     int sm_count = 0;
+    int smem_optin = 0;                    // cudaDevAttrMaxSharedMemoryPerBlockOptin: every dynamic-smem kernel is opted in to it ONCE at create
     cudaStream_t stream = nullptr;
     // join / frustum / pose of a window run on their own stream, concurrently with raster + propagation of the next
     // window (the chains are independent once a window's track tables exist)
@@ -150,6 +151,9 @@ struct movfe_ctx {
     int32_t *d_ninl = nullptr;         // [S][F]
     int32_t *d_match = nullptr;        // [S][F][max_tracks]
     uint8_t *d_outlier = nullptr;      // [S][F][max_tracks]
+    void    *d_map_stage = nullptr;    // staging of movfe_set_map_points_batch (host hand-over of all streams' local maps)
+    void    *h_map_meta = nullptr;
+    size_t   map_stage_bytes = 0;
     void    *d_pose_scratch = nullptr;
     size_t   pose_scratch_bytes = 0;
     // split pose chain (join kernels + small solver kernels, pose.cu): correspondences of one frame per stream
@@ -218,6 +222,18 @@ static inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 gr
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// Opts a kernel in to the largest dynamic shared memory the device allows beside the kernel's static allocation. Called
+// once per kernel at movfe_create (the attribute is per function and process-wide; the value is the same from every context).
+template <typename K>
+static inline cudaError_t optin_dynamic_smem(K kernel, int smem_optin, int *dynamic_limit = nullptr) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    const int lim = smem_optin - (int)fa.sharedSizeBytes;
+    if (dynamic_limit) *dynamic_limit = lim;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+}
+
 // RAII span: records an event pair around a stage when profiling is on, and always counts kernel launches.
 struct ProfScope {
     movfe_ctx *ctx;
@@ -256,6 +272,8 @@ int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_r
 int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 size_t movfe_extract_scratch_bytes(const movfe_ctx *ctx);
 int movfe_extract_init(movfe_ctx *ctx);
+int movfe_pose_init(movfe_ctx *ctx);    // pose.cu
+int movfe_bucket_init(movfe_ctx *ctx);  // bucket.cu
 // match.cu / pose.cu
 int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 size_t movfe_pose_scratch_bytes(const movfe_ctx *ctx);

@@ -1401,12 +1401,11 @@ int movfe_extract_init(movfe_ctx *ctx) {
     MOVFE_CUDA(ctx, cudaMemsetAsync(e.lk.dropped, 0, sizeof(unsigned long long), ctx->stream));
     // the attributes are per function and process-wide: set once to the device limit, never per launch (contexts on other
     // host threads launch the same kernels)
-    int dev = 0, optin = 0;
-    MOVFE_CUDA(ctx, cudaGetDevice(&dev));
-    MOVFE_CUDA(ctx, cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    if ((int)sort_smem(c.max_tracks) > optin) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "max_tracks=%d needs %zu bytes of shared memory, the device has %d", c.max_tracks, sort_smem(c.max_tracks), optin);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(sort_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+    int fin_limit = 0;
+    MOVFE_CUDA(ctx, optin_dynamic_smem(finalize_kernel, ctx->smem_optin, &fin_limit));
+    if ((int)sort_smem(c.max_tracks) > fin_limit)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "max_tracks=%d needs %zu bytes of shared memory, the device allows %d", c.max_tracks, sort_smem(c.max_tracks), fin_limit);
+    MOVFE_CUDA(ctx, optin_dynamic_smem(sort_only_kernel, ctx->smem_optin));
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }

@@ -481,7 +481,8 @@ int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w) {
         }
     if (nw == 4 && ntc % 4 != 0 && ntc > 4) nw = 8;
     const size_t smem = (size_t)nw * sizeof(WarpScratch) + ((size_t)2 * ntc * TQ_STRIDE + GRID_CHUNK_CAP) * sizeof(uint32_t);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > (size_t)ctx->smem_optin) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "grid: %zu bytes of shared memory per CTA exceed the device limit %d", smem, ctx->smem_optin);
+    MOVFE_CUDA(ctx, optin_dynamic_smem(grid_kernel, ctx->smem_optin));  // same value from every context
     if ((size_t)p.n_out * nxs > 65535 || p.S > 65535) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "grid: launch grid out of range");
     dim3 blocks(nsb, p.n_out * nxs, p.S);
     grid_kernel<<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid);

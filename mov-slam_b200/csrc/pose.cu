@@ -894,6 +894,16 @@ size_t movfe_pose_scratch_bytes(const movfe_ctx *ctx) {
 
 int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes);
 
+// Dynamic shared memory of every kernel of this file is opted in to the device limit once, at create: the attribute is per
+// function and process-wide, so setting it per launch would race between contexts on different host threads.
+int movfe_pose_init(movfe_ctx *ctx) {
+    MOVFE_CUDA(ctx, optin_dynamic_smem(track_poses_kernel, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(tp_join_kernel, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(tp_solve_kernel, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(join_kernel, ctx->smem_optin));
+    return MOVFE_OK;
+}
+
 int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
     const movfe_config &c = ctx->cfg;
     TrackPoseParams p;
@@ -919,7 +929,6 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     if (smem + fa.sharedSizeBytes > (size_t)optin)
         MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "track_poses: max_tracks=%d / max_map_points=%d need %zu bytes of shared memory per stream (limit %zu)",
                    c.max_tracks, c.max_map_points, smem, (size_t)optin - fa.sharedSizeBytes);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(track_poses_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // one chain per frame, each released by the event recorded after that frame's finalize: the pose chain of frame f
     // runs beside the propagation of frame f+1 instead of after the window
     const bool split = ctx->pose_split && ctx->d_pairs != nullptr && ctx->h_nmap_max <= 4096;  // larger maps: wide fused CTAs
@@ -928,10 +937,6 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     // solver CTAs are sized by the correspondence count, which only the device knows: one launch per size class, the CTAs
     // of the other class leave at once (the classes a context can need follow from the largest local map installed)
     const int n_cls = ctx->h_nmap_max <= 64 ? 1 : 2;
-    if (split) {
-        MOVFE_CUDA(ctx, cudaFuncSetAttribute(tp_join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_join));
-        MOVFE_CUDA(ctx, cudaFuncSetAttribute(tp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve));
-    }
     for (int k = 0; k < n_frames; k++) {
         for (int g = 0; g < ctx->n_groups; g++)  // every group of streams has finished this frame's table
             MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(size_t)g * c.window_frames + ctx->ev_of_frame[(first_frame + k) % c.window_frames]], 0));
@@ -992,6 +997,75 @@ extern "C" int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nmap + stream, &nn, 4, cudaMemcpyHostToDevice, ctx->pose_stream));
     MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_nkf + stream, &nk, 4, cudaMemcpyHostToDevice, ctx->pose_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    return MOVFE_OK;
+}
+
+namespace {
+// packed maps of all streams -> the per-stream tables (one CTA per stream, 32-bit words: a map point is 10 of them)
+__global__ void map_install_kernel(const uint32_t *__restrict__ src, const int64_t *__restrict__ off, const int32_t *__restrict__ n_kf,
+                                   int max_map, uint32_t *__restrict__ d_map, int32_t *__restrict__ d_nmap, int32_t *__restrict__ d_nkf) {
+    const int s = blockIdx.x;
+    const int64_t o = off[s];
+    const int n = (int)min((int64_t)max_map, off[s + 1] - o);
+    const uint32_t *from = src + o * 10;
+    uint32_t *to = d_map + (size_t)s * max_map * 10;
+    for (int i = threadIdx.x; i < n * 10; i += blockDim.x) to[i] = from[i];
+    if (threadIdx.x == 0) {
+        d_nmap[s] = n;
+        d_nkf[s] = min(n_kf[s], n);
+    }
+}
+}  // namespace
+
+extern "C" int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point *pts, const int64_t *off, const int32_t *n_keyframe_points,
+                                          int max_points_per_stream, int on_device) {
+    static_assert(sizeof(movfe_map_point) == 40, "map point = 10 words");
+    if (!ctx || !off || !n_keyframe_points) return MOVFE_E_INVALID;
+    const movfe_config &c = ctx->cfg;
+    const int S = c.n_streams;
+    if (max_points_per_stream < 0 || max_points_per_stream > c.max_map_points)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "set_map_points_batch: %d points per stream, capacity %d", max_points_per_stream, c.max_map_points);
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    cudaStream_t st = ctx->pose_stream;  // ordered with the pose chains that read the maps
+    const movfe_map_point *d_pts = pts;
+    const int64_t *d_off = off;
+    const int32_t *d_nkf = n_keyframe_points;
+    if (!on_device) {
+        int64_t total = off[S];
+        for (int s = 0; s < S; s++) {
+            const int64_t n = off[s + 1] - off[s];
+            if (n < 0 || n > max_points_per_stream)
+                MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "set_map_points_batch: stream %d has %lld points, the call allows %d", s, (long long)n, max_points_per_stream);
+        }
+        if (total > 0 && !pts) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "set_map_points_batch: null points");
+        const size_t b_pts = ((size_t)total * sizeof(movfe_map_point) + 255) & ~(size_t)255, b_off = ((size_t)(S + 1) * 8 + 255) & ~(size_t)255;
+        const size_t need = b_pts + b_off + (size_t)S * 4;
+        if (ctx->map_stage_bytes < need) {
+            MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+            if (ctx->d_map_stage) cudaFree(ctx->d_map_stage);
+            if (ctx->h_map_meta) cudaFreeHost(ctx->h_map_meta);
+            ctx->d_map_stage = nullptr;
+            ctx->h_map_meta = nullptr;
+            ctx->map_stage_bytes = 0;
+            MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_map_stage, need + need / 2));
+            MOVFE_CUDA(ctx, cudaMallocHost(&ctx->h_map_meta, b_off + (size_t)S * 4));
+            ctx->map_stage_bytes = need + need / 2;
+        } else {
+            MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // the previous hand-over has left the staging buffers
+        }
+        uint8_t *base = (uint8_t *)ctx->d_map_stage;
+        memcpy(ctx->h_map_meta, off, (size_t)(S + 1) * 8);
+        memcpy((uint8_t *)ctx->h_map_meta + b_off, n_keyframe_points, (size_t)S * 4);
+        if (total > 0) MOVFE_CUDA(ctx, cudaMemcpyAsync(base, pts, (size_t)total * sizeof(movfe_map_point), cudaMemcpyHostToDevice, st));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(base + b_pts, ctx->h_map_meta, b_off + (size_t)S * 4, cudaMemcpyHostToDevice, st));
+        d_pts = (const movfe_map_point *)base;
+        d_off = (const int64_t *)(base + b_pts);
+        d_nkf = (const int32_t *)(base + b_pts + b_off);
+    }
+    ctx->h_nmap_max = std::max(ctx->h_nmap_max, max_points_per_stream);
+    map_install_kernel<<<S, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_pts), d_off, d_nkf, std::max(c.max_map_points, 1),
+                                          reinterpret_cast<uint32_t *>(ctx->d_map), ctx->d_nmap, ctx->d_nkf);
+    MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
 
@@ -1105,7 +1179,12 @@ extern "C" int movfe_join(movfe_ctx *ctx, int n_problems, const int32_t *track_i
     const int nt = track_off[n_problems], np = probe_off[n_problems];
     int max_n = 0;
     for (int i = 0; i < n_problems; i++) max_n = std::max(max_n, track_off[i + 1] - track_off[i]);
-    if (max_n > 16384) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "join: %d tracks in one problem (limit 16384)", max_n);
+    {   // the hash table of one problem lives in shared memory: (2 * pow2(2n) + n) ints
+        const size_t need_smem = ((size_t)2 * pow2_at_least(2 * std::max(max_n, 1)) + std::max(max_n, 1)) * sizeof(int);
+        if (need_smem > (size_t)ctx->smem_optin)
+            MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "join: %d tracks in one problem need %zu bytes of shared memory (device limit %d: about 8192 tracks)",
+                       max_n, need_smem, ctx->smem_optin);
+    }
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     const size_t need = (size_t)nt * 8 + (size_t)np * 5 + (size_t)(n_problems + 1) * 12 + 8 * 256;
     int rc = movfe_ensure_op_scratch(ctx, need);
@@ -1127,7 +1206,6 @@ extern "C" int movfe_join(movfe_ctx *ctx, int n_problems, const int32_t *track_i
     MOVFE_CUDA(ctx, cudaMemcpyAsync(d_poff, probe_off, (size_t)(n_problems + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
     const int cap = pow2_at_least(2 * std::max(max_n, 1));
     const size_t smem = ((size_t)2 * cap + std::max(max_n, 1)) * sizeof(int);
-    MOVFE_CUDA(ctx, cudaFuncSetAttribute(join_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         ProfScope prof(ctx, MOVFE_STAGE_POSE);
         prof.launches(1);

@@ -36,12 +36,18 @@ ingest_kernel(const uint4 *__restrict__ recs16, int64_t n_records, const int64_t
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t w0 = ((int64_t)blockIdx.x * INGEST_WARPS + warp) * INGEST_REC_PER_WARP;  // first record of this warp
     if (w0 >= n_records) return;
-    const int64_t total16 = (n_records * 40 + 15) / 16;  // staging buffers are padded to a 16-byte multiple
-    const int64_t base16 = w0 * 40 / 16;                 // 2560*k/16: exact
+    const int64_t full16 = n_records * 40 / 16;  // 128-bit words that lie wholly inside the record array
+    const int64_t base16 = w0 * 40 / 16;         // 2560*k/16: exact
 #pragma unroll
     for (int i = 0; i < 5; i++) {
         const int q = i * 32 + lane;
-        if (base16 + q < total16) stage[warp][q] = __ldg(&recs16[base16 + q]);
+        if (base16 + q < full16) {
+            stage[warp][q] = __ldg(&recs16[base16 + q]);
+        } else if (base16 + q == full16 && (n_records & 1)) {
+            // an odd record count ends in the middle of a word: only its first 8 bytes belong to the caller's array
+            const uint2 h = __ldg(reinterpret_cast<const uint2 *>(&recs16[base16 + q]));
+            stage[warp][q] = make_uint4(h.x, h.y, 0u, 0u);
+        }
     }
     __syncwarp();
     const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage[warp]);

@@ -66,6 +66,7 @@ def load():
     L.movfe_set_camera.argtypes = [vp, vp, vp, C.c_float]
     L.movfe_set_map_points.argtypes = [vp, i32, vp, i32, i32]
     L.movfe_set_pose.argtypes = [vp, i32, vp]
+    L.movfe_set_map_points_batch.argtypes = [vp, vp, vp, vp, i32, i32]
     L.movfe_track_poses.argtypes = [vp, i64, i32]
     L.movfe_download_poses.argtypes = [vp, i64, i32, vp, vp]
     L.movfe_download_matches.argtypes = [vp, i32, i64, vp, vp, i32]
@@ -85,7 +86,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_frames_pushed", "movfe_raster",
            "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
            "movfe_rejected_records", "movfe_set_tracks", "movfe_set_lk_results", "movfe_dropped_lk_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
-           "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_pose",
+           "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
            "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read"]
@@ -267,6 +268,16 @@ class Context:
     def set_map_points(self, stream, pts, n_keyframe_points):
         pts = np.ascontiguousarray(pts, T.MAP_POINT)
         self._ck(self.L.movfe_set_map_points(self.h, stream, _p(pts), len(pts), n_keyframe_points))
+
+    def set_map_points_batch(self, pts, off, n_kf, max_points_per_stream, on_device=False):
+        """Local maps of all streams at once; host numpy arrays, or raw device pointers with on_device=True."""
+        if not on_device:
+            pts = np.ascontiguousarray(pts, T.MAP_POINT)
+            off = np.ascontiguousarray(off, np.int64)
+            n_kf = np.ascontiguousarray(n_kf, np.int32)
+            assert len(off) == self.S + 1 and len(n_kf) == self.S
+            self._keep_map = (pts, off, n_kf)       # host arrays must stay unchanged until the next synchronising call
+        self._ck(self.L.movfe_set_map_points_batch(self.h, _p(pts), _p(off), _p(n_kf), int(max_points_per_stream), int(on_device)))
 
     def set_pose(self, stream, pose):
         pose = np.ascontiguousarray(pose, T.POSE)

@@ -7,6 +7,7 @@
 // Used as the timed CPU baseline and as the checker for the batched GPU pipeline.
 #include "oracle.h"
 
+#include <chrono>
 #include <cstring>
 #include <vector>
 
@@ -23,7 +24,23 @@ extern "C" int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_reco
                                 const uint8_t *frame_flags, const uint8_t *grey, const movfe_track *seed_tracks,
                                 int n_seed, const movfe_map_point *map_pts, int n_map, const movfe_pose *pose0,
                                 orc_frontend_out *out) {
+    return orc_frontend_run_sched(cfg, recs, rec_off, frame_flags, grey, seed_tracks, n_seed, map_pts, n_map, pose0, 0, nullptr,
+                                  nullptr, nullptr, nullptr, 0, nullptr, out);
+}
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int orc_frontend_run_sched(const orc_frontend_cfg *cfg, const movfe_mv_record *recs, const int64_t *rec_off,
+                                      const uint8_t *frame_flags, const uint8_t *grey, const movfe_track *seed_tracks,
+                                      int n_seed, const movfe_map_point *map_pts, int n_map, const movfe_pose *pose0,
+                                      int n_sched, const int32_t *sched_frame, const int64_t *sched_off,
+                                      const movfe_map_point *sched_pts, const int32_t *sched_nkf, int timed_from,
+                                      double *tail_times, orc_frontend_out *out) {
     const int W = cfg->width, H = cfg->height, NF = cfg->n_frames;
+    int n_kf_points = cfg->n_kf_points;
+    int next_sched = 0;
     orc_clip *clip = orc_raster_clip(W, H, NF, recs, rec_off, frame_flags, cfg->max_ref);
 
     std::vector<uint8_t> flat;
@@ -52,6 +69,18 @@ extern "C" int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_reco
     std::vector<uint8_t> outl;
 
     for (int f = 0; f < NF; f++) {
+        if (tail_times && f == timed_from) tail_times[0] = now_s();
+        // the local map handed over by the mapping side before this frame (keyframe insertion -> UpdateLocalPoints,
+        // Tracking.cc:947-1107,1171-1198: out of scope, so its result arrives as a schedule)
+        while (next_sched < n_sched && sched_frame[next_sched] <= f) {
+            if (sched_frame[next_sched] == f) {
+                pts.assign(sched_pts + sched_off[next_sched], sched_pts + sched_off[next_sched + 1]);
+                n_map = (int)pts.size();
+                n_kf_points = sched_nkf[next_sched];
+                proj.resize(n_map);
+            }
+            next_sched++;
+        }
         const uint8_t *img = grey ? grey + (size_t)f * W * H : flat.data();
         // seed_tracks (if any) are the table of the frame before the clip (Frame::mpPrevFrame of frame 0)
         const int n = orc_extract_frame(W, H, frame_flags[f], img, orc_clip_grid(clip, f), orc_clip_hops(clip, f),
@@ -73,7 +102,7 @@ extern "C" int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_reco
                 return (int)(go.size() / 2);
             };
             // TrackReferenceKeyFrame
-            orc_search_by_keyframe(cur.data(), n, pts.data(), cfg->n_kf_points < n_map ? cfg->n_kf_points : n_map, match.data());
+            orc_search_by_keyframe(cur.data(), n, pts.data(), n_kf_points < n_map ? n_kf_points : n_map, match.data());
             int P = gather();
             orc_pose_optimize(&cfg->cam, &cfg->pose_params, gx.data(), go.data(), P, &pose, outl.data(), nullptr);
             // TrackLocalMap / SearchLocalPoints
@@ -94,6 +123,7 @@ extern "C" int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_reco
         prev.swap(cur);
         n_prev = n;
     }
+    if (tail_times) tail_times[1] = now_s();
     if (out && out->last_tracks) std::memcpy(out->last_tracks, prev.data(), sizeof(movfe_track) * (size_t)n_prev);
     orc_clip_free(clip);
     return n_prev;

@@ -153,6 +153,17 @@ int orc_frontend_run(const orc_frontend_cfg *cfg, const movfe_mv_record *recs, c
                      const movfe_map_point *map_pts, int n_map, const movfe_pose *pose0,
                      orc_frontend_out *out);
 
+/* The same with (a) a schedule of local maps: before frame sched_frame[i] (ascending) the map becomes
+ * sched_pts[sched_off[i] .. sched_off[i+1]) with sched_nkf[i] keyframe points - what the mapping side (out of scope)
+ * hands the tracker after a keyframe insertion; (b) wall-clock stamps: tail_times[0] when frame `timed_from` starts,
+ * tail_times[1] at the end (steady_clock seconds; may be NULL) - bench.py times only the frames the GPU arm times. */
+int orc_frontend_run_sched(const orc_frontend_cfg *cfg, const movfe_mv_record *recs, const int64_t *rec_off,
+                           const uint8_t *frame_flags, const uint8_t *grey, const movfe_track *seed_tracks, int n_seed,
+                           const movfe_map_point *map_pts, int n_map, const movfe_pose *pose0,
+                           int n_sched, const int32_t *sched_frame, const int64_t *sched_off,
+                           const movfe_map_point *sched_pts, const int32_t *sched_nkf, int timed_from,
+                           double *tail_times, orc_frontend_out *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,8 @@ def lib():
         L.orc_pose_optimize.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp]
         L.orc_frontend_run.restype = i32
         L.orc_frontend_run.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp]
+        L.orc_frontend_run_sched.restype = i32
+        L.orc_frontend_run_sched.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, i32, vp, vp, vp, vp, i32, vp, vp]
         _LIB = L
     return _LIB
 
@@ -290,7 +292,9 @@ class _FrontendOut(C.Structure):
 
 def frontend_run(width, height, recs, rec_off, frame_flags, grey, seed_tracks, map_pts, pose0, cam, pose_params,
                  max_ref=3, max_tracks=4096, threshold=25, coverage_threshold=0.20, n_kf_points=0,
-                 viewing_cos_limit=0.5):
+                 viewing_cos_limit=0.5, map_schedule=None, timed_from=0):
+    """map_schedule: [(frame, MAP_POINT array, n_kf_points), ...] (ascending frames): the local map installed before that
+    frame. The result carries tail_times = steady-clock seconds at the start of frame `timed_from` and at the end."""
     nf = len(frame_flags)
     cfg = np.zeros((), FRONTEND_CFG)
     cfg["width"], cfg["height"], cfg["n_frames"], cfg["max_ref"], cfg["max_tracks"] = width, height, nf, max_ref, max_tracks
@@ -310,6 +314,14 @@ def frontend_run(width, height, recs, rec_off, frame_flags, grey, seed_tracks, m
     last = np.zeros(max_tracks, T.TRACK)
     hashes = np.zeros(nf, np.uint64)
     out = _FrontendOut(poses.ctypes.data, n_tracks.ctypes.data, n_inl.ctypes.data, last.ctypes.data, hashes.ctypes.data)
-    n_last = lib().orc_frontend_run(_p(cfg), _p(recs), _p(rec_off), _p(frame_flags), _p(grey), _p(seeds),
-                                    0 if seeds is None else len(seeds), _p(mp), len(mp), _p(pose0), C.byref(out))
-    return dict(poses=poses, n_tracks=n_tracks, n_inliers=n_inl, last_tracks=last[:n_last].copy(), track_hash=hashes)
+    sched = map_schedule or []
+    s_frame = np.array([f for f, _, _ in sched], np.int32)
+    s_nkf = np.array([k for _, _, k in sched], np.int32)
+    s_off = np.cumsum([0] + [len(m) for _, m, _ in sched]).astype(np.int64)
+    s_pts = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(m, T.MAP_POINT) for _, m, _ in sched])) if sched else np.zeros(0, T.MAP_POINT)
+    tail = np.zeros(2, np.float64)
+    n_last = lib().orc_frontend_run_sched(_p(cfg), _p(recs), _p(rec_off), _p(frame_flags), _p(grey), _p(seeds),
+                                          0 if seeds is None else len(seeds), _p(mp), len(mp), _p(pose0), len(sched), _p(s_frame),
+                                          _p(s_off), _p(s_pts), _p(s_nkf), int(timed_from), _p(tail), C.byref(out))
+    return dict(poses=poses, n_tracks=n_tracks, n_inliers=n_inl, last_tracks=last[:n_last].copy(), track_hash=hashes,
+                tail_times=tail)
