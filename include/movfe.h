@@ -53,6 +53,12 @@ typedef struct movfe_config {
  * of window k (raster results are double-buffered). With this flag every movfe_raster first waits for all propagation
  * and pose work enqueued so far, so that the raster kernels run alone - bench.py uses it to time grid_kernel for the roofline. */
 #define MOVFE_CFG_SERIAL_RASTER 1
+/* Fused (grid-free) mode: VideoImage::mvi, the per-pixel slot grid, is not materialised. Propagation reads the grid at one
+ * pixel per track (src/MOVExtractor.cc:264-272) and at the 16-px lattice of a back-fill pass (:431), so the raster stage keeps
+ * only the ordered per-32x32-tile hop queues it builds anyway and every lookup resolves its four slots from its tile's queue.
+ * Results are bit-identical to the grid path (tests/test_pipeline_gpu.py); 16*W*H bytes per frame are never written and the
+ * grid's memory (2 x 16 W H F S bytes) is not allocated. movfe_download_grid and movfe_extract_frame are unavailable. */
+#define MOVFE_CFG_NO_GRID 2
 
 /* -- lifetime -------------------------------------------------------------------------------------------- */
 int         movfe_create(const movfe_config *cfg, movfe_ctx **out);
@@ -154,6 +160,11 @@ int movfe_download_matches(movfe_ctx *ctx, int stream, int64_t frame, int32_t *m
 #define MOVFE_STAGE_EXTRACT  3   /* propagation kernels */
 #define MOVFE_STAGE_POSE     4   /* join / frustum / pose kernels */
 #define MOVFE_N_STAGES       5
+/* Workload counters since the last reset (synchronises): out[0] tracks looked up in the slot grid, [1] candidate hops of those
+ * tracks, [2] pose solves, [3] correspondences of those solves, [4] passes over the correspondences (Gauss-Newton iterations +
+ * re-classifications), [5] hops of the rastered frames, [6] frames rastered, [7] reserved. bench.py turns them into the
+ * per-frame figures SURVEY.md 8d's byte formulas need. */
+int movfe_workload_stats(movfe_ctx *ctx, uint64_t *out /* 8 */, int reset);
 int movfe_profile_enable(movfe_ctx *ctx, int on);
 /* Waits for the stream, then adds up the event-timed milliseconds and kernel launches per stage since the last
  * reset. ms / launches have MOVFE_N_STAGES entries (either may be NULL). */

@@ -31,7 +31,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     for (int g = 1; g < movfe_ctx::MAX_GROUPS; g++)
         if (ctx->ext_stream[g]) cudaStreamSynchronize(ctx->ext_stream[g]);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    void *bufs[] = {ctx->d_stage[0], ctx->d_stage[1], ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected,
+    void *bufs[] = {ctx->d_stage[0], ctx->d_stage[1], ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, ctx->d_grey, ctx->d_rejected, ctx->d_stats,
                     ctx->d_tracks, ctx->d_ntracks,
                     ctx->d_cur_id, ctx->d_ext_scratch, ctx->d_map, ctx->d_nmap, ctx->d_nkf, ctx->d_pose_cur,
                     ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier, ctx->d_pose_scratch, ctx->d_op, ctx->d_pairs, ctx->d_npairs};
@@ -41,7 +41,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     if (ctx->h_map_meta) cudaFreeHost(ctx->h_map_meta);
     for (RasterBuf &w : ctx->rb) {
         void *wb[] = {w.d_seg_cnt, w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
-                      w.d_chunk_bbox, w.d_grid};
+                      w.d_chunk_bbox, w.d_grid, w.d_tq_cnt, w.d_tq_ent};
         for (void *b : wb)
             if (b) cudaFree(b);
         if (w.done) cudaEventDestroy(w.done);
@@ -122,6 +122,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     int prio_lo = 0, prio_hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     ctx->serial_raster = (c.flags & MOVFE_CFG_SERIAL_RASTER) != 0;
+    ctx->fused = (c.flags & MOVFE_CFG_NO_GRID) != 0;
     // pose chain and propagation share the high priority (a pose stream ABOVE propagation measured slower: 4.86-5.05 ms per
     // step against 4.75 ms)
     const int prio_prop = prio_hi;
@@ -178,6 +179,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->RING = 2 * c.window_frames + ctx->LA;
     ctx->NB = (c.height + 7) / 8;
     ctx->NT = (c.width + 31) / 32;
+    ctx->NTR = (c.height + 31) / 32;
     ctx->max_hops = c.max_records_per_frame * (ctx->K + 1);
     ctx->max_kps = c.max_records_per_frame * (ctx->K + 1);
     ctx->max_chunks = (ctx->max_hops + 31) / 32;
@@ -194,6 +196,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(dalloc(&ctx->d_rec_cnt, S * RING));
     CK(dalloc(&ctx->d_fflags, S * RING));
     if (c.has_grey) CK(dalloc(&ctx->d_grey, S * RING * (size_t)c.height * ctx->grey_pitch));
+    CK(dalloc(&ctx->d_stats, 8));
+    CK(cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)));
     CK(dalloc(&ctx->d_rejected, 1));
     CK(cudaMemset(ctx->d_rejected, 0, sizeof(unsigned long long)));
     CK(cudaMemset(ctx->d_rec_cnt, 0, S * RING * sizeof(int32_t)));
@@ -211,7 +215,13 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
         CK(dalloc(&w.d_hop_rect, S * F * ctx->max_hops));
         CK(dalloc(&w.d_kps, S * F * ctx->max_kps));
         CK(dalloc(&w.d_chunk_bbox, S * F * ctx->max_chunks));
-        CK(dalloc(&w.d_grid, S * F * plane));
+        if (ctx->fused) {
+            const size_t tiles = (size_t)ctx->NT * ctx->NTR;
+            CK(dalloc(&w.d_tq_cnt, S * F * tiles));
+            CK(dalloc(&w.d_tq_ent, S * F * tiles * MOVFE_TILE_Q));
+        } else {
+            CK(dalloc(&w.d_grid, S * F * plane));
+        }
     }
     // track tables
     ctx->TSLOTS = 2 * c.window_frames + 1;
@@ -485,6 +495,7 @@ extern "C" int movfe_download_grid(movfe_ctx *ctx, int stream, int64_t frame, in
     if (rc) return rc;
     const size_t plane = (size_t)ctx->cfg.width * ctx->cfg.height;
     const RasterBuf &w = ctx->rb[ctx->rb_cur];
+    if (ctx->fused) MOVFE_FAIL(ctx, MOVFE_E_STATE, "download_grid: the context was created with MOVFE_CFG_NO_GRID (the slot grid is not materialised)");
     MOVFE_CUDA(ctx, cudaMemcpyAsync(out, w.d_grid + ((size_t)stream * w.nout + fi) * plane, plane * sizeof(int4),
                                     cudaMemcpyDeviceToHost, ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
@@ -529,6 +540,15 @@ extern "C" int64_t movfe_rejected_records(movfe_ctx *ctx) {
     if (cudaMemcpyAsync(&v, ctx->d_rejected, sizeof v, cudaMemcpyDeviceToHost, ctx->raster_stream) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(ctx->raster_stream) != cudaSuccess) return -1;
     return (int64_t)v;
+}
+
+extern "C" int movfe_workload_stats(movfe_ctx *ctx, uint64_t *out, int reset) {
+    if (!ctx || !out) return MOVFE_E_INVALID;
+    int rc = movfe_synchronize(ctx);
+    if (rc) return rc;
+    MOVFE_CUDA(ctx, cudaMemcpy(out, ctx->d_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) MOVFE_CUDA(ctx, cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)));
+    return MOVFE_OK;
 }
 
 extern "C" int movfe_profile_enable(movfe_ctx *ctx, int on) {

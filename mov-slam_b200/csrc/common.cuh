@@ -30,6 +30,23 @@ struct __align__(8) HopRect {
     int16_t x0, y0, x1, y1;
 };
 
+// ---- fused (grid-free) mode: per-tile hop queues instead of the per-pixel slot grid ---------------------------------------
+// Propagation looks the slot grid up at a few thousand pixels per frame (one per track, plus the 16-px lattice of a back-fill
+// pass) out of W*H. In fused mode (MOVFE_CFG_NO_GRID) the raster stage stops after its phase 1 and stores, for every 32x32
+// pixel tile, the ordered queue of the hops whose rectangle meets the tile; a query resolves the four slots of ONE pixel
+// from its tile's queue (first three covering hops in order + the last one, VideoDecoder.cc:336-343). The 16 bytes per
+// pixel of the grid are never written: SURVEY.md 8d charges this mode 40 M + 12 Hops for the raster term.
+#define MOVFE_TILE_Q 186   // queue capacity per tile (6 chunks of 31); fuller tiles are resolved from the frame's hop list
+struct TileQueues {
+    const int32_t *cnt;    // [tiles] entries queued (> MOVFE_TILE_Q or < 0: overflow)
+    const uint2 *ent;      // [tiles][MOVFE_TILE_Q]  x = x0 | x1 << 16 (pixels), y = hop | r0 << 22 | r1 << 27 (rows inside the tile row)
+    const struct HopRect *rects;  // the frame's hop rectangles (overflow path)
+    int n_hops, NT;        // NT: tiles per tile row
+};
+
+// Slots of pixel (x, y): what VideoImage::mvi.at<Vec4i>(y, x) holds in the reference.
+__device__ __forceinline__ int4 resolve_slots(const TileQueues &q, int x, int y);
+
 // Per-frame class counts produced by the count pass (index into cls_cnt[frame][...]):
 //   [0..K]        valid P-branch records with ref >= k          -> hop segment k of frame (f-k)
 //   [K+1]         valid records that push their block into this frame's kps (not "chained")
@@ -53,7 +70,9 @@ struct RasterBuf {
     HopRect    *d_hop_rect = nullptr;
     movfe_rect *d_kps = nullptr;    // [S][F][max_kps]
     int2    *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  extent of every 32-hop chunk: (ymin | ymax<<16, xmin | xmax<<16)
-    int4    *d_grid = nullptr;      // [S][F][H*W]
+    int4    *d_grid = nullptr;      // [S][F][H*W]   (grid-output mode)
+    int32_t *d_tq_cnt = nullptr;    // [S][F][tiles]                (fused mode)
+    uint2   *d_tq_ent = nullptr;    // [S][F][tiles][MOVFE_TILE_Q]  (fused mode)
     cudaEvent_t done = nullptr;      // recorded on raster_stream: the buffer is complete
     cudaEvent_t consumed = nullptr;  // recorded on stream after the last propagation launch that read it
     bool    consumed_valid = false;
@@ -63,6 +82,8 @@ struct movfe_ctx {
     movfe_config cfg;
     int K = 0, LA = 0, RING = 0, NIN = 0;  // max_ref, look-ahead frames, ring depth, max input frames per window
     int NB = 0, NT = 0;                    // 8-row bands per frame, 32-px tiles per band
+    int NTR = 0;                           // 32-row tile rows per frame
+    bool fused = false;                    // MOVFE_CFG_NO_GRID: per-tile hop queues instead of the slot grid
     int max_hops = 0, max_kps = 0, max_chunks = 0;
     int rseg = 0, n_rseg = 1;              // records per count/emit segment (multiple of 512), segments per frame
     int sm_count = 0;
@@ -163,6 +184,11 @@ struct movfe_ctx {
     bool     pose_split = false;       // MOVFE_POSE_SPLIT=1: join kernels + small solver kernels instead of the fused
                                        // one-kernel-per-frame chain (measured slower under load)
 
+    // workload counters (movfe_workload_stats): diagnostic integer atomics, never on the data path
+    //  [0] tracks looked up   [1] candidate hops of those tracks   [2] pose solves   [3] correspondences of those solves
+    //  [4] passes over the correspondences (GN iterations + re-classifications)   [5] hops of rastered frames   [6] frames rastered
+    unsigned long long *d_stats = nullptr;
+
     // instrumentation
     bool prof_on = false;
     struct ProfSpan { int stage; cudaEvent_t a, b; };
@@ -189,6 +215,42 @@ struct movfe_ctx {
         cudaError_t _e = (expr);                                                               \
         if (_e != cudaSuccess) MOVFE_FAIL(ctx, MOVFE_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+
+__device__ __forceinline__ int4 resolve_slots(const TileQueues &q, int x, int y) {
+    int4 s = make_int4(-1, -1, -1, -1);
+    int c = 0;
+    const int tile = (y >> 5) * q.NT + (x >> 5);
+    const int n = __ldg(&q.cnt[tile]);
+    if (n >= 0 && n <= MOVFE_TILE_Q) {
+        const uint2 *e = q.ent + (size_t)tile * MOVFE_TILE_Q;
+        const unsigned ry = (unsigned)(y & 31);
+        for (int i = 0; i < n; i++) {
+            const uint2 w = __ldg(&e[i]);
+            const unsigned x0 = w.x & 0xffffu, x1 = w.x >> 16, r0 = (w.y >> 22) & 31u, r1 = w.y >> 27;
+            if ((unsigned)x >= x0 && (unsigned)x <= x1 && ry >= r0 && ry <= r1) {
+                const int h = (int)(w.y & 0x3fffffu);
+                if (c == 0) s.x = h;
+                else if (c == 1) s.y = h;
+                else if (c == 2) s.z = h;
+                else s.w = h;
+                c++;
+            }
+        }
+    } else {  // more hops meet the tile than a queue holds: the frame's whole hop list, in order
+        for (int h = 0; h < q.n_hops; h++) {
+            const int2 r = __ldg(reinterpret_cast<const int2 *>(q.rects + h));
+            const int x0 = (int16_t)(r.x & 0xffff), y0 = r.x >> 16, x1 = (int16_t)(r.y & 0xffff), y1 = r.y >> 16;
+            if (x >= x0 && x <= x1 && y >= y0 && y <= y1) {
+                if (c == 0) s.x = h;
+                else if (c == 1) s.y = h;
+                else if (c == 2) s.z = h;
+                else s.w = h;
+                c++;
+            }
+        }
+    }
+    return s;
+}
 
 // 128-bit streaming store: the slot grid is written once and not re-read by the writer.
 __device__ __forceinline__ void st_cs_v4(int4 *p, int4 v) {

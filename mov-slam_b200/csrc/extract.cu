@@ -48,8 +48,30 @@ struct ExtParams {
     int thr;         // EXPRESS threshold
     int has_grey;
     int use_lk;      // this frame consumes the host LK results installed with movfe_set_lk_results
+    int fused;       // MOVFE_CFG_NO_GRID: slots come from the per-tile hop queues (common.cuh: resolve_slots), not from a slot grid
+    int NT, tiles;   // tiles per tile row / per frame
     double cov_thr;
 };
+
+// raster results of one frame as the propagation kernels read them: the slot grid (grid-output mode) or the tile queues
+struct SlotSource {
+    const int4 *grid;
+    const int32_t *tq_cnt;
+    const uint2 *tq_ent;
+    const HopRect *hop_rect;
+    const int32_t *nhops;
+};
+
+__device__ __forceinline__ TileQueues frame_queues(const ExtParams &p, const SlotSource &src, int s) {
+    const size_t fr = (size_t)s * p.n_out + p.fi;
+    TileQueues q;
+    q.cnt = src.tq_cnt + fr * p.tiles;
+    q.ent = src.tq_ent + fr * p.tiles * MOVFE_TILE_Q;
+    q.rects = src.hop_rect + fr * p.max_hops;
+    q.n_hops = src.nhops[s * p.n_in + p.fi];
+    q.NT = p.NT;
+    return q;
+}
 
 // Host LK hand-over (movfe_set_lk_results), per stream. n < 0: nothing installed for this frame.
 struct LkBuf {
@@ -416,9 +438,9 @@ __device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, i
 template <int PITCH>
 __global__ void __launch_bounds__(CAND_THREADS, CAND_MINB)
 cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
-            const uint16_t *__restrict__ order, const int4 *__restrict__ grid, const movfe_hop *__restrict__ hops,
+            const uint16_t *__restrict__ order, SlotSource src, const movfe_hop *__restrict__ hops,
             const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
-            int2 *__restrict__ cinfo, int32_t *__restrict__ claim) {
+            int2 *__restrict__ cinfo, int32_t *__restrict__ claim, unsigned long long *__restrict__ stats) {
     __shared__ int sm[CAND_WARPS][CW_WORDS][32];
     pdl_wait();     // the previous frame's finalize_kernel wrote the tables read below
     pdl_trigger();  // after the wait: at most one dependent grid is resident and waiting
@@ -428,7 +450,9 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;  // I frame: nothing is propagated
     const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
     const uint16_t *ord = order + (size_t)s * p.maxT;
-    const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
+    const int4 *g = p.fused ? nullptr : src.grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
+    TileQueues tq = {};
+    if (p.fused) tq = frame_queues(p, src, s);
     const movfe_hop *hp = hops + ((size_t)s * p.n_out + p.fi) * p.max_hops;
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     movfe_track *st = stage + (size_t)s * p.maxT;
@@ -458,7 +482,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         if (alive) {
             const int x = (int)ptx, y = (int)pty;  // :264
             if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
-            else sl = __ldg(&g[(size_t)y * p.W + x]);
+            else sl = p.fused ? resolve_slots(tq, x, y) : __ldg(&g[(size_t)y * p.W + x]);
         }
         if (sl.x == -1) alive = false;  // :265-268
         const int sj[4] = {sl.x, sl.y, sl.z, sl.w};
@@ -466,6 +490,14 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         vj[0] = alive;
 #pragma unroll
         for (int j = 1; j < 4; j++) vj[j] = vj[j - 1] && sj[j] != -1;  // :277-278 stop at the first empty slot
+        {   // workload counters (diagnostic): tracks looked up and their candidate hops
+            const int nt = __reduce_add_sync(0xffffffffu, alive ? 1 : 0);
+            const int nc = __reduce_add_sync(0xffffffffu, (int)vj[0] + (int)vj[1] + (int)vj[2] + (int)vj[3]);
+            if (lane == 0 && nt) {
+                atomicAdd(&stats[0], (unsigned long long)nt);
+                atomicAdd(&stats[1], (unsigned long long)nc);
+            }
+        }
         int4 hv[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) hv[j] = vj[j] ? __ldg(reinterpret_cast<const int4 *>(hp + sj[j])) : make_int4(0, 0, -1, 0);
@@ -972,7 +1004,7 @@ __device__ void fill_keys(const movfe_track *__restrict__ tab, int from, int n, 
 }
 
 // 16-px lattice walk shared by the coverage back-fill (:418-451) and the I-frame seeding (:123-157).
-__device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img, const int4 *__restrict__ g, bool need_uncovered,
+__device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img, const int4 *__restrict__ g, const TileQueues &tq, bool need_uncovered,
                              uint32_t track_flags, movfe_track *__restrict__ cur, int &n_out, int &id, uint32_t (*scratch)[8],
                              int *lat_flag) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -988,7 +1020,7 @@ __device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img
             x = 8 + 16 * (b % gw);
             if (rect_in_bounds(x - 8, y - 8, 16, 16, p.W, p.H)) {
                 if (express_birth<16, 16, 0>(img, (unsigned)((y - 8) * p.P + (x - 8)), p.P, p.thr, scratch[warp], lane, d) &&
-                    !(need_uncovered && __ldg(&g[(size_t)y * p.W + x]).x >= 0))
+                    !(need_uncovered && (p.fused ? resolve_slots(tq, x, y).x : __ldg(&g[(size_t)y * p.W + x]).x) >= 0))
                     pass = true;
             }
         }
@@ -1025,7 +1057,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                 int32_t *__restrict__ cur_id, uint16_t *__restrict__ order, const movfe_track *__restrict__ stage,
                 const int2 *__restrict__ cinfo, int32_t *__restrict__ claim, const movfe_rect *__restrict__ kps,
                 const int32_t *__restrict__ nkps, const double *__restrict__ cov, const uint8_t *__restrict__ birth_flag,
-                const uint32_t *__restrict__ birth_desc, const int4 *__restrict__ grid,
+                const uint32_t *__restrict__ birth_desc, SlotSource src,
                 const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, LkBuf lk) {
     extern __shared__ unsigned long long keys[];  // general sort: keys[N]; run sort: age[maxT] pk[maxT] run_start[maxT] hist[32][264]
     __shared__ int wsum[FIN_WARPS];
@@ -1050,7 +1082,9 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     int n_out = 0;    // logical size of the new table (entries beyond maxT are dropped)
     int n_keyed = 0;  // entries whose sort key is already in shared memory
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
-    const int4 *g = grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
+    const int4 *g = p.fused ? nullptr : src.grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
+    TileQueues tq = {};
+    if (p.fused) tq = frame_queues(p, src, s);
     const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
     const int lk_n = p.use_lk ? lk.n[s] : -1;
     const uint8_t *lk_st = lk.status + (size_t)s * p.maxT;
@@ -1241,10 +1275,10 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
         n_keyed = min(n_out, p.maxT);
         // coverage back-fill (:418-451)
         if (img && (cov[s * p.n_in + p.fi] < p.cov_thr || mov_cnt < 60))
-            lattice_pass(p, img, g, true, MOVFE_TRACK_COVERAGE, cur, n_out, id, scratch, lat_flag);
+            lattice_pass(p, img, g, tq, true, MOVFE_TRACK_COVERAGE, cur, n_out, id, scratch, lat_flag);
     } else if (n_prev == 0 && img) {
         // I frame without previous features: seeding on the 16-px lattice (:123-157)
-        lattice_pass(p, img, g, false, 0u, cur, n_out, id, scratch, lat_flag);
+        lattice_pass(p, img, g, tq, false, 0u, cur, n_out, id, scratch, lat_flag);
     } else if (n_prev > 0) {
         // I frame with previous features (:81-120): every track of the previous table, in TABLE order, is carried to its LK
         // position with block and descriptor kept, age + 1, qIndx = its index; no seeding happens
@@ -1455,6 +1489,10 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.thr = c.express_threshold;
         p.has_grey = c.has_grey;
         p.use_lk = (k == 0 && ctx->lk_pending) ? 1 : 0;
+        p.fused = ctx->fused ? 1 : 0;
+        p.NT = ctx->NT;
+        p.tiles = ctx->NT * ctx->NTR;
+        const SlotSource src = {w.d_grid, w.d_tq_cnt, w.d_tq_ent, w.d_hop_rect, w.d_nhops};
         p.P = ctx->grey_pitch;
         p.cov_thr = c.coverage_threshold;
         const bool batch_end = !pdl_cand || (k + 1) % ctx->ev_batch == 0 || k == n_frames - 1;
@@ -1467,7 +1505,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
 #define MOVFE_CAND(PITCH)                                                                                              \
     MOVFE_CUDA(ctx, launch_pdl(pdl_cand, cand_kernel<PITCH>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
-                               w.d_grid, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim))
+                               src, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim, ctx->d_stats))
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
             case 2048: MOVFE_CAND(2048); break;
@@ -1490,7 +1528,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         }
         MOVFE_CUDA(ctx, launch_pdl(pdl, finalize_kernel, dim3(ns), dim3(FIN_THREADS), sort_smem(c.max_tracks), gs, p, ctx->d_tracks,
                                    ctx->d_ntracks, ctx->d_cur_id, e.order, e.stage, e.cinfo, e.claim, w.d_kps, w.d_nkps, w.d_cov,
-                                   e.birth_flag, e.birth_desc, w.d_grid, ctx->d_grey, ctx->d_fflags, e.lk));
+                                   e.birth_flag, e.birth_desc, src, ctx->d_grey, ctx->d_fflags, e.lk));
         prof.launches(nl);
         // the tables up to frame a are complete for this group: the pose stream may start on them while propagation goes on.
         // One event per ev_batch frames (and at the end of the call): an event record between two kernels breaks their
@@ -1663,6 +1701,7 @@ extern "C" int movfe_extract_frame(movfe_ctx *ctx, uint32_t frame_flags, const u
     if (grey && grey_stride == 0) grey_stride = c.width;
     if (grey && grey_stride < c.width) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "extract_frame: grey_stride %d below the frame width %d", grey_stride, c.width);
     if (c.n_streams != 1) MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract_frame: the context must have exactly one stream");
+    if (ctx->fused) MOVFE_FAIL(ctx, MOVFE_E_STATE, "extract_frame: takes a slot grid from the host; the context was created with MOVFE_CFG_NO_GRID");
     if (!grid || !current_id || !out || n_hops < 0 || n_kps < 0 || n_prev < 0 || (n_hops && !hops) || (n_kps && !kps) || (n_prev && !prev))
         MOVFE_FAIL(ctx, MOVFE_E_INVALID, "extract_frame: bad argument");
     if ((c.has_grey != 0) != (grey != nullptr))

@@ -27,6 +27,7 @@ constexpr int GRID_MAX_WARPS = 16;
 constexpr int GRID_CHUNK_CAP = 1024;   // surviving 32-hop chunk ids per band
 constexpr int TILE_CHUNKS = 6;         // a tile's candidates: up to 6 chunks of 31
 constexpr int TILE_Q = 31 * TILE_CHUNKS;
+static_assert(TILE_Q == MOVFE_TILE_Q, "queue capacity shared with the fused-mode queries (common.cuh)");
 constexpr int TQ_STRIDE = TILE_Q + 6;  // queue words per tile
 constexpr int CELL_CAP = 128;          // (column run, row run) cells resolved per batch
 constexpr int SB_ROWS = 32;            // rows a CTA owns = rows of a tile
@@ -220,10 +221,12 @@ __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, c
     }
 }
 
-// grid = (32-row bands, frames of the window x x-splits, streams)
+// grid = (32-row bands, frames of the window x x-splits, streams). FUSED: stop after phase 1 and store the per-tile queues
+// (tq_cnt / tq_ent, common.cuh: TileQueues) instead of resolving and writing every pixel.
+template <bool FUSED>
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
 grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
-            const int2 *__restrict__ chunk_bbox, int4 *__restrict__ grid) {
+            const int2 *__restrict__ chunk_bbox, int4 *__restrict__ grid, int32_t *__restrict__ tq_cnt, uint2 *__restrict__ tq_ent, int NT) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -381,6 +384,21 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
     }
     __syncthreads();
 
+    if (FUSED) {
+        // ---- fused mode: the queues ARE the result ---------------------------------------------------------------------
+        const int ntr = (p.H + SB_ROWS - 1) / SB_ROWS;
+        for (int t = warp; t < ntl; t += nwarps) {
+            const size_t tile = ((size_t)sg * ntr + band) * NT + (size_t)xs * NTC + t;
+            const int nq = __shfl_sync(0xffffffffu, run_total, t);
+            if (lane == 0) tq_cnt[tile] = direct ? -1 : nq;
+            if (!direct) {
+                const uint32_t *qx = tq_x + t * TQ_STRIDE, *qi = tq_i + t * TQ_STRIDE;
+                uint2 *o = tq_ent + tile * TILE_Q;
+                for (int e = lane; e < min(nq, TILE_Q); e += 32) o[e] = make_uint2(qx[e], qi[e]);
+            }
+        }
+        return;
+    }
     // ---- phase 2: a warp takes 32x32-pixel tiles of the band; no block barrier from here on -----------------------
     const int nrows = yhi - ylo + 1;
     for (int t = warp; t < ntl; t += nwarps) {
@@ -482,10 +500,16 @@ int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w) {
     if (nw == 4 && ntc % 4 != 0 && ntc > 4) nw = 8;
     const size_t smem = (size_t)nw * sizeof(WarpScratch) + ((size_t)2 * ntc * TQ_STRIDE + GRID_CHUNK_CAP) * sizeof(uint32_t);
     if (smem > (size_t)ctx->smem_optin) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "grid: %zu bytes of shared memory per CTA exceed the device limit %d", smem, ctx->smem_optin);
-    MOVFE_CUDA(ctx, optin_dynamic_smem(grid_kernel, ctx->smem_optin));  // same value from every context
+    MOVFE_CUDA(ctx, optin_dynamic_smem(grid_kernel<false>, ctx->smem_optin));  // same value from every context
+    MOVFE_CUDA(ctx, optin_dynamic_smem(grid_kernel<true>, ctx->smem_optin));
     if ((size_t)p.n_out * nxs > 65535 || p.S > 65535) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "grid: launch grid out of range");
     dim3 blocks(nsb, p.n_out * nxs, p.S);
-    grid_kernel<<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid);
+    if (ctx->fused)
+        grid_kernel<true><<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, nullptr, w.d_tq_cnt,
+                                                                          w.d_tq_ent, ctx->NT);
+    else
+        grid_kernel<false><<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid, nullptr,
+                                                                           nullptr, ctx->NT);
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }

@@ -638,7 +638,8 @@ __global__ void __launch_bounds__(TP_THREADS, MOVFE_TP_MINB)
 track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
                    const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
                    movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses, int32_t *__restrict__ ninl,
-                   int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out, int32_t *__restrict__ skip_tag) {
+                   int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out, int32_t *__restrict__ skip_tag,
+                   unsigned long long *__restrict__ stats) {
     extern __shared__ int hsm[];  // keys[cap] vals[cap] first[maxMap] | pairs: x y z u v idx [maxMap] out[maxMap]
     __shared__ SolverShared sh;
     __shared__ int wsum[TP_WARPS];
@@ -668,6 +669,11 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
                        first, match);
             int np = gather_pairs(tr, n, match, mp, cx, cy, cz, cu, cv, cidx, p.maxMap, wsum);
             pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
+            if (threadIdx.x == 0) {  // workload counters (diagnostic)
+                atomicAdd(&stats[2], 1ull);
+                atomicAdd(&stats[3], (unsigned long long)np);
+                atomicAdd(&stats[4], (unsigned long long)sh.stats[2]);
+            }
             // --- TrackLocalMap / SearchLocalPoints (Tracking.cc:1109-1158)
             const int frame_tag = 1;  // tags are cleared again below, so one value is enough
             for (int i = threadIdx.x; i < np; i += blockDim.x) tag[match[cidx[i]]] = frame_tag;  // mnLastFrameSeen = current frame
@@ -683,6 +689,11 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
             join_frame(tr, n, mp, n_map, [&](int i) { return cout[i] != 0; }, false, keys, vals, cap, first, match);
             np = gather_pairs(tr, n, match, mp, cx, cy, cz, cu, cv, cidx, p.maxMap, wsum);
             n_inl = pose_solve(src, np, p.cam, p.pp, pc, cout, nullptr, sh);
+            if (threadIdx.x == 0) {
+                atomicAdd(&stats[2], 1ull);
+                atomicAdd(&stats[3], (unsigned long long)np);
+                atomicAdd(&stats[4], (unsigned long long)sh.stats[2]);
+            }
             // Frame::mvbOutlier (Optimizer.cc:452-456): true everywhere, false for the inliers
             for (int t = threadIdx.x; t < n; t += blockDim.x) outl[t] = 1;
             __syncthreads();
@@ -948,7 +959,7 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
             prof.launches(1);
             track_poses_kernel<<<c.n_streams, TP_THREADS, smem, ctx->pose_stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap,
                                                                                     ctx->d_nkf, ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl,
-                                                                                    ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch);
+                                                                                    ctx->d_match, ctx->d_outlier, (int32_t *)ctx->d_pose_scratch, ctx->d_stats);
         } else {
             prof.launches(2 + 2 * n_cls);
             int32_t *tags = (int32_t *)ctx->d_pose_scratch;

@@ -267,7 +267,8 @@ __global__ void seg_sum_kernel(WinParams p, int n_rseg, const int32_t *__restric
 // ------------------------------------------------------------------------------------------------- bases -----
 __global__ void bases_kernel(WinParams p, const int32_t *__restrict__ cls_cnt, const int64_t *__restrict__ area,
                              int32_t *__restrict__ hop_base, int32_t *__restrict__ kps_base,
-                             int32_t *__restrict__ nhops, int32_t *__restrict__ nkps, double *__restrict__ cov) {
+                             int32_t *__restrict__ nhops, int32_t *__restrict__ nkps, double *__restrict__ cov,
+                             unsigned long long *__restrict__ stats) {
     const int sg = blockIdx.x * blockDim.x + threadIdx.x;
     if (sg >= p.S * p.n_in) return;
     const int s = sg / p.n_in, g = sg - s * p.n_in;
@@ -279,6 +280,10 @@ __global__ void bases_kernel(WinParams p, const int32_t *__restrict__ cls_cnt, c
     }
     hop_base[(size_t)sg * (K + 2) + K + 1] = hb;
     nhops[sg] = hb < p.max_hops ? hb : p.max_hops;
+    if (g < p.n_out) {  // workload counters (diagnostic)
+        atomicAdd(&stats[5], (unsigned long long)(hb < p.max_hops ? hb : p.max_hops));
+        atomicAdd(&stats[6], 1ull);
+    }
     int kb = 0;
     kps_base[(size_t)sg * (K + 2) + 0] = 0;
     kb = cls_cnt[(size_t)sg * MAXCLS + K + 1];  // own
@@ -498,7 +503,7 @@ int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n
     count_kernel<<<gseg, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->rseg, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_seg_cnt);
     seg_sum_kernel<<<SF, 32, 0, ctx->raster_stream>>>(p, ctx->n_rseg, w.d_seg_cnt, w.d_cls_cnt, w.d_area, ctx->d_rejected);
     bases_kernel<<<(SF + 127) / 128, 128, 0, ctx->raster_stream>>>(p, w.d_cls_cnt, w.d_area, w.d_hop_base,
-                                                            w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov);
+                                                            w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, ctx->d_stats);
     emit_kernel<<<gseg, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->rseg, w.d_seg_cnt, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags,
                                                        w.d_hop_base, w.d_kps_base, w.d_hops, w.d_hop_rect, w.d_kps);
     {

@@ -76,6 +76,7 @@ def load():
     L.movfe_track_feature_grid.argtypes = [vp, i32, i64, vp, vp, i32]
     L.movfe_features_in_area.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp]
     L.movfe_pose_optimize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.movfe_workload_stats.argtypes = [vp, vp, i32]
     L.movfe_profile_enable.argtypes = [vp, i32]
     L.movfe_profile_read.argtypes = [vp, vp, vp, i32]
     _LIB = L
@@ -89,7 +90,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
-           "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read"]
+           "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read", "movfe_workload_stats"]
 
 
 def _p(a):
@@ -101,15 +102,17 @@ def _p(a):
 
 
 CFG_SERIAL_RASTER = 1   # MOVFE_CFG_SERIAL_RASTER
+CFG_NO_GRID = 2         # MOVFE_CFG_NO_GRID
 
 
 class Context:
     def __init__(self, n_streams, width, height, max_records_per_frame=4800, max_ref=3, window_frames=16,
                  max_tracks=4096, max_map_points=4096, express_threshold=25, coverage_threshold=0.20, has_grey=True,
-                 device=0, serial_raster=False):
+                 device=0, serial_raster=False, output_grid=True):
         self.L = load()
         self.cfg = Config(device, n_streams, width, height, max_records_per_frame, max_ref, window_frames, max_tracks,
-                          max_map_points, express_threshold, coverage_threshold, int(bool(has_grey)), CFG_SERIAL_RASTER if serial_raster else 0)
+                          max_map_points, express_threshold, coverage_threshold, int(bool(has_grey)),
+                          (CFG_SERIAL_RASTER if serial_raster else 0) | (0 if output_grid else CFG_NO_GRID))
         h = C.c_void_p()
         rc = self.L.movfe_create(C.byref(self.cfg), C.byref(h))
         if rc != 0:
@@ -142,6 +145,15 @@ class Context:
         return self.L.movfe_cuda_stream(self.h)
 
     STAGES = ("ingest", "hops", "grid", "extract", "pose")
+
+    def workload_stats(self, reset=True):
+        """Per-frame workload figures from the device counters (movfe_workload_stats)."""
+        c = np.zeros(8, np.uint64)
+        self._ck(self.L.movfe_workload_stats(self.h, _p(c), int(reset)))
+        c = c.astype(np.float64)
+        return {"tracks_looked_up": c[0], "candidates_per_track": c[1] / max(c[0], 1.0), "pose_solves": c[2],
+                "pose_correspondences": c[3] / max(c[2], 1.0), "pose_passes_per_solve": c[4] / max(c[2], 1.0),
+                "hops_per_frame": c[5] / max(c[6], 1.0), "frames_rastered": c[6]}
 
     def profile_enable(self, on=True):
         self._ck(self.L.movfe_profile_enable(self.h, int(on)))

@@ -142,7 +142,7 @@ typedef struct orc_frontend_out {
     int32_t    *n_tracks;         /* n_frames */
     int32_t    *n_inliers;        /* n_frames (second PoseOptimization) */
     movfe_track *last_tracks;     /* max_tracks: table of the last frame */
-    uint64_t   *track_hash;       /* n_frames: FNV-1a over the frame's track table (may be NULL) */
+    uint64_t   *track_hash;       /* n_frames: checksum of the frame's track table (frontend.cc: table_checksum; may be NULL) */
 } orc_frontend_out;
 
 /* Runs raster -> extract -> [join(kf) -> pose -> frustum -> join(local) -> pose] per frame, as Tracking.cc

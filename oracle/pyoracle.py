@@ -325,3 +325,11 @@ def frontend_run(width, height, recs, rec_off, frame_flags, grey, seed_tracks, m
                                           _p(s_off), _p(s_pts), _p(s_nkf), int(timed_from), _p(tail), C.byref(out))
     return dict(poses=poses, n_tracks=n_tracks, n_inliers=n_inl, last_tracks=last[:n_last].copy(), track_hash=hashes,
                 tail_times=tail)
+
+
+def table_checksum(tracks):
+    """numpy mirror of frontend.cc::table_checksum (what frontend_run's track_hash holds per frame)."""
+    w = np.ascontiguousarray(tracks, T.TRACK).view(np.uint64).ravel()
+    i = np.arange(len(w), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return int(np.sum((w ^ (i * np.uint64(0x9E3779B97F4A7C15))) * (np.uint64(2) * i + np.uint64(1)), dtype=np.uint64))

@@ -13,9 +13,12 @@ from gpu_util import assert_tracks_equal, oracle_tracks, pack_streams
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("serial_raster,env", [(False, {}), (True, {}), (False, {"MOVFE_POSE_SPLIT": "1"}),
-                                               (False, {"MOVFE_PDL": "1"}), (False, {"MOVFE_EXTRACT_GROUPS": "3"})])
-def test_pipelined_windows_match_oracle(orc, serial_raster, env, monkeypatch):
+@pytest.mark.parametrize("serial_raster,env,output_grid", [(False, {}, True), (True, {}, True), (False, {"MOVFE_POSE_SPLIT": "1"}, True),
+                                                           (False, {"MOVFE_PDL": "1"}, True), (False, {"MOVFE_EXTRACT_GROUPS": "3"}, True),
+                                                           (False, {}, False), (True, {}, False), (False, {"MOVFE_PDL": "1"}, False)])
+def test_pipelined_windows_match_oracle(orc, serial_raster, env, output_grid, monkeypatch):
+    """output_grid False = MOVFE_CFG_NO_GRID, the fused mode bench.py's headline uses: slots resolved from the per-tile hop
+    queues, same tables bit for bit."""
     for k, v in env.items():      # development switches of the library, read at movfe_create: every path stays parity-tested
         monkeypatch.setenv(k, v)
     W, H, F, K, NW, S, NB = 640, 480, 8, 3, 6, 12, 3
@@ -31,10 +34,11 @@ def test_pipelined_windows_match_oracle(orc, serial_raster, env, monkeypatch):
     cam, pp = specs[0].camera(), T.pose_params()
 
     ctx = lib.Context(S, W, H, max_records_per_frame=4800, max_ref=K, window_frames=F, max_tracks=8192, max_map_points=2048,
-                      has_grey=True, serial_raster=serial_raster)
+                      has_grey=True, serial_raster=serial_raster, output_grid=output_grid)
     ctx.set_camera(cam, pp, 0.5)
+    off = np.cumsum([0] + [len(maps[s % NB]) for s in range(S)]).astype(np.int64)   # all streams' maps in one call
+    ctx.set_map_points_batch(np.concatenate([maps[s % NB] for s in range(S)]), off, [len(maps[s % NB]) // 2 for s in range(S)], 2048)
     for s in range(S):
-        ctx.set_map_points(s, maps[s % NB], len(maps[s % NB]) // 2)
         ctx.set_pose(s, synth.pose_struct(synth.pose_at(specs[s % NB], 0)))
 
     def push(f0, f1):
