@@ -73,6 +73,8 @@ def lib(variant="plain"):
         L.ref_extract_frame.restype = i32
         L.ref_extract_frame.argtypes = [i32, i32, u32, vp, vp, vp, i32, vp, i32, f64, vp, i32, i32, i32, i32, vp, vp, vp, i32, f64, f64,
                                         vp, vp, i32, vp]
+        L.ref_frontend_run.restype = i32
+        L.ref_frontend_run.argtypes = [i32, i32, i32, vp, vp, vp, vp, i32, i32, f64, vp, vp, vp, vp]
         L.ref_search_by_video_feature.restype = i32
         L.ref_search_by_video_feature.argtypes = [vp, i32, vp, vp, i32, i32, f32, vp]
         L.ref_search_by_keyframe.restype = i32
@@ -228,3 +230,20 @@ def search_for_initialization(f1, f2, prev_matched):
     m = np.zeros(len(f1), np.int32)
     n = lib().ref_search_for_initialization(_p(f1), len(f1), _p(f2), len(f2), _p(pm), _p(m))
     return n, m, pm
+
+
+def frontend_run(width, height, recs, rec_off, frame_flags, grey, qlen=12, threshold=25, coverage_threshold=0.20, variant="canon"):
+    """The reference's own decoder + extractor loop over a clip (LK loses every point). -> dict(n_tracks, track_hash,
+    seconds_decoder, seconds_extractor)."""
+    nf = len(frame_flags)
+    recs = np.ascontiguousarray(recs, T.MV_RECORD)
+    rec_off = np.ascontiguousarray(rec_off, np.int64)
+    frame_flags = np.ascontiguousarray(frame_flags, np.uint8)
+    grey = None if grey is None else np.ascontiguousarray(grey, np.uint8)
+    nt = np.zeros(nf, np.int32)
+    hs = np.zeros(nf, np.uint64)
+    td, te = C.c_double(), C.c_double()
+    n = lib(variant).ref_frontend_run(width, height, nf, _p(recs), _p(rec_off), _p(frame_flags), _p(grey), qlen, threshold,
+                                      float(coverage_threshold), C.byref(td), C.byref(te), _p(nt), _p(hs))
+    assert n == nf, (n, nf)
+    return dict(n_tracks=nt, track_hash=hs, seconds_decoder=td.value, seconds_extractor=te.value)

@@ -8,6 +8,7 @@
 // This file only marshals flat arrays (include/movfe_types.h) into the reference's containers and back; it holds no
 // algorithm. tests/test_ref_parity.py compares the oracle (oracle/*.cc) against it; nothing under mov-slam_b200/ may
 // load it.
+#include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -291,6 +292,66 @@ int ref_extract_frame(int width, int height, uint32_t frame_flags, const uint8_t
     const int n = (int)vf.size();
     for (int i = 0; i < n && i < capacity; i++) out[i] = to_track(vf[i]);
     return n;
+}
+
+// The reference's own per-frame loop over a clip, as its mains drive it (Examples/Monocular/mono_video_tartan.cc:71-100 up to the
+// Frame constructor): VideoDecoder::NextImage -> MOVExtractor::operator() with the previous frame's table. LK returns "lost" for
+// every point (nothing injected). Timed inside with steady_clock like the mains do (:73-86). checksums: per frame, the table
+// checksum of oracle/frontend.cc (recomputed here over the converted tables). Returns the number of frames processed.
+int ref_frontend_run(int width, int height, int n_frames, const movfe_mv_record *recs, const int64_t *rec_off, const uint8_t *frame_flags,
+                     const uint8_t *grey, int qlen, int threshold, double coverage_threshold, double *seconds_decoder, double *seconds_extractor,
+                     int32_t *n_tracks, uint64_t *checksums) {
+    using namespace MOV_SLAM;
+    using clk = std::chrono::steady_clock;
+    std::vector<uint8_t> is_p(n_frames);
+    std::vector<const uint8_t *> luma(n_frames, nullptr), side(n_frames, nullptr);
+    std::vector<int> side_bytes(n_frames, 0);
+    for (int f = 0; f < n_frames; f++) {
+        is_p[f] = (frame_flags[f] & MOVFE_FRAME_P) ? 1 : 0;
+        if (grey) luma[f] = grey + (size_t)f * width * height;
+        if ((frame_flags[f] & MOVFE_FRAME_MV) && rec_off[f + 1] > rec_off[f]) {
+            side[f] = reinterpret_cast<const uint8_t *>(recs + rec_off[f]);
+            side_bytes[f] = (int)((rec_off[f + 1] - rec_off[f]) * (int64_t)sizeof(movfe_mv_record));
+        }
+    }
+    fake_av_clip fc = {width, height, n_frames, is_p.data(), luma.data(), side.data(), side_bytes.data()};
+    fake_av_install(&fc);
+    VideoDecoder dec("fake://clip", qlen);
+    if (!dec.Init()) return -1;
+    MOVExtractor ext(threshold, coverage_threshold, 0.25);
+    ext.mCurrentId = 0;
+    cvstub::lk_queue().clear();
+    std::shared_ptr<Frame> prev;
+    double t_dec = 0, t_ext = 0;
+    int done = 0;
+    while (true) {
+        const auto a = clk::now();
+        std::shared_ptr<MotionVectorImage> smv = dec.NextImage(true);
+        const auto b = clk::now();
+        t_dec += std::chrono::duration<double>(b - a).count();
+        if (!smv) break;
+        std::shared_ptr<Frame> F(new Frame());
+        F->imageCols = width;
+        F->imageRows = height;
+        F->imgLeft = smv->imGray;
+        const auto c = clk::now();
+        F->N = ext(smv, F->mvKeys, F->mvVF, F->mvVFMap, F->mDescriptors, prev.get());
+        t_ext += std::chrono::duration<double>(clk::now() - c).count();
+        if (n_tracks) n_tracks[done] = (int32_t)F->mvVF.size();
+        if (checksums) {
+            std::vector<movfe_track> tab;
+            for (const auto &vf : F->mvVF) tab.push_back(to_track(vf));
+            const uint64_t *w = reinterpret_cast<const uint64_t *>(tab.data());
+            uint64_t h = 0;
+            for (size_t i = 0; i < tab.size() * 8; i++) h += (w[i] ^ (i * 0x9E3779B97F4A7C15ull)) * (2 * i + 1);
+            checksums[done] = h;
+        }
+        prev = F;
+        done++;
+    }
+    if (seconds_decoder) *seconds_decoder = t_dec;
+    if (seconds_extractor) *seconds_extractor = t_ext;
+    return done;
 }
 
 // ---------------------------------------------------------------------------------------------------- MOVMatcher -----
