@@ -252,6 +252,56 @@ __device__ __forceinline__ int4 resolve_slots(const TileQueues &q, int x, int y)
     return s;
 }
 
+// The same for a whole warp: lane t asks for pixel (x, y) when `want` is set. The requests are served one after the other by
+// all 32 lanes, 32 queue entries per step (one coalesced 256-byte load), because the tracks of a warp sit in unrelated tiles
+// and a lane streaming its own tile's queue costs one L1 wavefront per lane and entry. Must be called by the full warp.
+__device__ __forceinline__ int4 resolve_slots_warp(const TileQueues &q, bool want, int x, int y, int lane) {
+    int4 mine = make_int4(-1, -1, -1, -1);
+    unsigned todo = __ballot_sync(0xffffffffu, want);
+    while (todo) {
+        const int t = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int xt = __shfl_sync(0xffffffffu, x, t), yt = __shfl_sync(0xffffffffu, y, t);
+        const int tile = (yt >> 5) * q.NT + (xt >> 5);
+        const int n = __ldg(&q.cnt[tile]);
+        const bool queued = n >= 0 && n <= MOVFE_TILE_Q;
+        const int total = queued ? n : q.n_hops;
+        const uint2 *e = q.ent + (size_t)tile * MOVFE_TILE_Q;
+        const unsigned ry = (unsigned)(yt & 31);
+        int s0 = -1, s1 = -1, s2 = -1, s3 = -1, c = 0;
+        for (int base = 0; base < total; base += 32) {
+            const int i = base + lane;
+            bool hit = false;
+            int h = -1;
+            if (i < total) {
+                if (queued) {
+                    const uint2 w = __ldg(&e[i]);
+                    const unsigned x0 = w.x & 0xffffu, x1 = w.x >> 16, r0 = (w.y >> 22) & 31u, r1 = w.y >> 27;
+                    hit = (unsigned)xt >= x0 && (unsigned)xt <= x1 && ry >= r0 && ry <= r1;
+                    h = (int)(w.y & 0x3fffffu);
+                } else {  // more hops meet the tile than a queue holds: the frame's hop list, in order
+                    const int2 r = __ldg(reinterpret_cast<const int2 *>(q.rects + i));
+                    const int x0 = (int16_t)(r.x & 0xffff), y0 = r.x >> 16, x1 = (int16_t)(r.y & 0xffff), y1 = r.y >> 16;
+                    hit = xt >= x0 && xt <= x1 && yt >= y0 && yt <= y1;
+                    h = i;
+                }
+            }
+            unsigned b = __ballot_sync(0xffffffffu, hit);  // entries are in hop order: lower lane = earlier hop
+            while (b && c < 3) {                          // warp-uniform
+                const int v = __shfl_sync(0xffffffffu, h, __ffs(b) - 1);
+                b &= b - 1;
+                if (c == 0) s0 = v;
+                else if (c == 1) s1 = v;
+                else s2 = v;
+                c++;
+            }
+            if (b) s3 = __shfl_sync(0xffffffffu, h, 31 - __clz(b));  // the last covering hop so far
+        }
+        if (lane == t) mine = make_int4(s0, s1, s2, s3);
+    }
+    return mine;
+}
+
 // 128-bit streaming store: the slot grid is written once and not re-read by the writer.
 __device__ __forceinline__ void st_cs_v4(int4 *p, int4 v) {
     asm volatile("st.global.cs.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

@@ -479,10 +479,11 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         const int mw = (int16_t)(a0.w & 0xffffu), mh = (int16_t)(a0.w >> 16);
         bool alive = act && !(a1.w & MOVFE_TRACK_COVERAGE);  // :258-262 coverage tracks go to the host LK step
         int4 sl = make_int4(-1, -1, -1, -1);
-        if (alive) {
+        {
             const int x = (int)ptx, y = (int)pty;  // :264
             if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
-            else sl = p.fused ? resolve_slots(tq, x, y) : __ldg(&g[(size_t)y * p.W + x]);
+            if (p.fused) sl = resolve_slots_warp(tq, alive, x, y, lane);  // warp-uniform branch
+            else if (alive) sl = __ldg(&g[(size_t)y * p.W + x]);
         }
         if (sl.x == -1) alive = false;  // :265-268
         const int sj[4] = {sl.x, sl.y, sl.z, sl.w};
