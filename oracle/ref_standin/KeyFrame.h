@@ -5,10 +5,17 @@
 #include "Frame.h"
 #include "MapPoint.h"
 namespace MOV_SLAM {
-class GeometricCamera {
+class GeometricCamera {   // include/CameraModels/GeometricCamera.h: the members the compiled sources and the shims touch
 public:
     virtual ~GeometricCamera() {}
     virtual Eigen::Vector2f project(const Eigen::Vector3f &) { return Eigen::Vector2f(); }
+    float getParameter(const int i) { return mvParameters[i]; }
+    size_t size() { return mvParameters.size(); }
+    unsigned int GetType() { return mnType; }
+    const static unsigned int CAM_PINHOLE = 0;
+    const static unsigned int CAM_FISHEYE = 1;
+    std::vector<float> mvParameters;
+    unsigned int mnType = 0;
 };
 class KeyFrame {
 public:

@@ -14,6 +14,14 @@ struct Matrix {
     Matrix() {
         for (int i = 0; i < R * C; i++) m[i] = T(0);
     }
+    Matrix(T a, T b) {
+        static_assert(R * C == 2, "two-element constructor");
+        m[0] = a, m[1] = b;
+    }
+    Matrix(T a, T b, T c) {
+        static_assert(R * C == 3, "three-element constructor");
+        m[0] = a, m[1] = b, m[2] = c;
+    }
     T &operator()(int i) { return m[i]; }
     const T &operator()(int i) const { return m[i]; }
     T &operator()(int r, int c) { return m[r * C + c]; }
@@ -50,6 +58,7 @@ typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<float, 2, 1> Vector2f;
 typedef Matrix<float, 3, 3> Matrix3f;
 typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 2, 1> Vector2d;
 typedef Matrix<double, 3, 3> Matrix3d;
 }  // namespace Eigen
 

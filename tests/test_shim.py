@@ -34,6 +34,37 @@ def test_shims_compile_and_link():
         assert sig in m
 
 
+def test_kannala_brandt8_camera_class_behind_the_reference_interface(orc):
+    """shim/KannalaBrandt8_movfe.h overrides every pure virtual of GeometricCamera (GeometricCamera.h:61-101; the check
+    program would not compile otherwise) and its projection / Jacobian equal the oracle's camera model, which the CUDA
+    solver is tested against."""
+    _build()
+    cam = T.camera(190, 190, 376, 240, k=(-0.01, 0.002, -0.0005, 0.0001), model=T.CAM_FISHEYE)
+    rng = np.random.Generator(np.random.PCG64(0x5A))
+    for _ in range(20):
+        X = rng.uniform([-3, -2, 0.5], [3, 2, 20])
+        r = subprocess.run([os.path.join(SHIM, "camera_iface_check"), "190", "190", "376", "240", "-0.01", "0.002", "-0.0005", "0.0001"] +
+                           ["%.17g" % v for v in X], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        v = [float(t) for t in r.stdout.split()]
+        assert np.abs(np.array(v[:2]) - orc.project(cam, X)).max() < 1e-9
+        assert np.abs(np.array(v[2:8]).reshape(2, 3) - orc.project_jac(cam, X)).max() < 1e-9
+        assert abs(v[8] - X[0] / X[2]) < 1e-4 and abs(v[9] - X[1] / X[2]) < 1e-4 and int(v[10]) == 1     # unproject, CAM_FISHEYE
+
+
+def test_shim_sources_compile_against_the_reference_headers():
+    """-DMOVFE_IN_TREE: the shim sources include the reference's OWN Frame.h / MOVExtractor.h / VideoDecoder.h (through the
+    oracle/_ref symlinks, third-party headers replaced by stand-ins) instead of standin/mov_slam_min.h."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "inc")
+    if not os.path.isdir("/root/reference/include"):
+        pytest.skip("/root/reference absent")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "-s", "ref"], check=True)
+    for src in ("MOVExtractor_movfe.cc", "VideoDecoder_movfe.cc", "shim_common.cc"):
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-DMOVFE_IN_TREE", "-I" + ref, "-I" + os.path.join(ROOT, "oracle", "ref_standin"),
+                            "-I" + os.path.join(ROOT, "include"), "-I" + SHIM, os.path.join(SHIM, src)], capture_output=True, text=True)
+        assert r.returncode == 0, (src, r.stderr[-3000:])
+
+
 def pseudo_lk(pts_xy):
     """mirror of test_shim.cc::pseudo_lk, the deterministic stand-in for cv::calcOpticalFlowPyrLK"""
     pts = np.asarray(pts_xy, np.float32).reshape(-1, 2)
