@@ -41,7 +41,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     if (ctx->h_map_meta) cudaFreeHost(ctx->h_map_meta);
     for (RasterBuf &w : ctx->rb) {
         void *wb[] = {w.d_seg_cnt, w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
-                      w.d_chunk_bbox, w.d_grid, w.d_tq_cnt, w.d_tq_ent};
+                      w.d_chunk_bbox, w.d_grid, w.d_tc_dim, w.d_tc_runs, w.d_tc_cells};
         for (void *b : wb)
             if (b) cudaFree(b);
         if (w.done) cudaEventDestroy(w.done);
@@ -217,8 +217,9 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
         CK(dalloc(&w.d_chunk_bbox, S * F * ctx->max_chunks));
         if (ctx->fused) {
             const size_t tiles = (size_t)ctx->NT * ctx->NTR;
-            CK(dalloc(&w.d_tq_cnt, S * F * tiles));
-            CK(dalloc(&w.d_tq_ent, S * F * tiles * MOVFE_TILE_Q));
+            CK(dalloc(&w.d_tc_dim, S * F * tiles));
+            CK(dalloc(&w.d_tc_runs, S * F * tiles * 64));
+            CK(dalloc(&w.d_tc_cells, S * F * tiles * MOVFE_TILE_CELLS));
         } else {
             CK(dalloc(&w.d_grid, S * F * plane));
         }

@@ -30,22 +30,24 @@ struct __align__(8) HopRect {
     int16_t x0, y0, x1, y1;
 };
 
-// ---- fused (grid-free) mode: per-tile hop queues instead of the per-pixel slot grid ---------------------------------------
+// ---- fused (grid-free) mode: per-tile cell tables instead of the per-pixel slot grid --------------------------------------
 // Propagation looks the slot grid up at a few thousand pixels per frame (one per track, plus the 16-px lattice of a back-fill
-// pass) out of W*H. In fused mode (MOVFE_CFG_NO_GRID) the raster stage stops after its phase 1 and stores, for every 32x32
-// pixel tile, the ordered queue of the hops whose rectangle meets the tile; a query resolves the four slots of ONE pixel
-// from its tile's queue (first three covering hops in order + the last one, VideoDecoder.cc:336-343). The 16 bytes per
-// pixel of the grid are never written: SURVEY.md 8d charges this mode 40 M + 12 Hops for the raster term.
-#define MOVFE_TILE_Q 186   // queue capacity per tile (6 chunks of 31); fuller tiles are resolved from the frame's hop list
-struct TileQueues {
-    const int32_t *cnt;    // [tiles] entries queued (> MOVFE_TILE_Q or < 0: overflow)
-    const uint2 *ent;      // [tiles][MOVFE_TILE_Q]  x = x0 | x1 << 16 (pixels), y = hop | r0 << 22 | r1 << 27 (rows inside the tile row)
-    const struct HopRect *rects;  // the frame's hop rectangles (overflow path)
-    int n_hops, NT;        // NT: tiles per tile row
+// pass) out of W*H. Hops are rectangles, so inside a 32x32 tile the slot vector only changes at block edges: the tile's
+// columns fall into a few runs with the same covering set, its rows too, and the slots are constant on every (row run,
+// column run) CELL - the raster kernel computes exactly these cells before it expands them to pixels (grid.cu). In fused mode
+// (MOVFE_CFG_NO_GRID) it stops there and stores, per tile, the run index of every column and row (64 bytes) and the cells'
+// slot vectors; a lookup is two dependent loads. The 16 bytes per pixel of the grid are never written: SURVEY.md 8d charges
+// this mode 40 M + 12 Hops for the raster term.
+#define MOVFE_TILE_CELLS 1024   // cell capacity of a tile (32 x 32: every pixel its own cell, the worst case)
+struct TileCells {
+    const int32_t *dim;    // [tiles] column runs | row runs << 8; 0: no hop meets the tile
+    const uint8_t *runs;   // [tiles][64] run index of column 0..31, then of row 0..31
+    const int4 *cells;     // [tiles][MOVFE_TILE_CELLS] slots of cell (row run * column runs + column run)
+    int NT;                // tiles per tile row
 };
 
 // Slots of pixel (x, y): what VideoImage::mvi.at<Vec4i>(y, x) holds in the reference.
-__device__ __forceinline__ int4 resolve_slots(const TileQueues &q, int x, int y);
+__device__ __forceinline__ int4 resolve_slots(const TileCells &q, int x, int y);
 
 // Per-frame class counts produced by the count pass (index into cls_cnt[frame][...]):
 //   [0..K]        valid P-branch records with ref >= k          -> hop segment k of frame (f-k)
@@ -71,8 +73,9 @@ struct RasterBuf {
     movfe_rect *d_kps = nullptr;    // [S][F][max_kps]
     int2    *d_chunk_bbox = nullptr;  // [S][F][max_chunks]  extent of every 32-hop chunk: (ymin | ymax<<16, xmin | xmax<<16)
     int4    *d_grid = nullptr;      // [S][F][H*W]   (grid-output mode)
-    int32_t *d_tq_cnt = nullptr;    // [S][F][tiles]                (fused mode)
-    uint2   *d_tq_ent = nullptr;    // [S][F][tiles][MOVFE_TILE_Q]  (fused mode)
+    int32_t *d_tc_dim = nullptr;    // [S][F][tiles]                    (fused mode: TileCells)
+    uint8_t *d_tc_runs = nullptr;   // [S][F][tiles][64]
+    int4    *d_tc_cells = nullptr;  // [S][F][tiles][MOVFE_TILE_CELLS]
     cudaEvent_t done = nullptr;      // recorded on raster_stream: the buffer is complete
     cudaEvent_t consumed = nullptr;  // recorded on stream after the last propagation launch that read it
     bool    consumed_valid = false;
@@ -83,7 +86,7 @@ struct movfe_ctx {
     int K = 0, LA = 0, RING = 0, NIN = 0;  // max_ref, look-ahead frames, ring depth, max input frames per window
     int NB = 0, NT = 0;                    // 8-row bands per frame, 32-px tiles per band
     int NTR = 0;                           // 32-row tile rows per frame
-    bool fused = false;                    // MOVFE_CFG_NO_GRID: per-tile hop queues instead of the slot grid
+    bool fused = false;                    // MOVFE_CFG_NO_GRID: per-tile cell tables instead of the slot grid
     int max_hops = 0, max_kps = 0, max_chunks = 0;
     int rseg = 0, n_rseg = 1;              // records per count/emit segment (multiple of 512), segments per frame
     int sm_count = 0;
@@ -216,90 +219,13 @@ struct movfe_ctx {
         if (_e != cudaSuccess) MOVFE_FAIL(ctx, MOVFE_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-__device__ __forceinline__ int4 resolve_slots(const TileQueues &q, int x, int y) {
-    int4 s = make_int4(-1, -1, -1, -1);
-    int c = 0;
+__device__ __forceinline__ int4 resolve_slots(const TileCells &q, int x, int y) {
     const int tile = (y >> 5) * q.NT + (x >> 5);
-    const int n = __ldg(&q.cnt[tile]);
-    if (n >= 0 && n <= MOVFE_TILE_Q) {
-        const uint2 *e = q.ent + (size_t)tile * MOVFE_TILE_Q;
-        const unsigned ry = (unsigned)(y & 31);
-        for (int i = 0; i < n; i++) {
-            const uint2 w = __ldg(&e[i]);
-            const unsigned x0 = w.x & 0xffffu, x1 = w.x >> 16, r0 = (w.y >> 22) & 31u, r1 = w.y >> 27;
-            if ((unsigned)x >= x0 && (unsigned)x <= x1 && ry >= r0 && ry <= r1) {
-                const int h = (int)(w.y & 0x3fffffu);
-                if (c == 0) s.x = h;
-                else if (c == 1) s.y = h;
-                else if (c == 2) s.z = h;
-                else s.w = h;
-                c++;
-            }
-        }
-    } else {  // more hops meet the tile than a queue holds: the frame's whole hop list, in order
-        for (int h = 0; h < q.n_hops; h++) {
-            const int2 r = __ldg(reinterpret_cast<const int2 *>(q.rects + h));
-            const int x0 = (int16_t)(r.x & 0xffff), y0 = r.x >> 16, x1 = (int16_t)(r.y & 0xffff), y1 = r.y >> 16;
-            if (x >= x0 && x <= x1 && y >= y0 && y <= y1) {
-                if (c == 0) s.x = h;
-                else if (c == 1) s.y = h;
-                else if (c == 2) s.z = h;
-                else s.w = h;
-                c++;
-            }
-        }
-    }
-    return s;
-}
-
-// The same for a whole warp: lane t asks for pixel (x, y) when `want` is set. The requests are served one after the other by
-// all 32 lanes, 32 queue entries per step (one coalesced 256-byte load), because the tracks of a warp sit in unrelated tiles
-// and a lane streaming its own tile's queue costs one L1 wavefront per lane and entry. Must be called by the full warp.
-__device__ __forceinline__ int4 resolve_slots_warp(const TileQueues &q, bool want, int x, int y, int lane) {
-    int4 mine = make_int4(-1, -1, -1, -1);
-    unsigned todo = __ballot_sync(0xffffffffu, want);
-    while (todo) {
-        const int t = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const int xt = __shfl_sync(0xffffffffu, x, t), yt = __shfl_sync(0xffffffffu, y, t);
-        const int tile = (yt >> 5) * q.NT + (xt >> 5);
-        const int n = __ldg(&q.cnt[tile]);
-        const bool queued = n >= 0 && n <= MOVFE_TILE_Q;
-        const int total = queued ? n : q.n_hops;
-        const uint2 *e = q.ent + (size_t)tile * MOVFE_TILE_Q;
-        const unsigned ry = (unsigned)(yt & 31);
-        int s0 = -1, s1 = -1, s2 = -1, s3 = -1, c = 0;
-        for (int base = 0; base < total; base += 32) {
-            const int i = base + lane;
-            bool hit = false;
-            int h = -1;
-            if (i < total) {
-                if (queued) {
-                    const uint2 w = __ldg(&e[i]);
-                    const unsigned x0 = w.x & 0xffffu, x1 = w.x >> 16, r0 = (w.y >> 22) & 31u, r1 = w.y >> 27;
-                    hit = (unsigned)xt >= x0 && (unsigned)xt <= x1 && ry >= r0 && ry <= r1;
-                    h = (int)(w.y & 0x3fffffu);
-                } else {  // more hops meet the tile than a queue holds: the frame's hop list, in order
-                    const int2 r = __ldg(reinterpret_cast<const int2 *>(q.rects + i));
-                    const int x0 = (int16_t)(r.x & 0xffff), y0 = r.x >> 16, x1 = (int16_t)(r.y & 0xffff), y1 = r.y >> 16;
-                    hit = xt >= x0 && xt <= x1 && yt >= y0 && yt <= y1;
-                    h = i;
-                }
-            }
-            unsigned b = __ballot_sync(0xffffffffu, hit);  // entries are in hop order: lower lane = earlier hop
-            while (b && c < 3) {                          // warp-uniform
-                const int v = __shfl_sync(0xffffffffu, h, __ffs(b) - 1);
-                b &= b - 1;
-                if (c == 0) s0 = v;
-                else if (c == 1) s1 = v;
-                else s2 = v;
-                c++;
-            }
-            if (b) s3 = __shfl_sync(0xffffffffu, h, 31 - __clz(b));  // the last covering hop so far
-        }
-        if (lane == t) mine = make_int4(s0, s1, s2, s3);
-    }
-    return mine;
+    const int dim = __ldg(&q.dim[tile]);
+    if (dim == 0) return make_int4(-1, -1, -1, -1);
+    const uint8_t *r = q.runs + (size_t)tile * 64;
+    const int cr = __ldg(&r[x & 31]), rr = __ldg(&r[32 + (y & 31)]);
+    return __ldg(&q.cells[(size_t)tile * MOVFE_TILE_CELLS + rr * (dim & 0xff) + cr]);
 }
 
 // 128-bit streaming store: the slot grid is written once and not re-read by the writer.

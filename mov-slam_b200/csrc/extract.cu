@@ -48,27 +48,25 @@ struct ExtParams {
     int thr;         // EXPRESS threshold
     int has_grey;
     int use_lk;      // this frame consumes the host LK results installed with movfe_set_lk_results
-    int fused;       // MOVFE_CFG_NO_GRID: slots come from the per-tile hop queues (common.cuh: resolve_slots), not from a slot grid
+    int fused;       // MOVFE_CFG_NO_GRID: slots come from the per-tile cell tables (common.cuh: resolve_slots), not from a slot grid
     int NT, tiles;   // tiles per tile row / per frame
     double cov_thr;
 };
 
-// raster results of one frame as the propagation kernels read them: the slot grid (grid-output mode) or the tile queues
+// raster results of one frame as the propagation kernels read them: the slot grid (grid-output mode) or the tile cell tables
 struct SlotSource {
     const int4 *grid;
-    const int32_t *tq_cnt;
-    const uint2 *tq_ent;
-    const HopRect *hop_rect;
-    const int32_t *nhops;
+    const int32_t *tc_dim;
+    const uint8_t *tc_runs;
+    const int4 *tc_cells;
 };
 
-__device__ __forceinline__ TileQueues frame_queues(const ExtParams &p, const SlotSource &src, int s) {
+__device__ __forceinline__ TileCells frame_cells(const ExtParams &p, const SlotSource &src, int s) {
     const size_t fr = (size_t)s * p.n_out + p.fi;
-    TileQueues q;
-    q.cnt = src.tq_cnt + fr * p.tiles;
-    q.ent = src.tq_ent + fr * p.tiles * MOVFE_TILE_Q;
-    q.rects = src.hop_rect + fr * p.max_hops;
-    q.n_hops = src.nhops[s * p.n_in + p.fi];
+    TileCells q;
+    q.dim = src.tc_dim + fr * p.tiles;
+    q.runs = src.tc_runs + fr * p.tiles * 64;
+    q.cells = src.tc_cells + fr * p.tiles * MOVFE_TILE_CELLS;
     q.NT = p.NT;
     return q;
 }
@@ -332,7 +330,8 @@ constexpr int CAND_THREADS = CAND_WARPS * 32;
 constexpr int CW_MXY = 0;    // [4] candidate rectangle origin, mx | my << 16
 constexpr int CW_INFO = 4;   // need (4 bits) | mw << 8 | mh << 16
 constexpr int CW_DESC = 5;   // [8] the track's previous descriptor (fetched at thread level, 32 tracks at once)
-constexpr int CW_WORDS = 13;
+constexpr int CW_HOP = 13;   // [4][3] the candidate hops' displacement (2 floats) and kps index: parked here across the warp-level loop
+constexpr int CW_WORDS = 25;
 
 // Loads of one candidate patch for the propagation kernel (mask pixels at column offset 1). For the shapes whose four
 // centre pixels lie inside the loaded 1..COLS columns the centre costs four shuffles instead of four more loads.
@@ -371,31 +370,32 @@ __device__ __forceinline__ Band cand_band(const int (&vals)[ROWS * COLS / 32], c
     return band_of(c4, thr);
 }
 
+// Candidates are evaluated two at a time (the loads of both are in flight together): four at a time keeps 48 registers of
+// pixels alive and halves the warps an SM can hold, and occupancy is what hides the L2 latency of these gathers.
 template <int ROWS, int COLS, int STRIDE>
-__device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int stride_rt, int thr, const int (&mxy)[4], unsigned need,
-                                         const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
+__device__ __forceinline__ void cand_eval_pair(const uint8_t *__restrict__ img, int stride_rt, int thr, const int (&mxy)[4], unsigned need, int j0,
+                                               const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best, int &chosen) {
     constexpr int IT = ROWS * COLS / 32;
-    int vals[4][IT], cen[4][4];
+    int vals[2][IT], cen[2][4];
     const int stride = STRIDE ? STRIDE : stride_rt;
-    // every needed candidate's loads are issued before any is consumed (the branches are warp-uniform)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if ((need >> j) & 1u) {
-            cand_issue<ROWS, COLS, STRIDE>(img, (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)), stride_rt, lane, vals[j], cen[j]);
+    for (int k = 0; k < 2; k++) {
+        const int j = j0 + k;
+        if ((need >> j) & 1u) {  // warp-uniform
+            cand_issue<ROWS, COLS, STRIDE>(img, (unsigned)((mxy[j] >> 16) * stride + (int16_t)(mxy[j] & 0xffff)), stride_rt, lane, vals[k], cen[k]);
         } else {
 #pragma unroll
-            for (int it = 0; it < IT; it++) vals[j][it] = 0;
+            for (int it = 0; it < IT; it++) vals[k][it] = 0;
 #pragma unroll
-            for (int q = 0; q < 4; q++) cen[j][q] = 0;
+            for (int q = 0; q < 4; q++) cen[k][q] = 0;
         }
     }
-    int chosen = -1;
-    best = 256;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int k = 0; k < 2; k++) {
+        const int j = j0 + k;
         if ((need >> j) & 1u) {  // warp-uniform
             uint32_t b[IT], d[8];
-            patch_words<IT>(vals[j], cand_band<ROWS, COLS>(vals[j], cen[j], thr), b);
+            patch_words<IT>(vals[k], cand_band<ROWS, COLS>(vals[k], cen[k], thr), b);
             desc_layout<ROWS, COLS>(b, d);
             const int dist = hamming256(pd, d);
             // :292-296 strict '<' from 256. Candidate 0 is also the default choice (:270), so taking it at dist == 256
@@ -404,10 +404,19 @@ __device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int st
                 best = dist;
                 chosen = j;
 #pragma unroll
-                for (int k = 0; k < 8; k++) best_d[k] = d[k];
+                for (int q = 0; q < 8; q++) best_d[q] = d[q];
             }
         }
     }
+}
+
+template <int ROWS, int COLS, int STRIDE>
+__device__ __forceinline__ int cand_eval(const uint8_t *__restrict__ img, int stride_rt, int thr, const int (&mxy)[4], unsigned need,
+                                         const uint32_t (&pd)[8], int lane, uint32_t (&best_d)[8], int &best) {
+    int chosen = -1;
+    best = 256;
+    cand_eval_pair<ROWS, COLS, STRIDE>(img, stride_rt, thr, mxy, need, 0, pd, lane, best_d, best, chosen);
+    if (need & 0xcu) cand_eval_pair<ROWS, COLS, STRIDE>(img, stride_rt, thr, mxy, need, 2, pd, lane, best_d, best, chosen);  // warp-uniform
     return chosen;
 }
 
@@ -451,8 +460,8 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
     const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
     const uint16_t *ord = order + (size_t)s * p.maxT;
     const int4 *g = p.fused ? nullptr : src.grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
-    TileQueues tq = {};
-    if (p.fused) tq = frame_queues(p, src, s);
+    TileCells tq = {};
+    if (p.fused) tq = frame_cells(p, src, s);
     const movfe_hop *hp = hops + ((size_t)s * p.n_out + p.fi) * p.max_hops;
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     movfe_track *st = stage + (size_t)s * p.maxT;
@@ -482,8 +491,7 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         {
             const int x = (int)ptx, y = (int)pty;  // :264
             if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
-            if (p.fused) sl = resolve_slots_warp(tq, alive, x, y, lane);  // warp-uniform branch
-            else if (alive) sl = __ldg(&g[(size_t)y * p.W + x]);
+            if (alive) sl = p.fused ? resolve_slots(tq, x, y) : __ldg(&g[(size_t)y * p.W + x]);
         }
         if (sl.x == -1) alive = false;  // :265-268
         const int sj[4] = {sl.x, sl.y, sl.z, sl.w};
@@ -503,20 +511,24 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
 #pragma unroll
         for (int j = 0; j < 4; j++) hv[j] = vj[j] ? __ldg(reinterpret_cast<const int4 *>(hp + sj[j])) : make_int4(0, 0, -1, 0);
         const float hw = (float)(mw / 2), hh = (float)(mh / 2);
-        float px[4], py[4];
         int mxy[4];
         unsigned need = 0;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            px[j] = __fadd_rn(ptx, __int_as_float(hv[j].x));  // :283
-            py[j] = __fadd_rn(pty, __int_as_float(hv[j].y));
-            const int mx = (int)__fsub_rn(px[j], hw), my = (int)__fsub_rn(py[j], hh);  // :284
+            const float px = __fadd_rn(ptx, __int_as_float(hv[j].x));  // :283
+            const float py = __fadd_rn(pty, __int_as_float(hv[j].y));
+            const int mx = (int)__fsub_rn(px, hw), my = (int)__fsub_rn(py, hh);  // :284
             mxy[j] = (int)((uint32_t)(mx & 0xffff) | ((uint32_t)my << 16));
             if (vj[j] && rect_in_bounds(mx, my, mw, mh, p.W, p.H)) need |= 1u << j;  // :286
+            // the hop itself is parked in shared memory: only the chosen one is needed again, after the warp-level loop
+            sm[warp][CW_HOP + 3 * j + 0][lane] = hv[j].x;
+            sm[warp][CW_HOP + 3 * j + 1][lane] = hv[j].y;
+            sm[warp][CW_HOP + 3 * j + 2][lane] = hv[j].z;
         }
         // chosen candidate when no descriptor is involved: single-candidate pixels keep slot 0 (:270); with several
         // candidates and a flat image every distance is 0, so the first in-bounds one wins
         int chosen = (!img && sl.y >= 0 && need) ? __ffs(need) - 1 : 0;
+        const bool multi = sl.y >= 0;
         const bool warp_job = alive && need != 0 && img != nullptr;
         if (warp_job) {
             // a later candidate whose block lands on the same pixels as an earlier in-bounds one has the same descriptor and
@@ -541,7 +553,8 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         }
         __syncwarp();
         // ---- warp level: descriptors of the candidate patches -------------------------------------------------------
-        uint32_t my_d[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        // The winning descriptor of track t goes straight to the staging record of its rank (written for every evaluated
+        // track; finalize only reads the records of tracks that pass bounds and gate).
         int my_best = 0;
         unsigned todo = __ballot_sync(0xffffffffu, warp_job);
         unsigned odd = 0;  // tracks whose block is none of the four H.264 shapes: second loop (its arrays live in local memory)
@@ -570,10 +583,11 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             else ch = cand_eval<8, 16, PITCH>(img, p.P, p.thr, cm, nd, pd, lane, bd, best);
             if (lane == t) {
                 // single-candidate pixels never compare (:272): slot 0 stays chosen; its descriptor is the one evaluated
-                if (sl.y >= 0 && ch >= 0) chosen = ch;
+                if (multi && ch >= 0) chosen = ch;
                 my_best = best;
-#pragma unroll
-                for (int k = 0; k < 8; k++) my_d[k] = bd[k];
+                uint4 *o = reinterpret_cast<uint4 *>(st + i);
+                o[2] = make_uint4(bd[0], bd[1], bd[2], bd[3]);
+                o[3] = make_uint4(bd[4], bd[5], bd[6], bd[7]);
             }
         }
         while (odd) {
@@ -590,25 +604,21 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             int best;
             const int ch = cand_eval_generic(img, p.P, p.thr, (info >> 8) & 0xff, info >> 16, cm, info & 0xf, pd, lane, bd, best);
             if (lane == t) {
-                if (sl.y >= 0 && ch >= 0) chosen = ch;
+                if (multi && ch >= 0) chosen = ch;
                 my_best = best;
-#pragma unroll
-                for (int k = 0; k < 8; k++) my_d[k] = bd[k];
+                uint4 *o = reinterpret_cast<uint4 *>(st + i);
+                o[2] = make_uint4(bd[0], bd[1], bd[2], bd[3]);
+                o[3] = make_uint4(bd[4], bd[5], bd[6], bd[7]);
             }
         }
         __syncwarp();
         // ---- thread level: move, bounds, gate, claim (:301-316) -------------------------------------------------------
         if (act) {
-            float cx = px[0], cy = py[0];
-            int cxy = mxy[0], cd = hv[0].z;
-#pragma unroll
-            for (int j = 1; j < 4; j++)
-                if (chosen == j) {
-                    cx = px[j];
-                    cy = py[j];
-                    cxy = mxy[j];
-                    cd = hv[j].z;
-                }
+            const float cx = __fadd_rn(ptx, __int_as_float(sm[warp][CW_HOP + 3 * chosen + 0][lane]));  // :303
+            const float cy = __fadd_rn(pty, __int_as_float(sm[warp][CW_HOP + 3 * chosen + 1][lane]));
+            const int cd = sm[warp][CW_HOP + 3 * chosen + 2][lane];
+            const int cmx = (int)__fsub_rn(cx, hw), cmy = (int)__fsub_rn(cy, hh);  // :304
+            const int cxy = (int)((uint32_t)(cmx & 0xffff) | ((uint32_t)cmy << 16));
             const bool inb = alive && ((need >> chosen) & 1u);  // :306 (the claim test itself happens in finalize)
             int fl = 0;
             if (inb) {
@@ -618,8 +628,10 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
                 uint4 *o = reinterpret_cast<uint4 *>(st + i);
                 o[0] = make_uint4(__float_as_uint(cx), __float_as_uint(cy), (uint32_t)cxy, a0.w);
                 o[1] = make_uint4(a1.x, a1.y + 1, (uint32_t)i, 0u);  // trackId, age + 1, qIndx, flags
-                o[2] = make_uint4(my_d[0], my_d[1], my_d[2], my_d[3]);
-                o[3] = make_uint4(my_d[4], my_d[5], my_d[6], my_d[7]);
+                if (!img) {  // MV-only mode: descriptors are all zero
+                    o[2] = make_uint4(0, 0, 0, 0);
+                    o[3] = make_uint4(0, 0, 0, 0);
+                }
                 if (cd >= 0 && cd < p.max_kps) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
             }
             if (a1.w & MOVFE_TRACK_COVERAGE) fl = 4;  // carried by the host LK step (:258-262), merged in finalize
@@ -1005,7 +1017,7 @@ __device__ void fill_keys(const movfe_track *__restrict__ tab, int from, int n, 
 }
 
 // 16-px lattice walk shared by the coverage back-fill (:418-451) and the I-frame seeding (:123-157).
-__device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img, const int4 *__restrict__ g, const TileQueues &tq, bool need_uncovered,
+__device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img, const int4 *__restrict__ g, const TileCells &tq, bool need_uncovered,
                              uint32_t track_flags, movfe_track *__restrict__ cur, int &n_out, int &id, uint32_t (*scratch)[8],
                              int *lat_flag) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1084,8 +1096,8 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     int n_keyed = 0;  // entries whose sort key is already in shared memory
     const uint8_t *img = p.has_grey ? grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H) : nullptr;
     const int4 *g = p.fused ? nullptr : src.grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
-    TileQueues tq = {};
-    if (p.fused) tq = frame_queues(p, src, s);
+    TileCells tq = {};
+    if (p.fused) tq = frame_cells(p, src, s);
     const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
     const int lk_n = p.use_lk ? lk.n[s] : -1;
     const uint8_t *lk_st = lk.status + (size_t)s * p.maxT;
@@ -1493,7 +1505,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         p.fused = ctx->fused ? 1 : 0;
         p.NT = ctx->NT;
         p.tiles = ctx->NT * ctx->NTR;
-        const SlotSource src = {w.d_grid, w.d_tq_cnt, w.d_tq_ent, w.d_hop_rect, w.d_nhops};
+        const SlotSource src = {w.d_grid, w.d_tc_dim, w.d_tc_runs, w.d_tc_cells};
         p.P = ctx->grey_pitch;
         p.cov_thr = c.coverage_threshold;
         const bool batch_end = !pdl_cand || (k + 1) % ctx->ev_batch == 0 || k == n_frames - 1;

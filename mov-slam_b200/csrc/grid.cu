@@ -27,7 +27,6 @@ constexpr int GRID_MAX_WARPS = 16;
 constexpr int GRID_CHUNK_CAP = 1024;   // surviving 32-hop chunk ids per band
 constexpr int TILE_CHUNKS = 6;         // a tile's candidates: up to 6 chunks of 31
 constexpr int TILE_Q = 31 * TILE_CHUNKS;
-static_assert(TILE_Q == MOVFE_TILE_Q, "queue capacity shared with the fused-mode queries (common.cuh)");
 constexpr int TQ_STRIDE = TILE_Q + 6;  // queue words per tile
 constexpr int CELL_CAP = 128;          // (column run, row run) cells resolved per batch
 constexpr int SB_ROWS = 32;            // rows a CTA owns = rows of a tile
@@ -135,9 +134,10 @@ __device__ __forceinline__ unsigned row_mask32(uint32_t wi) {
 __constant__ uint32_t c_magic[33] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
 
 // Fast path of one 32x32 tile whose candidates (at most NCH chunks of 31) are queued in shared memory.
-template <int NCH>
+// FUSED: the cells are the result (common.cuh: TileCells) - run maps to `runs`, slot vectors to `cells`, nothing per pixel.
+template <int NCH, bool FUSED>
 __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, const uint32_t *qi, int nq, int tx, int lane, unsigned lt,
-                                          int4 *out, int W, int nrows, bool xin) {
+                                          int4 *out, int W, int nrows, bool xin, int32_t *dim, uint8_t *runs, int4 *cells) {
     const int nchk = (nq + 30) / 31;
     unsigned col[NCH], row[NCH];  // lane = column (row): candidates of the chunk covering it
     int idx[NCH];                         // lane 30-i: hop index of candidate i of the chunk; lane 31: -1
@@ -175,6 +175,11 @@ __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, c
     const int mycc = __popc(cb & le) - 1;  // run of column `lane`
     if (dcol) ws.repc[mycc] = (uint8_t)lane;
     if (drow) ws.repr[__popc(rb & le) - 1] = (uint8_t)lane;
+    if (FUSED) {
+        runs[lane] = (uint8_t)mycc;
+        runs[32 + lane] = (uint8_t)(__popc(rb & le) - 1);
+        if (lane == 0) *dim = ncc | (nrc << 8);
+    }
     __syncwarp();
     // cells are numbered densely, cell j = (row run j / ncc, column run j % ncc); 32 cells are resolved per fold pass,
     // up to CELL_CAP per batch. j / ncc by a multiply: exact for j < 2048 (ncc <= 32).
@@ -201,8 +206,13 @@ __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, c
                         fold<false, true>(st, m, idx[c]);
                     }
                 }
-            if (valid) ws.tab[j] = make_int4(st.s0, st.s1, st.s2, st.s3);
+            if (FUSED) {
+                if (valid) cells[kr0 * ncc + j] = make_int4(st.s0, st.s1, st.s2, st.s3);
+            } else if (valid) {
+                ws.tab[j] = make_int4(st.s0, st.s1, st.s2, st.s3);
+            }
         }
+        if (FUSED) continue;  // warp-uniform
         __syncwarp();
         // the rows of these runs: one table read per run and column, one 128-bit store per pixel
         const int y0 = ws.repr[kr0], y1 = min(kr1 < nrc ? (int)ws.repr[kr1] : 32, nrows);
@@ -221,12 +231,13 @@ __device__ __forceinline__ void fast_tile(WarpScratch &ws, const uint32_t *qx, c
     }
 }
 
-// grid = (32-row bands, frames of the window x x-splits, streams). FUSED: stop after phase 1 and store the per-tile queues
-// (tq_cnt / tq_ent, common.cuh: TileQueues) instead of resolving and writing every pixel.
+// grid = (32-row bands, frames of the window x x-splits, streams). FUSED: the per-tile cell tables (common.cuh: TileCells) are
+// stored instead of expanding them to pixels.
 template <bool FUSED>
 __global__ void __launch_bounds__(GRID_MAX_WARPS * 32, 2)
 grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects, const int32_t *__restrict__ nhops,
-            const int2 *__restrict__ chunk_bbox, int4 *__restrict__ grid, int32_t *__restrict__ tq_cnt, uint2 *__restrict__ tq_ent, int NT) {
+            const int2 *__restrict__ chunk_bbox, int4 *__restrict__ grid, int32_t *__restrict__ tc_dim, uint8_t *__restrict__ tc_runs,
+            int4 *__restrict__ tc_cells, int NT) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -384,44 +395,43 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
     }
     __syncthreads();
 
-    if (FUSED) {
-        // ---- fused mode: the queues ARE the result ---------------------------------------------------------------------
-        const int ntr = (p.H + SB_ROWS - 1) / SB_ROWS;
-        for (int t = warp; t < ntl; t += nwarps) {
-            const size_t tile = ((size_t)sg * ntr + band) * NT + (size_t)xs * NTC + t;
-            const int nq = __shfl_sync(0xffffffffu, run_total, t);
-            if (lane == 0) tq_cnt[tile] = direct ? -1 : nq;
-            if (!direct) {
-                const uint32_t *qx = tq_x + t * TQ_STRIDE, *qi = tq_i + t * TQ_STRIDE;
-                uint2 *o = tq_ent + tile * TILE_Q;
-                for (int e = lane; e < min(nq, TILE_Q); e += 32) o[e] = make_uint2(qx[e], qi[e]);
-            }
-        }
-        return;
-    }
     // ---- phase 2: a warp takes 32x32-pixel tiles of the band; no block barrier from here on -----------------------
     const int nrows = yhi - ylo + 1;
     for (int t = warp; t < ntl; t += nwarps) {
         const int tx = X0 + t * 32;
         const int x = tx + lane;
         const bool xin = x < p.W;
-        int4 *out = grid + ((size_t)sg * p.H + ylo) * p.W + x;
+        int4 *out = FUSED ? nullptr : grid + ((size_t)sg * p.H + ylo) * p.W + x;
         uint32_t *qx = tq_x + t * TQ_STRIDE, *qi = tq_i + t * TQ_STRIDE;
         const int nq = __shfl_sync(0xffffffffu, run_total, t);
         const bool overflow = direct || nq > TILE_Q;
+        // fused mode: this tile's cell table
+        const size_t tile = FUSED ? ((size_t)sg * gridDim.x + band) * NT + (size_t)xs * NTC + t : 0;
+        int32_t *dim = FUSED ? tc_dim + tile : nullptr;
+        uint8_t *runs = FUSED ? tc_runs + tile * 64 : nullptr;
+        int4 *cells = FUSED ? tc_cells + tile * MOVFE_TILE_CELLS : nullptr;
         if (!overflow && nq == 0) {
             // no hop touches the tile (I frames, intra blocks): the implicit fill
-            const int4 v = make_int4(-1, -1, -1, -1);
-            if (xin)
-                for (int y = 0; y < nrows; y++) st_cs_v4(out + (size_t)y * p.W, v);
+            if (FUSED) {
+                if (lane == 0) *dim = 0;
+            } else {
+                const int4 v = make_int4(-1, -1, -1, -1);
+                if (xin)
+                    for (int y = 0; y < nrows; y++) st_cs_v4(out + (size_t)y * p.W, v);
+            }
         } else if (!overflow) {
             // ---- fast path: specialised for the usual one or two chunks of candidates ------------------------------
-            if (nq <= 62) fast_tile<2>(ws, qx, qi, nq, tx, lane, lt, out, p.W, nrows, xin);
-            else fast_tile<TILE_CHUNKS>(ws, qx, qi, nq, tx, lane, lt, out, p.W, nrows, xin);
+            if (nq <= 62) fast_tile<2, FUSED>(ws, qx, qi, nq, tx, lane, lt, out, p.W, nrows, xin, dim, runs, cells);
+            else fast_tile<TILE_CHUNKS, FUSED>(ws, qx, qi, nq, tx, lane, lt, out, p.W, nrows, xin, dim, runs, cells);
         } else {
             // slow path (more than 186 candidates in one tile, or the chunk list did not fit): one row at a time,
             // streaming the band's chunks again from global memory and folding 31 candidates per step.
             const int n_src = direct ? nchunks : n_cl;
+            if (FUSED) {  // every pixel its own cell: identity run maps
+                runs[lane] = (uint8_t)lane;
+                runs[32 + lane] = (uint8_t)lane;
+                if (lane == 0) *dim = 32 | (32 << 8);
+            }
             for (int y = 0; y < nrows; y++) {
                 Slots st = {-1, -1, -1, -1, 0};
                 int nq2 = 0;
@@ -474,7 +484,8 @@ grid_kernel(WinParams p, int nxs, int NTC, const HopRect *__restrict__ hop_rects
                         __syncwarp();
                     }
                 }
-                if (xin) st_cs_v4(out + (size_t)y * p.W, make_int4(st.s0, st.s1, st.s2, st.s3));
+                if (FUSED) cells[y * 32 + lane] = make_int4(st.s0, st.s1, st.s2, st.s3);
+                else if (xin) st_cs_v4(out + (size_t)y * p.W, make_int4(st.s0, st.s1, st.s2, st.s3));
             }
         }
         __syncwarp();
@@ -505,11 +516,11 @@ int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w) {
     if ((size_t)p.n_out * nxs > 65535 || p.S > 65535) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "grid: launch grid out of range");
     dim3 blocks(nsb, p.n_out * nxs, p.S);
     if (ctx->fused)
-        grid_kernel<true><<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, nullptr, w.d_tq_cnt,
-                                                                          w.d_tq_ent, ctx->NT);
+        grid_kernel<true><<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, nullptr, w.d_tc_dim,
+                                                                          w.d_tc_runs, w.d_tc_cells, ctx->NT);
     else
         grid_kernel<false><<<blocks, nw * 32, smem, ctx->raster_stream>>>(p, nxs, ntc, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox, w.d_grid, nullptr,
-                                                                           nullptr, ctx->NT);
+                                                                           nullptr, nullptr, ctx->NT);
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
