@@ -157,6 +157,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     ctx->ev_of_frame.assign(c.window_frames, 0);
     if (const char *e = getenv("MOVFE_EVENT_BATCH")) ctx->ev_batch = std::max(1, atoi(e));
     if (const char *e = getenv("MOVFE_PDL")) ctx->pdl_mode = atoi(e);
+    if (const char *e = getenv("MOVFE_CAND_PIPE")) ctx->cand_pipe = atoi(e) != 0;
     ctx->ev_frame.resize((size_t)ctx->n_groups * c.window_frames, nullptr);
     for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &pl : ctx->pose_launches) {
@@ -195,7 +196,9 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(dalloc(&ctx->d_rec, S * RING * c.max_records_per_frame));
     CK(dalloc(&ctx->d_rec_cnt, S * RING));
     CK(dalloc(&ctx->d_fflags, S * RING));
-    if (c.has_grey) CK(dalloc(&ctx->d_grey, S * RING * (size_t)c.height * ctx->grey_pitch));
+    // + 16 rows: the window pipeline of cand_kernel fetches 16 rows for every block shape (8-row blocks near the bottom of the
+    // last plane read past it; the extra rows are never used)
+    if (c.has_grey) CK(dalloc(&ctx->d_grey, S * RING * (size_t)c.height * ctx->grey_pitch + 16 * (size_t)ctx->grey_pitch));
     CK(dalloc(&ctx->d_stats, 8));
     CK(cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)));
     CK(dalloc(&ctx->d_rejected, 1));

@@ -441,16 +441,65 @@ __device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, i
     return chosen;
 }
 
+
+// ---- asynchronous patch staging (PIPE variant of cand_kernel) -----------------------------------------------------------
+// The candidate patches are gathers whose latency (an L2 round trip each) is what bounds propagation. Instead of holding the
+// pixels of the patches in flight in registers, a warp keeps PF_DEPTH patch WINDOWS in flight as asynchronous global->shared
+// copies (cp.async, 16 bytes per lane: one instruction fetches a 32-byte x 16-row window that contains the block's columns
+// 1..cols and its centre pixels), and reads a window's pixels from shared memory when it has landed. No registers are tied
+// up by the loads, so twice as many warps fit on an SM, and the depth of the prefetch no longer depends on how many
+// candidates a track happens to have.
+constexpr int PF_DEPTH = 4;
+constexpr int WIN_ROW = 32, WIN_ROWS = 16, WIN_BYTES = WIN_ROW * WIN_ROWS;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// window of the block at (mx, my): rows my .. my+15, bytes xa .. xa+31 with xa = (mx + 1) & ~15
+__device__ __forceinline__ void window_issue(const uint8_t *__restrict__ img, int stride, int mx, int my, uint8_t *win, int lane) {
+    const int xa = (mx + 1) & ~15;
+    cp_async16(win + (lane >> 1) * WIN_ROW + (lane & 1) * 16, img + (size_t)(my + (lane >> 1)) * stride + xa + (lane & 1) * 16);
+}
+
+// descriptor of a ROWS x COLS block from its staged window (EXPRESS.h:79-110: centre, band, out-of-band bits of columns 1..COLS)
+template <int ROWS, int COLS>
+__device__ __forceinline__ void window_descriptor(const uint8_t *win, int mx, int thr, int lane, uint32_t (&desc)[8]) {
+    constexpr int IT = ROWS * COLS / 32, LC = COLS == 16 ? 4 : 3;
+    const int xo = mx - ((mx + 1) & ~15);  // window byte of the block's column 0 (-1 .. 14)
+    constexpr int cr = ROWS / 2, cc = COLS / 2;  // compute_center: at(row = cols/2, col = rows/2) and its upper-left neighbours
+    const int center = ((int)win[cc * WIN_ROW + xo + cr] + (int)win[(cc - 1) * WIN_ROW + xo + cr - 1] + (int)win[cc * WIN_ROW + xo + cr - 1] +
+                        (int)win[(cc - 1) * WIN_ROW + xo + cr]) / 4;
+    Band bd;
+    bd.low = (uint8_t)(center - thr);
+    bd.high = (uint8_t)(center + thr);
+    const uint8_t *pq = win + (lane >> LC) * WIN_ROW + xo + 1 + (lane & (COLS - 1));
+    int vals[IT];
+#pragma unroll
+    for (int it = 0; it < IT; it++) vals[it] = pq[it * (32 >> LC) * WIN_ROW];
+    uint32_t b[IT];
+    patch_words<IT>(vals, bd, b);
+    desc_layout<ROWS, COLS>(b, desc);
+}
+
 #ifndef CAND_MINB
 #define CAND_MINB (16 / MOVFE_CAND_WARPS)  // 128 registers per thread
 #endif
-template <int PITCH>
-__global__ void __launch_bounds__(CAND_THREADS, CAND_MINB)
+#ifndef CAND_PIPE_MINB
+#define CAND_PIPE_MINB (2 * CAND_MINB)
+#endif
+template <int PITCH, bool PIPE>
+__global__ void __launch_bounds__(CAND_THREADS, PIPE ? CAND_PIPE_MINB : CAND_MINB)
 cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
             const uint16_t *__restrict__ order, SlotSource src, const movfe_hop *__restrict__ hops,
             const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
             int2 *__restrict__ cinfo, int32_t *__restrict__ claim, unsigned long long *__restrict__ stats) {
     __shared__ int sm[CAND_WARPS][CW_WORDS][32];
+    __shared__ __align__(16) uint8_t swin[PIPE ? CAND_WARPS : 1][PF_DEPTH][WIN_BYTES];  // PIPE: patch windows in flight
+    __shared__ uint8_t slist[PIPE ? CAND_WARPS : 1][128];                              // PIPE: the chunk's (track | candidate << 5) list
     pdl_wait();     // the previous frame's finalize_kernel wrote the tables read below
     pdl_trigger();  // after the wait: at most one dependent grid is resident and waiting
     const int s = p.s0 + blockIdx.y;
@@ -558,7 +607,89 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
         int my_best = 0;
         unsigned todo = __ballot_sync(0xffffffffu, warp_job);
         unsigned odd = 0;  // tracks whose block is none of the four H.264 shapes: second loop (its arrays live in local memory)
-        while (todo) {
+        if (PIPE) {
+            // the chunk's evaluations as one flat list in (track, candidate) order: PF_DEPTH windows are always in flight
+            const int stride = PITCH ? PITCH : p.P;
+            int info = warp_job ? sm[warp][CW_INFO][lane] : 0;
+            const bool std_shape = ((info >> 8 & 0xff) == 16 || (info >> 8 & 0xff) == 8) && ((info >> 16) == 16 || (info >> 16) == 8);
+            odd = __ballot_sync(0xffffffffu, warp_job && !std_shape);
+            const unsigned mine = (warp_job && std_shape) ? (unsigned)(info & 0xf) : 0u;
+            int cnt = __popc(mine), incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const int n_ev = __shfl_sync(0xffffffffu, incl, 31);
+            {
+                int pos = incl - cnt;
+                unsigned m = mine;
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    slist[warp][pos++] = (uint8_t)(lane | (j << 5));
+                }
+            }
+            __syncwarp();
+            auto issue = [&](int k) {
+                const int e = slist[warp][k], t = e & 31, j = e >> 5;
+                const int m = sm[warp][CW_MXY + j][t];
+                window_issue(img, stride, (int16_t)(m & 0xffff), m >> 16, swin[warp][k % PF_DEPTH], lane);
+            };
+#pragma unroll
+            for (int k = 0; k < PF_DEPTH; k++) {
+                if (k < n_ev) issue(k);
+                cp_async_commit();
+            }
+            int cur_t = -1, best = 256, ch = -1;
+            uint32_t bd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            auto flush = [&]() {  // the finished track's verdict goes to its lane, its descriptor to its staging record
+                if (lane == cur_t) {
+                    if (multi && ch >= 0) chosen = ch;  // single-candidate pixels never compare (:272): slot 0 stays chosen
+                    my_best = best;
+                    uint4 *o = reinterpret_cast<uint4 *>(st + i);
+                    o[2] = make_uint4(bd[0], bd[1], bd[2], bd[3]);
+                    o[3] = make_uint4(bd[4], bd[5], bd[6], bd[7]);
+                }
+            };
+            for (int k = 0; k < n_ev; k++) {
+                cp_async_wait<PF_DEPTH - 1>();  // all but the newest PF_DEPTH-1 groups have landed: window k is complete
+                __syncwarp();
+                const int e = slist[warp][k], t = e & 31, j = e >> 5;
+                if (t != cur_t) {  // warp-uniform
+                    if (cur_t >= 0) flush();
+                    cur_t = t;
+                    best = 256;
+                    ch = -1;
+                }
+                const int tinfo = sm[warp][CW_INFO][t];
+                const int tw = (tinfo >> 8) & 0xff, th = tinfo >> 16;
+                const int mx = (int16_t)(sm[warp][CW_MXY + j][t] & 0xffff);
+                const uint8_t *win = swin[warp][k % PF_DEPTH];
+                uint32_t d[8];
+                if (tw == 16 && th == 16) window_descriptor<16, 16>(win, mx, p.thr, lane, d);
+                else if (tw == 8 && th == 8) window_descriptor<8, 8>(win, mx, p.thr, lane, d);
+                else if (tw == 8 && th == 16) window_descriptor<16, 8>(win, mx, p.thr, lane, d);
+                else window_descriptor<8, 16>(win, mx, p.thr, lane, d);
+                int dist = 0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) dist += __popc((uint32_t)sm[warp][CW_DESC + q][t] ^ d[q]);
+                // :292-296 strict '<' from 256; candidate 0 is also the default choice (:270), see cand_eval_pair
+                if (j == 0 || dist < best) {
+                    best = dist;
+                    ch = j;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) bd[q] = d[q];
+                }
+                __syncwarp();  // every lane has read window k before its buffer is refilled
+                if (k + PF_DEPTH < n_ev) issue(k + PF_DEPTH);
+                cp_async_commit();
+            }
+            if (cur_t >= 0) flush();
+            cp_async_wait<0>();
+            todo = 0;
+        }
+        while (!PIPE && todo) {
             const int t = __ffs(todo) - 1;
             todo &= todo - 1;
             const int info = sm[warp][CW_INFO][t];
@@ -1517,7 +1648,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         const int bps = std::max(4, (64 * ctx->sm_count + c.n_streams * CAND_WARPS - 1) / (c.n_streams * CAND_WARPS));
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
 #define MOVFE_CAND(PITCH)                                                                                              \
-    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, cand_kernel<PITCH>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
+    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
                                src, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim, ctx->d_stats))
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
