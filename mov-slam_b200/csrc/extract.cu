@@ -449,7 +449,7 @@ __device__ __noinline__ int cand_eval_generic(const uint8_t *__restrict__ img, i
 // 1..cols and its centre pixels), and reads a window's pixels from shared memory when it has landed. No registers are tied
 // up by the loads, so twice as many warps fit on an SM, and the depth of the prefetch no longer depends on how many
 // candidates a track happens to have.
-constexpr int PF_DEPTH = 4;
+constexpr int PF_DEPTH = 8;   // even: two windows are consumed per step (one per half-warp)
 constexpr int WIN_ROW = 32, WIN_ROWS = 16, WIN_BYTES = WIN_ROW * WIN_ROWS;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -459,9 +459,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// window of the block at (mx, my): rows my .. my+15, bytes xa .. xa+31 with xa = (mx + 1) & ~15
-__device__ __forceinline__ void window_issue(const uint8_t *__restrict__ img, int stride, int mx, int my, uint8_t *win, int lane) {
-    const int xa = (mx + 1) & ~15;
+// window: rows my .. my+15, bytes xa .. xa+31 (xa a multiple of 16). Propagation reads a block's columns 1..cols: xa = (mx + 1) & ~15;
+// births read columns 0..cols: xa = mx & ~15.
+__device__ __forceinline__ void window_issue(const uint8_t *__restrict__ img, int stride, int xa, int my, uint8_t *win, int lane) {
     cp_async16(win + (lane >> 1) * WIN_ROW + (lane & 1) * 16, img + (size_t)(my + (lane >> 1)) * stride + xa + (lane & 1) * 16);
 }
 
@@ -483,6 +483,64 @@ __device__ __forceinline__ void window_descriptor(const uint8_t *win, int mx, in
     uint32_t b[IT];
     patch_words<IT>(vals, bd, b);
     desc_layout<ROWS, COLS>(b, desc);
+}
+
+
+// ---- SWAR evaluation of a staged window: a HALF-WARP per patch, a lane per block row, 16 pixels per lane -------------------
+// One lane compares its row's pixels four to a 32-bit word (per-byte subtract and compare without carries between bytes) and
+// ends with the row's out-of-band bits; the 256-bit descriptor is those rows side by side, so the Hamming distance to the
+// track's previous descriptor is one popcount per lane and a half-warp sum. A quarter of the instructions of the
+// pixel-per-lane form (eight byte loads, compares and ballots per lane and patch), and two patches per warp step.
+struct BandSwar {
+    uint32_t lowm;   // (low replicated) & 0x7f7f7f7f
+    uint32_t nlow;   // ~(low replicated)
+    uint32_t k4;     // per byte 0x7f - (t & 0x7f), t = high - low; 0x80 when every pixel is out of band (low > high: uint8 wrap)
+    bool big;        // t >= 128
+};
+__device__ __forceinline__ BandSwar band_swar(int center, int thr) {
+    const int low = (uint8_t)(center - thr), high = (uint8_t)(center + thr);  // EXPRESS.h:93-94, wrap included
+    BandSwar b;
+    const bool all = low > high;  // (low > p) || (high < p) holds for every p
+    const uint32_t l4 = all ? 0u : (uint32_t)low * 0x01010101u;
+    const int t = high - low;
+    b.lowm = l4 & 0x7f7f7f7fu;
+    b.nlow = ~l4;
+    b.k4 = all ? 0x80808080u : (uint32_t)(0x7f - (t & 0x7f)) * 0x01010101u;
+    b.big = !all && t >= 128;
+    return b;
+}
+// bit 7 of byte k: pixel k of v lies outside [low, high]
+__device__ __forceinline__ uint32_t oob4(uint32_t v, const BandSwar &b) {
+    const uint32_t H = 0x80808080u;
+    const uint32_t d = ((v | H) - b.lowm) ^ ((v ^ b.nlow) & H);  // per-byte v - low (mod 256)
+    const uint32_t g = (d & ~H) + b.k4;                          // bit 7: (d & 0x7f) > (t & 0x7f)   [or always, k4 = 0x80]
+    return (b.big ? (g & d) : (g | d)) & H;                      // d > t
+}
+// the four bit-7 flags of a word as a nibble (pixel k -> bit k)
+__device__ __forceinline__ uint32_t nib(uint32_t r) { return ((r >> 7) * 0x10204080u) >> 28; }
+
+// Out-of-band bits of row `r` of the rows x cols block whose column 0 sits at window byte xo (-1..14): columns 1..cols, i.e.
+// window bytes xo+1 .. xo+cols (the p++-before-read of EXPRESS.h:98-109). 0 for rows outside the block.
+__device__ __forceinline__ uint32_t row_bits(const uint8_t *win, int xo, int r, int rows, int cols, const BandSwar &b) {
+    if (r >= rows) return 0u;
+    const int sft = xo + 1;                      // 0..15
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(win + r * WIN_ROW) + (sft >> 2);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];   // (sft >> 2) + 4 <= 7: inside the 32-byte row
+    const int bs = (sft & 3) * 8;
+    const uint32_t p0 = __funnelshift_r(w0, w1, bs), p1 = __funnelshift_r(w1, w2, bs), p2 = __funnelshift_r(w2, w3, bs), p3 = __funnelshift_r(w3, w4, bs);
+    const uint32_t m = nib(oob4(p0, b)) | (nib(oob4(p1, b)) << 4) | (nib(oob4(p2, b)) << 8) | (nib(oob4(p3, b)) << 12);
+    return m & ((1u << cols) - 1u);
+}
+
+// Half-warp-wide: the 16 half-words of the block's descriptor (bit y*rows + x, OR-ed: EXPRESS.h:106), half-word q in lane q of
+// the half. `row` = row_bits of this lane's row. rows == 16: half-word y is row y. rows == 8: rows are 8 bits apart and, for
+// 16-column blocks, overlap their successor by 8 bits.
+__device__ __forceinline__ uint32_t desc_halfword(uint32_t row, int rows, int hl) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, row, 1, 16);
+    const uint32_t byte = (row & 0xffu) | (hl > 0 ? (up >> 8) : 0u);          // byte hl of the 8-row layout (hl = 0..8)
+    const uint32_t b0 = __shfl_sync(0xffffffffu, byte, 2 * hl, 16), b1 = __shfl_sync(0xffffffffu, byte, 2 * hl + 1, 16);
+    const uint32_t hw8 = hl < 8 ? (b0 | (b1 << 8)) : 0u;                        // lanes 8..15: 2*hl wraps, nothing there
+    return rows == 16 ? row : hw8;
 }
 
 #ifndef CAND_MINB
@@ -634,55 +692,71 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             auto issue = [&](int k) {
                 const int e = slist[warp][k], t = e & 31, j = e >> 5;
                 const int m = sm[warp][CW_MXY + j][t];
-                window_issue(img, stride, (int16_t)(m & 0xffff), m >> 16, swin[warp][k % PF_DEPTH], lane);
+                window_issue(img, stride, ((int16_t)(m & 0xffff) + 1) & ~15, m >> 16, swin[warp][k % PF_DEPTH], lane);
             };
 #pragma unroll
             for (int k = 0; k < PF_DEPTH; k++) {
                 if (k < n_ev) issue(k);
                 cp_async_commit();
             }
+            // two evaluations per step: half-warp h takes list entry k + h, lane hl of the half takes block row hl
+            const int half = lane >> 4, hl = lane & 15;
             int cur_t = -1, best = 256, ch = -1;
-            uint32_t bd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            auto flush = [&]() {  // the finished track's verdict goes to its lane, its descriptor to its staging record
+            auto flush = [&]() {  // the finished track's verdict goes to its lane (its descriptor is already in its staging record)
                 if (lane == cur_t) {
                     if (multi && ch >= 0) chosen = ch;  // single-candidate pixels never compare (:272): slot 0 stays chosen
                     my_best = best;
-                    uint4 *o = reinterpret_cast<uint4 *>(st + i);
-                    o[2] = make_uint4(bd[0], bd[1], bd[2], bd[3]);
-                    o[3] = make_uint4(bd[4], bd[5], bd[6], bd[7]);
                 }
             };
-            for (int k = 0; k < n_ev; k++) {
-                cp_async_wait<PF_DEPTH - 1>();  // all but the newest PF_DEPTH-1 groups have landed: window k is complete
+            const bool swar_ok = p.thr >= 0;  // (the band arithmetic below covers every threshold; kept as a switch for A/B)
+            for (int k = 0; k < n_ev; k += 2) {
+                cp_async_wait<PF_DEPTH - 2>();  // all but the newest PF_DEPTH-2 groups have landed: windows k and k+1 are complete
                 __syncwarp();
-                const int e = slist[warp][k], t = e & 31, j = e >> 5;
-                if (t != cur_t) {  // warp-uniform
-                    if (cur_t >= 0) flush();
-                    cur_t = t;
-                    best = 256;
-                    ch = -1;
-                }
+                const int ke = k + half;
+                const bool on = ke < n_ev;
+                const int e = on ? slist[warp][ke] : 0, t = e & 31, j = e >> 5;
                 const int tinfo = sm[warp][CW_INFO][t];
-                const int tw = (tinfo >> 8) & 0xff, th = tinfo >> 16;
+                const int cols = (tinfo >> 8) & 0xff, rows = tinfo >> 16;   // block width / height
                 const int mx = (int16_t)(sm[warp][CW_MXY + j][t] & 0xffff);
-                const uint8_t *win = swin[warp][k % PF_DEPTH];
-                uint32_t d[8];
-                if (tw == 16 && th == 16) window_descriptor<16, 16>(win, mx, p.thr, lane, d);
-                else if (tw == 8 && th == 8) window_descriptor<8, 8>(win, mx, p.thr, lane, d);
-                else if (tw == 8 && th == 16) window_descriptor<16, 8>(win, mx, p.thr, lane, d);
-                else window_descriptor<8, 16>(win, mx, p.thr, lane, d);
-                int dist = 0;
+                const uint8_t *win = swin[warp][ke % PF_DEPTH];
+                const int xo = mx - ((mx + 1) & ~15);
+                // compute_center (EXPRESS.h:79-88): at(row = cols/2, col = rows/2) and its upper-left neighbours
+                const int cr = rows >> 1, cc = cols >> 1;
+                const int center = ((int)win[cc * WIN_ROW + xo + cr] + (int)win[(cc - 1) * WIN_ROW + xo + cr - 1] +
+                                    (int)win[cc * WIN_ROW + xo + cr - 1] + (int)win[(cc - 1) * WIN_ROW + xo + cr]) / 4;
+                const BandSwar bd = band_swar(center, p.thr);
+                const uint32_t row = swar_ok ? row_bits(win, xo, hl, rows, cols, bd) : 0u;
+                const uint32_t hw = desc_halfword(row, rows, hl);
+                // previous descriptor, half-word hl (bitset<256> bit i at word i>>5, bit i&31)
+                const uint32_t pw = (uint32_t)sm[warp][CW_DESC + (hl >> 1)][t];
+                const uint32_t pdh = (hl & 1) ? (pw >> 16) : (pw & 0xffffu);
+                const int part = on ? __popc(hw ^ pdh) : 0;
+                const int dist = __reduce_add_sync(half ? 0xffff0000u : 0x0000ffffu, part);
+                const int d0v = __shfl_sync(0xffffffffu, dist, 0), d1v = __shfl_sync(0xffffffffu, dist, 16);
+                const int e1 = __shfl_sync(0xffffffffu, e, 16), e0 = __shfl_sync(0xffffffffu, e, 0);
 #pragma unroll
-                for (int q = 0; q < 8; q++) dist += __popc((uint32_t)sm[warp][CW_DESC + q][t] ^ d[q]);
-                // :292-296 strict '<' from 256; candidate 0 is also the default choice (:270), see cand_eval_pair
-                if (j == 0 || dist < best) {
-                    best = dist;
-                    ch = j;
-#pragma unroll
-                    for (int q = 0; q < 8; q++) bd[q] = d[q];
+                for (int h = 0; h < 2; h++) {  // the two results are folded in list order (warp-uniform)
+                    if (k + h >= n_ev) break;
+                    const int eh = h ? e1 : e0, th = eh & 31, jh = eh >> 5, dh = h ? d1v : d0v;
+                    if (th != cur_t) {
+                        if (cur_t >= 0) flush();
+                        cur_t = th;
+                        best = 256;
+                        ch = -1;
+                    }
+                    // :292-296 strict '<' from 256; candidate 0 is also the default choice (:270), see cand_eval_pair
+                    if (jh == 0 || dh < best) {
+                        best = dh;
+                        ch = jh;
+                        // the winner so far: its descriptor goes to the track's staging record, half-word hl from lane hl of half h
+                        // (a later, better candidate of the same track overwrites it: same warp, program order)
+                        if (half == h) reinterpret_cast<uint16_t *>((st + c * 32 + th)->desc)[hl] = (uint16_t)hw;
+                    }
                 }
-                __syncwarp();  // every lane has read window k before its buffer is refilled
+                __syncwarp();  // every lane has read windows k, k+1 before their buffers are refilled
                 if (k + PF_DEPTH < n_ev) issue(k + PF_DEPTH);
+                cp_async_commit();
+                if (k + PF_DEPTH + 1 < n_ev) issue(k + PF_DEPTH + 1);
                 cp_async_commit();
             }
             if (cur_t >= 0) flush();
@@ -846,13 +920,16 @@ __device__ __forceinline__ bool express_birth(const uint8_t *__restrict__ img, u
     return ok;
 }
 
-template <int PITCH>
+constexpr int BIRTH_KPW = 8;  // PIPE: kps entries a warp takes per round (finer than 32: the unclaimed blocks are spread unevenly)
+
+template <int PITCH, bool PIPE>
 __global__ void __launch_bounds__(CAND_THREADS, 32 / MOVFE_CAND_WARPS)  // 64 registers per thread
 birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
              const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
              uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
     __shared__ uint32_t scratch[CAND_WARPS][8];
     __shared__ int sm[CAND_WARPS][2][32];
+    __shared__ __align__(16) uint8_t swin[PIPE ? CAND_WARPS : 1][PF_DEPTH][WIN_BYTES];  // PIPE: block windows in flight (cp.async)
     pdl_wait();  // cand_kernel wrote the claims
     pdl_trigger();
     const int s = p.s0 + blockIdx.y;
@@ -861,12 +938,13 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
     if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;
     const uint8_t *img = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H);
     const movfe_rect *kp = kps + ((size_t)s * p.n_out + p.fi) * p.max_kps;
-    for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n; c += gridDim.x * CAND_WARPS) {
-        const int i = c * 32 + lane;
+    constexpr int KPW = PIPE ? BIRTH_KPW : 32;
+    for (int c = blockIdx.x * CAND_WARPS + warp; c * KPW < n; c += gridDim.x * CAND_WARPS) {
+        const int i = c * KPW + lane;
         // thread level: which blocks are unclaimed and inside the image (:381,:388)
         bool job = false;
         int2 r = make_int2(0, 0);
-        if (i < n) {
+        if (lane < KPW && i < n) {
             r = __ldg(reinterpret_cast<const int2 *>(kp + i));  // x | y << 16, w | h << 16
             const int x = (int16_t)(r.x & 0xffff), y = r.x >> 16, w = (int16_t)(r.y & 0xffff), h = r.y >> 16;
             const bool claimed = claim[(size_t)s * p.max_kps + i] != 0x7fffffff;  // lbFound[i]
@@ -878,7 +956,66 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
         __syncwarp();
         unsigned todo = __ballot_sync(0xffffffffu, job);
         unsigned odd = 0;  // blocks of none of the four H.264 shapes: second loop (the generic mask indexes its array dynamically)
-        while (todo) {
+        const int stride = PITCH ? PITCH : p.P;
+        auto publish = [&](int t, const uint32_t (&d)[8]) {
+            if (lane == 0) {
+                const size_t o = (size_t)s * p.max_kps + (c * KPW + t);
+                birth_flag[o] = 1;
+                uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
+                bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
+                bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
+            }
+        };
+        if (PIPE) {
+            // the round's standard-shape blocks, PF_DEPTH windows in flight (the same staging as cand_kernel)
+            unsigned std_m = 0;
+            {
+                const int w = (int16_t)(r.y & 0xffff), h = r.y >> 16;
+                const bool stdsh = (w == 16 || w == 8) && (h == 16 || h == 8);
+                std_m = __ballot_sync(0xffffffffu, job && stdsh);
+                odd = todo & ~std_m;
+            }
+            auto issue = [&](int t, int slot) {
+                const int rx = sm[warp][0][t];
+                const int x = (int16_t)(rx & 0xffff), y = rx >> 16;
+                window_issue(img, stride, x & ~15, y, swin[warp][slot], lane);
+            };
+            unsigned pend = std_m;  // blocks whose window has not been requested yet
+#pragma unroll
+            for (int k = 0; k < PF_DEPTH; k++) {
+                if (pend) {
+                    issue(__ffs(pend) - 1, k);
+                    pend &= pend - 1;
+                }
+                cp_async_commit();
+            }
+            int k = 0;
+            for (unsigned run = std_m; run; run &= run - 1, k++) {
+                const int t = __ffs(run) - 1;
+                cp_async_wait<PF_DEPTH - 1>();
+                __syncwarp();
+                const int rx = sm[warp][0][t], ry = sm[warp][1][t];
+                const int x = (int16_t)(rx & 0xffff), w = (int16_t)(ry & 0xffff), h = ry >> 16;
+                const uint8_t *win = swin[warp][k % PF_DEPTH];
+                const unsigned xo = (unsigned)(x & 15);
+                uint32_t d[8];
+                bool pass;
+                if (w == 16 && h == 16) pass = express_birth<16, 16, WIN_ROW>(win, xo, WIN_ROW, p.thr, scratch[warp], lane, d);
+                else if (w == 8 && h == 8) pass = express_birth<8, 8, WIN_ROW>(win, xo, WIN_ROW, p.thr, scratch[warp], lane, d);
+                else if (w == 8 && h == 16) pass = express_birth<16, 8, WIN_ROW>(win, xo, WIN_ROW, p.thr, scratch[warp], lane, d);
+                else pass = express_birth<8, 16, WIN_ROW>(win, xo, WIN_ROW, p.thr, scratch[warp], lane, d);
+                if (pass) publish(t, d);
+                __syncwarp();  // every lane has read the window before its buffer is refilled
+                if (pend) {
+                    issue(__ffs(pend) - 1, k % PF_DEPTH);
+                    pend &= pend - 1;
+                }
+                cp_async_commit();
+            }
+            cp_async_wait<0>();
+            todo = 0;
+        }
+        while (!PIPE && todo) {
             const int t = __ffs(todo) - 1;
             todo &= todo - 1;
             const int rx = sm[warp][0][t], ry = sm[warp][1][t];
@@ -887,7 +1024,6 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
                 odd |= 1u << t;
                 continue;
             }
-            const int stride = PITCH ? PITCH : p.P;
             const unsigned origin = (unsigned)(y * stride + x);
             uint32_t d[8];
             bool pass;
@@ -895,32 +1031,19 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
             else if (w == 8 && h == 8) pass = express_birth<8, 8, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
             else if (w == 8 && h == 16) pass = express_birth<16, 8, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
             else pass = express_birth<8, 16, PITCH>(img, origin, p.P, p.thr, scratch[warp], lane, d);
-            if (pass && lane == 0) {
-                const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
-                birth_flag[o] = 1;
-                uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
-                bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
-                bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
-            }
+            if (pass) publish(t, d);
         }
         while (odd) {
             const int t = __ffs(odd) - 1;
             odd &= odd - 1;
             const int rx = sm[warp][0][t], ry = sm[warp][1][t];
             const int x = (int16_t)(rx & 0xffff), y = rx >> 16, w = (int16_t)(ry & 0xffff), h = ry >> 16;
-            const int stride = PITCH ? PITCH : p.P;
             const uint8_t *roi = img + (unsigned)(y * stride + x);
             uint32_t d[8];
             const bool pass = express_test(roi, stride, h, w, p.thr, scratch[warp], lane);  // :391
             if (pass) {
                 express_mask(roi, stride, h, w, express_band(roi, stride, h, w, p.thr), 1, false, d, lane);
-                if (lane == 0) {
-                    const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
-                    birth_flag[o] = 1;
-                    uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
-                    bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
-                    bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
-                }
+                publish(t, d);
             }
         }
         __syncwarp();
@@ -1211,6 +1334,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
     uint16_t *s_pk = reinterpret_cast<uint16_t *>(s_age + p.maxT);
     uint16_t *s_run = s_pk + p.maxT;
     int *s_hist = reinterpret_cast<int *>(s_run + p.maxT);
+    uint16_t *s_src = reinterpret_cast<uint16_t *>(s_hist + FIN_WARPS * HIST_STRIDE);  // [FIN_THREADS * FIN_IPT] ranks that survive a round
     pdl_wait();  // cand_kernel / birth_kernel wrote the staging tables
     pdl_trigger();
     const int s = p.s0 + blockIdx.x;
@@ -1283,7 +1407,9 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
             }
             rekey_all = true;
         }
-        // survivors in sorted order (:254-334): a thread owns FIN_IPT consecutive ranks, so one block scan orders a round
+        // survivors in sorted order (:254-334): a thread owns FIN_IPT consecutive ranks, so one block scan orders a round.
+        // The scan only produces the list of surviving ranks (shared memory); the 64-byte records are then moved by ALL
+        // threads, one record each per step, instead of by the few threads whose ranks survived, eight in a row.
         for (int base = 0; base < n_prev; base += FIN_THREADS * FIN_IPT) {
             const int i0 = base + threadIdx.x * FIN_IPT;
             int2 c[FIN_IPT];
@@ -1298,28 +1424,31 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                 }
             }
             int tot;
-            int pos = n_out + block_excl_scan(__popc(accm), wsum, tot);  // barriers: every claim test is done
+            int pos = block_excl_scan(__popc(accm), wsum, tot);  // barriers: every claim test is done
 #pragma unroll
             for (int e = 0; e < FIN_IPT; e++) {
                 if ((c[e].y & 1) && c[e].x >= 0 && c[e].x < p.max_kps) cl[c[e].x] = 0x7fffffff;  // claims are per frame
-                if ((accm >> e) & 1u) {
-                    if (pos < p.maxT) {
-                        const uint4 *src = reinterpret_cast<const uint4 *>(st + i0 + e);
-                        const uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3];
-                        uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
-                        dst[0] = r0;
-                        dst[1] = r1;
-                        dst[2] = r2;
-                        dst[3] = r3;
-                        const int pc = __popc(r2.x) + __popc(r2.y) + __popc(r2.z) + __popc(r2.w) + __popc(r3.x) + __popc(r3.y) +
-                                       __popc(r3.z) + __popc(r3.w);
-                        s_age[pos] = max((int)r1.y, 0);
-                        s_pk[pos] = (uint16_t)(256 - pc);
-                    }
-                    pos++;
+                if ((accm >> e) & 1u) s_src[pos++] = (uint16_t)(i0 + e - base);
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < tot; k += FIN_THREADS) {
+                const int dpos = n_out + k;
+                if (dpos < p.maxT) {
+                    const uint4 *src = reinterpret_cast<const uint4 *>(st + base + s_src[k]);
+                    const uint4 r0 = src[0], r1 = src[1], r2 = src[2], r3 = src[3];
+                    uint4 *dst = reinterpret_cast<uint4 *>(cur + dpos);
+                    dst[0] = r0;
+                    dst[1] = r1;
+                    dst[2] = r2;
+                    dst[3] = r3;
+                    const int pc = __popc(r2.x) + __popc(r2.y) + __popc(r2.z) + __popc(r2.w) + __popc(r3.x) + __popc(r3.y) +
+                                   __popc(r3.z) + __popc(r3.w);
+                    s_age[dpos] = max((int)r1.y, 0);
+                    s_pk[dpos] = (uint16_t)(256 - pc);
                 }
             }
             n_out += tot;
+            __syncthreads();  // s_src is reused by the next round / the births
         }
         // coverage tracks (:337-377): the i-th coverage track in sorted order owns LK result i; carried ones follow the
         // propagated survivors, keep block and descriptor, age + 1, coverage flag, qIndx = i
@@ -1386,34 +1515,35 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
                 int tot;
                 int r = block_excl_scan(__popc(bm), wsum, tot);
 #pragma unroll
-                for (int e = 0; e < FIN_IPT; e++) {
-                    if ((bm >> e) & 1u) {
-                        const int pos = n_out + r;
-                        if (pos < p.maxT) {
-                            const int i = i0 + e;
-                            const movfe_rect mb = kp[i];
-                            const uint4 *dp = reinterpret_cast<const uint4 *>(birth_desc + ((size_t)s * p.max_kps + i) * 8);
-                            const uint4 d0 = dp[0], d1 = dp[1];
-                            // (mb.br() + mb.tl()) * 0.5 on Point_<int>: saturate_cast<int>(double) rounds half to even (:385)
-                            const float fx = (float)__double2int_rn((mb.x + mb.w + mb.x) * 0.5);
-                            const float fy = (float)__double2int_rn((mb.y + mb.h + mb.y) * 0.5);
-                            uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
-                            dst[0] = make_uint4(__float_as_uint(fx), __float_as_uint(fy), (uint32_t)(uint16_t)mb.x | ((uint32_t)(uint16_t)mb.y << 16),
-                                                (uint32_t)(uint16_t)mb.w | ((uint32_t)(uint16_t)mb.h << 16));
-                            dst[1] = make_uint4((uint32_t)(id + r + 1), 0u, (uint32_t)-1, 0u);  // ++mCurrentId, age 0, qIndx -1
-                            dst[2] = d0;
-                            dst[3] = d1;
-                            const int pc = __popc(d0.x) + __popc(d0.y) + __popc(d0.z) + __popc(d0.w) + __popc(d1.x) + __popc(d1.y) +
-                                           __popc(d1.z) + __popc(d1.w);
-                            s_age[pos] = 0;
-                            s_pk[pos] = (uint16_t)(256 - pc);
-                        }
-                        r++;
+                for (int e = 0; e < FIN_IPT; e++)
+                    if ((bm >> e) & 1u) s_src[r++] = (uint16_t)(i0 + e - base);
+                __syncthreads();
+                for (int k = threadIdx.x; k < tot; k += FIN_THREADS) {  // one new track per thread and step
+                    const int pos = n_out + k;
+                    if (pos < p.maxT) {
+                        const int i = base + s_src[k];
+                        const movfe_rect mb = kp[i];
+                        const uint4 *dp = reinterpret_cast<const uint4 *>(birth_desc + ((size_t)s * p.max_kps + i) * 8);
+                        const uint4 d0 = dp[0], d1 = dp[1];
+                        // (mb.br() + mb.tl()) * 0.5 on Point_<int>: saturate_cast<int>(double) rounds half to even (:385)
+                        const float fx = (float)__double2int_rn((mb.x + mb.w + mb.x) * 0.5);
+                        const float fy = (float)__double2int_rn((mb.y + mb.h + mb.y) * 0.5);
+                        uint4 *dst = reinterpret_cast<uint4 *>(cur + pos);
+                        dst[0] = make_uint4(__float_as_uint(fx), __float_as_uint(fy), (uint32_t)(uint16_t)mb.x | ((uint32_t)(uint16_t)mb.y << 16),
+                                            (uint32_t)(uint16_t)mb.w | ((uint32_t)(uint16_t)mb.h << 16));
+                        dst[1] = make_uint4((uint32_t)(id + k + 1), 0u, (uint32_t)-1, 0u);  // ++mCurrentId, age 0, qIndx -1
+                        dst[2] = d0;
+                        dst[3] = d1;
+                        const int pc = __popc(d0.x) + __popc(d0.y) + __popc(d0.z) + __popc(d0.w) + __popc(d1.x) + __popc(d1.y) +
+                                       __popc(d1.z) + __popc(d1.w);
+                        s_age[pos] = 0;
+                        s_pk[pos] = (uint16_t)(256 - pc);
                     }
                 }
                 n_out += tot;
                 id += tot;
                 mov_cnt += tot;
+                __syncthreads();
             }
         }
         n_keyed = min(n_out, p.maxT);
@@ -1550,7 +1680,7 @@ size_t sort_smem(int maxT) {
     int N = SORT_MIN_N;
     while (N < maxT) N <<= 1;
     const size_t general = (size_t)N * sizeof(unsigned long long);
-    const size_t runs = (size_t)maxT * 8 + (size_t)FIN_WARPS * HIST_STRIDE * sizeof(int);
+    const size_t runs = (size_t)maxT * 8 + (size_t)FIN_WARPS * HIST_STRIDE * sizeof(int) + (size_t)FIN_THREADS * 8 * sizeof(uint16_t);
     return std::max(general, runs);
 }
 
@@ -1658,9 +1788,10 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
 #undef MOVFE_CAND
         int nl = 2;
         if (c.has_grey) {
-            dim3 gb(std::min((ctx->max_kps + CAND_THREADS - 1) / CAND_THREADS, bps), ns);
+            const int kpw = ctx->cand_pipe ? BIRTH_KPW : 32;
+            dim3 gb(std::min((ctx->max_kps + kpw * CAND_WARPS - 1) / (kpw * CAND_WARPS), ctx->cand_pipe ? 2 * bps : bps), ns);
 #define MOVFE_BIRTH(PITCH)                                                                                             \
-    MOVFE_CUDA(ctx, launch_pdl(pdl, birth_kernel<PITCH>, gb, dim3(CAND_THREADS), 0, gs, p, w.d_kps, w.d_nkps, ctx->d_grey,  \
+    MOVFE_CUDA(ctx, launch_pdl(pdl, ctx->cand_pipe ? birth_kernel<PITCH, true> : birth_kernel<PITCH, false>, gb, dim3(CAND_THREADS), 0, gs, p, w.d_kps, w.d_nkps, ctx->d_grey,  \
                                ctx->d_fflags, e.claim, e.birth_flag, e.birth_desc))
             switch (ctx->grey_pitch) {
                 case 1024: MOVFE_BIRTH(1024); break;
