@@ -37,8 +37,11 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
                     ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier, ctx->d_pose_scratch, ctx->d_op, ctx->d_pairs, ctx->d_npairs};
     for (void *b : bufs)
         if (b) cudaFree(b);
-    if (ctx->d_map_stage) cudaFree(ctx->d_map_stage);
-    if (ctx->h_map_meta) cudaFreeHost(ctx->h_map_meta);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->d_map_stage[b]) cudaFree(ctx->d_map_stage[b]);
+        if (ctx->h_map_meta[b]) cudaFreeHost(ctx->h_map_meta[b]);
+        if (ctx->ev_map_staged[b]) cudaEventDestroy(ctx->ev_map_staged[b]);
+    }
     for (RasterBuf &w : ctx->rb) {
         void *wb[] = {w.d_seg_cnt, w.d_cls_cnt, w.d_area, w.d_hop_base, w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, w.d_hops, w.d_hop_rect, w.d_kps,
                       w.d_chunk_bbox, w.d_grid, w.d_tc_dim, w.d_tc_runs, w.d_tc_cells};

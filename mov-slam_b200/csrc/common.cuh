@@ -176,9 +176,13 @@ struct movfe_ctx {
     int32_t *d_ninl = nullptr;         // [S][F]
     int32_t *d_match = nullptr;        // [S][F][max_tracks]
     uint8_t *d_outlier = nullptr;      // [S][F][max_tracks]
-    void    *d_map_stage = nullptr;    // staging of movfe_set_map_points_batch (host hand-over of all streams' local maps)
-    void    *h_map_meta = nullptr;
-    size_t   map_stage_bytes = 0;
+    // staging of movfe_set_map_points_batch (host hand-over of all streams' local maps), double-buffered so that a
+    // hand-over never waits for the pose chain that consumed the previous one
+    void    *d_map_stage[2] = {nullptr, nullptr};
+    void    *h_map_meta[2] = {nullptr, nullptr};
+    size_t   map_stage_bytes[2] = {0, 0};
+    cudaEvent_t ev_map_staged[2] = {nullptr, nullptr};   // recorded on the pose stream after the install kernel read buffer b
+    int      map_parity = 0;
     void    *d_pose_scratch = nullptr;
     size_t   pose_scratch_bytes = 0;
     // split pose chain (join kernels + small solver kernels, pose.cu): correspondences of one frame per stream

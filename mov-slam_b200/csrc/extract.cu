@@ -715,9 +715,10 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
                 const int ke = k + half;
                 const bool on = ke < n_ev;
                 const int e = on ? slist[warp][ke] : 0, t = e & 31, j = e >> 5;
-                const int tinfo = sm[warp][CW_INFO][t];
+                // (an idle half - odd list length - computes on a 16x16 dummy: the per-track words of lane 0 may be stale)
+                const int tinfo = on ? sm[warp][CW_INFO][t] : ((16 << 8) | (16 << 16));
                 const int cols = (tinfo >> 8) & 0xff, rows = tinfo >> 16;   // block width / height
-                const int mx = (int16_t)(sm[warp][CW_MXY + j][t] & 0xffff);
+                const int mx = on ? (int16_t)(sm[warp][CW_MXY + j][t] & 0xffff) : 0;
                 const uint8_t *win = swin[warp][ke % PF_DEPTH];
                 const int xo = mx - ((mx + 1) & ~15);
                 // compute_center (EXPRESS.h:79-88): at(row = cols/2, col = rows/2) and its upper-left neighbours
@@ -730,9 +731,10 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
                 // previous descriptor, half-word hl (bitset<256> bit i at word i>>5, bit i&31)
                 const uint32_t pw = (uint32_t)sm[warp][CW_DESC + (hl >> 1)][t];
                 const uint32_t pdh = (hl & 1) ? (pw >> 16) : (pw & 0xffffu);
+                // both halves' distances from one warp-wide sum: half 1 counts in the upper 16 bits (a distance is at most 256)
                 const int part = on ? __popc(hw ^ pdh) : 0;
-                const int dist = __reduce_add_sync(half ? 0xffff0000u : 0x0000ffffu, part);
-                const int d0v = __shfl_sync(0xffffffffu, dist, 0), d1v = __shfl_sync(0xffffffffu, dist, 16);
+                const unsigned both = __reduce_add_sync(0xffffffffu, (unsigned)part << (16 * half));
+                const int d0v = (int)(both & 0xffffu), d1v = (int)(both >> 16);
                 const int e1 = __shfl_sync(0xffffffffu, e, 16), e0 = __shfl_sync(0xffffffffu, e, 0);
 #pragma unroll
                 for (int h = 0; h < 2; h++) {  // the two results are folded in list order (warp-uniform)

@@ -1041,6 +1041,7 @@ extern "C" int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point 
     const movfe_map_point *d_pts = pts;
     const int64_t *d_off = off;
     const int32_t *d_nkf = n_keyframe_points;
+    int staged = -1;
     if (!on_device) {
         int64_t total = off[S];
         for (int s = 0; s < S; s++) {
@@ -1051,24 +1052,27 @@ extern "C" int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point 
         if (total > 0 && !pts) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "set_map_points_batch: null points");
         const size_t b_pts = ((size_t)total * sizeof(movfe_map_point) + 255) & ~(size_t)255, b_off = ((size_t)(S + 1) * 8 + 255) & ~(size_t)255;
         const size_t need = b_pts + b_off + (size_t)S * 4;
-        if (ctx->map_stage_bytes < need) {
-            MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
-            if (ctx->d_map_stage) cudaFree(ctx->d_map_stage);
-            if (ctx->h_map_meta) cudaFreeHost(ctx->h_map_meta);
-            ctx->d_map_stage = nullptr;
-            ctx->h_map_meta = nullptr;
-            ctx->map_stage_bytes = 0;
-            MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_map_stage, need + need / 2));
-            MOVFE_CUDA(ctx, cudaMallocHost(&ctx->h_map_meta, b_off + (size_t)S * 4));
-            ctx->map_stage_bytes = need + need / 2;
-        } else {
-            MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // the previous hand-over has left the staging buffers
+        const int b = ctx->map_parity;
+        ctx->map_parity ^= 1;
+        if (!ctx->ev_map_staged[b]) MOVFE_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_map_staged[b], cudaEventDisableTiming));
+        // buffer b was last used two hand-overs ago: its install kernel has normally long finished
+        if (ctx->map_stage_bytes[b]) MOVFE_CUDA(ctx, cudaEventSynchronize(ctx->ev_map_staged[b]));
+        if (ctx->map_stage_bytes[b] < need) {
+            if (ctx->d_map_stage[b]) cudaFree(ctx->d_map_stage[b]);
+            if (ctx->h_map_meta[b]) cudaFreeHost(ctx->h_map_meta[b]);
+            ctx->d_map_stage[b] = nullptr;
+            ctx->h_map_meta[b] = nullptr;
+            ctx->map_stage_bytes[b] = 0;
+            MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_map_stage[b], need + need / 2));
+            MOVFE_CUDA(ctx, cudaMallocHost(&ctx->h_map_meta[b], b_off + (size_t)S * 4));
+            ctx->map_stage_bytes[b] = need + need / 2;
         }
-        uint8_t *base = (uint8_t *)ctx->d_map_stage;
-        memcpy(ctx->h_map_meta, off, (size_t)(S + 1) * 8);
-        memcpy((uint8_t *)ctx->h_map_meta + b_off, n_keyframe_points, (size_t)S * 4);
+        uint8_t *base = (uint8_t *)ctx->d_map_stage[b];
+        memcpy(ctx->h_map_meta[b], off, (size_t)(S + 1) * 8);
+        memcpy((uint8_t *)ctx->h_map_meta[b] + b_off, n_keyframe_points, (size_t)S * 4);
         if (total > 0) MOVFE_CUDA(ctx, cudaMemcpyAsync(base, pts, (size_t)total * sizeof(movfe_map_point), cudaMemcpyHostToDevice, st));
-        MOVFE_CUDA(ctx, cudaMemcpyAsync(base + b_pts, ctx->h_map_meta, b_off + (size_t)S * 4, cudaMemcpyHostToDevice, st));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(base + b_pts, ctx->h_map_meta[b], b_off + (size_t)S * 4, cudaMemcpyHostToDevice, st));
+        staged = b;
         d_pts = (const movfe_map_point *)base;
         d_off = (const int64_t *)(base + b_pts);
         d_nkf = (const int32_t *)(base + b_pts + b_off);
@@ -1077,6 +1081,7 @@ extern "C" int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point 
     map_install_kernel<<<S, 256, 0, st>>>(reinterpret_cast<const uint32_t *>(d_pts), d_off, d_nkf, std::max(c.max_map_points, 1),
                                           reinterpret_cast<uint32_t *>(ctx->d_map), ctx->d_nmap, ctx->d_nkf);
     MOVFE_CUDA(ctx, cudaGetLastError());
+    if (staged >= 0) MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_map_staged[staged], st));
     return MOVFE_OK;
 }
 
