@@ -643,15 +643,22 @@ def run_product(args, cfg):
     def push_host(k):
         push_np(ctx, host[k])
 
+    def map_host(k):
+        m = host[k]["map"]
+        ctx.set_map_points_batch(m["pts"].numpy().view(T.MAP_POINT), m["off"].numpy(), m["nkf"].numpy(), MAPCAP)
+
     push_host(0)
+    map_host(0)
 
     def step_host(k):
         first = F * (k + 1)
-        m = host[k]["map"]
         ctx.raster(first, F)
         ctx.extract(first, F)
-        ctx.set_map_points_batch(m["pts"].numpy().view(T.MAP_POINT), m["off"].numpy(), m["nkf"].numpy(), MAPCAP)
         ctx.track_poses(first, F)
+        # the next window's inputs: its local maps first (a small copy that must not queue behind the big one: the pose chain
+        # of window k+1 waits for it), then records + grey planes; both are one step's inputs, counted in h2d_bytes_per_step
+        if k + 1 < n_steps:
+            map_host(k + 1)
         push_host(k + 1)
         last["poses"], last["ninl"] = ctx.poses(first, F)      # device->host read of the step's result (synchronises)
 

@@ -27,6 +27,7 @@
 #include <cstdio>
 
 #include "common.cuh"
+#include "express_lane.cuh"
 
 namespace {
 
@@ -543,11 +544,146 @@ __device__ __forceinline__ uint32_t desc_halfword(uint32_t row, int rows, int hl
     return rows == 16 ? row : hw8;
 }
 
+// Thread-level state of one track across the phases of the candidate kernels (lane = sorted rank inside the warp's 32-track chunk).
+struct TrackState {
+    uint4 a0, a1;    // pt_x, pt_y, mb.x | mb.y << 16, mb.w | mb.h << 16;  track_id, age, q_indx, flags
+    float ptx, pty, hw, hh;
+    unsigned need;   // candidates whose block lies inside the image (:286)
+    int chosen;
+    bool act, alive, multi, warp_job;
+};
+
+// ---- thread level: the track's own chain order -> track -> slots -> up to four hops; candidate rectangles, previous descriptor and the
+// hops themselves are parked in the warp's shared-memory words smw[CW_*][lane] for the warp-level phase.
+__device__ __forceinline__ TrackState track_chain(const ExtParams &p, const movfe_track *__restrict__ prev, const uint16_t *__restrict__ ord,
+                                                  const int4 *__restrict__ g, const TileCells &tq, const movfe_hop *__restrict__ hp, bool has_img,
+                                                  unsigned long long *__restrict__ stats, int i, int n_prev, int lane, int (*smw)[32]) {
+    TrackState ts;
+    ts.act = i < n_prev;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0), d0 = a0, d1 = a0;
+    if (ts.act) {
+        const int oidx = ord[i];
+        const uint4 *tp = reinterpret_cast<const uint4 *>(prev + oidx);
+        a0 = __ldg(tp);      // pt_x, pt_y, mb.x | mb.y << 16, mb.w | mb.h << 16
+        a1 = __ldg(tp + 1);  // track_id, age, q_indx, flags
+        if (has_img) {       // previous descriptor: one more dependent latency if it were fetched per track at warp level
+            d0 = __ldg(tp + 2);
+            d1 = __ldg(tp + 3);
+        }
+    }
+    ts.a0 = a0;
+    ts.a1 = a1;
+    const float ptx = __uint_as_float(a0.x), pty = __uint_as_float(a0.y);
+    const int mw = (int16_t)(a0.w & 0xffffu), mh = (int16_t)(a0.w >> 16);
+    bool alive = ts.act && !(a1.w & MOVFE_TRACK_COVERAGE);  // :258-262 coverage tracks go to the host LK step
+    int4 sl = make_int4(-1, -1, -1, -1);
+    {
+        const int x = (int)ptx, y = (int)pty;  // :264
+        if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
+        if (alive) sl = p.fused ? resolve_slots(tq, x, y) : __ldg(&g[(size_t)y * p.W + x]);
+    }
+    if (sl.x == -1) alive = false;  // :265-268
+    const int sj[4] = {sl.x, sl.y, sl.z, sl.w};
+    bool vj[4];
+    vj[0] = alive;
+#pragma unroll
+    for (int j = 1; j < 4; j++) vj[j] = vj[j - 1] && sj[j] != -1;  // :277-278 stop at the first empty slot
+    {   // workload counters (diagnostic): tracks looked up and their candidate hops
+        const int nt = __reduce_add_sync(0xffffffffu, alive ? 1 : 0);
+        const int nc = __reduce_add_sync(0xffffffffu, (int)vj[0] + (int)vj[1] + (int)vj[2] + (int)vj[3]);
+        if (lane == 0 && nt) {
+            atomicAdd(&stats[0], (unsigned long long)nt);
+            atomicAdd(&stats[1], (unsigned long long)nc);
+        }
+    }
+    int4 hv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) hv[j] = vj[j] ? __ldg(reinterpret_cast<const int4 *>(hp + sj[j])) : make_int4(0, 0, -1, 0);
+    const float hw = (float)(mw / 2), hh = (float)(mh / 2);
+    int mxy[4];
+    unsigned need = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float px = __fadd_rn(ptx, __int_as_float(hv[j].x));  // :283
+        const float py = __fadd_rn(pty, __int_as_float(hv[j].y));
+        const int mx = (int)__fsub_rn(px, hw), my = (int)__fsub_rn(py, hh);  // :284
+        mxy[j] = (int)((uint32_t)(mx & 0xffff) | ((uint32_t)my << 16));
+        if (vj[j] && rect_in_bounds(mx, my, mw, mh, p.W, p.H)) need |= 1u << j;  // :286
+        // the hop itself is parked in shared memory: only the chosen one is needed again, after the warp-level phase
+        smw[CW_HOP + 3 * j + 0][lane] = hv[j].x;
+        smw[CW_HOP + 3 * j + 1][lane] = hv[j].y;
+        smw[CW_HOP + 3 * j + 2][lane] = hv[j].z;
+    }
+    // chosen candidate when no descriptor is involved: single-candidate pixels keep slot 0 (:270); with several
+    // candidates and a flat image every distance is 0, so the first in-bounds one wins
+    ts.chosen = (!has_img && sl.y >= 0 && need) ? __ffs(need) - 1 : 0;
+    ts.multi = sl.y >= 0;
+    ts.warp_job = alive && need != 0 && has_img;
+    if (ts.warp_job) {
+        // a later candidate whose block lands on the same pixels as an earlier in-bounds one has the same descriptor and
+        // distance, and the strict '<' of :292 never prefers it: it is not evaluated
+        unsigned need_eval = need;
+#pragma unroll
+        for (int j = 1; j < 4; j++)
+#pragma unroll
+            for (int k = 0; k < j; k++)
+                if (((need >> k) & 1u) && mxy[j] == mxy[k]) need_eval &= ~(1u << j);
+#pragma unroll
+        for (int j = 0; j < 4; j++) smw[CW_MXY + j][lane] = mxy[j];
+        smw[CW_INFO][lane] = (int)need_eval | (mw << 8) | (mh << 16);
+        smw[CW_DESC + 0][lane] = (int)d0.x;
+        smw[CW_DESC + 1][lane] = (int)d0.y;
+        smw[CW_DESC + 2][lane] = (int)d0.z;
+        smw[CW_DESC + 3][lane] = (int)d0.w;
+        smw[CW_DESC + 4][lane] = (int)d1.x;
+        smw[CW_DESC + 5][lane] = (int)d1.y;
+        smw[CW_DESC + 6][lane] = (int)d1.z;
+        smw[CW_DESC + 7][lane] = (int)d1.w;
+    }
+    ts.ptx = ptx;
+    ts.pty = pty;
+    ts.hw = hw;
+    ts.hh = hh;
+    ts.need = need;
+    ts.alive = alive;
+    return ts;
+}
+
+// ---- thread level: move, bounds, gate, claim (:301-316). my_best: distance of the chosen candidate's descriptor (with an image).
+__device__ __forceinline__ void track_move(const ExtParams &p, const TrackState &ts, int my_best, bool has_img, movfe_track *__restrict__ st,
+                                           int2 *__restrict__ ci, int32_t *__restrict__ cl, int i, int lane, int (*smw)[32]) {
+    if (!ts.act) return;
+    const int chosen = ts.chosen;
+    const float cx = __fadd_rn(ts.ptx, __int_as_float(smw[CW_HOP + 3 * chosen + 0][lane]));  // :303
+    const float cy = __fadd_rn(ts.pty, __int_as_float(smw[CW_HOP + 3 * chosen + 1][lane]));
+    const int cd = smw[CW_HOP + 3 * chosen + 2][lane];
+    const int cmx = (int)__fsub_rn(cx, ts.hw), cmy = (int)__fsub_rn(cy, ts.hh);  // :304
+    const int cxy = (int)((uint32_t)(cmx & 0xffff) | ((uint32_t)cmy << 16));
+    const bool inb = ts.alive && ((ts.need >> chosen) & 1u);  // :306 (the claim test itself happens in finalize)
+    int fl = 0;
+    if (inb) {
+        fl = 1;
+        // with an image the chosen candidate's descriptor was evaluated at warp level (need bit set => warp job)
+        if (!has_img || my_best <= 40) fl |= 2;  // :311-316
+        uint4 *o = reinterpret_cast<uint4 *>(st + i);
+        o[0] = make_uint4(__float_as_uint(cx), __float_as_uint(cy), (uint32_t)cxy, ts.a0.w);
+        o[1] = make_uint4(ts.a1.x, ts.a1.y + 1, (uint32_t)i, 0u);  // trackId, age + 1, qIndx, flags
+        if (!has_img) {  // MV-only mode: descriptors are all zero
+            o[2] = make_uint4(0, 0, 0, 0);
+            o[3] = make_uint4(0, 0, 0, 0);
+        }
+        if (cd >= 0 && cd < p.max_kps) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
+    }
+    if (ts.a1.w & MOVFE_TRACK_COVERAGE) fl = 4;  // carried by the host LK step (:258-262), merged in finalize
+    ci[i] = make_int2(ts.alive ? cd : -1, fl);
+}
+
+
 #ifndef CAND_MINB
 #define CAND_MINB (16 / MOVFE_CAND_WARPS)  // 128 registers per thread
 #endif
 #ifndef CAND_PIPE_MINB
-#define CAND_PIPE_MINB (2 * CAND_MINB)
+#define CAND_PIPE_MINB 6  // 80 registers per thread: no spills; 64 registers (8 CTAs) spill 200 bytes and measure 5-9 % slower
 #endif
 template <int PITCH, bool PIPE>
 __global__ void __launch_bounds__(CAND_THREADS, PIPE ? CAND_PIPE_MINB : CAND_MINB)
@@ -577,87 +713,9 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
 
     for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n_prev; c += gridDim.x * CAND_WARPS) {
         const int i = c * 32 + lane;  // sorted rank
-        // ---- thread level: the track's own chain ------------------------------------------------------------------
-        const bool act = i < n_prev;
-        int oidx = 0;
-        uint4 a0 = make_uint4(0, 0, 0, 0), a1 = make_uint4(0, 0, 0, 0), d0 = a0, d1 = a0;
-        if (act) {
-            oidx = ord[i];
-            const uint4 *tp = reinterpret_cast<const uint4 *>(prev + oidx);
-            a0 = __ldg(tp);      // pt_x, pt_y, mb.x | mb.y << 16, mb.w | mb.h << 16
-            a1 = __ldg(tp + 1);  // track_id, age, q_indx, flags
-            if (img) {           // previous descriptor: one more dependent latency if it were fetched per track below
-                d0 = __ldg(tp + 2);
-                d1 = __ldg(tp + 3);
-            }
-        }
-        const float ptx = __uint_as_float(a0.x), pty = __uint_as_float(a0.y);
-        const int mw = (int16_t)(a0.w & 0xffffu), mh = (int16_t)(a0.w >> 16);
-        bool alive = act && !(a1.w & MOVFE_TRACK_COVERAGE);  // :258-262 coverage tracks go to the host LK step
-        int4 sl = make_int4(-1, -1, -1, -1);
-        {
-            const int x = (int)ptx, y = (int)pty;  // :264
-            if (x < 0 || y < 0 || x >= p.W || y >= p.H) alive = false;  // unchecked .at<>() in the reference (UB)
-            if (alive) sl = p.fused ? resolve_slots(tq, x, y) : __ldg(&g[(size_t)y * p.W + x]);
-        }
-        if (sl.x == -1) alive = false;  // :265-268
-        const int sj[4] = {sl.x, sl.y, sl.z, sl.w};
-        bool vj[4];
-        vj[0] = alive;
-#pragma unroll
-        for (int j = 1; j < 4; j++) vj[j] = vj[j - 1] && sj[j] != -1;  // :277-278 stop at the first empty slot
-        {   // workload counters (diagnostic): tracks looked up and their candidate hops
-            const int nt = __reduce_add_sync(0xffffffffu, alive ? 1 : 0);
-            const int nc = __reduce_add_sync(0xffffffffu, (int)vj[0] + (int)vj[1] + (int)vj[2] + (int)vj[3]);
-            if (lane == 0 && nt) {
-                atomicAdd(&stats[0], (unsigned long long)nt);
-                atomicAdd(&stats[1], (unsigned long long)nc);
-            }
-        }
-        int4 hv[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) hv[j] = vj[j] ? __ldg(reinterpret_cast<const int4 *>(hp + sj[j])) : make_int4(0, 0, -1, 0);
-        const float hw = (float)(mw / 2), hh = (float)(mh / 2);
-        int mxy[4];
-        unsigned need = 0;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float px = __fadd_rn(ptx, __int_as_float(hv[j].x));  // :283
-            const float py = __fadd_rn(pty, __int_as_float(hv[j].y));
-            const int mx = (int)__fsub_rn(px, hw), my = (int)__fsub_rn(py, hh);  // :284
-            mxy[j] = (int)((uint32_t)(mx & 0xffff) | ((uint32_t)my << 16));
-            if (vj[j] && rect_in_bounds(mx, my, mw, mh, p.W, p.H)) need |= 1u << j;  // :286
-            // the hop itself is parked in shared memory: only the chosen one is needed again, after the warp-level loop
-            sm[warp][CW_HOP + 3 * j + 0][lane] = hv[j].x;
-            sm[warp][CW_HOP + 3 * j + 1][lane] = hv[j].y;
-            sm[warp][CW_HOP + 3 * j + 2][lane] = hv[j].z;
-        }
-        // chosen candidate when no descriptor is involved: single-candidate pixels keep slot 0 (:270); with several
-        // candidates and a flat image every distance is 0, so the first in-bounds one wins
-        int chosen = (!img && sl.y >= 0 && need) ? __ffs(need) - 1 : 0;
-        const bool multi = sl.y >= 0;
-        const bool warp_job = alive && need != 0 && img != nullptr;
-        if (warp_job) {
-            // a later candidate whose block lands on the same pixels as an earlier in-bounds one has the same descriptor and
-            // distance, and the strict '<' of :292 never prefers it: it is not evaluated
-            unsigned need_eval = need;
-#pragma unroll
-            for (int j = 1; j < 4; j++)
-#pragma unroll
-                for (int k = 0; k < j; k++)
-                    if (((need >> k) & 1u) && mxy[j] == mxy[k]) need_eval &= ~(1u << j);
-#pragma unroll
-            for (int j = 0; j < 4; j++) sm[warp][CW_MXY + j][lane] = mxy[j];
-            sm[warp][CW_INFO][lane] = (int)need_eval | (mw << 8) | (mh << 16);
-            sm[warp][CW_DESC + 0][lane] = (int)d0.x;
-            sm[warp][CW_DESC + 1][lane] = (int)d0.y;
-            sm[warp][CW_DESC + 2][lane] = (int)d0.z;
-            sm[warp][CW_DESC + 3][lane] = (int)d0.w;
-            sm[warp][CW_DESC + 4][lane] = (int)d1.x;
-            sm[warp][CW_DESC + 5][lane] = (int)d1.y;
-            sm[warp][CW_DESC + 6][lane] = (int)d1.z;
-            sm[warp][CW_DESC + 7][lane] = (int)d1.w;
-        }
+        TrackState ts = track_chain(p, prev, ord, g, tq, hp, img != nullptr, stats, i, n_prev, lane, sm[warp]);
+        const bool warp_job = ts.warp_job, multi = ts.multi;
+        int chosen = ts.chosen;
         __syncwarp();
         // ---- warp level: descriptors of the candidate patches -------------------------------------------------------
         // The winning descriptor of track t goes straight to the staging record of its rank (written for every evaluated
@@ -819,31 +877,208 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
             }
         }
         __syncwarp();
-        // ---- thread level: move, bounds, gate, claim (:301-316) -------------------------------------------------------
-        if (act) {
-            const float cx = __fadd_rn(ptx, __int_as_float(sm[warp][CW_HOP + 3 * chosen + 0][lane]));  // :303
-            const float cy = __fadd_rn(pty, __int_as_float(sm[warp][CW_HOP + 3 * chosen + 1][lane]));
-            const int cd = sm[warp][CW_HOP + 3 * chosen + 2][lane];
-            const int cmx = (int)__fsub_rn(cx, hw), cmy = (int)__fsub_rn(cy, hh);  // :304
-            const int cxy = (int)((uint32_t)(cmx & 0xffff) | ((uint32_t)cmy << 16));
-            const bool inb = alive && ((need >> chosen) & 1u);  // :306 (the claim test itself happens in finalize)
-            int fl = 0;
-            if (inb) {
-                fl = 1;
-                // with an image the chosen candidate's descriptor was evaluated above (need bit set => warp job)
-                if (!img || my_best <= 40) fl |= 2;  // :311-316
-                uint4 *o = reinterpret_cast<uint4 *>(st + i);
-                o[0] = make_uint4(__float_as_uint(cx), __float_as_uint(cy), (uint32_t)cxy, a0.w);
-                o[1] = make_uint4(a1.x, a1.y + 1, (uint32_t)i, 0u);  // trackId, age + 1, qIndx, flags
-                if (!img) {  // MV-only mode: descriptors are all zero
-                    o[2] = make_uint4(0, 0, 0, 0);
-                    o[3] = make_uint4(0, 0, 0, 0);
-                }
-                if (cd >= 0 && cd < p.max_kps) atomicMin(&cl[cd], i);  // first-come in sorted order (:306-309)
-            }
-            if (a1.w & MOVFE_TRACK_COVERAGE) fl = 4;  // carried by the host LK step (:258-262), merged in finalize
-            ci[i] = make_int2(alive ? cd : -1, fl);
+        ts.chosen = chosen;
+        track_move(p, ts, my_best, img != nullptr, st, ci, cl, i, lane, sm[warp]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- cand_lane_kernel -----
+// The same propagation step with the descriptors evaluated at THREAD level (express_lane.cuh): a lane pair per candidate block,
+// one lane per 8-row half, 16 blocks per warp step. The warp-level forms above pay a set of warp-wide shuffles, ballots and
+// bookkeeping per block (cand_kernel<.., true>: ~85 warp instructions per block, instruction issue is what bounds it); here the
+// block's pixels are compared four to an instruction by one lane and nothing crosses lanes until the distance of a block is the
+// sum of its two halves. The windows are staged with 8-byte cp.async copies, 24 bytes per row from an 8-byte aligned column, so
+// that a row is three conflict-free 64-bit shared loads.
+constexpr int LN_BATCH = 16;                       // blocks per warp step
+constexpr int LN_LIST = 128;                       // evaluations of a 32-track chunk (4 candidates each)
+constexpr int CW_BEST = CW_WORDS;                  // one more parked word per track: (best distance << 3 | candidate) of the evaluations so far
+constexpr int CWL_WORDS = CW_WORDS + 1;
+#ifndef CAND_LANE_MINB
+#define CAND_LANE_MINB 5
+#endif
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// Stages the windows of `n` (<= BATCH) list entries into the warp's window slots: 48 copies of 8 bytes per window (16 rows x 3),
+// two windows per three warp-wide copies, no predicates: an odd last window is fetched twice (the second copy lands in an unused
+// slot), and the rows below an 8-row block are fetched like the others (the grey ring ends with 16 rows of slack).
+// org[k] = byte offset of the window's first row in the grey plane.
+struct StageLane {
+    unsigned src[3], dst[3];  // byte offsets of this lane's three copies: source relative to the window origin, destination in the pair's slots
+    bool second[3];           // the copy belongs to the second window of the pair
+};
+__device__ __forceinline__ StageLane stage_lane(int stride, int lane) {
+    StageLane sl;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int m = lane + 32 * i;  // 0..95: copy m of the window pair
+        const int which = m >= 48 ? 1 : 0, mm = m - 48 * which, row = mm / 3, part = mm - 3 * row;
+        sl.second[i] = which != 0;
+        sl.src[i] = (unsigned)(row * stride + part * 8);
+        sl.dst[i] = (unsigned)(which * (xl::WIN_STRIDE * 4) + mm * 8);
+    }
+    return sl;
+}
+template <int BATCH>
+__device__ __forceinline__ void stage_windows(const uint8_t *__restrict__ img, const StageLane &sl, const uint32_t *org, int n, uint32_t *win) {
+#pragma unroll
+    for (int pp = 0; pp < BATCH / 2; pp++) {
+        if (2 * pp >= n) break;  // warp-uniform
+        const uint32_t o0 = org[2 * pp], o1 = org[min(2 * pp + 1, n - 1)];
+        uint8_t *dst = reinterpret_cast<uint8_t *>(win) + pp * (2 * xl::WIN_STRIDE * 4);
+#pragma unroll
+        for (int i = 0; i < 3; i++) cp_async8(dst + sl.dst[i], img + ((sl.second[i] ? o1 : o0) + sl.src[i]));
+    }
+    cp_async_commit();
+}
+
+template <int PITCH>
+__global__ void __launch_bounds__(CAND_THREADS, CAND_LANE_MINB)
+cand_lane_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
+                 const uint16_t *__restrict__ order, SlotSource src, const movfe_hop *__restrict__ hops,
+                 const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
+                 int2 *__restrict__ cinfo, int32_t *__restrict__ claim, unsigned long long *__restrict__ stats) {
+    __shared__ int sm[CAND_WARPS][CWL_WORDS][32];
+    __shared__ __align__(16) uint32_t swin[CAND_WARPS][LN_BATCH * xl::WIN_STRIDE];
+    __shared__ uint32_t sorg[CAND_WARPS][LN_LIST];   // window origin of every evaluation of the chunk, in (track, candidate) order
+    __shared__ uint8_t slist[CAND_WARPS][LN_LIST];   // track | candidate << 5
+    pdl_wait();     // the previous frame's finalize_kernel wrote the tables read below
+    pdl_trigger();
+    const int s = p.s0 + blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_prev = ntracks[s * p.TSLOTS + p.tslot_prev];
+    if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;  // I frame: nothing is propagated
+    const movfe_track *prev = tracks + ((size_t)s * p.TSLOTS + p.tslot_prev) * p.maxT;
+    const uint16_t *ord = order + (size_t)s * p.maxT;
+    const int4 *g = p.fused ? nullptr : src.grid + ((size_t)s * p.n_out + p.fi) * ((size_t)p.W * p.H);
+    TileCells tq = {};
+    if (p.fused) tq = frame_cells(p, src, s);
+    const movfe_hop *hp = hops + ((size_t)s * p.n_out + p.fi) * p.max_hops;
+    const uint8_t *img = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H);  // this kernel is only launched with an image
+    movfe_track *st = stage + (size_t)s * p.maxT;
+    int2 *ci = cinfo + (size_t)s * p.maxT;
+    int32_t *cl = claim + (size_t)s * p.max_kps;
+    const int stride = PITCH ? PITCH : p.P;
+    const int q = lane >> 1, half = lane & 1;
+    const StageLane stl = stage_lane(stride, lane);
+
+    for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n_prev; c += gridDim.x * CAND_WARPS) {
+        const int i = c * 32 + lane;  // sorted rank
+        TrackState ts = track_chain(p, prev, ord, g, tq, hp, true, stats, i, n_prev, lane, sm[warp]);
+        // ---- the chunk's evaluations as one flat list in (track, candidate) order ------------------------------------------------
+        const int info = ts.warp_job ? sm[warp][CW_INFO][lane] : 0;
+        const int tw = (info >> 8) & 0xff, th = info >> 16;
+        const bool std_shape = (tw == 16 || tw == 8) && (th == 16 || th == 8);
+        unsigned odd = __ballot_sync(0xffffffffu, ts.warp_job && !std_shape);  // none of the four H.264 shapes: warp-level loop below
+        const unsigned mine = (ts.warp_job && std_shape) ? (unsigned)(info & 0xf) : 0u;
+        const int cnt = __popc(mine);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
+        const int n_ev = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            int pos = incl - cnt;
+            unsigned m = mine;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int mv = sm[warp][CW_MXY + j][lane];
+                const int mx = (int16_t)(mv & 0xffff), my = mv >> 16;
+                slist[warp][pos] = (uint8_t)(lane | (j << 5));
+                sorg[warp][pos] = (uint32_t)(my * stride + ((mx + 1) & ~7));
+                pos++;
+            }
+        }
+        __syncwarp();
+        // ---- lane level: a lane pair per block, 16 blocks per step --------------------------------------------------------------
+        int carry_t = -1, carry_key = 0;   // the track whose evaluations straddle two steps: its best key so far (warp-uniform)
+        for (int b0 = 0; b0 < n_ev; b0 += LN_BATCH) {
+            const int nb = min(LN_BATCH, n_ev - b0);
+            stage_windows<LN_BATCH>(img, stl, sorg[warp] + b0, nb, swin[warp]);
+            const bool on = q < nb;
+            const int e = on ? slist[warp][b0 + q] : 0, t = e & 31, j = e >> 5;
+            // (an idle pair computes on a 16x16 dummy: the per-track words of lane 0 may be stale)
+            const int tinfo = on ? sm[warp][CW_INFO][t] : ((16 << 8) | (16 << 16));
+            const int cols = (tinfo >> 8) & 0xff, rows = tinfo >> 16;
+            const int mx = on ? (int16_t)(sm[warp][CW_MXY + j][t] & 0xffff) : 0;
+            const int xw = (mx + 1) & ~7;
+            uint32_t pd[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) pd[k] = (uint32_t)sm[warp][CW_DESC + 4 * half + k][t];
+            cp_async_wait<0>();
+            __syncwarp();
+            const uint32_t *win = swin[warp] + q * xl::WIN_STRIDE;
+            const xl::Band bd = xl::band_of(xl::centre_of(win, mx - xw, rows, cols), p.thr);
+            uint32_t d[4];
+            xl::half_descriptor(win, mx + 1 - xw, rows, cols, half, bd, d);
+            if (half && rows == 8) d[0] = d[1] = d[2] = d[3] = 0;  // an 8-row block has no second half
+            // (desc1 ^ desc2).count() (EXPRESS.h:112-115): this half's four words, the block's distance is the sum of both halves
+            int part = __popc(d[0] ^ pd[0]) + __popc(d[1] ^ pd[1]) + __popc(d[2] ^ pd[2]) + __popc(d[3] ^ pd[3]);
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            // :292-296: candidates in order, strict '<' from 256, candidate 0 is the default choice (:270): the winner is the smallest
+            // (distance, candidate) key. Evaluations of a track are adjacent list entries: a segmented minimum over <= 3 neighbours.
+            const int key = on ? ((part << 3) | j) : 0x7fff;
+            const int tk = on ? ((t << 16) | key) : (0xff << 16) | 0x7fff;
+            int seg_min = 0x7fff;  // best key of the OTHER evaluations of this track in this step
+#pragma unroll
+            for (int dlt = 1; dlt <= 3; dlt++) {
+                const int up = __shfl_up_sync(0xffffffffu, tk, 2 * dlt), dn = __shfl_down_sync(0xffffffffu, tk, 2 * dlt);
+                if (q >= dlt && (up >> 16) == t) seg_min = min(seg_min, up & 0xffff);
+                if (q + dlt < LN_BATCH && (dn >> 16) == t) seg_min = min(seg_min, dn & 0xffff);
+            }
+            const int prior = (on && t == carry_t) ? carry_key : 0x7fff;  // this track's best key of the previous step
+            const bool winner = on && key < seg_min && key < prior;
+            if (winner) {
+                // the best descriptor so far goes to the track's staging record (a better candidate of a later step overwrites it:
+                // same warp, program order); the key is parked for the track's own lane
+                reinterpret_cast<uint4 *>((st + c * 32 + t)->desc)[half] = make_uint4(d[0], d[1], d[2], d[3]);
+                if (!half) sm[warp][CW_BEST][t] = key;
+            }
+            // the last block's track may continue in the next step
+            const int last = 2 * (nb - 1);
+            const int lt = __shfl_sync(0xffffffffu, t, last), lk = __shfl_sync(0xffffffffu, min(min(key, seg_min), prior), last);
+            carry_t = lt;
+            carry_key = lk;
+            __syncwarp();  // every lane has read its window before the slots are refilled
+        }
+        __syncwarp();
+        int my_best = 0;
+        if (ts.warp_job && std_shape) {
+            const int key = sm[warp][CW_BEST][lane];
+            const int dist = key >> 3, j = key & 7;
+            // single-candidate pixels never compare (:272): slot 0 stays chosen. A first evaluated candidate j > 0 at distance 256
+            // is not taken by the strict '<' (its track fails the bounds test of :306 at slot 0 anyway).
+            if (ts.multi && (dist < 256 || j == 0)) ts.chosen = j;
+            my_best = dist;
+        }
+        while (odd) {
+            const int t = __ffs(odd) - 1;
+            odd &= odd - 1;
+            int cm[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) cm[j] = sm[warp][CW_MXY + j][t];
+            const int oinfo = sm[warp][CW_INFO][t];
+            uint32_t pd[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) pd[k] = (uint32_t)sm[warp][CW_DESC + k][t];
+            uint32_t bd[8];
+            int best;
+            const int ch = cand_eval_generic(img, p.P, p.thr, (oinfo >> 8) & 0xff, oinfo >> 16, cm, oinfo & 0xf, pd, lane, bd, best);
+            if (lane == t) {
+                if (ts.multi && ch >= 0) ts.chosen = ch;
+                my_best = best;
+                uint4 *o = reinterpret_cast<uint4 *>(st + i);
+                o[2] = make_uint4(bd[0], bd[1], bd[2], bd[3]);
+                o[3] = make_uint4(bd[4], bd[5], bd[6], bd[7]);
+            }
+        }
+        __syncwarp();
+        track_move(p, ts, my_best, true, st, ci, cl, i, lane, sm[warp]);
     }
 }
 
@@ -1050,6 +1285,121 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
         }
         __syncwarp();
     }
+}
+
+// --------------------------------------------------------------------------------------- birth_lane_kernel -----
+// compute_express + descriptor of the unclaimed in-bounds kps blocks at THREAD level (express_lane.cuh: block_express), a lane
+// per block, 32 blocks per warp step. A warp scans its share of the kps list 32 entries at a time and gathers the jobs in a list;
+// whenever 32 have come together their windows are staged and every lane evaluates one block on its own: no ballots, no
+// transposes, the diagonal walk is a carry-save sum of the block's shifted rows.
+constexpr int BL_BATCH = 32;
+constexpr size_t BL_SMEM = (size_t)CAND_WARPS * BL_BATCH * xl::WIN_STRIDE * sizeof(uint32_t);
+constexpr int BL_CHUNKS_PER_WARP = 2;  // grid sizing: kps chunks a warp scans (more: fuller steps; fewer: more warps in flight)
+
+template <int PITCH>
+__global__ void __launch_bounds__(CAND_THREADS, 4)
+birth_lane_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
+                  const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
+                  uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
+    extern __shared__ __align__(16) uint32_t swin_all[];  // [CAND_WARPS][BL_BATCH * xl::WIN_STRIDE]: 49 KB, above the static limit
+    uint32_t (*swin)[BL_BATCH * xl::WIN_STRIDE] = reinterpret_cast<uint32_t (*)[BL_BATCH * xl::WIN_STRIDE]>(swin_all);
+    __shared__ uint32_t sorg[CAND_WARPS][2 * BL_BATCH];  // job list: window origin in the grey plane
+    __shared__ uint32_t sinf[CAND_WARPS][2 * BL_BATCH];  //           kps index | (x & 7) << 20 | (w == 16) << 23 | (h == 16) << 24
+    __shared__ uint32_t scratch[CAND_WARPS][8];
+    __shared__ int sm[CAND_WARPS][2][32];
+    pdl_wait();  // cand_kernel wrote the claims
+    pdl_trigger();
+    const int s = p.s0 + blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = nkps[s * p.n_in + p.fi];
+    if (!(fflags[s * p.RING + p.gslot] & MOVFE_FRAME_P)) return;
+    const uint8_t *img = grey + ((size_t)s * p.RING + p.gslot) * ((size_t)p.P * p.H);
+    const movfe_rect *kp = kps + ((size_t)s * p.n_out + p.fi) * p.max_kps;
+    const int stride = PITCH ? PITCH : p.P;
+    const StageLane stl = stage_lane(stride, lane);
+    const unsigned lt = lanemask_lt();
+    int n_jobs = 0;  // warp-uniform: entries of the job list
+
+    auto run_step = [&](int nb) {  // evaluates list entries [0, nb), nb <= BL_BATCH
+        stage_windows<BL_BATCH>(img, stl, sorg[warp], nb, swin[warp]);
+        const bool on = lane < nb;
+        const uint32_t inf = on ? sinf[warp][lane] : ((1u << 23) | (1u << 24));  // an idle lane computes on a 16x16 dummy
+        const int cols = (inf >> 23) & 1u ? 16 : 8, rows = (inf >> 24) & 1u ? 16 : 8;
+        cp_async_wait<0>();
+        __syncwarp();
+        uint32_t d[8];
+        const bool pass = xl::block_express(swin[warp] + lane * xl::WIN_STRIDE, (int)((inf >> 20) & 7u), rows, cols, p.thr, d);  // :391
+        if (on && pass) {
+            const size_t o = (size_t)s * p.max_kps + (inf & 0xfffffu);
+            birth_flag[o] = 1;
+            uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
+            bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
+            bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
+        }
+        __syncwarp();  // every lane has read its window before the slots are refilled
+    };
+
+    for (int c = blockIdx.x * CAND_WARPS + warp; c * 32 < n; c += gridDim.x * CAND_WARPS) {
+        const int i = c * 32 + lane;
+        // thread level: which blocks are unclaimed and inside the image (:381,:388)
+        bool job = false;
+        int2 r = make_int2(0, 0);
+        if (i < n) {
+            r = __ldg(reinterpret_cast<const int2 *>(kp + i));  // x | y << 16, w | h << 16
+            const int x = (int16_t)(r.x & 0xffff), y = r.x >> 16, w = (int16_t)(r.y & 0xffff), h = r.y >> 16;
+            const bool claimed = claim[(size_t)s * p.max_kps + i] != 0x7fffffff;  // lbFound[i]
+            job = !claimed && rect_in_bounds(x, y, w, h, p.W, p.H);
+            birth_flag[(size_t)s * p.max_kps + i] = 0;
+        }
+        const int x = (int16_t)(r.x & 0xffff), y = r.x >> 16, w = (int16_t)(r.y & 0xffff), h = r.y >> 16;
+        const bool stdsh = (w == 16 || w == 8) && (h == 16 || h == 8);
+        const unsigned std_m = __ballot_sync(0xffffffffu, job && stdsh);
+        unsigned odd = __ballot_sync(0xffffffffu, job && !stdsh);
+        if (job && stdsh) {
+            const int pos = n_jobs + __popc(std_m & lt);
+            sorg[warp][pos] = (uint32_t)(y * stride + (x & ~7));
+            sinf[warp][pos] = (uint32_t)i | ((uint32_t)(x & 7) << 20) | (w == 16 ? 1u << 23 : 0u) | (h == 16 ? 1u << 24 : 0u);
+        }
+        n_jobs += __popc(std_m);
+        __syncwarp();
+        if (n_jobs >= BL_BATCH) {  // warp-uniform
+            run_step(BL_BATCH);
+            n_jobs -= BL_BATCH;
+            const uint32_t o = lane < n_jobs ? sorg[warp][BL_BATCH + lane] : 0u, f = lane < n_jobs ? sinf[warp][BL_BATCH + lane] : 0u;
+            __syncwarp();
+            if (lane < n_jobs) {
+                sorg[warp][lane] = o;
+                sinf[warp][lane] = f;
+            }
+            __syncwarp();
+        }
+        if (odd) {  // blocks of none of the four H.264 shapes: the warp-level generic test
+            sm[warp][0][lane] = r.x;
+            sm[warp][1][lane] = r.y;
+            __syncwarp();
+            while (odd) {
+                const int t = __ffs(odd) - 1;
+                odd &= odd - 1;
+                const int rx = sm[warp][0][t], ry = sm[warp][1][t];
+                const int ox = (int16_t)(rx & 0xffff), oy = rx >> 16, ow = (int16_t)(ry & 0xffff), oh = ry >> 16;
+                const uint8_t *roi = img + (unsigned)(oy * stride + ox);
+                uint32_t d[8];
+                const bool pass = express_test(roi, stride, oh, ow, p.thr, scratch[warp], lane);  // :391
+                if (pass) {
+                    express_mask(roi, stride, oh, ow, express_band(roi, stride, oh, ow, p.thr), 1, false, d, lane);
+                    if (lane == 0) {
+                        const size_t o = (size_t)s * p.max_kps + (c * 32 + t);
+                        birth_flag[o] = 1;
+                        uint4 *bd4 = reinterpret_cast<uint4 *>(birth_desc + o * 8);
+                        bd4[0] = make_uint4(d[0], d[1], d[2], d[3]);
+                        bd4[1] = make_uint4(d[4], d[5], d[6], d[7]);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+    if (n_jobs > 0) run_step(n_jobs);
 }
 
 // --------------------------------------------------------------------------------------- finalize_kernel -----
@@ -1716,6 +2066,9 @@ int movfe_extract_init(movfe_ctx *ctx) {
     if ((int)sort_smem(c.max_tracks) > fin_limit)
         MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "max_tracks=%d needs %zu bytes of shared memory, the device allows %d", c.max_tracks, sort_smem(c.max_tracks), fin_limit);
     MOVFE_CUDA(ctx, optin_dynamic_smem(sort_only_kernel, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(birth_lane_kernel<0>, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(birth_lane_kernel<1024>, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(birth_lane_kernel<2048>, ctx->smem_optin));
     MOVFE_CUDA(ctx, cudaGetLastError());
     return MOVFE_OK;
 }
@@ -1779,8 +2132,10 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         // grid-stride over tracks / kps: enough CTAs to fill the chip, never one CTA per (mostly empty) capacity slot
         const int bps = std::max(4, (64 * ctx->sm_count + c.n_streams * CAND_WARPS - 1) / (c.n_streams * CAND_WARPS));
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
+        // thread-level descriptors (cand_lane_kernel / birth_lane_kernel) need an image and a threshold below 128
+        const bool lane_mode = ctx->cand_lane && c.has_grey && c.express_threshold >= 0 && c.express_threshold <= xl::MAX_THR;
 #define MOVFE_CAND(PITCH)                                                                                              \
-    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
+    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, lane_mode ? cand_lane_kernel<PITCH> : ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
                                src, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim, ctx->d_stats))
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
@@ -1790,10 +2145,10 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
 #undef MOVFE_CAND
         int nl = 2;
         if (c.has_grey) {
-            const int kpw = ctx->cand_pipe ? BIRTH_KPW : 32;
-            dim3 gb(std::min((ctx->max_kps + kpw * CAND_WARPS - 1) / (kpw * CAND_WARPS), ctx->cand_pipe ? 2 * bps : bps), ns);
+            const int kpw = lane_mode ? 32 * BL_CHUNKS_PER_WARP : ctx->cand_pipe ? BIRTH_KPW : 32;
+            dim3 gb(std::min((ctx->max_kps + kpw * CAND_WARPS - 1) / (kpw * CAND_WARPS), (ctx->cand_pipe && !lane_mode) ? 2 * bps : bps), ns);
 #define MOVFE_BIRTH(PITCH)                                                                                             \
-    MOVFE_CUDA(ctx, launch_pdl(pdl, ctx->cand_pipe ? birth_kernel<PITCH, true> : birth_kernel<PITCH, false>, gb, dim3(CAND_THREADS), 0, gs, p, w.d_kps, w.d_nkps, ctx->d_grey,  \
+    MOVFE_CUDA(ctx, launch_pdl(pdl, lane_mode ? birth_lane_kernel<PITCH> : ctx->cand_pipe ? birth_kernel<PITCH, true> : birth_kernel<PITCH, false>, gb, dim3(CAND_THREADS), lane_mode ? BL_SMEM : 0, gs, p, w.d_kps, w.d_nkps, ctx->d_grey,  \
                                ctx->d_fflags, e.claim, e.birth_flag, e.birth_desc))
             switch (ctx->grey_pitch) {
                 case 1024: MOVFE_BIRTH(1024); break;
