@@ -267,6 +267,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(dalloc(&ctx->d_npairs, S));
     CK(cudaMemset(ctx->d_npairs, 0, S * sizeof(int32_t)));
     if (const char *e = getenv("MOVFE_POSE_SPLIT")) ctx->pose_split = atoi(e) != 0;
+    if (const char *e = getenv("MOVFE_POSE_V1")) ctx->pose_v1 = atoi(e) != 0;
+    if (const char *e = getenv("MOVFE_POSE_GROUP")) ctx->pose_group = std::max(1, atoi(e));
     ctx->pose_scratch_bytes = movfe_pose_scratch_bytes(ctx);
     CK(cudaMalloc(&ctx->d_pose_scratch, std::max<size_t>(ctx->pose_scratch_bytes, 16)));
     CK(cudaMemset(ctx->d_pose_scratch, 0, std::max<size_t>(ctx->pose_scratch_bytes, 16)));

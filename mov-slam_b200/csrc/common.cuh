@@ -190,6 +190,8 @@ struct movfe_ctx {
     float   *d_pairs = nullptr;        // [S][6][max_map_points]: x y z u v idx
     int32_t *d_npairs = nullptr;       // [S]
     int      h_nmap_max = 0;           // largest local map installed so far (sizes the solver CTAs)
+    bool     pose_v1 = false;          // MOVFE_POSE_V1=1: the first form of the fused pose chain (one launch per frame, joins over the whole track table)
+    int      pose_group = 4;           // MOVFE_POSE_GROUP: frames per launch pair of the second form
     bool     pose_split = false;       // MOVFE_POSE_SPLIT=1: join kernels + small solver kernels instead of the fused
                                        // one-kernel-per-frame chain (measured slower under load)
 

@@ -717,6 +717,354 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
     }
 }
 
+// ================================================================================== pose chain, second form ======
+// The first form above (kept behind MOVFE_POSE_V1=1 for A/B runs) walks the whole track table of a frame - thousands of
+// 64-byte records - three times per join and seventeen block scans per gather, and every Gauss-Newton pass parks the CTA at
+// three barriers around a one-thread 6x6 solve. It runs beside propagation but was the longer of the two chains.
+// Second form:
+//  * tp_prep_kernel (wide: one CTA per frame and stream, all frames of a window at once, nothing pose-dependent): for every
+//    local map point the FIRST track carrying its id (F.mvVFMap, MOVExtractor.cc:330) and the first map point of its id group.
+//    What remains of a join is then work on the few hundred map points only: the last eligible point of an id group owns
+//    the group's track (MOVMatcher.h:35-103 walk the points in order and overwrite).
+//  * the pairs are put in keypoint order (Optimizer.cc:404-413) through a bitmap of the matched tracks: one popcount prefix.
+//  * pose_solve2: every pass ends at ONE barrier; each warp then adds the per-warp partial sums in the fixed order and solves
+//    the 6x6 system itself (identical arithmetic in every thread, so the poses stay bit-identical across the CTA), and the
+//    re-classification that closes a round is fused into the first pass of the next round (same pose, same residuals).
+// Sums are formed in the same order as in the first form, so both give the same bits.
+struct Solver2Shared {
+    double part[2][TP_WARPS][32];  // per-warp partial sums (21 JtJ + 6 Jtr + outlier count), double-buffered by pass parity
+    double tot[TP_WARPS][28];      // each warp's own copy of the totals
+    double Rt[TP_WARPS][12];       // each warp's own copy of the pose
+    int ipart[2][TP_WARPS];
+};
+
+template <typename Src>
+__device__ int pose_solve2(const Src &src, int n, const movfe_camera &cam_, const movfe_pose_params &pp, movfe_pose *pose,
+                           uint8_t *outlier, int (&stats)[4], Solver2Shared &sh) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const CamD cam = widen(cam_);
+    const float repErrorF = pp.is_lost ? (float)pp.reprojection_error_lost : (float)pp.reprojection_error;  // Optimizer.cc:423-427
+    const double delta = repErrorF, chi2thr = delta * delta;
+    const int its = pp.iteration_count / 4 > 1 ? pp.iteration_count / 4 : 1;
+    const int nw = min((n + 31) >> 5, (int)(blockDim.x >> 5));  // warps that own points
+    const int nthr = nw * 32;
+    double *Rt = sh.Rt[warp];
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) outlier[i] = 0;
+    if (lane < 9) Rt[lane] = pose->R[lane];
+    else if (lane < 12) Rt[lane] = pose->t[lane - 9];
+    __syncthreads();
+    if (n < 4) return 0;  // Optimizer.cc:415-418
+    int n_bad = 0, pass = 0;
+    bool pending = false;  // a round has ended: every correspondence is to be re-classified at the current pose
+    bool stop = false;
+    for (int round = 0; round < 4 && !stop; round++) {
+        const bool robust = round < 3;
+        for (int it = 0; it < its; it++) {
+            double acc[27];
+#pragma unroll
+            for (int q = 0; q < 27; q++) acc[q] = 0.0;
+            int bad = 0;
+            if (warp < nw) {
+                for (int i = threadIdx.x; i < n; i += nthr) {
+                    float X0, X1, X2, ou, ov;
+                    src.get(i, X0, X1, X2, ou, ov);
+                    if (pending) {
+                        const bool b = classify_point(cam, Rt, Rt + 9, X0, X1, X2, ou, ov, chi2thr);
+                        outlier[i] = b ? 1 : 0;  // only this thread reads it back in later passes
+                        bad += b;
+                        if (b) continue;
+                    } else if (outlier[i]) {
+                        continue;
+                    }
+                    accumulate_point(cam, Rt, Rt + 9, X0, X1, X2, ou, ov, robust, delta, acc);
+                }
+                const double v = warp_reduce27(acc, lane);
+                sh.part[pass & 1][warp][lane] = v;
+                if (pending) {
+                    for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+                    if (lane == 0) sh.ipart[pass & 1][warp] = bad;
+                }
+            }
+            __syncthreads();  // the only barrier of a pass (the partials of the pass after next go to this buffer again: by then
+                              // every warp has passed the next barrier, i.e. has finished reading these)
+            if (lane < 27) {
+                double v = 0;
+                for (int w = 0; w < nw; w++) v += sh.part[pass & 1][w][lane];
+                sh.tot[warp][lane] = v;
+            }
+            stats[2]++;
+            if (pending) {
+                n_bad = 0;
+                for (int w = 0; w < nw; w++) n_bad += sh.ipart[pass & 1][w];
+                stats[1]++;
+                pending = false;
+                if (n - n_bad < 3) {  // the first form leaves the rounds here, before another iteration
+                    stop = true;
+                    pass++;
+                    break;
+                }
+            }
+            pass++;
+            __syncwarp();
+            stats[0]++;
+            double dx[6];
+            int flag;
+            if (!solve6_d(sh.tot[warp], &sh.tot[warp][21], dx)) {
+                flag = 2;
+                stats[3]++;
+            } else {
+                double dR[9], dt[3], Rn[9], tn[3];
+                se3_exp_d(dx, dR, dt);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) Rn[i * 3 + j] = dR[i * 3] * Rt[j] + dR[i * 3 + 1] * Rt[3 + j] + dR[i * 3 + 2] * Rt[6 + j];
+#pragma unroll
+                for (int r = 0; r < 3; r++) tn[r] = dR[r * 3] * Rt[9] + dR[r * 3 + 1] * Rt[10] + dR[r * 3 + 2] * Rt[11] + dt[r];
+                __syncwarp();  // every lane has read the old pose
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) Rt[i] = Rn[i];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) Rt[9 + i] = tn[i];
+                }
+                double m = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) m = fmax(m, fabs(dx[a]));
+                flag = m < 1e-10 ? 1 : 0;
+            }
+            __syncwarp();
+            if (flag) break;
+        }
+        if (!stop) pending = true;
+    }
+    if (pending) {  // the classification that closes the last round
+        int bad = 0;
+        if (warp < nw) {
+            for (int i = threadIdx.x; i < n; i += nthr) {
+                float X0, X1, X2, ou, ov;
+                src.get(i, X0, X1, X2, ou, ov);
+                const bool b = classify_point(cam, Rt, Rt + 9, X0, X1, X2, ou, ov, chi2thr);
+                outlier[i] = b ? 1 : 0;
+                bad += b;
+            }
+            for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+            if (lane == 0) sh.ipart[pass & 1][warp] = bad;
+        }
+        __syncthreads();
+        n_bad = 0;
+        for (int w = 0; w < nw; w++) n_bad += sh.ipart[pass & 1][w];
+        stats[1]++;
+        stats[2]++;
+    }
+    if (threadIdx.x < 9) pose->R[threadIdx.x] = Rt[threadIdx.x];
+    else if (threadIdx.x < 12) pose->t[threadIdx.x - 9] = Rt[threadIdx.x];
+    __syncthreads();  // outlier[] and the pose are visible to the whole CTA
+    return n - n_bad;
+}
+
+// first track / group leader of every map point of one (frame, stream): (first track index + 1) | leader point << 16
+__global__ void __launch_bounds__(TP_THREADS)
+tp_prep_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
+               const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, uint32_t *__restrict__ first_track,
+               int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out) {
+    extern __shared__ int hsm[];  // keys[cap] ftrack[cap] leader[cap]
+    int *keys = hsm, *ftrack = hsm + p.hash_cap, *leader = hsm + 2 * p.hash_cap;
+    const int k = blockIdx.x, s = blockIdx.y;
+    const movfe_map_point *mp = map + (size_t)s * p.maxMap;
+    const int n_map = nmap[s];
+    const int ts = (p.tslot0 + k) % p.TSLOTS;
+    const movfe_track *tr = tracks + ((size_t)s * p.TSLOTS + ts) * p.maxT;
+    const int n = ntracks[s * p.TSLOTS + ts];
+    int32_t *match = match_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
+    uint8_t *outl = outlier_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
+    uint32_t *ft = first_track + ((size_t)s * p.F + p.out0 + k) * p.maxMap;
+    // SearchByVideoFeature(KF, F, matches) starts from an all-NULL vector (MOVMatcher.h:76), mvbOutlier from all true (Optimizer.cc:452)
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        match[t] = -1;
+        outl[t] = 1;
+    }
+    int cap = 2;
+    while (cap < 2 * n_map) cap <<= 1;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        keys[i] = HASH_EMPTY;
+        ftrack[i] = 0x7fffffff;
+        leader[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
+        const int id = mp[i].track_id;
+        if (id == HASH_EMPTY) continue;
+        unsigned h = hash_id(id) & (cap - 1);
+        while (true) {
+            const int prev = atomicCAS(&keys[h], HASH_EMPTY, id);
+            if (prev == HASH_EMPTY || prev == id) {
+                atomicMin(&leader[h], i);
+                break;
+            }
+            h = (h + 1) & (cap - 1);
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const int id = tr[t].track_id;
+        if (id == HASH_EMPTY) continue;
+        unsigned h = hash_id(id) & (cap - 1);
+        while (true) {
+            const int kk = keys[h];
+            if (kk == id) {
+                atomicMin(&ftrack[h], t);  // integer min: the first index wins whatever the thread order
+                break;
+            }
+            if (kk == HASH_EMPTY) break;
+            h = (h + 1) & (cap - 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
+        const int id = mp[i].track_id;
+        uint32_t v = 0;
+        if (id != HASH_EMPTY) {
+            unsigned h = hash_id(id) & (cap - 1);
+            while (keys[h] != id) h = (h + 1) & (cap - 1);
+            const int f = ftrack[h];
+            v = (f == 0x7fffffff ? 0u : (uint32_t)(f + 1)) | ((uint32_t)leader[h] << 16);
+        }
+        ft[i] = v;
+    }
+}
+
+// keypoint-ordered (map point, keypoint) pairs of a join result: win[g] = the map point that owns the track of id group g
+// (set at the group's leader only), -1 elsewhere. Returns the pair count. bits/pref: maxT/32 words each.
+__device__ int gather_pairs2(const movfe_track *__restrict__ tr, const movfe_map_point *__restrict__ mp, int n_map, const uint32_t *pk,
+                             const int *win, uint32_t *bits, int *pref, int n_words, float *cx, float *cy, float *cz, float *cu, float *cv,
+                             int *cidx, int *cm, int cap, int *wsum, int32_t *__restrict__ match) {
+    for (int w = threadIdx.x; w < n_words; w += blockDim.x) bits[w] = 0;
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_map; g += blockDim.x)
+        if (win[g] >= 0) {
+            const int t = (int)(pk[g] & 0xffffu) - 1;
+            atomicOr(&bits[t >> 5], 1u << (t & 31));
+        }
+    __syncthreads();
+    int n_pairs = 0;
+    for (int base = 0; base < n_words; base += TP_THREADS) {
+        const int w = base + threadIdx.x;
+        const int c = w < n_words ? __popc(bits[w]) : 0;
+        int tot;
+        const int e = n_pairs + tp_excl_scan(c, wsum, tot);
+        if (w < n_words) pref[w] = e;
+        n_pairs += tot;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < n_map; g += blockDim.x) {
+        const int m = win[g];
+        if (m < 0) continue;
+        const int t = (int)(pk[g] & 0xffffu) - 1;
+        const int pos = pref[t >> 5] + __popc(bits[t >> 5] & ((1u << (t & 31)) - 1u));
+        match[t] = m;
+        if (pos < cap) {
+            cx[pos] = mp[m].pos[0];
+            cy[pos] = mp[m].pos[1];
+            cz[pos] = mp[m].pos[2];
+            const float2 pt = *reinterpret_cast<const float2 *>(&tr[t].pt_x);
+            cu[pos] = pt.x;
+            cv[pos] = pt.y;
+            cidx[pos] = t;
+            cm[pos] = m;
+        }
+    }
+    __syncthreads();
+    return min(n_pairs, cap);
+}
+
+__global__ void __launch_bounds__(TP_THREADS, MOVFE_TP_MINB)
+track_poses2_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks,
+                    const movfe_map_point *__restrict__ map, const int32_t *__restrict__ nmap, const int32_t *__restrict__ nkf,
+                    const uint32_t *__restrict__ first_track, movfe_pose *__restrict__ pose_cur, movfe_pose *__restrict__ poses,
+                    int32_t *__restrict__ ninl, int32_t *__restrict__ match_out, uint8_t *__restrict__ outlier_out,
+                    unsigned long long *__restrict__ stats) {
+    extern __shared__ int hsm[];  // pk win1 win2 cidx cm [maxMap] | x y z u v [maxMap] | bits pref [maxT/32] | cout tag [maxMap bytes]
+    __shared__ Solver2Shared sh;
+    __shared__ int wsum[TP_WARPS];
+    const int M = p.maxMap, NWORDS = (p.maxT + 31) / 32;
+    uint32_t *pk = reinterpret_cast<uint32_t *>(hsm);
+    int *win1 = hsm + M, *win2 = hsm + 2 * M, *cidx = hsm + 3 * M, *cm = hsm + 4 * M;
+    float *cx = reinterpret_cast<float *>(hsm + 5 * M), *cy = cx + M, *cz = cy + M, *cu = cz + M, *cv = cu + M;
+    uint32_t *bits = reinterpret_cast<uint32_t *>(cv + M);
+    int *pref = reinterpret_cast<int *>(bits + NWORDS);
+    uint8_t *cout = reinterpret_cast<uint8_t *>(pref + NWORDS), *tag = cout + M;
+    const int s = blockIdx.x;
+    const movfe_map_point *mp = map + (size_t)s * p.maxMap;
+    const int n_map = nmap[s], n_kf = min(nkf[s], n_map);
+    movfe_pose *pc = pose_cur + s;
+    const CompactSrc src{cx, cy, cz, cu, cv};
+
+    for (int k = 0; k < p.n_frames; k++) {
+        const int ts = (p.tslot0 + k) % p.TSLOTS;
+        const movfe_track *tr = tracks + ((size_t)s * p.TSLOTS + ts) * p.maxT;
+        const int n = ntracks[s * p.TSLOTS + ts];
+        int32_t *match = match_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
+        uint8_t *outl = outlier_out + ((size_t)s * p.F + p.out0 + k) * p.maxT;
+        const uint32_t *ft = first_track + ((size_t)s * p.F + p.out0 + k) * p.maxMap;
+        int n_inl = 0;
+        if (n > 0 && n_map > 0) {
+            const int n_words = (n + 31) >> 5;
+            int st[4];
+            // --- TrackReferenceKeyFrame: SearchByVideoFeature(KF, F, matches) (MOVMatcher.h:70-103)
+            for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
+                pk[i] = ft[i];
+                win1[i] = -1;
+                win2[i] = -1;
+                tag[i] = 0;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_kf; i += blockDim.x)
+                if (!(mp[i].flags & (MOVFE_MP_NULL | MOVFE_MP_BAD)) && (pk[i] & 0xffffu)) atomicMax(&win1[pk[i] >> 16], i);  // the last point of a group wins
+            __syncthreads();
+            int np = gather_pairs2(tr, mp, n_map, pk, win1, bits, pref, n_words, cx, cy, cz, cu, cv, cidx, cm, M, wsum, match);
+            pose_solve2(src, np, p.cam, p.pp, pc, cout, st, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
+            if (threadIdx.x == 0) {  // workload counters (diagnostic)
+                atomicAdd(&stats[2], 1ull);
+                atomicAdd(&stats[3], (unsigned long long)np);
+                atomicAdd(&stats[4], (unsigned long long)st[2]);
+            }
+            // --- TrackLocalMap / SearchLocalPoints (Tracking.cc:1109-1158)
+            for (int i = threadIdx.x; i < np; i += blockDim.x) tag[cm[i]] = 1;  // mnLastFrameSeen = current frame
+            __syncthreads();
+            const FrustumPose fp = frustum_pose(*pc);
+            // isInFrustum for every local point (:1136-1151); in view and not bad -> eligible (MOVMatcher.h:43-49, far filter off).
+            // The Frame overload keeps the earlier matches: a group without an eligible point keeps its owner.
+            for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
+                const movfe_map_point m = mp[i];
+                const movfe_projection pr = frustum_point(fp, p.cam, p.W, p.H, p.view_cos, m, tag[i] != 0);
+                if (pr.in_view && !(m.flags & MOVFE_MP_BAD) && (pk[i] & 0xffffu)) atomicMax(&win2[pk[i] >> 16], i);
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_map; i += blockDim.x)
+                if (win2[i] >= 0) win1[i] = win2[i];
+            __syncthreads();
+            np = gather_pairs2(tr, mp, n_map, pk, win1, bits, pref, n_words, cx, cy, cz, cu, cv, cidx, cm, M, wsum, match);
+            n_inl = pose_solve2(src, np, p.cam, p.pp, pc, cout, st, sh);
+            if (threadIdx.x == 0) {
+                atomicAdd(&stats[2], 1ull);
+                atomicAdd(&stats[3], (unsigned long long)np);
+                atomicAdd(&stats[4], (unsigned long long)st[2]);
+            }
+            // Frame::mvbOutlier (Optimizer.cc:452-456): true everywhere (tp_prep_kernel), false for the inliers;
+            // < 4 pairs: the frame is left untouched
+            for (int i = threadIdx.x; i < np; i += blockDim.x) outl[cidx[i]] = np >= 4 ? cout[i] : 0;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            poses[(size_t)s * p.F + p.out0 + k] = *pc;
+            ninl[(size_t)s * p.F + p.out0 + k] = n_inl;
+        }
+        __syncthreads();
+    }
+}
+
 // ---- the same per-frame chain as four launches (movfe_track_poses_launch, split mode) ------------------------------
 // The fused kernel above keeps 256 threads x 128 registers resident per stream for the whole frame, although the two
 // solves - most of its time - are a one-warp job between barriers; those registers are what the propagation CTAs on the
@@ -899,8 +1247,12 @@ int pow2_at_least(int v) {
 
 }  // namespace
 
+static size_t pose_tag_bytes(const movfe_ctx *ctx) {
+    return ((size_t)ctx->cfg.n_streams * std::max(ctx->cfg.max_map_points, 1) * sizeof(int32_t) + 255) & ~(size_t)255;  // skip tags (first form)
+}
 size_t movfe_pose_scratch_bytes(const movfe_ctx *ctx) {
-    return (size_t)ctx->cfg.n_streams * std::max(ctx->cfg.max_map_points, 1) * sizeof(int32_t);  // skip tags
+    // + first track / group leader of every map point, per frame of a window (tp_prep_kernel)
+    return pose_tag_bytes(ctx) + (size_t)ctx->cfg.n_streams * ctx->cfg.window_frames * std::max(ctx->cfg.max_map_points, 1) * sizeof(uint32_t);
 }
 
 int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes);
@@ -909,6 +1261,8 @@ int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes);
 // function and process-wide, so setting it per launch would race between contexts on different host threads.
 int movfe_pose_init(movfe_ctx *ctx) {
     MOVFE_CUDA(ctx, optin_dynamic_smem(track_poses_kernel, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(track_poses2_kernel, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(tp_prep_kernel, ctx->smem_optin));
     MOVFE_CUDA(ctx, optin_dynamic_smem(tp_join_kernel, ctx->smem_optin));
     MOVFE_CUDA(ctx, optin_dynamic_smem(tp_solve_kernel, ctx->smem_optin));
     MOVFE_CUDA(ctx, optin_dynamic_smem(join_kernel, ctx->smem_optin));
@@ -948,7 +1302,35 @@ int movfe_track_poses_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) 
     // solver CTAs are sized by the correspondence count, which only the device knows: one launch per size class, the CTAs
     // of the other class leave at once (the classes a context can need follow from the largest local map installed)
     const int n_cls = ctx->h_nmap_max <= 64 ? 1 : 2;
-    for (int k = 0; k < n_frames; k++) {
+    // second form (default): one wide preparation launch for the frames of the call, then one persistent CTA per stream
+    const size_t smem_prep = (size_t)3 * p.hash_cap * sizeof(int);
+    const size_t smem2 = ((size_t)10 * p.maxMap + 2 * (size_t)((p.maxT + 31) / 32)) * sizeof(int) + (size_t)2 * p.maxMap;
+    cudaFuncAttributes fa2;
+    MOVFE_CUDA(ctx, cudaFuncGetAttributes(&fa2, track_poses2_kernel));
+    const bool second = !ctx->pose_v1 && !split && p.maxMap <= 0xffff && p.maxT < 0xffff && smem_prep <= (size_t)optin &&
+                        smem2 + fa2.sharedSizeBytes <= (size_t)optin;
+    if (second) {
+        // a few frames per launch pair: the chain of the first frames of a window starts while propagation is still on the
+        // later ones, and what is left after the window's last table is one group, not a whole window
+        uint32_t *ft = (uint32_t *)((uint8_t *)ctx->d_pose_scratch + pose_tag_bytes(ctx));
+        for (int k0 = 0; k0 < n_frames; k0 += ctx->pose_group) {
+            const int ng = std::min(ctx->pose_group, n_frames - k0);
+            for (int k = k0; k < k0 + ng; k++)
+                for (int g = 0; g < ctx->n_groups; g++)  // every group of streams has finished the tables of these frames
+                    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(size_t)g * c.window_frames + ctx->ev_of_frame[(first_frame + k) % c.window_frames]], 0));
+            ProfScope prof(ctx, MOVFE_STAGE_POSE, ctx->pose_stream);
+            prof.launches(2);
+            p.n_frames = ng;
+            p.tslot0 = (int)((first_frame + k0) % p.TSLOTS);
+            p.out0 = k0;
+            tp_prep_kernel<<<dim3(ng, c.n_streams), TP_THREADS, smem_prep, ctx->pose_stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap, ft,
+                                                                                                ctx->d_match, ctx->d_outlier);
+            track_poses2_kernel<<<c.n_streams, TP_THREADS, smem2, ctx->pose_stream>>>(p, ctx->d_tracks, ctx->d_ntracks, ctx->d_map, ctx->d_nmap, ctx->d_nkf, ft,
+                                                                                      ctx->d_pose_cur, ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier,
+                                                                                      ctx->d_stats);
+        }
+    }
+    for (int k = 0; k < n_frames && !second; k++) {
         for (int g = 0; g < ctx->n_groups; g++)  // every group of streams has finished this frame's table
             MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->pose_stream, ctx->ev_frame[(size_t)g * c.window_frames + ctx->ev_of_frame[(first_frame + k) % c.window_frames]], 0));
         p.n_frames = 1;

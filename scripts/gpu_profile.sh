@@ -18,7 +18,7 @@ fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $OUT/launches_$TAG.csv \
       python bench.py --steps 2 --warmup 2 > $OUT/ncu_launches_$TAG.log 2>&1; echo "ncu launches rc=$?"
-  for KS in ${NCU_KERNELS:-cand_kernel:136 birth_kernel:136 finalize_kernel:136 track_poses_kernel:56 grid_kernel:8}; do
+  for KS in ${NCU_KERNELS:-cand_lane_kernel:136 birth_lane_kernel:136 finalize_kernel:136 track_poses2_kernel:14 tp_prep_kernel:14 grid_kernel:8}; do
     K=${KS%%:*}; SKIP=${KS##*:}
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K --launch-skip $SKIP -c 1 \
         -o $OUT/${K}_$TAG -f python bench.py --steps 2 --warmup 2 > $OUT/ncu_${K}_$TAG.log 2>&1; echo "ncu $K rc=$?"
