@@ -162,6 +162,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     if (const char *e = getenv("MOVFE_PDL")) ctx->pdl_mode = atoi(e);
     if (const char *e = getenv("MOVFE_CAND_PIPE")) ctx->cand_pipe = atoi(e) != 0;
     if (const char *e = getenv("MOVFE_CAND_LANE")) ctx->cand_lane = atoi(e) != 0;
+    if (const char *e = getenv("MOVFE_BIRTH_CHUNKS")) ctx->birth_chunks = std::max(1, atoi(e));
     ctx->ev_frame.resize((size_t)ctx->n_groups * c.window_frames, nullptr);
     for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &pl : ctx->pose_launches) {

@@ -890,11 +890,15 @@ cand_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int32_t *
 // sum of its two halves. The windows are staged with 8-byte cp.async copies, 24 bytes per row from an 8-byte aligned column, so
 // that a row is three conflict-free 64-bit shared loads.
 constexpr int LN_BATCH = 16;                       // blocks per warp step
+#ifndef LN_BUFS
+#define LN_BUFS 1   // 2: the next step's windows are staged while this step is evaluated - measured 2.5 % slower (3 CTAs per SM instead of 5)
+#endif
 constexpr int LN_LIST = 128;                       // evaluations of a 32-track chunk (4 candidates each)
 constexpr int CW_BEST = CW_WORDS;                  // one more parked word per track: (best distance << 3 | candidate) of the evaluations so far
 constexpr int CWL_WORDS = CW_WORDS + 1;
+constexpr size_t LN_SMEM = (size_t)CAND_WARPS * LN_BUFS * LN_BATCH * xl::WIN_STRIDE * sizeof(uint32_t);
 #ifndef CAND_LANE_MINB
-#define CAND_LANE_MINB 5
+#define CAND_LANE_MINB (LN_BUFS == 2 ? 3 : 5)  // CTAs per SM that the shared memory of the window slots allows
 #endif
 
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
@@ -941,7 +945,9 @@ cand_lane_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int3
                  const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, movfe_track *__restrict__ stage,
                  int2 *__restrict__ cinfo, int32_t *__restrict__ claim, unsigned long long *__restrict__ stats) {
     __shared__ int sm[CAND_WARPS][CWL_WORDS][32];
-    __shared__ __align__(16) uint32_t swin[CAND_WARPS][LN_BATCH * xl::WIN_STRIDE];
+    // window slots, double-buffered: the next step's windows land while this step is evaluated (dynamic: above the static limit)
+    extern __shared__ __align__(16) uint32_t swin_all[];
+    uint32_t (*swin)[LN_BUFS][LN_BATCH * xl::WIN_STRIDE] = reinterpret_cast<uint32_t (*)[LN_BUFS][LN_BATCH * xl::WIN_STRIDE]>(swin_all);
     __shared__ uint32_t sorg[CAND_WARPS][LN_LIST];   // window origin of every evaluation of the chunk, in (track, candidate) order
     __shared__ uint8_t slist[CAND_WARPS][LN_LIST];   // track | candidate << 5
     pdl_wait();     // the previous frame's finalize_kernel wrote the tables read below
@@ -997,9 +1003,15 @@ cand_lane_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int3
         __syncwarp();
         // ---- lane level: a lane pair per block, 16 blocks per step --------------------------------------------------------------
         int carry_t = -1, carry_key = 0;   // the track whose evaluations straddle two steps: its best key so far (warp-uniform)
-        for (int b0 = 0; b0 < n_ev; b0 += LN_BATCH) {
+        if (LN_BUFS == 2 && n_ev > 0) stage_windows<LN_BATCH>(img, stl, sorg[warp], min(LN_BATCH, n_ev), swin[warp][0]);
+        for (int b0 = 0, bi = 0; b0 < n_ev; b0 += LN_BATCH, bi++) {
             const int nb = min(LN_BATCH, n_ev - b0);
-            stage_windows<LN_BATCH>(img, stl, sorg[warp] + b0, nb, swin[warp]);
+            if (LN_BUFS == 2) {  // the next step's windows: one commit group per step, empty at the end
+                if (b0 + LN_BATCH < n_ev) stage_windows<LN_BATCH>(img, stl, sorg[warp] + b0 + LN_BATCH, min(LN_BATCH, n_ev - b0 - LN_BATCH), swin[warp][(bi + 1) & 1]);
+                else cp_async_commit();
+            } else {
+                stage_windows<LN_BATCH>(img, stl, sorg[warp] + b0, nb, swin[warp][0]);
+            }
             const bool on = q < nb;
             const int e = on ? slist[warp][b0 + q] : 0, t = e & 31, j = e >> 5;
             // (an idle pair computes on a 16x16 dummy: the per-track words of lane 0 may be stale)
@@ -1010,9 +1022,9 @@ cand_lane_kernel(ExtParams p, const movfe_track *__restrict__ tracks, const int3
             uint32_t pd[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) pd[k] = (uint32_t)sm[warp][CW_DESC + 4 * half + k][t];
-            cp_async_wait<0>();
+            cp_async_wait<LN_BUFS - 1>();  // all but the newest group: this step's windows have landed
             __syncwarp();
-            const uint32_t *win = swin[warp] + q * xl::WIN_STRIDE;
+            const uint32_t *win = swin[warp][LN_BUFS == 2 ? (bi & 1) : 0] + q * xl::WIN_STRIDE;
             const xl::Band bd = xl::band_of(xl::centre_of(win, mx - xw, rows, cols), p.thr);
             uint32_t d[4];
             xl::half_descriptor(win, mx + 1 - xw, rows, cols, half, bd, d);
@@ -1294,7 +1306,6 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
 // transposes, the diagonal walk is a carry-save sum of the block's shifted rows.
 constexpr int BL_BATCH = 32;
 constexpr size_t BL_SMEM = (size_t)CAND_WARPS * BL_BATCH * xl::WIN_STRIDE * sizeof(uint32_t);
-constexpr int BL_CHUNKS_PER_WARP = 2;  // grid sizing: kps chunks a warp scans (more: fuller steps; fewer: more warps in flight)
 
 template <int PITCH>
 __global__ void __launch_bounds__(CAND_THREADS, 4)
@@ -2067,6 +2078,9 @@ int movfe_extract_init(movfe_ctx *ctx) {
         MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "max_tracks=%d needs %zu bytes of shared memory, the device allows %d", c.max_tracks, sort_smem(c.max_tracks), fin_limit);
     MOVFE_CUDA(ctx, optin_dynamic_smem(sort_only_kernel, ctx->smem_optin));
     MOVFE_CUDA(ctx, optin_dynamic_smem(birth_lane_kernel<0>, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(cand_lane_kernel<0>, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(cand_lane_kernel<1024>, ctx->smem_optin));
+    MOVFE_CUDA(ctx, optin_dynamic_smem(cand_lane_kernel<2048>, ctx->smem_optin));
     MOVFE_CUDA(ctx, optin_dynamic_smem(birth_lane_kernel<1024>, ctx->smem_optin));
     MOVFE_CUDA(ctx, optin_dynamic_smem(birth_lane_kernel<2048>, ctx->smem_optin));
     MOVFE_CUDA(ctx, cudaGetLastError());
@@ -2135,7 +2149,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         // thread-level descriptors (cand_lane_kernel / birth_lane_kernel) need an image and a threshold below 128
         const bool lane_mode = ctx->cand_lane && c.has_grey && c.express_threshold >= 0 && c.express_threshold <= xl::MAX_THR;
 #define MOVFE_CAND(PITCH)                                                                                              \
-    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, lane_mode ? cand_lane_kernel<PITCH> : ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
+    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, lane_mode ? cand_lane_kernel<PITCH> : ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), lane_mode ? LN_SMEM : 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
                                src, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim, ctx->d_stats))
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
@@ -2145,7 +2159,7 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
 #undef MOVFE_CAND
         int nl = 2;
         if (c.has_grey) {
-            const int kpw = lane_mode ? 32 * BL_CHUNKS_PER_WARP : ctx->cand_pipe ? BIRTH_KPW : 32;
+            const int kpw = lane_mode ? 32 * ctx->birth_chunks : ctx->cand_pipe ? BIRTH_KPW : 32;
             dim3 gb(std::min((ctx->max_kps + kpw * CAND_WARPS - 1) / (kpw * CAND_WARPS), (ctx->cand_pipe && !lane_mode) ? 2 * bps : bps), ns);
 #define MOVFE_BIRTH(PITCH)                                                                                             \
     MOVFE_CUDA(ctx, launch_pdl(pdl, lane_mode ? birth_lane_kernel<PITCH> : ctx->cand_pipe ? birth_kernel<PITCH, true> : birth_kernel<PITCH, false>, gb, dim3(CAND_THREADS), lane_mode ? BL_SMEM : 0, gs, p, w.d_kps, w.d_nkps, ctx->d_grey,  \
