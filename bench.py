@@ -150,7 +150,13 @@ def pack_window(cfg, clips, S, f0, f1, pinned=True):
             grey.numpy()[s] = clips[s % len(clips)]["grey"][f0:f1]
         pos += len(r)
     ov[S * n] = pos
-    return dict(recs=recs, off=off, flags=flags, grey=grey, n_records=tot, n=n)
+    out = dict(recs=recs, off=off, flags=flags, grey=grey, n_records=tot, n=n)
+    if pinned:   # the form the decoder shim hands over: 16-byte records, packed while the side data is copied out of the AVFrame
+        from movfe import lib
+        recs16 = torch.empty(max(tot, 1) * 16, dtype=torch.uint8, pin_memory=True)
+        lib.pack_records(rv, recs16.numpy()[:tot * 16].view(T.PACKED_RECORD))
+        out["recs16"] = recs16
+    return out
 
 
 def local_map(cfg, spec, table, frame):
@@ -488,7 +494,7 @@ def run_product(args, cfg):
     torch.cuda.synchronize()
     h0 = host[0]
     map_bytes = int(h0["map"]["pts"].numel() + h0["map"]["off"].numel() * 8 + h0["map"]["nkf"].numel() * 4)
-    h2d = int(h0["n_records"] * 40 + h0["off"].numel() * 8 + h0["flags"].numel() + (h0["grey"].numel() if h0["grey"] is not None else 0) + map_bytes)
+    h2d = int(h0["n_records"] * (40 if os.environ.get("BENCH_E2E_RECORDS40") else 16) + h0["off"].numel() * 8 + h0["flags"].numel() + (h0["grey"].numel() if h0["grey"] is not None else 0) + map_bytes)
     d2h = int(np.zeros((S, F), T.POSE).nbytes + np.zeros((S, F), np.int32).nbytes)
 
     def barrier():
@@ -640,8 +646,15 @@ def run_product(args, cfg):
     ext = setup(ctx)
     last = {}
 
+    packed_push = not os.environ.get("BENCH_E2E_RECORDS40")      # development: push the 40-byte records instead
+
     def push_host(k):
-        push_np(ctx, host[k])
+        w = host[k]
+        if packed_push:
+            ctx.push_frames_packed(w["n"], w["recs16"].numpy()[:w["n_records"] * 16].view(T.PACKED_RECORD), w["off"].numpy(), w["flags"].numpy(),
+                                   None if w["grey"] is None else w["grey"].numpy())
+        else:
+            push_np(ctx, w)
 
     def map_host(k):
         m = host[k]["map"]
@@ -698,7 +711,8 @@ def run_product(args, cfg):
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_wall_ms / args.steps, "median_inliers_last_step": med_inl,
                         "h2d_gbs": h2d / 1e9 / (e2e_wall_ms / args.steps / 1e3), "host_read_gbs_aggregate": world * h2d / 1e9 / (e2e_wall_ms / args.steps / 1e3),
-                        "bound": "host->device copy of the step's inputs (records + full grey planes) over PCIe",
+                        "bound": "host->device copy of the step's inputs (16-byte packed records + full grey planes + local maps) over PCIe",
+                        "records": "movfe_push_frames_packed: 16-byte records (movfe_pack_records, done by the decoder shim while it copies the side data)" if packed_push else "movfe_push_frames: 40-byte records",
                         "pipelining": "push of window k+1 overlaps compute of window k; poses of window k read back every step"},
                 "gpu_launches": int(sum(launches.values())), "roofline": roofline, "parity_check": parity,
                 "raster_mode": "fused (slots resolved from per-tile hop queues; no slot grid in HBM)" if fused else "grid output",

@@ -87,6 +87,12 @@ int     movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_record *r
 int     movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs,
                                  const int64_t *d_rec_off, int64_t n_records, const uint8_t *d_frame_flags,
                                  const uint8_t *d_grey);
+/* The same hand-over with 16-byte records (movfe_packed_record): the shim packs while it copies the side data out of the
+ * AVFrame (it has to copy it anyway - the side data belongs to the frame), and the push moves 16 instead of 40 bytes per
+ * record. movfe_pack_records is plain host code (no GPU involved); results are identical to pushing the 40-byte records. */
+void    movfe_pack_records(const movfe_mv_record *recs, int64_t n_records, movfe_packed_record *out);
+int     movfe_push_frames_packed(movfe_ctx *ctx, int n_frames, const movfe_packed_record *recs, const int64_t *rec_off,
+                                 const uint8_t *frame_flags, const uint8_t *grey);
 int64_t movfe_frames_pushed(const movfe_ctx *ctx);
 
 /* -- raster: replaces the MV loop of VideoDecoder::NextImage (src/VideoDecoder.cc:211-350).

@@ -375,14 +375,14 @@ extern "C" int movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movf
     MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
     rc = wait_ring_readers(ctx, n_frames);
     if (rc) return rc;
-    rc = movfe_ingest_launch(ctx, n_frames, d_recs, d_rec_off, n_records, d_frame_flags, d_grey);
+    rc = movfe_ingest_launch(ctx, n_frames, d_recs, false, d_rec_off, n_records, d_frame_flags, d_grey);
     if (rc) return rc;
     ctx->pushed += n_frames;
     return MOVFE_OK;
 }
 
-extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_record *recs, const int64_t *rec_off,
-                                 const uint8_t *frame_flags, const uint8_t *grey) {
+static int push_host(movfe_ctx *ctx, int n_frames, const void *recs, size_t rec_size, const int64_t *rec_off,
+                     const uint8_t *frame_flags, const uint8_t *grey) {
     int rc = check_push(ctx, n_frames);
     if (rc) return rc;
     if (!rec_off || !frame_flags) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: null pointer");
@@ -391,7 +391,7 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
     const int64_t n_records = rec_off[n_seg];
     if (n_records < 0 || (n_records > 0 && !recs)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: bad record offsets");
     // staging layout: [records, padded to 16 B][offsets][flags, padded to 16 B][grey planes]
-    const size_t rec_bytes = ((size_t)n_records * sizeof(movfe_mv_record) + 15) & ~(size_t)15;
+    const size_t rec_bytes = ((size_t)n_records * rec_size + 15) & ~(size_t)15;
     const size_t off_bytes = ((n_seg + 1) * sizeof(int64_t) + 15) & ~(size_t)15;
     const size_t flag_bytes = (n_seg + 15) & ~(size_t)15;
     const bool with_grey = ctx->cfg.has_grey && grey;
@@ -406,7 +406,7 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
     uint8_t *base = (uint8_t *)ctx->d_stage[b];
     cudaStream_t cs = ctx->copy_stream;
     if (n_records > 0)
-        MOVFE_CUDA(ctx, cudaMemcpyAsync(base, recs, (size_t)n_records * sizeof(movfe_mv_record), cudaMemcpyHostToDevice, cs));
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(base, recs, (size_t)n_records * rec_size, cudaMemcpyHostToDevice, cs));
     // offsets and flags are small and usually live on the caller's stack: they go through a pinned copy owned by the
     // context (reused only after ev_consumed[b], like the device buffer). Records and grey planes are the caller's to keep.
     if (ctx->h_meta_bytes[b] < off_bytes + flag_bytes) {
@@ -433,7 +433,7 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_copied[b], 0));
     rc = wait_ring_readers(ctx, n_frames);
     if (rc) return rc;
-    rc = movfe_ingest_launch(ctx, n_frames, (const movfe_mv_record *)base, (const int64_t *)(base + rec_bytes), n_records,
+    rc = movfe_ingest_launch(ctx, n_frames, base, rec_size == sizeof(movfe_packed_record), (const int64_t *)(base + rec_bytes), n_records,
                              base + rec_bytes + off_bytes, d_grey);
     if (rc) return rc;
     MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->raster_stream));
@@ -441,6 +441,34 @@ extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_re
     ctx->push_parity ^= 1;
     ctx->pushed += n_frames;
     return MOVFE_OK;
+}
+
+extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_record *recs, const int64_t *rec_off,
+                                 const uint8_t *frame_flags, const uint8_t *grey) {
+    return push_host(ctx, n_frames, recs, sizeof(movfe_mv_record), rec_off, frame_flags, grey);
+}
+
+extern "C" int movfe_push_frames_packed(movfe_ctx *ctx, int n_frames, const movfe_packed_record *recs, const int64_t *rec_off,
+                                        const uint8_t *frame_flags, const uint8_t *grey) {
+    return push_host(ctx, n_frames, recs, sizeof(movfe_packed_record), rec_off, frame_flags, grey);
+}
+
+// Host code: the 40-byte side-data record -> the 16 bytes the path reads (the same repacking ingest_kernel does on the device).
+extern "C" void movfe_pack_records(const movfe_mv_record *recs, int64_t n_records, movfe_packed_record *out) {
+    for (int64_t i = 0; i < n_records; i++) {
+        const movfe_mv_record &r = recs[i];
+        movfe_packed_record o;
+        o.src_x = r.src_x;
+        o.src_y = r.src_y;
+        o.dst_x = r.dst_x;
+        o.dst_y = r.dst_y;
+        o.w = r.w;
+        o.h = r.h;
+        o.source_sign = r.source < 0 ? -1 : (r.source > 0 ? 1 : 0);
+        o.reserved = 0;
+        o.ref = r.ref;
+        out[i] = o;
+    }
 }
 
 extern "C" int movfe_raster(movfe_ctx *ctx, int64_t first_frame, int n_out) {

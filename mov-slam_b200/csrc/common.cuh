@@ -23,6 +23,7 @@ struct __align__(16) Rec16 {
     int32_t ref;
 };
 static_assert(sizeof(Rec16) == 16, "Rec16 must be one 128-bit word");
+static_assert(sizeof(movfe_packed_record) == sizeof(Rec16), "movfe_packed_record is the public name of Rec16");
 
 // Inclusive pixel rectangle a hop covers in its target frame's slot grid (VideoDecoder.cc:295-306,330-333).
 // Empty rectangles are {0, 32767, -1, -32768} so that no overlap test ever accepts them.
@@ -313,7 +314,7 @@ struct WinParams {
 int movfe_grid_launch(movfe_ctx *ctx, const WinParams &p, RasterBuf &w);
 // raster.cu
 int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n_out, int n_in);
-int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs, const int64_t *d_rec_off,
+int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const void *d_recs, bool packed, const int64_t *d_rec_off,
                         int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey);
 // extract.cu
 int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);

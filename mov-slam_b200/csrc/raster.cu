@@ -85,6 +85,29 @@ ingest_kernel(const uint4 *__restrict__ recs16, int64_t n_records, const int64_t
     }
 }
 
+// 16-byte records as the host packed them (movfe_push_frames_packed): one 128-bit load and store per record.
+__global__ void __launch_bounds__(256)
+ingest_packed_kernel(const uint4 *__restrict__ recs, int64_t n_records, const int64_t *__restrict__ rec_off, int n_seg, int n_frames,
+                     int64_t first_abs, int RING, int maxM, Rec16 *__restrict__ d_rec, unsigned long long *__restrict__ rejected) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_records) return;
+    uint4 r = __ldg(&recs[i]);
+    r.z &= 0x00ffffffu;  // the reserved byte is not part of the record
+    int lo = 0, hi = n_seg;  // segment (stream, frame) of record i: invariant rec_off[lo] <= i < rec_off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&rec_off[mid]) <= i) lo = mid; else hi = mid;
+    }
+    const int s = lo / n_frames, f = lo - s * n_frames;
+    const int64_t pos = i - __ldg(&rec_off[lo]);
+    if (pos < maxM) {
+        const int slot = (int)((first_abs + f) % RING);
+        reinterpret_cast<uint4 *>(d_rec)[((size_t)s * RING + slot) * maxM + pos] = r;
+    } else {
+        atomicAdd(rejected, 1ull);  // error counter only; never on the data path
+    }
+}
+
 __global__ void ingest_meta_kernel(const int64_t *__restrict__ rec_off, const uint8_t *__restrict__ flags, int n_seg,
                                    int n_frames, int64_t first_abs, int RING, int maxM, int32_t *__restrict__ rec_cnt,
                                    uint8_t *__restrict__ fflags) {
@@ -441,13 +464,17 @@ __global__ void bbox_kernel(WinParams p, const HopRect *__restrict__ hop_rects, 
 }  // namespace
 
 // ----------------------------------------------------------------------------------------------- launchers -----
-int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const movfe_mv_record *d_recs, const int64_t *d_rec_off,
+int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const void *d_recs, bool packed, const int64_t *d_rec_off,
                         int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey) {
     const movfe_config &c = ctx->cfg;
     const int n_seg = c.n_streams * n_frames;
     ProfScope prof(ctx, MOVFE_STAGE_INGEST, ctx->raster_stream);
     prof.launches(n_records > 0 ? 2 : 1);
-    if (n_records > 0) {
+    if (n_records > 0 && packed) {
+        ingest_packed_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->raster_stream>>>(
+            reinterpret_cast<const uint4 *>(d_recs), n_records, d_rec_off, n_seg, n_frames, ctx->pushed, ctx->RING, c.max_records_per_frame,
+            ctx->d_rec, ctx->d_rejected);
+    } else if (n_records > 0) {
         const int64_t warps = (n_records + INGEST_REC_PER_WARP - 1) / INGEST_REC_PER_WARP;
         const int blocks = (int)((warps + INGEST_WARPS - 1) / INGEST_WARPS);
         ingest_kernel<<<blocks, INGEST_WARPS * 32, 0, ctx->raster_stream>>>(

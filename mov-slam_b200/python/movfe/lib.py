@@ -46,6 +46,9 @@ def load():
     L.movfe_cuda_stream.argtypes = [vp]
     L.movfe_push_frames.argtypes = [vp, i32, vp, vp, vp, vp]
     L.movfe_push_frames_device.argtypes = [vp, i32, vp, vp, i64, vp, vp]
+    L.movfe_push_frames_packed.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.movfe_pack_records.argtypes = [vp, i64, vp]
+    L.movfe_pack_records.restype = None
     L.movfe_frames_pushed.restype = i64
     L.movfe_frames_pushed.argtypes = [vp]
     L.movfe_raster.argtypes = [vp, i64, i32]
@@ -84,13 +87,23 @@ def load():
 
 
 EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchronize", "movfe_fence", "movfe_cuda_stream",
-           "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_frames_pushed", "movfe_raster",
+           "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_push_frames_packed", "movfe_pack_records", "movfe_frames_pushed", "movfe_raster",
            "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
            "movfe_rejected_records", "movfe_set_tracks", "movfe_set_lk_results", "movfe_dropped_lk_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
            "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read", "movfe_workload_stats"]
+
+
+def pack_records(recs, out=None):
+    """movfe_pack_records: 40-byte side-data records -> the 16-byte form movfe_push_frames_packed takes (host code)."""
+    recs = np.ascontiguousarray(recs, T.MV_RECORD)
+    if out is None:
+        out = np.empty(len(recs), T.PACKED_RECORD)
+    assert out.dtype == T.PACKED_RECORD and len(out) >= len(recs) and out.flags.c_contiguous
+    load().movfe_pack_records(recs.ctypes.data_as(C.c_void_p), len(recs), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 def _p(a):
@@ -175,6 +188,17 @@ class Context:
             grey = np.ascontiguousarray(grey, np.uint8)
             assert grey.size == self.S * n_frames * self.W * self.H
         self._ck(self.L.movfe_push_frames(self.h, n_frames, _p(recs), _p(rec_off), _p(frame_flags), _p(grey)))
+
+    def push_frames_packed(self, n_frames, recs, rec_off, frame_flags, grey=None):
+        """16-byte records (movfe_pack_records / pack_records below) instead of the 40-byte side-data form."""
+        recs = np.ascontiguousarray(recs, T.PACKED_RECORD)
+        rec_off = np.ascontiguousarray(rec_off, np.int64)
+        frame_flags = np.ascontiguousarray(frame_flags, np.uint8)
+        assert len(rec_off) == self.S * n_frames + 1 and len(frame_flags) == self.S * n_frames
+        if grey is not None:
+            grey = np.ascontiguousarray(grey, np.uint8)
+            assert grey.size == self.S * n_frames * self.W * self.H
+        self._ck(self.L.movfe_push_frames_packed(self.h, n_frames, _p(recs), _p(rec_off), _p(frame_flags), _p(grey)))
 
     def push_frames_device(self, n_frames, d_recs, d_rec_off, n_records, d_flags, d_grey=None):
         self._ck(self.L.movfe_push_frames_device(self.h, n_frames, _p(d_recs), _p(d_rec_off), n_records, _p(d_flags),

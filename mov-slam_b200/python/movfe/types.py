@@ -8,6 +8,8 @@ MV_RECORD = np.dtype({
     "offsets": [0, 4, 5, 6, 8, 10, 12, 16, 24, 28, 32, 36],
     "itemsize": 40,
 })
+PACKED_RECORD = np.dtype([("src_x", "<i2"), ("src_y", "<i2"), ("dst_x", "<i2"), ("dst_y", "<i2"), ("w", "u1"), ("h", "u1"),
+                          ("source_sign", "i1"), ("reserved", "u1"), ("ref", "<i4")])
 HOP = np.dtype([("mv_x", "<f4"), ("mv_y", "<f4"), ("d_indx", "<i4"), ("_pad", "<i4")])
 RECT = np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2")])
 TRACK = np.dtype([("pt_x", "<f4"), ("pt_y", "<f4"), ("mb", RECT), ("track_id", "<i4"), ("age", "<i4"),
@@ -24,7 +26,7 @@ POSE_PARAMS = np.dtype([("is_lost", "<i4"), ("iteration_count", "<i4"), ("reproj
 
 RELOC_SEED = np.dtype([("track_id", "<i4"), ("q_indx", "<i4"), ("x", "<f4"), ("y", "<f4")])
 assert RELOC_SEED.itemsize == 16
-assert MV_RECORD.itemsize == 40 and HOP.itemsize == 16 and RECT.itemsize == 8 and TRACK.itemsize == 64
+assert PACKED_RECORD.itemsize == 16 and MV_RECORD.itemsize == 40 and HOP.itemsize == 16 and RECT.itemsize == 8 and TRACK.itemsize == 64
 assert MAP_POINT.itemsize == 40 and PROJECTION.itemsize == 20 and CAMERA.itemsize == 36
 assert POSE.itemsize == 96 and POSE_PARAMS.itemsize == 40
 

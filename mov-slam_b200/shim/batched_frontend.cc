@@ -93,7 +93,7 @@ int main(int argc, char **argv) {
     // stream-major packing of frames [f0, f1) of S streams that all replay the clip; three rotating buffers because a
     // host buffer must stay unchanged until the second following push
     struct Pack {
-        std::vector<movfe_mv_record> r;
+        std::vector<movfe_packed_record> r;  // 16-byte records: packed while the side data is copied (what a decoder pool does)
         std::vector<int64_t> o;
         std::vector<uint8_t> fl, g;
     } packs[3];
@@ -105,12 +105,14 @@ int main(int argc, char **argv) {
         pk.g.resize((size_t)S * n * plane);
         for (int s = 0; s < S; s++)
             for (int f = f0; f < f1; f++) {
-                pk.r.insert(pk.r.end(), recs.begin() + off[f], recs.begin() + off[f + 1]);
+                const size_t at = pk.r.size();
+                pk.r.resize(at + (size_t)(off[f + 1] - off[f]));
+                movfe_pack_records(recs.data() + off[f], off[f + 1] - off[f], pk.r.data() + at);
                 pk.o.push_back((int64_t)pk.r.size());
                 pk.fl.push_back(flags[f]);
                 memcpy(&pk.g[((size_t)s * n + (f - f0)) * plane], &grey[(size_t)f * plane], plane);
             }
-        return movfe_push_frames(ctx, n, pk.r.data(), pk.o.data(), pk.fl.data(), pk.g.data());
+        return movfe_push_frames_packed(ctx, n, pk.r.data(), pk.o.data(), pk.fl.data(), pk.g.data());
     };
     CK(push(0, F + LA));
     std::vector<movfe_pose> poses((size_t)S * F);

@@ -19,7 +19,7 @@ def pack_streams(per_stream, n_frames, f0, f1):
 
 
 def run_raster_clip(per_stream, W, H, n_frames, window, max_ref, max_records=4800, grey=None, collect=True, ctx=None,
-                    **ctx_kw):
+                    packed=False, **ctx_kw):
     """Pushes and rasterises the clip window by window. Returns {(s,f): dict(grid,hops,kps,cov)} and the ctx."""
     S = len(per_stream)
     own = ctx is None
@@ -38,7 +38,10 @@ def run_raster_clip(per_stream, W, H, n_frames, window, max_ref, max_records=480
             g = None
             if grey is not None:
                 g = np.stack([grey[s][pushed:want] for s in range(S)])
-            ctx.push_frames(want - pushed, r, o, fl, g)
+            if packed:      # 16-byte records, packed on the host (movfe_pack_records)
+                ctx.push_frames_packed(want - pushed, lib.pack_records(r), o, fl, g)
+            else:
+                ctx.push_frames(want - pushed, r, o, fl, g)
             pushed = want
         ctx.raster(first, n_out)
         if collect:

@@ -78,3 +78,24 @@ def test_product_never_touches_the_oracle():
                     continue
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "liboracle" not in txt and "pyoracle" not in txt and "orc_" not in txt, os.path.join(dp, fn)
+
+
+def test_pack_records_is_the_seven_fields_the_path_reads():
+    """movfe_pack_records (host code, no GPU): the 16-byte record carries source sign, block size, both centres and ref."""
+    rng = np.random.default_rng(5)
+    n = 1000
+    r = np.zeros(n, T.MV_RECORD)
+    r["source"] = rng.integers(-3, 4, n)
+    r["w"] = rng.choice([4, 8, 16], n)
+    r["h"] = rng.choice([4, 8, 16], n)
+    for k in ("src_x", "src_y", "dst_x", "dst_y"):
+        r[k] = rng.integers(-300, 2000, n)
+    r["ref"] = rng.integers(-1, 12, n)
+    r["flags"] = rng.integers(0, 1 << 40, n)
+    r["motion_x"] = rng.integers(-500, 500, n)
+    p = lib.pack_records(r)
+    assert p.dtype.itemsize == 16
+    for k in ("src_x", "src_y", "dst_x", "dst_y", "w", "h", "ref"):
+        assert np.array_equal(p[k], r[k]), k
+    assert np.array_equal(p["source_sign"], np.sign(r["source"]))
+    assert not p["reserved"].any()

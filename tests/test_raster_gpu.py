@@ -184,3 +184,17 @@ def test_single_frame_pushes_full_ref_range(orc):
         got[(0, f)] = dict(grid=ctx.grid(0, f), hops=ctx.hops(0, f), kps=ctx.kps(0, f), cov=ctx.raster_counts(0, f)[2])
         assert_raster_equal(clip, got, 0, f)
     ctx.close()
+
+
+def test_packed_push_equals_record_push(orc):
+    """movfe_push_frames_packed (16-byte records packed by movfe_pack_records on the host) gives the raster results of the
+    40-byte push, bit for bit: hop lists, kps, slot grids and coverage against the oracle."""
+    W, H, NF, K = 320, 240, 9, 3
+    spec = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED00C7)
+    stream = synth.make_records(spec)
+    got, ctx = run_raster_clip([stream, stream], W, H, NF, window=4, max_ref=K, packed=True)
+    ctx.close()
+    clip = orc.Clip(W, H, *stream, K)
+    for s in range(2):
+        for f in range(NF):
+            assert_raster_equal(clip, got, s, f)
