@@ -131,7 +131,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     const int prio_prop = prio_hi;
     CK(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_prop));
     CK(cudaStreamCreateWithPriority(&ctx->pose_stream, cudaStreamNonBlocking, prio_hi));
-    CK(cudaStreamCreateWithPriority(&ctx->raster_stream, cudaStreamNonBlocking, prio_lo));
+    // MOVFE_RASTER_PRIO=1 (development): the raster stream at the propagation priority
+    CK(cudaStreamCreateWithPriority(&ctx->raster_stream, cudaStreamNonBlocking, (getenv("MOVFE_RASTER_PRIO") && atoi(getenv("MOVFE_RASTER_PRIO"))) ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_lo));
     CK(cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_serial, cudaEventDisableTiming));
@@ -145,9 +146,11 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
         CK(cudaEventCreateWithFlags(&el.done, cudaEventDisableTiming));
     }
     {
-        // groups of independent propagation chains (MOVFE_EXTRACT_GROUPS, default 1: on B200 with 64 streams of C2 the
-        // launches already fill the chip, and 2..8 groups measured the same or slower - profiles/README.md)
-        int g = 1;
+        // groups of independent propagation chains (MOVFE_EXTRACT_GROUPS). With the thread-level kernels a chain is bound by
+        // latency, not by issue slots, and its per-stream finalize launch leaves most SMs idle: three chains measured 3-4 %
+        // faster than one at 64 streams (1 / 2 / 3 / 4 / 8 groups: 3.40 / 3.36 / 3.27 / 3.33 / 3.62 ms per step - the host's
+        // launch rate takes over beyond four). Contexts with few streams keep one chain.
+        int g = c.n_streams >= 24 ? 3 : 1;
         if (const char *e = getenv("MOVFE_EXTRACT_GROUPS")) g = atoi(e);
         ctx->n_groups = std::max(1, std::min(std::min(g, c.n_streams), (int)movfe_ctx::MAX_GROUPS));
     }
