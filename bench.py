@@ -737,6 +737,7 @@ def main():
     claim_stdout()
     if args.config in ("C1", "C5"):
         import bench_extra
+        bench_extra.bench._JSON_FD = _JSON_FD      # bench_extra imports this file as module `bench`: same stdout duplicate
         return bench_extra.run(args)
     cfg = dict(CONFIGS[args.config])
     if F_ENV:

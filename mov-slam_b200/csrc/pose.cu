@@ -89,6 +89,37 @@ __device__ __forceinline__ void project_jac_d(const CamD &c, double x, double y,
     J[5] = -c.fy * y / (z * z);
 }
 
+// project_d + project_jac_d of the fisheye model in one go: radius, angle and polynomial are shared (sqrt and atan2 are most
+// of the per-point cost of a KannalaBrandt8 solve). The same expressions, so the same bits as the two separate calls.
+__device__ __forceinline__ void project_with_jac_kb8(const CamD &c, double x, double y, double z, double &u, double &v, double J[6]) {
+    const double r2 = x * x + y * y;
+    const double r = sqrt(r2);
+    const double theta = atan2(r, z);
+    const double t2 = theta * theta;
+    const double f = theta * (1.0 + t2 * (c.k0 + t2 * (c.k1 + t2 * (c.k2 + t2 * c.k3))));
+    const double s = r > 1e-12 ? f / r : 1.0;
+    u = c.fx * s * x + c.cx;
+    v = c.fy * s * y + c.cy;
+    if (r >= 1e-8) {
+        const double fd = 1.0 + t2 * (3 * c.k0 + t2 * (5 * c.k1 + t2 * (7 * c.k2 + t2 * 9 * c.k3)));
+        const double D = r2 + z * z;
+        const double r3 = r2 * r;
+        J[0] = c.fx * (fd * z * x * x / (r2 * D) + f * y * y / r3);
+        J[1] = c.fx * (fd * z * x * y / (r2 * D) - f * x * y / r3);
+        J[2] = -c.fx * fd * x / D;
+        J[3] = c.fy * (fd * z * x * y / (r2 * D) - f * x * y / r3);
+        J[4] = c.fy * (fd * z * y * y / (r2 * D) + f * x * x / r3);
+        J[5] = -c.fy * fd * y / D;
+    } else {  // on the optical axis: the pinhole Jacobian (project_jac_d)
+        J[0] = c.fx / z;
+        J[1] = 0;
+        J[2] = -c.fx * x / (z * z);
+        J[3] = 0;
+        J[4] = c.fy / z;
+        J[5] = -c.fy * y / (z * z);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ frustum ----
 __device__ __forceinline__ float dot3f(const float a[3], const float b[3]) {
     // Eigen 3.4's unrolled 3-vector reduction: c0 + (c1 + c2) (see oracle/match.cc)
@@ -301,8 +332,7 @@ __device__ __forceinline__ void accumulate_point(const CamD &cam, const double *
     double u, v, J0[6], J1[6];
     if (cam.model == MOVFE_CAM_FISHEYE) {
         double Jp[6];
-        project_d(cam, x, y, z, u, v);
-        project_jac_d(cam, x, y, z, Jp);
+        project_with_jac_kb8(cam, x, y, z, u, v, Jp);
         // J = -Jp * [ -[Xc]x | I ]  (OptimizableTypes.cpp:63-68)
         const double D[3][6] = {{0, z, -y, 1, 0, 0}, {-z, 0, x, 0, 1, 0}, {y, -x, 0, 0, 0, 1}};
 #pragma unroll
@@ -742,7 +772,7 @@ struct Solver2Shared {
 
 template <typename Src>
 __device__ int pose_solve2(const Src &src, int n, const movfe_camera &cam_, const movfe_pose_params &pp, movfe_pose *pose,
-                           uint8_t *outlier, int (&stats)[4], Solver2Shared &sh) {
+                           uint8_t *outlier, int (&stats)[4], int &executed, Solver2Shared &sh) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const CamD cam = widen(cam_);
     const float repErrorF = pp.is_lost ? (float)pp.reprojection_error_lost : (float)pp.reprojection_error;  // Optimizer.cc:423-427
@@ -751,7 +781,8 @@ __device__ int pose_solve2(const Src &src, int n, const movfe_camera &cam_, cons
     const int nw = min((n + 31) >> 5, (int)(blockDim.x >> 5));  // warps that own points
     const int nthr = nw * 32;
     double *Rt = sh.Rt[warp];
-    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;  // iterations, classifications, their sum, solver failures (the oracle's counters)
+    executed = 0;                                   // passes over the correspondences actually made (a fused pass counts once)
     for (int i = threadIdx.x; i < n; i += blockDim.x) outlier[i] = 0;
     if (lane < 9) Rt[lane] = pose->R[lane];
     else if (lane < 12) Rt[lane] = pose->t[lane - 9];
@@ -795,7 +826,7 @@ __device__ int pose_solve2(const Src &src, int n, const movfe_camera &cam_, cons
                 for (int w = 0; w < nw; w++) v += sh.part[pass & 1][w][lane];
                 sh.tot[warp][lane] = v;
             }
-            stats[2]++;
+            executed++;
             if (pending) {
                 n_bad = 0;
                 for (int w = 0; w < nw; w++) n_bad += sh.ipart[pass & 1][w];
@@ -858,8 +889,9 @@ __device__ int pose_solve2(const Src &src, int n, const movfe_camera &cam_, cons
         n_bad = 0;
         for (int w = 0; w < nw; w++) n_bad += sh.ipart[pass & 1][w];
         stats[1]++;
-        stats[2]++;
+        executed++;
     }
+    stats[2] = stats[0] + stats[1];
     if (threadIdx.x < 9) pose->R[threadIdx.x] = Rt[threadIdx.x];
     else if (threadIdx.x < 12) pose->t[threadIdx.x - 9] = Rt[threadIdx.x];
     __syncthreads();  // outlier[] and the pose are visible to the whole CTA
@@ -1013,7 +1045,7 @@ track_poses2_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, c
         int n_inl = 0;
         if (n > 0 && n_map > 0) {
             const int n_words = (n + 31) >> 5;
-            int st[4];
+            int st[4], passes;
             // --- TrackReferenceKeyFrame: SearchByVideoFeature(KF, F, matches) (MOVMatcher.h:70-103)
             for (int i = threadIdx.x; i < n_map; i += blockDim.x) {
                 pk[i] = ft[i];
@@ -1026,11 +1058,11 @@ track_poses2_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, c
                 if (!(mp[i].flags & (MOVFE_MP_NULL | MOVFE_MP_BAD)) && (pk[i] & 0xffffu)) atomicMax(&win1[pk[i] >> 16], i);  // the last point of a group wins
             __syncthreads();
             int np = gather_pairs2(tr, mp, n_map, pk, win1, bits, pref, n_words, cx, cy, cz, cu, cv, cidx, cm, M, wsum, match);
-            pose_solve2(src, np, p.cam, p.pp, pc, cout, st, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
+            pose_solve2(src, np, p.cam, p.pp, pc, cout, st, passes, sh);  // pose := last frame's pose is already in pc (Tracking.cc:807)
             if (threadIdx.x == 0) {  // workload counters (diagnostic)
                 atomicAdd(&stats[2], 1ull);
                 atomicAdd(&stats[3], (unsigned long long)np);
-                atomicAdd(&stats[4], (unsigned long long)st[2]);
+                atomicAdd(&stats[4], (unsigned long long)passes);
             }
             // --- TrackLocalMap / SearchLocalPoints (Tracking.cc:1109-1158)
             for (int i = threadIdx.x; i < np; i += blockDim.x) tag[cm[i]] = 1;  // mnLastFrameSeen = current frame
@@ -1048,11 +1080,11 @@ track_poses2_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, c
                 if (win2[i] >= 0) win1[i] = win2[i];
             __syncthreads();
             np = gather_pairs2(tr, mp, n_map, pk, win1, bits, pref, n_words, cx, cy, cz, cu, cv, cidx, cm, M, wsum, match);
-            n_inl = pose_solve2(src, np, p.cam, p.pp, pc, cout, st, sh);
+            n_inl = pose_solve2(src, np, p.cam, p.pp, pc, cout, st, passes, sh);
             if (threadIdx.x == 0) {
                 atomicAdd(&stats[2], 1ull);
                 atomicAdd(&stats[3], (unsigned long long)np);
-                atomicAdd(&stats[4], (unsigned long long)st[2]);
+                atomicAdd(&stats[4], (unsigned long long)passes);
             }
             // Frame::mvbOutlier (Optimizer.cc:452-456): true everywhere (tp_prep_kernel), false for the inliers;
             // < 4 pairs: the frame is left untouched
@@ -1233,12 +1265,19 @@ __global__ void __launch_bounds__(TP_THREADS)
 pose_kernel(const float *__restrict__ pts, const float *__restrict__ obs, const int32_t *__restrict__ off, movfe_camera cam,
             movfe_pose_params pp, movfe_pose *__restrict__ poses, uint8_t *__restrict__ outlier, int32_t *__restrict__ n_inl,
             int32_t *__restrict__ stats) {
-    __shared__ SolverShared sh;
+    __shared__ Solver2Shared sh;
     const int pidx = blockIdx.x;
     const int b = off[pidx], n = off[pidx + 1] - b;
     DirectSrc src{pts + 3 * (size_t)b, obs + 2 * (size_t)b};
-    const int r = pose_solve(src, n, cam, pp, poses + pidx, outlier + b, stats ? stats + 4 * pidx : nullptr, sh);
-    if (threadIdx.x == 0) n_inl[pidx] = r;
+    int st[4], passes;
+    const int r = pose_solve2(src, n, cam, pp, poses + pidx, outlier + b, st, passes, sh);  // outlier flags live in global memory here
+    if (threadIdx.x == 0) {
+        n_inl[pidx] = r;
+        if (stats) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) stats[4 * pidx + k] = st[k];
+        }
+    }
 }
 
 int pow2_at_least(int v) {

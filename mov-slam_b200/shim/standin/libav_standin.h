@@ -92,7 +92,8 @@ typedef struct fake_av_clip {
     const uint8_t *const *side;      /* n_frames pointers to AVMotionVector arrays (NULL: no side data) */
     const int *side_bytes;           /* n_frames */
 } fake_av_clip;
-void fake_av_install(const fake_av_clip *clip);
+void fake_av_install(const fake_av_clip *clip);                    /* clip 0: url "fake://clip" */
+void fake_av_install_clip(int id, const fake_av_clip *clip);      /* clip id: url "fake://clip/<id>" (one decoder per stream) */
 
 #ifdef __cplusplus
 }

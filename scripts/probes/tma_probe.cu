@@ -14,8 +14,9 @@
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // bisect kernels: mode 1 = mbarrier only, mode 2 = 1-D bulk copy, mode 3 = tensor copy without .tile
-__global__ void bisect(int mode, int txb, const __grid_constant__ CUtensorMap pmap, const uint8_t *src, int x, int y, uint8_t *out, int *status) {
-    __shared__ __align__(128) uint8_t box[512];
+__global__ void bisect(int mode, int txb, const __grid_constant__ CUtensorMap pmap, const uint8_t *src, int x, int y, uint8_t *out, int *status, int dstoff) {
+    __shared__ __align__(128) uint8_t boxbuf[1024];
+    uint8_t *box = boxbuf + dstoff;   // DSTOFF: destination alignment experiments (the PTX manual asks for 128 bytes)
     __shared__ uint64_t bar;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1) : "memory");
@@ -35,6 +36,8 @@ __global__ void bisect(int mode, int txb, const __grid_constant__ CUtensorMap pm
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(txb) : "memory");
             cute::SM90_TMA_LOAD_2D::copy(&pmap, &bar, 0ull, box, x, y);
 #endif
+        } else if (mode == 6) {
+            // nothing here: mode 6 issues from a converged warp below (elect.sync), as CUTLASS does
         } else if (mode == 4) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(txb) : "memory");
             asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(box)),
@@ -43,6 +46,16 @@ __global__ void bisect(int mode, int txb, const __grid_constant__ CUtensorMap pm
         } else {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(txb) : "memory");
             asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(box)),
+                         "l"(reinterpret_cast<uint64_t>(&pmap)), "r"(x), "r"(y), "r"(smem_u32(&bar))
+                         : "memory");
+        }
+    }
+    if (mode == 6 && threadIdx.x < 32) {
+        uint32_t elected = 0;
+        asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+        if (elected) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar)), "r"(txb) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(box)),
                          "l"(reinterpret_cast<uint64_t>(&pmap)), "r"(x), "r"(y), "r"(smem_u32(&bar))
                          : "memory");
         }
@@ -119,17 +132,17 @@ int main() {
     printf("encode: %d box %dx%d l2p %d\n", (int)r, BW, BH, l2p);
     { const uint64_t *w = (const uint64_t *)&map; for (int i = 0; i < 16; i++) printf("%016llx%c", (unsigned long long)w[i], i % 4 == 3 ? '\n' : ' '); }
     cudaMemcpy(dmap, &map, sizeof map, cudaMemcpyHostToDevice);
-    const int x = 37, y = 5;
+    const int x = getenv("X") ? atoi(getenv("X")) : 37, y = 5;
     if (getenv("BISECT") && getenv("CLUSTER")) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(1); cfg.blockDim = dim3(32);
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t le = cudaLaunchKernelEx(&cfg, bisect, atoi(getenv("BISECT")), BW * BH, map, (const uint8_t *)(d + y * P), x, y, dout, dst);
+        cudaError_t le = cudaLaunchKernelEx(&cfg, bisect, atoi(getenv("BISECT")), BW * BH, map, (const uint8_t *)(d + y * P), x, y, dout, dst, getenv("DSTOFF") ? atoi(getenv("DSTOFF")) : 0);
         printf("launchEx: %s\n", cudaGetErrorString(le));
     } else
-    if (getenv("BISECT")) bisect<<<1, 32>>>(atoi(getenv("BISECT")), BW * BH, map, d + y * P, x, y, dout, dst);
+    if (getenv("BISECT")) bisect<<<1, 32>>>(atoi(getenv("BISECT")), BW * BH, map, d + y * P, x, y, dout, dst, getenv("DSTOFF") ? atoi(getenv("DSTOFF")) : 0);
     else if (getenv("GLOBAL_MAP")) probe<false><<<1, 32>>>(map, dmap, x, y, dout, dst);
     else probe<true><<<1, 32>>>(map, dmap, x, y, dout, dst);
     e = cudaDeviceSynchronize();
