@@ -89,10 +89,12 @@ int     movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movfe_mv_re
                                  const uint8_t *d_grey);
 /* The same hand-over with 16-byte records (movfe_packed_record): the shim packs while it copies the side data out of the
  * AVFrame (it has to copy it anyway - the side data belongs to the frame), and the push moves 16 instead of 40 bytes per
- * record. movfe_pack_records is plain host code (no GPU involved); results are identical to pushing the 40-byte records. */
+ * record. movfe_pack_records is plain host code (no GPU involved); results are identical to pushing the 40-byte records.
+ * grey_stride: bytes between the rows of a luma plane (AVFrame::linesize[0] / cv::Mat::step; 0 = width); a plane is grey_stride *
+ * height bytes and the planes follow each other without gaps. The rows go straight into the device's pitched ring. */
 void    movfe_pack_records(const movfe_mv_record *recs, int64_t n_records, movfe_packed_record *out);
 int     movfe_push_frames_packed(movfe_ctx *ctx, int n_frames, const movfe_packed_record *recs, const int64_t *rec_off,
-                                 const uint8_t *frame_flags, const uint8_t *grey);
+                                 const uint8_t *frame_flags, const uint8_t *grey, int grey_stride);
 int64_t movfe_frames_pushed(const movfe_ctx *ctx);
 
 /* -- raster: replaces the MV loop of VideoDecoder::NextImage (src/VideoDecoder.cc:211-350).

@@ -165,6 +165,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     if (const char *e = getenv("MOVFE_PDL")) ctx->pdl_mode = atoi(e);
     if (const char *e = getenv("MOVFE_CAND_PIPE")) ctx->cand_pipe = atoi(e) != 0;
     if (const char *e = getenv("MOVFE_CAND_LANE")) ctx->cand_lane = atoi(e) != 0;
+    if (const char *e = getenv("MOVFE_GREY_DIRECT")) ctx->grey_direct = atoi(e) != 0;
     if (const char *e = getenv("MOVFE_BIRTH_CHUNKS")) ctx->birth_chunks = std::max(1, atoi(e));
     ctx->ev_frame.resize((size_t)ctx->n_groups * c.window_frames, nullptr);
     for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -343,7 +344,8 @@ int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes) { return ensure_op(ctx
 // the primary stream) that read the grey planes / frame flags of those frames must have finished. Launches are ordered on
 // one stream, so waiting for the newest launch that starts at or before the last overwritten frame covers all of them;
 // when that launch has already left the bookkeeping ring, its oldest entry (a later launch) stands in for it.
-static int wait_ring_readers(movfe_ctx *ctx, int n_frames) {
+static int wait_ring_readers(movfe_ctx *ctx, int n_frames, cudaStream_t waiter = nullptr) {
+    if (!waiter) waiter = ctx->raster_stream;
     const int64_t last_overwritten = ctx->pushed + n_frames - 1 - ctx->RING;
     if (last_overwritten < 0 || ctx->ext_launch_count == 0) return MOVFE_OK;
     const int N = movfe_ctx::N_EXT_LAUNCHES;
@@ -357,7 +359,7 @@ static int wait_ring_readers(movfe_ctx *ctx, int n_frames) {
         }
     }
     if (!pick && ctx->ext_launch_count > N) pick = &ctx->ext_launches[ctx->ext_launch_head];  // oldest entry
-    if (pick) MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, pick->done, 0));
+    if (pick) MOVFE_CUDA(ctx, cudaStreamWaitEvent(waiter, pick->done, 0));
     return MOVFE_OK;
 }
 
@@ -385,7 +387,7 @@ extern "C" int movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movf
 }
 
 static int push_host(movfe_ctx *ctx, int n_frames, const void *recs, size_t rec_size, const int64_t *rec_off,
-                     const uint8_t *frame_flags, const uint8_t *grey) {
+                     const uint8_t *frame_flags, const uint8_t *grey, int grey_stride) {
     int rc = check_push(ctx, n_frames);
     if (rc) return rc;
     if (!rec_off || !frame_flags) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: null pointer");
@@ -398,7 +400,13 @@ static int push_host(movfe_ctx *ctx, int n_frames, const void *recs, size_t rec_
     const size_t off_bytes = ((n_seg + 1) * sizeof(int64_t) + 15) & ~(size_t)15;
     const size_t flag_bytes = (n_seg + 15) & ~(size_t)15;
     const bool with_grey = ctx->cfg.has_grey && grey;
-    const size_t grey_bytes = with_grey ? n_seg * (size_t)ctx->cfg.width * ctx->cfg.height : 0;
+    if (grey_stride == 0) grey_stride = ctx->cfg.width;
+    if (with_grey && grey_stride < ctx->cfg.width) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "push: grey_stride %d below the frame width %d", grey_stride, ctx->cfg.width);
+    // luma planes: straight into the pitched ring with one strided copy per stream (AVFrame::linesize / cv::Mat::step rows are
+    // taken as they are), or - the planes tightly packed, unless MOVFE_GREY_DIRECT=1 - through the staging buffer + grey_ingest_kernel
+    // (one flat copy moves faster over PCIe than 64 strided ones: common.cuh)
+    const bool direct = with_grey && (ctx->grey_direct || grey_stride != ctx->cfg.width);
+    const size_t grey_bytes = (with_grey && !direct) ? n_seg * (size_t)ctx->cfg.width * ctx->cfg.height : 0;
     const size_t total = rec_bytes + off_bytes + flag_bytes + grey_bytes + 16;
     const int b = ctx->push_parity;
     rc = ensure_stage(ctx, b, total);
@@ -428,9 +436,28 @@ static int push_host(movfe_ctx *ctx, int n_frames, const void *recs, size_t rec_
     memcpy((uint8_t *)ctx->h_meta[b] + off_bytes, frame_flags, n_seg);
     MOVFE_CUDA(ctx, cudaMemcpyAsync(base + rec_bytes, ctx->h_meta[b], off_bytes + flag_bytes, cudaMemcpyHostToDevice, cs));
     uint8_t *d_grey = nullptr;
-    if (with_grey) {
+    if (with_grey && !direct) {
         d_grey = base + rec_bytes + off_bytes + flag_bytes;
         MOVFE_CUDA(ctx, cudaMemcpyAsync(d_grey, grey, grey_bytes, cudaMemcpyHostToDevice, cs));
+    } else if (with_grey) {
+        // the ring slots of these frames may still be read by the propagation of the window they held, or be written by the
+        // ingest kernels of the previous push (staged planes): the copies wait for both, nothing else
+        rc = wait_ring_readers(ctx, n_frames, cs);
+        if (rc) return rc;
+        if (ctx->stage_used[b ^ 1]) MOVFE_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_consumed[b ^ 1], 0));
+        const int W = ctx->cfg.width, H = ctx->cfg.height, R = ctx->RING;
+        const size_t P = (size_t)ctx->grey_pitch;
+        for (int st = 0; st < ctx->cfg.n_streams; st++) {
+            int f = 0;
+            while (f < n_frames) {  // consecutive frames are consecutive slots until the ring wraps: at most two copies per stream
+                const int slot = (int)((ctx->pushed + f) % R);
+                const int cnt = std::min(n_frames - f, R - slot);
+                MOVFE_CUDA(ctx, cudaMemcpy2DAsync(ctx->d_grey + ((size_t)st * R + slot) * H * P, P,
+                                                  grey + ((size_t)st * n_frames + f) * (size_t)grey_stride * H, (size_t)grey_stride, (size_t)W,
+                                                  (size_t)cnt * H, cudaMemcpyHostToDevice, cs));
+                f += cnt;
+            }
+        }
     }
     MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_copied[b], 0));
@@ -448,12 +475,12 @@ static int push_host(movfe_ctx *ctx, int n_frames, const void *recs, size_t rec_
 
 extern "C" int movfe_push_frames(movfe_ctx *ctx, int n_frames, const movfe_mv_record *recs, const int64_t *rec_off,
                                  const uint8_t *frame_flags, const uint8_t *grey) {
-    return push_host(ctx, n_frames, recs, sizeof(movfe_mv_record), rec_off, frame_flags, grey);
+    return push_host(ctx, n_frames, recs, sizeof(movfe_mv_record), rec_off, frame_flags, grey, 0);
 }
 
 extern "C" int movfe_push_frames_packed(movfe_ctx *ctx, int n_frames, const movfe_packed_record *recs, const int64_t *rec_off,
-                                        const uint8_t *frame_flags, const uint8_t *grey) {
-    return push_host(ctx, n_frames, recs, sizeof(movfe_packed_record), rec_off, frame_flags, grey);
+                                        const uint8_t *frame_flags, const uint8_t *grey, int grey_stride) {
+    return push_host(ctx, n_frames, recs, sizeof(movfe_packed_record), rec_off, frame_flags, grey, grey_stride);
 }
 
 // Host code: the 40-byte side-data record -> the 16 bytes the path reads (the same repacking ingest_kernel does on the device).

@@ -46,7 +46,7 @@ def load():
     L.movfe_cuda_stream.argtypes = [vp]
     L.movfe_push_frames.argtypes = [vp, i32, vp, vp, vp, vp]
     L.movfe_push_frames_device.argtypes = [vp, i32, vp, vp, i64, vp, vp]
-    L.movfe_push_frames_packed.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.movfe_push_frames_packed.argtypes = [vp, i32, vp, vp, vp, vp, i32]
     L.movfe_pack_records.argtypes = [vp, i64, vp]
     L.movfe_pack_records.restype = None
     L.movfe_frames_pushed.restype = i64
@@ -189,16 +189,17 @@ class Context:
             assert grey.size == self.S * n_frames * self.W * self.H
         self._ck(self.L.movfe_push_frames(self.h, n_frames, _p(recs), _p(rec_off), _p(frame_flags), _p(grey)))
 
-    def push_frames_packed(self, n_frames, recs, rec_off, frame_flags, grey=None):
-        """16-byte records (movfe_pack_records / pack_records below) instead of the 40-byte side-data form."""
+    def push_frames_packed(self, n_frames, recs, rec_off, frame_flags, grey=None, grey_stride=0):
+        """16-byte records (movfe_pack_records / pack_records below) instead of the 40-byte side-data form; grey_stride = bytes
+        between the rows of a luma plane (0 = width)."""
         recs = np.ascontiguousarray(recs, T.PACKED_RECORD)
         rec_off = np.ascontiguousarray(rec_off, np.int64)
         frame_flags = np.ascontiguousarray(frame_flags, np.uint8)
         assert len(rec_off) == self.S * n_frames + 1 and len(frame_flags) == self.S * n_frames
         if grey is not None:
             grey = np.ascontiguousarray(grey, np.uint8)
-            assert grey.size == self.S * n_frames * self.W * self.H
-        self._ck(self.L.movfe_push_frames_packed(self.h, n_frames, _p(recs), _p(rec_off), _p(frame_flags), _p(grey)))
+            assert grey.size == self.S * n_frames * (grey_stride or self.W) * self.H
+        self._ck(self.L.movfe_push_frames_packed(self.h, n_frames, _p(recs), _p(rec_off), _p(frame_flags), _p(grey), grey_stride))
 
     def push_frames_device(self, n_frames, d_recs, d_rec_off, n_records, d_flags, d_grey=None):
         self._ck(self.L.movfe_push_frames_device(self.h, n_frames, _p(d_recs), _p(d_rec_off), n_records, _p(d_flags),

@@ -112,7 +112,7 @@ int main(int argc, char **argv) {
                 pk.fl.push_back(flags[f]);
                 memcpy(&pk.g[((size_t)s * n + (f - f0)) * plane], &grey[(size_t)f * plane], plane);
             }
-        return movfe_push_frames_packed(ctx, n, pk.r.data(), pk.o.data(), pk.fl.data(), pk.g.data());
+        return movfe_push_frames_packed(ctx, n, pk.r.data(), pk.o.data(), pk.fl.data(), pk.g.data(), 0);
     };
     CK(push(0, F + LA));
     std::vector<movfe_pose> poses((size_t)S * F);

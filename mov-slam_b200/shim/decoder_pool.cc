@@ -229,7 +229,7 @@ int DecoderPool::next_window(int n_frames, HostWindow &w) {
 int DecoderPool::push_next_window(movfe_ctx *ctx, int n_frames, HostWindow &w) {
     const int n = next_window(n_frames, w);
     if (n <= 0) return 0;
-    const int rc = movfe_push_frames_packed(ctx, n, w.recs.data(), w.rec_off.data(), w.flags.data(), w.grey.data());
+    const int rc = movfe_push_frames_packed(ctx, n, w.recs.data(), w.rec_off.data(), w.flags.data(), w.grey.data(), 0);
     return rc == MOVFE_OK ? n : -std::abs(rc);
 }
 

@@ -71,7 +71,7 @@ def assert_raster_equal(orc_clip, got, s, f):
 
 
 def run_frontend_clip(per_stream, W, H, n_frames, window, max_ref, grey=None, seeds=None, max_records=4800,
-                      max_tracks=4096, threshold=25, coverage_threshold=0.20, poses=False, ctx_hook=None):
+                      max_tracks=4096, threshold=25, coverage_threshold=0.20, poses=False, ctx_hook=None, grey_stride=0):
     """Raster + extract (+ pose tracking) window by window. Returns ({(s,f): tracks}, extra, ctx)."""
     S = len(per_stream)
     ctx = lib.Context(S, W, H, max_records_per_frame=max_records, max_ref=max_ref, window_frames=window,
@@ -91,7 +91,12 @@ def run_frontend_clip(per_stream, W, H, n_frames, window, max_ref, grey=None, se
         if want > pushed:
             r, o, fl = pack_streams(per_stream, n_frames, pushed, want)
             g = None if grey is None else np.stack([grey[s][pushed:want] for s in range(S)])
-            ctx.push_frames(want - pushed, r, o, fl, g)
+            if grey_stride:     # rows of grey_stride bytes (AVFrame::linesize), the padding filled with junk; 16-byte records
+                gp = np.full(g.shape[:3] + (grey_stride,), 0xA5, np.uint8)
+                gp[..., :W] = g
+                ctx.push_frames_packed(want - pushed, lib.pack_records(r), o, fl, gp, grey_stride)
+            else:
+                ctx.push_frames(want - pushed, r, o, fl, g)
             pushed = want
         ctx.raster(first, n_out)
         ctx.extract(first, n_out)

@@ -109,3 +109,22 @@ def test_decoder_context_feeding_extractor_context(orc):
         prev_g, prev_w = got, want
     for c in (rctx, ectx, octx):
         c.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"MOVFE_GREY_DIRECT": "1"}])
+def test_strided_luma_planes(orc, env, monkeypatch):
+    """Luma planes whose rows are grey_stride > width bytes apart (AVFrame::linesize, cv::Mat::step) go straight into the device's
+    pitched ring (movfe_push_frames_packed); the ring wraps several times over the clip. Tables bit-exact. MOVFE_GREY_DIRECT=1 sends
+    tightly packed planes the same way (the seeding push of other tests); strided ones always go row by row."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    W, H, NF, K = 320, 240, 26, 2
+    specs = [synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED00D1 + s, phase=0.3 * s) for s in range(2)]
+    streams = [synth.make_records(sp) for sp in specs]
+    greys = [synth.make_grey(sp) for sp in specs]
+    got, _, ctx = run_frontend_clip(streams, W, H, NF, 3, K, grey=greys, grey_stride=W + 48)
+    ctx.close()
+    for s in range(2):
+        want = oracle_tracks(orc, streams[s], W, H, K, grey=greys[s])
+        for f in range(NF):
+            assert_tracks_equal(got[(s, f)], want[f], (s, f))
