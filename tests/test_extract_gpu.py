@@ -111,8 +111,8 @@ def test_decoder_context_feeding_extractor_context(orc):
         c.close()
 
 
-@pytest.mark.parametrize("env", [{}, {"MOVFE_GREY_DIRECT": "1"}])
-def test_strided_luma_planes(orc, env, monkeypatch):
+@pytest.mark.parametrize("pad,env", [(48, {}), (0, {"MOVFE_GREY_DIRECT": "1"})])
+def test_strided_luma_planes(orc, pad, env, monkeypatch):
     """Luma planes whose rows are grey_stride > width bytes apart (AVFrame::linesize, cv::Mat::step) go straight into the device's
     pitched ring (movfe_push_frames_packed); the ring wraps several times over the clip. Tables bit-exact. MOVFE_GREY_DIRECT=1 sends
     tightly packed planes the same way (the seeding push of other tests); strided ones always go row by row."""
@@ -122,7 +122,7 @@ def test_strided_luma_planes(orc, env, monkeypatch):
     specs = [synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED00D1 + s, phase=0.3 * s) for s in range(2)]
     streams = [synth.make_records(sp) for sp in specs]
     greys = [synth.make_grey(sp) for sp in specs]
-    got, _, ctx = run_frontend_clip(streams, W, H, NF, 3, K, grey=greys, grey_stride=W + 48)
+    got, _, ctx = run_frontend_clip(streams, W, H, NF, 3, K, grey=greys, grey_stride=(W + pad) if pad else 0)
     ctx.close()
     for s in range(2):
         want = oracle_tracks(orc, streams[s], W, H, K, grey=greys[s])
