@@ -13,6 +13,8 @@
 #include <algorithm>
 #include <cstdio>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace {
@@ -1280,6 +1282,169 @@ pose_kernel(const float *__restrict__ pts, const float *__restrict__ obs, const 
     }
 }
 
+// ------------------------------------------------------------------ PoseOptimization by a thread-block cluster -----
+// Large problems (20 000 correspondences per frame) with one CTA each leave the FP64 pipes of an SM to
+// eight warps and 20 SMs of the chip to nobody (128 problems per GPU). Here a CLUSTER of CTAs owns a problem: every CTA
+// accumulates its share of the correspondences, the per-warp partial sums stay in each CTA's shared memory, and after ONE
+// cluster barrier per pass every warp of every CTA adds all of them - its own CTA's and, through distributed shared memory,
+// the other CTAs' - in the same fixed order and solves the 6x6 system itself, so all CTAs walk the same poses without a
+// word of global traffic. Same pass schedule as pose_solve2 (classification fused into the next round's first pass).
+template <typename Src>
+__device__ int pose_solve_cluster(const Src &src, int n, const movfe_camera &cam_, const movfe_pose_params &pp, movfe_pose *pose,
+                                  uint8_t *outlier, int (&stats)[4], Solver2Shared &sh) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int NW = TP_WARPS;
+    const CamD cam = widen(cam_);
+    const float repErrorF = pp.is_lost ? (float)pp.reprojection_error_lost : (float)pp.reprojection_error;  // Optimizer.cc:423-427
+    const double delta = repErrorF, chi2thr = delta * delta;
+    const int its = pp.iteration_count / 4 > 1 ? pp.iteration_count / 4 : 1;
+    const int first = rank * TP_THREADS + threadIdx.x, stride = CL * TP_THREADS;  // this thread's correspondences
+    double *Rt = sh.Rt[warp];
+    stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    for (int i = first; i < n; i += stride) outlier[i] = 0;
+    if (lane < 9) Rt[lane] = pose->R[lane];
+    else if (lane < 12) Rt[lane] = pose->t[lane - 9];
+    // the other CTAs' partial-sum buffers (distributed shared memory)
+    const double *rpart[8];
+    const int *ripart[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        rpart[r] = r < CL ? cluster.map_shared_rank(&sh.part[0][0][0], r) : nullptr;
+        ripart[r] = r < CL ? cluster.map_shared_rank(&sh.ipart[0][0], r) : nullptr;
+    }
+    cluster.sync();  // every CTA has read the initial pose before the last pass's writer (rank 0) can overwrite it
+    if (n < 4) return 0;  // Optimizer.cc:415-418
+    int n_bad = 0, pass = 0;
+    bool pending = false, stop = false;
+    for (int round = 0; round < 4 && !stop; round++) {
+        const bool robust = round < 3;
+        for (int it = 0; it < its; it++) {
+            double acc[27];
+#pragma unroll
+            for (int q = 0; q < 27; q++) acc[q] = 0.0;
+            int bad = 0;
+            for (int i = first; i < n; i += stride) {
+                float X0, X1, X2, ou, ov;
+                src.get(i, X0, X1, X2, ou, ov);
+                if (pending) {
+                    const bool b = classify_point(cam, Rt, Rt + 9, X0, X1, X2, ou, ov, chi2thr);
+                    outlier[i] = b ? 1 : 0;  // only this thread reads it back in later passes
+                    bad += b;
+                    if (b) continue;
+                } else if (outlier[i]) {
+                    continue;
+                }
+                accumulate_point(cam, Rt, Rt + 9, X0, X1, X2, ou, ov, robust, delta, acc);
+            }
+            const double v = warp_reduce27(acc, lane);
+            sh.part[pass & 1][warp][lane] = v;
+            if (pending) {
+                for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+                if (lane == 0) sh.ipart[pass & 1][warp] = bad;
+            }
+            cluster.sync();  // the only barrier of a pass; partials are double-buffered by pass parity (pose_solve2)
+            if (lane < 27) {
+                double tot = 0;
+                for (int r = 0; r < CL; r++)
+                    for (int w = 0; w < NW; w++) tot += rpart[r][((pass & 1) * NW + w) * 32 + lane];
+                sh.tot[warp][lane] = tot;
+            }
+            if (pending) {
+                n_bad = 0;
+                for (int r = 0; r < CL; r++)
+                    for (int w = 0; w < NW; w++) n_bad += ripart[r][(pass & 1) * NW + w];
+                stats[1]++;
+                pending = false;
+                if (n - n_bad < 3) {
+                    stop = true;
+                    pass++;
+                    break;
+                }
+            }
+            pass++;
+            __syncwarp();
+            stats[0]++;
+            double dx[6];
+            int flag;
+            if (!solve6_d(sh.tot[warp], &sh.tot[warp][21], dx)) {
+                flag = 2;
+                stats[3]++;
+            } else {
+                double dR[9], dt[3], Rn[9], tn[3];
+                se3_exp_d(dx, dR, dt);
+#pragma unroll
+                for (int i = 0; i < 3; i++)
+#pragma unroll
+                    for (int j = 0; j < 3; j++) Rn[i * 3 + j] = dR[i * 3] * Rt[j] + dR[i * 3 + 1] * Rt[3 + j] + dR[i * 3 + 2] * Rt[6 + j];
+#pragma unroll
+                for (int r = 0; r < 3; r++) tn[r] = dR[r * 3] * Rt[9] + dR[r * 3 + 1] * Rt[10] + dR[r * 3 + 2] * Rt[11] + dt[r];
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 9; i++) Rt[i] = Rn[i];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) Rt[9 + i] = tn[i];
+                }
+                double m = 0;
+#pragma unroll
+                for (int a = 0; a < 6; a++) m = fmax(m, fabs(dx[a]));
+                flag = m < 1e-10 ? 1 : 0;
+            }
+            __syncwarp();
+            if (flag) break;
+        }
+        if (!stop) pending = true;
+    }
+    if (pending) {  // the classification that closes the last round
+        int bad = 0;
+        for (int i = first; i < n; i += stride) {
+            float X0, X1, X2, ou, ov;
+            src.get(i, X0, X1, X2, ou, ov);
+            const bool b = classify_point(cam, Rt, Rt + 9, X0, X1, X2, ou, ov, chi2thr);
+            outlier[i] = b ? 1 : 0;
+            bad += b;
+        }
+        for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        if (lane == 0) sh.ipart[pass & 1][warp] = bad;
+        cluster.sync();
+        n_bad = 0;
+        for (int r = 0; r < CL; r++)
+            for (int w = 0; w < NW; w++) n_bad += ripart[r][(pass & 1) * NW + w];
+        stats[1]++;
+    }
+    stats[2] = stats[0] + stats[1];
+    if (rank == 0) {
+        if (threadIdx.x < 9) pose->R[threadIdx.x] = Rt[threadIdx.x];
+        else if (threadIdx.x < 12) pose->t[threadIdx.x - 9] = Rt[threadIdx.x];
+    }
+    cluster.sync();  // no CTA leaves while another may still read its shared memory
+    return n - n_bad;
+}
+
+__global__ void __launch_bounds__(TP_THREADS, MOVFE_TP_MINB)
+pose_cluster_kernel(const float *__restrict__ pts, const float *__restrict__ obs, const int32_t *__restrict__ off, movfe_camera cam,
+                    movfe_pose_params pp, movfe_pose *__restrict__ poses, uint8_t *__restrict__ outlier, int32_t *__restrict__ n_inl,
+                    int32_t *__restrict__ stats) {
+    __shared__ Solver2Shared sh;
+    namespace cg = cooperative_groups;
+    const int CL = (int)cg::this_cluster().num_blocks();
+    const int pidx = blockIdx.x / CL;
+    const int b = off[pidx], n = off[pidx + 1] - b;
+    DirectSrc src{pts + 3 * (size_t)b, obs + 2 * (size_t)b};
+    int st[4];
+    const int r = pose_solve_cluster(src, n, cam, pp, poses + pidx, outlier + b, st, sh);
+    if (cg::this_cluster().block_rank() == 0 && threadIdx.x == 0) {
+        n_inl[pidx] = r;
+        if (stats) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) stats[4 * pidx + k] = st[k];
+        }
+    }
+}
+
 int pow2_at_least(int v) {
     int c = 2;
     while (c < v) c <<= 1;
@@ -1682,7 +1847,28 @@ extern "C" int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_c
     {
         ProfScope prof(ctx, MOVFE_STAGE_POSE);
         prof.launches(1);
-        pose_kernel<<<n_problems, TP_THREADS, 0, ctx->stream>>>(d_pts, d_obs, d_off, *cam, *pp, d_pose, d_out, d_ninl, d_stats);
+        // large problems: a cluster of CTAs per problem (pose_solve_cluster); MOVFE_POSE_CLUSTER=n forces the size (1 = off)
+        int max_n = 0;
+        for (int i = 0; i < n_problems; i++) max_n = std::max(max_n, off[i + 1] - off[i]);
+        int cl = max_n >= 4096 ? ((int64_t)n_problems * 2 <= 2 * (int64_t)ctx->sm_count ? 2 : 1) : 1;
+        if (const char *e = getenv("MOVFE_POSE_CLUSTER")) cl = std::max(1, std::min(8, atoi(e)));
+        if (cl > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(n_problems * cl));
+            cfg.blockDim = dim3(TP_THREADS);
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)cl;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            MOVFE_CUDA(ctx, cudaLaunchKernelEx(&cfg, pose_cluster_kernel, (const float *)d_pts, (const float *)d_obs, (const int32_t *)d_off, *cam, *pp,
+                                               d_pose, d_out, d_ninl, d_stats));
+        } else {
+            pose_kernel<<<n_problems, TP_THREADS, 0, ctx->stream>>>(d_pts, d_obs, d_off, *cam, *pp, d_pose, d_out, d_ninl, d_stats);
+        }
     }
     MOVFE_CUDA(ctx, cudaGetLastError());
     MOVFE_CUDA(ctx, cudaMemcpyAsync(poses, d_pose, (size_t)n_problems * sizeof(movfe_pose), cudaMemcpyDeviceToHost, ctx->stream));

@@ -54,8 +54,13 @@ def test_c4_1080p_dense_4x4(orc):
     ctx.close()
 
 
-def test_c5_pose_stress_fisheye(orc):
-    """20 000 correspondences per problem, KannalaBrandt8 (k from SURVEY.md 8d), sigma 0.5 px + 10 % gross outliers."""
+@pytest.mark.parametrize("cluster", [None, "1", "4"])
+def test_c5_pose_stress_fisheye(orc, cluster, monkeypatch):
+    """20 000 correspondences per problem, KannalaBrandt8 (k from SURVEY.md 8d), sigma 0.5 px + 10 % gross outliers. Default: a
+    cluster of two CTAs per problem adding its partial sums through distributed shared memory (pose_solve_cluster); MOVFE_POSE_CLUSTER=1
+    one CTA per problem, =4 four."""
+    if cluster:
+        monkeypatch.setenv("MOVFE_POSE_CLUSTER", cluster)
     cam = T.camera(190.0, 190.0, 376.0, 240.0, k=(-0.01, 0.002, -0.0005, 0.0001), model=T.CAM_FISHEYE)
     pp = T.pose_params()
     ctx = lib.Context(1, 752, 480, has_grey=False)
