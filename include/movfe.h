@@ -155,6 +155,19 @@ int movfe_set_map_points(movfe_ctx *ctx, int stream, const movfe_map_point *pts,
  * movfe_track_poses: frames tracked after the call see the new maps. */
 int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point *pts, const int64_t *off, const int32_t *n_keyframe_points,
                                int max_points_per_stream, int on_device);
+/* -- local map building on the device: replaces Tracking::UpdateLocalPoints (src/Tracking.cc:1171-1198) for batched callers.
+ *    The map points of a stream live in a device-resident STORE (movfe_set_map_store: `first_index`.. are the caller's own point
+ *    indices; call it again to patch points the mapping side added, moved or culled - flags carry MOVFE_MP_BAD). A local map is
+ *    then built from INDEX lists: for every stream the map-point matches of its local keyframes, concatenated in the order the
+ *    caller walks them (the reference: mvpLocalKeyFrames reversed, each keyframe's GetMapPointMatches() in order; a NULL entry
+ *    is -1). The kernel skips NULL and bad points, keeps the FIRST occurrence of every point in order (mnTrackReferenceForFrame)
+ *    and installs the result as the stream's local map, as movfe_set_map_points would; n_keyframe_entries[s] leading list
+ *    entries are the reference keyframe's list (their surviving points become the local map's keyframe prefix). 4 bytes per
+ *    list entry cross PCIe instead of 40 per point. idx: all lists, stream-major; off: n_streams + 1 offsets. */
+int movfe_reserve_map_store(movfe_ctx *ctx, int max_points_per_stream);
+int movfe_set_map_store(movfe_ctx *ctx, int stream, int first_index, const movfe_map_point *pts, int n);
+int movfe_update_local_points(movfe_ctx *ctx, const int32_t *idx, const int64_t *off, const int32_t *n_keyframe_entries);
+int movfe_download_map_points(movfe_ctx *ctx, int stream, movfe_map_point *out, int capacity, int32_t *n_keyframe_points);
 int movfe_set_pose(movfe_ctx *ctx, int stream, const movfe_pose *pose);
 int movfe_track_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 int movfe_download_poses(movfe_ctx *ctx, int64_t first_frame, int n_frames, movfe_pose *poses /* S*n */,

@@ -188,6 +188,14 @@ struct movfe_ctx {
     size_t   map_stage_bytes[2] = {0, 0};
     cudaEvent_t ev_map_staged[2] = {nullptr, nullptr};   // recorded on the pose stream after the install kernel read buffer b
     int      map_parity = 0;
+    // device-resident map-point store + scratch of movfe_update_local_points (allocated by movfe_reserve_map_store)
+    movfe_map_point *d_store = nullptr;    // [S][store_cap]
+    int32_t *d_store_stamp = nullptr;      // [S][store_cap] first list position of a point (0x7fffffff between calls)
+    int      store_cap = 0;
+    int32_t *d_lp_idx = nullptr;           // staged index lists
+    int64_t *d_lp_off = nullptr;           // [S + 1] offsets, then [S] keyframe entry counts as int32
+    size_t   lp_idx_cap = 0;
+    void    *h_lp_meta = nullptr;          // pinned copy of offsets + counts
     void    *d_pose_scratch = nullptr;
     size_t   pose_scratch_bytes = 0;
     // split pose chain (join kernels + small solver kernels, pose.cu): correspondences of one frame per stream

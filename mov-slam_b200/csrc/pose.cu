@@ -1614,6 +1614,167 @@ __global__ void map_install_kernel(const uint32_t *__restrict__ src, const int64
         d_nkf[s] = min(n_kf[s], n);
     }
 }
+// ------------------------------------------------------------------------ local map building (UpdateLocalPoints) -----
+// One CTA per stream. The list is walked twice: first every non-NULL, non-bad entry bids for its point with its list position
+// (integer atomicMin: the first occurrence wins whatever the thread order), then the entries that own their point are compacted
+// in list order into the stream's local map; a third walk puts the stamps back.
+constexpr int LP_THREADS = 1024;
+__global__ void __launch_bounds__(LP_THREADS)
+local_points_kernel(const movfe_map_point *__restrict__ store, int32_t *__restrict__ stamp, int store_cap, const int32_t *__restrict__ idx,
+                    const int64_t *__restrict__ off, const int32_t *__restrict__ n_kf_entries, int max_map, movfe_map_point *__restrict__ d_map,
+                    int32_t *__restrict__ d_nmap, int32_t *__restrict__ d_nkf) {
+    __shared__ int wsum[LP_THREADS / 32];
+    __shared__ int s_total, s_first;
+    const int s = blockIdx.x;
+    const movfe_map_point *st = store + (size_t)s * store_cap;
+    int32_t *sp = stamp + (size_t)s * store_cap;
+    const int32_t *L = idx + off[s];
+    const int m = (int)(off[s + 1] - off[s]), n_first = n_kf_entries[s];
+    movfe_map_point *out = d_map + (size_t)s * max_map;
+    auto valid = [&](int j, int &i) {
+        i = L[j];
+        return i >= 0 && i < store_cap && !(st[i].flags & MOVFE_MP_BAD);  // :1187-1191
+    };
+    for (int j = threadIdx.x; j < m; j += LP_THREADS) {
+        int i;
+        if (valid(j, i)) atomicMin(&sp[i], j);
+    }
+    if (threadIdx.x == 0) {
+        s_total = 0;
+        s_first = 0;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = 0; base < m; base += LP_THREADS) {
+        const int j = base + threadIdx.x;
+        int i = -1;
+        const bool keep = j < m && valid(j, i) && sp[i] == j;  // first occurrence (mnTrackReferenceForFrame, :1189-1195)
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int before = s_total, tot = 0;
+        for (int w = 0; w < LP_THREADS / 32; w++) {
+            const int c = wsum[w];
+            before += w < warp ? c : 0;
+            tot += c;
+        }
+        const int pos = before + __popc(b & ((1u << lane) - 1u));
+        if (keep && pos < max_map) {
+            out[pos] = st[i];  // mvpLocalMapPoints.push_back(pMP) (:1194)
+            if (j < n_first) atomicMax(&s_first, pos + 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_total += tot;
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < m; j += LP_THREADS) {
+        int i;
+        if (valid(j, i)) sp[i] = 0x7fffffff;
+    }
+    if (threadIdx.x == 0) {
+        d_nmap[s] = min(s_total, max_map);
+        d_nkf[s] = s_first;
+    }
+}
+}  // namespace
+
+extern "C" int movfe_reserve_map_store(movfe_ctx *ctx, int max_points_per_stream) {
+    if (!ctx || max_points_per_stream < 1) return MOVFE_E_INVALID;
+    if (max_points_per_stream <= ctx->store_cap) return MOVFE_OK;
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    const size_t S = ctx->cfg.n_streams, n = S * (size_t)max_points_per_stream;
+    movfe_map_point *ns = nullptr;
+    int32_t *nst = nullptr;
+    MOVFE_CUDA(ctx, cudaMalloc(&ns, n * sizeof(movfe_map_point)));
+    MOVFE_CUDA(ctx, cudaMalloc(&nst, n * sizeof(int32_t)));
+    MOVFE_CUDA(ctx, cudaMemsetAsync(ns, 0xff, n * sizeof(movfe_map_point), ctx->pose_stream));  // flags all set: every slot starts as a bad point
+    MOVFE_CUDA(ctx, cudaMemsetAsync(nst, 0x7f, n * sizeof(int32_t), ctx->pose_stream));         // 0x7f7f7f7f: above every list position
+    if (ctx->d_store)  // keep what was installed
+        MOVFE_CUDA(ctx, cudaMemcpy2DAsync(ns, (size_t)max_points_per_stream * sizeof(movfe_map_point), ctx->d_store,
+                                          (size_t)ctx->store_cap * sizeof(movfe_map_point), (size_t)ctx->store_cap * sizeof(movfe_map_point), S,
+                                          cudaMemcpyDeviceToDevice, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    if (ctx->d_store) cudaFree(ctx->d_store);
+    if (ctx->d_store_stamp) cudaFree(ctx->d_store_stamp);
+    ctx->d_store = ns;
+    ctx->d_store_stamp = nst;
+    ctx->store_cap = max_points_per_stream;
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_set_map_store(movfe_ctx *ctx, int stream, int first_index, const movfe_map_point *pts, int n) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (stream < 0 || stream >= ctx->cfg.n_streams || first_index < 0 || n < 0 || (n > 0 && !pts)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "set_map_store: bad argument");
+    if (first_index + n > ctx->store_cap)
+        MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "set_map_store: points [%d, %d) exceed the reserved store of %d points per stream (movfe_reserve_map_store)",
+                   first_index, first_index + n, ctx->store_cap);
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    if (n > 0) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_store + (size_t)stream * ctx->store_cap + first_index, pts, (size_t)n * sizeof(movfe_map_point),
+                                        cudaMemcpyHostToDevice, ctx->pose_stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));  // the array is the caller's
+    }
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_update_local_points(movfe_ctx *ctx, const int32_t *idx, const int64_t *off, const int32_t *n_keyframe_entries) {
+    if (!ctx || !off || !n_keyframe_entries) return MOVFE_E_INVALID;
+    if (!ctx->d_store) MOVFE_FAIL(ctx, MOVFE_E_STATE, "update_local_points: no map store (movfe_reserve_map_store / movfe_set_map_store)");
+    const movfe_config &c = ctx->cfg;
+    const int S = c.n_streams;
+    const int64_t total = off[S];
+    if (total < 0 || (total > 0 && !idx)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "update_local_points: bad offsets");
+    for (int s = 0; s < S; s++)
+        if (off[s + 1] < off[s] || n_keyframe_entries[s] < 0) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "update_local_points: bad list of stream %d", s);
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    cudaStream_t st = ctx->pose_stream;  // ordered with the pose chains that read the local maps
+    const size_t meta = (size_t)(S + 1) * 8 + (size_t)S * 4;
+    if (ctx->lp_idx_cap < (size_t)total || !ctx->d_lp_off) {
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->d_lp_idx) cudaFree(ctx->d_lp_idx);
+        ctx->d_lp_idx = nullptr;
+        ctx->lp_idx_cap = 0;
+        const size_t want = (size_t)total + (size_t)total / 2 + 1024;
+        MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_lp_idx, want * sizeof(int32_t)));
+        ctx->lp_idx_cap = want;
+        if (!ctx->d_lp_off) MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_lp_off, meta));
+        if (!ctx->h_lp_meta) MOVFE_CUDA(ctx, cudaMallocHost(&ctx->h_lp_meta, meta));
+    } else {
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // the previous call's copies out of the pinned buffer have completed
+    }
+    memcpy(ctx->h_lp_meta, off, (size_t)(S + 1) * 8);
+    memcpy((uint8_t *)ctx->h_lp_meta + (size_t)(S + 1) * 8, n_keyframe_entries, (size_t)S * 4);
+    if (total > 0) MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_lp_idx, idx, (size_t)total * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(ctx->d_lp_off, ctx->h_lp_meta, meta, cudaMemcpyHostToDevice, st));
+    local_points_kernel<<<S, LP_THREADS, 0, st>>>(ctx->d_store, ctx->d_store_stamp, ctx->store_cap, ctx->d_lp_idx, ctx->d_lp_off,
+                                                  reinterpret_cast<const int32_t *>(ctx->d_lp_off + S + 1), std::max(c.max_map_points, 1), ctx->d_map,
+                                                  ctx->d_nmap, ctx->d_nkf);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    ctx->h_nmap_max = std::max(ctx->h_nmap_max, c.max_map_points);
+    if (total > 0) MOVFE_CUDA(ctx, cudaStreamSynchronize(st));  // idx is the caller's array
+    return MOVFE_OK;
+}
+
+extern "C" int movfe_download_map_points(movfe_ctx *ctx, int stream, movfe_map_point *out, int capacity, int32_t *n_keyframe_points) {
+    if (!ctx) return MOVFE_E_INVALID;
+    if (stream < 0 || stream >= ctx->cfg.n_streams || capacity < 0 || (capacity > 0 && !out)) MOVFE_FAIL(ctx, MOVFE_E_INVALID, "download_map_points: bad argument");
+    MOVFE_CUDA(ctx, cudaSetDevice(ctx->cfg.device));
+    int32_t n = 0, nk = 0;
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(&n, ctx->d_nmap + stream, 4, cudaMemcpyDeviceToHost, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaMemcpyAsync(&nk, ctx->d_nkf + stream, 4, cudaMemcpyDeviceToHost, ctx->pose_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    if (n > capacity) MOVFE_FAIL(ctx, MOVFE_E_CAPACITY, "download_map_points: %d points, capacity %d", n, capacity);
+    if (n > 0) {
+        MOVFE_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_map + (size_t)stream * std::max(ctx->cfg.max_map_points, 1), (size_t)n * sizeof(movfe_map_point),
+                                        cudaMemcpyDeviceToHost, ctx->pose_stream));
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    }
+    if (n_keyframe_points) *n_keyframe_points = nk;
+    return n;
+}
+
+namespace {
 }  // namespace
 
 extern "C" int movfe_set_map_points_batch(movfe_ctx *ctx, const movfe_map_point *pts, const int64_t *off, const int32_t *n_keyframe_points,

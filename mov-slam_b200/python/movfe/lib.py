@@ -69,6 +69,10 @@ def load():
     L.movfe_set_camera.argtypes = [vp, vp, vp, C.c_float]
     L.movfe_set_map_points.argtypes = [vp, i32, vp, i32, i32]
     L.movfe_set_pose.argtypes = [vp, i32, vp]
+    L.movfe_reserve_map_store.argtypes = [vp, i32]
+    L.movfe_set_map_store.argtypes = [vp, i32, i32, vp, i32]
+    L.movfe_update_local_points.argtypes = [vp, vp, vp, vp]
+    L.movfe_download_map_points.argtypes = [vp, i32, vp, i32, vp]
     L.movfe_set_map_points_batch.argtypes = [vp, vp, vp, vp, i32, i32]
     L.movfe_track_poses.argtypes = [vp, i64, i32]
     L.movfe_download_poses.argtypes = [vp, i64, i32, vp, vp]
@@ -90,7 +94,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_version", "movfe_push_frames", "movfe_push_frames_device", "movfe_push_frames_packed", "movfe_pack_records", "movfe_frames_pushed", "movfe_raster",
            "movfe_raster_counts", "movfe_download_grid", "movfe_download_hops", "movfe_download_kps",
            "movfe_rejected_records", "movfe_set_tracks", "movfe_set_lk_results", "movfe_dropped_lk_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
-           "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_set_pose",
+           "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_reserve_map_store", "movfe_set_map_store", "movfe_update_local_points", "movfe_download_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
            "movfe_pose_optimize", "movfe_profile_enable", "movfe_profile_read", "movfe_workload_stats"]
@@ -315,6 +319,28 @@ class Context:
             assert len(off) == self.S + 1 and len(n_kf) == self.S
             self._keep_map = (pts, off, n_kf)       # host arrays must stay unchanged until the next synchronising call
         self._ck(self.L.movfe_set_map_points_batch(self.h, _p(pts), _p(off), _p(n_kf), int(max_points_per_stream), int(on_device)))
+
+    # -- device-side Tracking::UpdateLocalPoints --------------------------------------------------------------------
+    def reserve_map_store(self, max_points_per_stream):
+        self._ck(self.L.movfe_reserve_map_store(self.h, int(max_points_per_stream)))
+
+    def set_map_store(self, stream, first_index, pts):
+        pts = np.ascontiguousarray(pts, T.MAP_POINT)
+        self._ck(self.L.movfe_set_map_store(self.h, stream, int(first_index), _p(pts), len(pts)))
+
+    def update_local_points(self, idx, off, n_kf_entries):
+        idx = np.ascontiguousarray(idx, np.int32)
+        off = np.ascontiguousarray(off, np.int64)
+        n_kf_entries = np.ascontiguousarray(n_kf_entries, np.int32)
+        assert len(off) == self.S + 1 and len(n_kf_entries) == self.S and len(idx) == off[-1]
+        self._ck(self.L.movfe_update_local_points(self.h, _p(idx), _p(off), _p(n_kf_entries)))
+
+    def map_points(self, stream, capacity=1 << 16):
+        out = np.zeros(capacity, T.MAP_POINT)
+        nk = C.c_int32()
+        n = self.L.movfe_download_map_points(self.h, stream, _p(out), capacity, C.byref(nk))
+        self._ck(n if n < 0 else 0)
+        return out[:n], nk.value
 
     def set_pose(self, stream, pose):
         pose = np.ascontiguousarray(pose, T.POSE)

@@ -224,3 +224,27 @@ extern "C" int orc_get_features_in_area(const movfe_track *tracks, int n, int wi
     }
     return cnt;
 }
+
+// Tracking::UpdateLocalPoints (src/Tracking.cc:1171-1198) on index lists: `idx` is the concatenation of the local keyframes'
+// GetMapPointMatches() in the order the reference walks them (mvpLocalKeyFrames reversed, each list in order; a NULL entry is -1),
+// `store` the stream's map points by index. mnTrackReferenceForFrame is modelled by a visited set. Returns the number of points
+// written to `out` (at most `capacity`); *n_from_first = how many of them came from the first n_first list entries.
+extern "C" int orc_update_local_points(const movfe_map_point *store, int n_store, const int32_t *idx, int n_idx, int n_first,
+                                       movfe_map_point *out, int capacity, int32_t *n_from_first) {
+    std::vector<char> seen((size_t)std::max(n_store, 1), 0);
+    int n = 0, first = 0;
+    for (int j = 0; j < n_idx; j++) {
+        const int i = idx[j];
+        if (i < 0 || i >= n_store) continue;               // if (!pMP) continue;                       :1187-1188
+        if (seen[(size_t)i]) continue;                     // mnTrackReferenceForFrame == current frame   :1189-1190
+        if (store[i].flags & MOVFE_MP_BAD) continue;       // if (!pMP->isBad())                         :1191
+        seen[(size_t)i] = 1;                               // mnTrackReferenceForFrame = mCurrentFrame.mnId :1195
+        if (n < capacity) {
+            out[n] = store[i];                             // mvpLocalMapPoints.push_back(pMP)            :1194
+            if (j < n_first) first = n + 1;
+        }
+        n++;
+    }
+    if (n_from_first) *n_from_first = first;
+    return n < capacity ? n : capacity;
+}

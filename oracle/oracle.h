@@ -97,6 +97,9 @@ int orc_search_by_video_feature(const movfe_track *tracks, int n_tracks, const m
 int orc_search_by_keyframe(const movfe_track *tracks, int n_tracks, const movfe_map_point *kf_pts, int n_pts,
                            int32_t *match);
 /* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize). prev_matched has n1*2 floats. */
+/* Tracking::UpdateLocalPoints (src/Tracking.cc:1171-1198) on index lists into a per-stream point store. */
+int orc_update_local_points(const movfe_map_point *store, int n_store, const int32_t *idx, int n_idx, int n_first,
+                            movfe_map_point *out, int capacity, int32_t *n_from_first);
 int orc_search_for_initialization(const movfe_track *f1, int n1, const movfe_track *f2, int n2,
                                   float *prev_matched, int32_t *matches12);
 

@@ -53,6 +53,7 @@ def lib():
         L.orc_extract_frame_lost.restype = i32
         L.orc_extract_frame_lost.argtypes = [i32, i32, C.c_uint32, vp, vp, vp, vp, i32, f64, vp, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         L.orc_frustum.argtypes = [vp, vp, i32, i32, f32, vp, i32, vp]
+        L.orc_update_local_points.argtypes = [vp, i32, vp, i32, i32, vp, i32, vp]
         L.orc_search_by_video_feature.restype = i32
         L.orc_search_by_video_feature.argtypes = [vp, i32, vp, vp, i32, i32, f32, vp]
         L.orc_search_by_keyframe.restype = i32
@@ -203,6 +204,15 @@ def search_by_keyframe(tracks, kf_pts):
     match = np.zeros(len(tracks), np.int32)
     n = lib().orc_search_by_keyframe(_p(tracks), len(tracks), _p(kf_pts), len(kf_pts), _p(match))
     return n, match
+
+
+def update_local_points(store, idx, n_first, capacity):
+    store = np.ascontiguousarray(store, T.MAP_POINT)
+    idx = np.ascontiguousarray(idx, np.int32)
+    out = np.zeros(max(capacity, 1), T.MAP_POINT)
+    nf = C.c_int32()
+    n = lib().orc_update_local_points(_p(store), len(store), _p(idx), len(idx), int(n_first), _p(out), int(capacity), C.byref(nf))
+    return out[:n], nf.value
 
 
 def search_for_initialization(f1, f2, prev_matched):

@@ -236,3 +236,17 @@ def test_se3_exp_small_and_large(orc):
     assert np.allclose(R, [[0, -1, 0], [1, 0, 0], [0, 0, 1]], atol=1e-15)
     assert np.allclose(R @ R.T, np.eye(3), atol=1e-15)
     assert np.allclose(t, [2 / np.pi, 2 / np.pi, 0], atol=1e-15)
+
+
+def test_update_local_points_walk(orc):
+    """Tracking::UpdateLocalPoints (src/Tracking.cc:1171-1198) on index lists: NULL entries and bad points are skipped, the
+    first occurrence of a point stays, in list order; a bad point is never marked as referenced."""
+    store = np.zeros(8, T.MAP_POINT)
+    store["track_id"] = np.arange(100, 108)
+    store["flags"][3] = T.MP_BAD
+    idx = [5, -1, 3, 5, 2, 3, 7, 2, 0, 99]                      # 99: outside the store = a dangling pointer, treated as NULL
+    out, n_first = orc.update_local_points(store, idx, n_first=5, capacity=16)
+    assert list(out["track_id"]) == [105, 102, 107, 100]
+    assert n_first == 2                                        # 105 and 102 came from the first five entries
+    out, n_first = orc.update_local_points(store, idx, n_first=5, capacity=3)
+    assert list(out["track_id"]) == [105, 102, 107] and n_first == 2

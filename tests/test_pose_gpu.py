@@ -237,3 +237,69 @@ def test_keyframe_join_and_initialization_search_parity(orc, ctx):
     hit = m12 >= 0
     got_prev[hit, 0], got_prev[hit, 1] = f2["pt_x"][m12[hit]], f2["pt_y"][m12[hit]]      # MOVMatcher.h:131-134, host side
     assert np.array_equal(got_prev, wprev)
+
+
+def test_update_local_points_on_device(orc):
+    """Tracking::UpdateLocalPoints (src/Tracking.cc:1171-1198) built on the device from index lists into a resident point store
+    (movfe_set_map_store / movfe_update_local_points): the installed local maps equal the oracle's walk - NULL entries, bad points,
+    duplicates across keyframes, a list longer than the local-map capacity, an empty list - and a pose chain run on them gives
+    the poses of a context that received the same maps through movfe_set_map_points."""
+    rng = np.random.default_rng(77)
+    S, W, H, NF, K, CAP, NSTORE = 3, 320, 240, 5, 2, 300, 1500
+    specs = [synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0A10 + s, fx=160.0, fy=160.0) for s in range(S)]
+    streams = [synth.make_records(sp) for sp in specs]
+    greys = [synth.make_grey(sp) for sp in specs]
+    want0 = [oracle_tracks(orc, streams[s], W, H, K, grey=greys[s])[0] for s in range(S)]
+    stores, lists, n_first, maps = [], [], [], []
+    for s in range(S):
+        base = synth.map_from_tracks(specs[s], want0[s], synth.pose_at(specs[s], 0))   # real points first, padding after
+        store = np.zeros(NSTORE, T.MAP_POINT)
+        store[:len(base)] = base[:NSTORE]
+        store["flags"][len(base):] = T.MP_BAD
+        bad = rng.choice(len(base), len(base) // 10, replace=False)
+        store["flags"][bad] |= T.MP_BAD
+        n_list = [900, 0, 2500][s]                                 # stream 1: nothing; stream 2: more survivors than CAP
+        idx = rng.integers(-1, len(base) + 20, n_list).astype(np.int32)    # -1 = NULL, >= len(base): culled padding
+        stores.append(store)
+        lists.append(idx)
+        n_first.append(min(n_list, 200))
+        maps.append(orc.update_local_points(store, idx, n_first[s], CAP))
+    off = np.cumsum([0] + [len(l) for l in lists]).astype(np.int64)
+    cam, pp = specs[0].camera(), T.pose_params()
+
+    def run(install):
+        ctx = lib.Context(S, W, H, max_records_per_frame=4800, max_ref=K, window_frames=NF, max_tracks=4096, max_map_points=CAP, has_grey=True)
+        ctx.set_camera(cam, pp, 0.5)
+        install(ctx)
+        got = [ctx.map_points(s) for s in range(S)]
+        for s in range(S):
+            ctx.set_pose(s, synth.pose_struct(synth.pose_at(specs[s], 0)))
+        from gpu_util import pack_streams
+        r, o, fl = pack_streams(streams, NF, 0, NF)
+        ctx.push_frames(NF, r, o, fl, np.stack([g[:NF] for g in greys]))
+        ctx.raster(0, NF)
+        ctx.extract(0, NF)
+        ctx.track_poses(0, NF)
+        P, ninl = ctx.poses(0, NF)
+        ctx.close()
+        return got, P, ninl
+
+    def by_lists(ctx):
+        ctx.reserve_map_store(NSTORE)
+        for s in range(S):
+            ctx.set_map_store(s, 0, stores[s][:700])
+            ctx.set_map_store(s, 700, stores[s][700:])       # patched in two pieces
+        ctx.update_local_points(np.concatenate(lists), off, n_first)
+
+    def by_points(ctx):
+        for s in range(S):
+            ctx.set_map_points(s, maps[s][0], maps[s][1])
+
+    got, P1, n1 = run(by_lists)
+    for s in range(S):
+        assert got[s][0].tobytes() == maps[s][0].tobytes(), (s, len(got[s][0]), len(maps[s][0]))
+        assert got[s][1] == maps[s][1], (s, got[s][1], maps[s][1])
+    assert len(maps[2][0]) == CAP and len(maps[1][0]) == 0 and 0 < len(maps[0][0]) < CAP
+    _, P2, n2 = run(by_points)
+    assert np.array_equal(n1, n2) and P1.tobytes() == P2.tobytes()
+    assert n1[0].max() > 20      # the chain really ran on these maps
