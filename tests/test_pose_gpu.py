@@ -245,7 +245,7 @@ def test_update_local_points_on_device(orc):
     duplicates across keyframes, a list longer than the local-map capacity, an empty list - and a pose chain run on them gives
     the poses of a context that received the same maps through movfe_set_map_points."""
     rng = np.random.default_rng(77)
-    S, W, H, NF, K, CAP, NSTORE = 3, 320, 240, 5, 2, 300, 1500
+    S, W, H, NF, K, CAP, NSTORE = 3, 320, 240, 5, 2, 60, 1500
     specs = [synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0A10 + s, fx=160.0, fy=160.0) for s in range(S)]
     streams = [synth.make_records(sp) for sp in specs]
     greys = [synth.make_grey(sp) for sp in specs]
@@ -258,11 +258,11 @@ def test_update_local_points_on_device(orc):
         store["flags"][len(base):] = T.MP_BAD
         bad = rng.choice(len(base), len(base) // 10, replace=False)
         store["flags"][bad] |= T.MP_BAD
-        n_list = [900, 0, 2500][s]                                 # stream 1: nothing; stream 2: more survivors than CAP
+        n_list = [45, 0, 2500][s]                                  # stream 1: nothing; stream 2: more survivors than CAP
         idx = rng.integers(-1, len(base) + 20, n_list).astype(np.int32)    # -1 = NULL, >= len(base): culled padding
         stores.append(store)
         lists.append(idx)
-        n_first.append(min(n_list, 200))
+        n_first.append(min(n_list, 20))
         maps.append(orc.update_local_points(store, idx, n_first[s], CAP))
     off = np.cumsum([0] + [len(l) for l in lists]).astype(np.int64)
     cam, pp = specs[0].camera(), T.pose_params()
@@ -302,4 +302,4 @@ def test_update_local_points_on_device(orc):
     assert len(maps[2][0]) == CAP and len(maps[1][0]) == 0 and 0 < len(maps[0][0]) < CAP
     _, P2, n2 = run(by_points)
     assert np.array_equal(n1, n2) and P1.tobytes() == P2.tobytes()
-    assert n1[0].max() > 20      # the chain really ran on these maps
+    assert n1[2].max() > 20      # the chain really ran on these maps
