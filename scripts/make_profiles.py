@@ -7,7 +7,7 @@
   kernel_traffic_r2.json                  dram__bytes_read + dram__bytes_write per launch of every captured kernel and per step of
                                           every stage (read by bench.py for roofline.traffic)
   sass_TAG_<kernel>.txt                   SASS of the hot kernels of the build the captures were taken from
-usage: python scripts/make_profiles.py TAG [launches per step of the propagation kernels = 16]"""
+usage: python scripts/make_profiles.py TAG [frames per step = 16] [propagation chains = 3: a launch covers 1/chains of the streams]"""
 import csv
 import json
 import os
@@ -19,8 +19,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT, PROF = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 TAG = sys.argv[1]
 F = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+G = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 # kernel -> (translation unit, stage, launches per step)
-KERNELS = {"cand_lane_kernel": ("extract", "extract", F), "birth_lane_kernel": ("extract", "extract", F), "finalize_kernel": ("extract", "extract", F),
+KERNELS = {"cand_lane_kernel": ("extract", "extract", F * G), "birth_lane_kernel": ("extract", "extract", F * G), "finalize_kernel": ("extract", "extract", F * G),
            "track_poses2_kernel": ("pose", "pose", F // 4), "tp_prep_kernel": ("pose", "pose", F // 4), "grid_kernel": ("grid", "grid", 1)}
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
 
