@@ -232,6 +232,16 @@ int movfe_features_in_area(movfe_ctx *ctx, int n_problems, const float *pts_xy, 
                            const int32_t *cell_start, const int32_t *cell_items, int n_queries,
                            const movfe_area_query *queries, int capacity, int32_t *out, int32_t *counts);
 /* Optimizer::PoseOptimization for n_problems correspondence sets (pts xyz float, obs uv float, packed). */
+/* -- pyramidal Lucas-Kanade: replaces cv::calcOpticalFlowPyrLK as the reference calls it for its carry-over branches
+ *    (src/MOVExtractor.cc:91-92 I-frame carry-over, :196-197 lost relocalisation, :347-348 coverage tracks: win_size 31, max_level 3,
+ *    max_count 20, epsilon 0.01, OPTFLOW_LK_GET_MIN_EIGENVALS, min_eig_threshold 1e-4; src/Frame.cc:305: win_size 21).
+ *    n_problems image pairs of the context's width x height (host memory, rows `stride` bytes apart, 0 = width; pair i at
+ *    prev + i*stride*height); the points of pair i are pts_xy[2*off[i] .. 2*off[i+1]). Per point: next position, status (1 =
+ *    tracked) and err = the minimum eigenvalue of the window's gradient matrix at level 0. OpenCV's arithmetic (fixed-point
+ *    bilinear weights, int16 Scharr derivatives, reflected image border, zero derivative border); positions agree with
+ *    OpenCV to ~1e-3 px. The results are what movfe_set_lk_results / movfe_extract_frame take. */
+int movfe_lk(movfe_ctx *ctx, int n_problems, const uint8_t *prev, const uint8_t *next, int stride, const float *pts_xy, const int32_t *off,
+             int win_size, int max_level, int max_count, double epsilon, double min_eig_threshold, float *out_xy, uint8_t *status, float *err);
 int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_camera *cam, const movfe_pose_params *pp,
                         const float *pts, const float *obs, const int32_t *off, movfe_pose *poses /* in/out */,
                         uint8_t *outlier, int32_t *n_inliers, int32_t *stats /* 4 per problem, may be NULL */);
