@@ -19,21 +19,42 @@
 namespace movfe_shim {
 
 lk_fn lk_override = nullptr;
+#ifdef MOVFE_IN_TREE
+bool use_gpu_lk = false;   // in the tree OpenCV is there: its own calcOpticalFlowPyrLK is the default (bit-for-bit the reference's results)
+#else
+bool use_gpu_lk = true;
+#endif
 
 // cv::calcOpticalFlowPyrLK(prev, next, pts, out, status, err, Size(31,31), 3, TermCriteria(COUNT+EPS, 20, 0.01),
 //                          OPTFLOW_LK_GET_MIN_EIGENVALS, 1e-4)  — MOVExtractor.cc:69,91-92
-static void run_lk(const cv::Mat &prev_img, const cv::Mat &next_img, const std::vector<cv::Point2f> &pts, std::vector<cv::Point2f> &out,
+// Three providers: a test hook; movfe_lk (the same tracker on the GPU: OpenCV's arithmetic restated, status flags equal and
+// positions within 5e-3 px of OpenCV's in the parity tests); OpenCV itself when built in the MoV-SLAM tree.
+static void run_lk(movfe_ctx *ctx, const cv::Mat &prev_img, const cv::Mat &next_img, const std::vector<cv::Point2f> &pts, std::vector<cv::Point2f> &out,
                    std::vector<unsigned char> &status) {
     if (lk_override) {
         lk_override(prev_img, next_img, pts, out, status);
         return;
+    }
+    if (use_gpu_lk && ctx && !pts.empty() && prev_img.data && next_img.data && prev_img.step == next_img.step) {
+        std::vector<float> in(2 * pts.size()), res(2 * pts.size()), err(pts.size());
+        for (size_t i = 0; i < pts.size(); i++) {
+            in[2 * i] = pts[i].x;
+            in[2 * i + 1] = pts[i].y;
+        }
+        status.assign(pts.size(), 0);
+        const int32_t off[2] = {0, (int32_t)pts.size()};
+        if (movfe_lk(ctx, 1, prev_img.data, next_img.data, (int)prev_img.step, in.data(), off, 31, 3, 20, 0.01, 1e-4, res.data(), status.data(), err.data()) == MOVFE_OK) {
+            out.resize(pts.size());
+            for (size_t i = 0; i < pts.size(); i++) out[i] = cv::Point2f(res[2 * i], res[2 * i + 1]);
+            return;
+        }
     }
 #ifdef MOVFE_IN_TREE
     std::vector<float> err;
     cv::TermCriteria criteria = cv::TermCriteria((cv::TermCriteria::COUNT) + (cv::TermCriteria::EPS), 20, 0.01);
     cv::calcOpticalFlowPyrLK(prev_img, next_img, pts, out, status, err, cv::Size(31, 31), 3, criteria, cv::OPTFLOW_LK_GET_MIN_EIGENVALS, 1e-4);
 #else
-    out.assign(pts.size(), cv::Point2f());  // no OpenCV outside the tree and no hook installed: every point is lost
+    out.assign(pts.size(), cv::Point2f());  // no OpenCV outside the tree, no hook, no usable images: every point is lost
     status.assign(pts.size(), 0);
 #endif
 }
@@ -78,7 +99,7 @@ int MOVExtractor::operator()(const shared_ptr<MotionVectorImage> &_smv, std::vec
         // I frame (:81-120): every previous track, in TABLE order (no sort on this branch), goes to LK
         if (!_prev_frame->mvVF.empty()) {
             for (const VideoFeature &pvf : _prev_frame->mvVF) pts.push_back(pvf.pt);
-            movfe_shim::run_lk(_prev_frame->imgLeft, imGrey, pts, pts_out, status);
+            movfe_shim::run_lk(ctx, _prev_frame->imgLeft, imGrey, pts, pts_out, status);
             hand_over();
         }
     } else if (_prev_frame) {
@@ -95,7 +116,7 @@ int MOVExtractor::operator()(const shared_ptr<MotionVectorImage> &_smv, std::vec
                 trackIds.push_back(pMP->mTrackId);
             }
             if (!kpts.empty()) {
-                movfe_shim::run_lk(lpLastKeyFrame->mImage, imGrey, kpts, kout, kstatus);
+                movfe_shim::run_lk(ctx, lpLastKeyFrame->mImage, imGrey, kpts, kout, kstatus);
                 const double thresholdDist = mRelocalizationDistance * sqrt(double(H * H + W * W));  // :201
                 for (size_t i = 0; i < kout.size(); i++) {
                     const cv::Point2f &ptL = kpts[i], &ptR = kout[i];
@@ -116,7 +137,7 @@ int MOVExtractor::operator()(const shared_ptr<MotionVectorImage> &_smv, std::vec
         for (const VideoFeature &pvf : _prev_frame->mvVF)
             if (pvf.coverage) pts.push_back(pvf.pt);
         if (!pts.empty()) {
-            movfe_shim::run_lk(_prev_frame->imgLeft, imGrey, pts, pts_out, status);
+            movfe_shim::run_lk(ctx, _prev_frame->imgLeft, imGrey, pts, pts_out, status);
             hand_over();
         }
     }

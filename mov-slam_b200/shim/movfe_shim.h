@@ -26,6 +26,7 @@ void fail(movfe_ctx *ctx, const char *what);  // prints movfe_last_error to stde
 typedef void (*lk_fn)(const cv::Mat &prev_img, const cv::Mat &next_img, const std::vector<cv::Point2f> &pts,
                       std::vector<cv::Point2f> &out, std::vector<unsigned char> &status);
 extern lk_fn lk_override;
+extern bool use_gpu_lk;   // movfe_lk instead of cv::calcOpticalFlowPyrLK at the reference's three call sites (default outside the MoV-SLAM tree)
 
 movfe_track pack(const MOV_SLAM::VideoFeature &vf);
 MOV_SLAM::VideoFeature unpack(const movfe_track &t, int index);

@@ -61,7 +61,8 @@ int main(int argc, char **argv) {
     const std::vector<int32_t> meta = slurp<int32_t>(dir + "/meta.bin");  // W H NF max_ref threshold n_map n_kf [cov_thr permille]
     const int W = meta[0], H = meta[1], NF = meta[2], K = meta[3], thr = meta[4], n_map = meta[5], n_kf = meta[6];
     const double cov_thr = meta.size() > 7 ? meta[7] / 1000.0 : 0.20;
-    movfe_shim::lk_override = pseudo_lk;
+    // SHIM_LK=gpu: no hook - the extractor shim's own provider, movfe_lk (the GPU tracker), runs at the reference's call sites
+    movfe_shim::lk_override = (getenv("SHIM_LK") && std::string(getenv("SHIM_LK")) == "gpu") ? nullptr : pseudo_lk;
     const std::vector<movfe_mv_record> recs = slurp<movfe_mv_record>(dir + "/recs.bin");
     const std::vector<int64_t> off = slurp<int64_t>(dir + "/off.bin");
     const std::vector<uint8_t> flags = slurp<uint8_t>(dir + "/flags.bin");

@@ -172,6 +172,51 @@ def test_shims_against_oracle(orc, tmp_path, cov_thr, iframe_at):
 
 
 @pytest.mark.gpu
+def test_extractor_shim_with_gpu_lk(orc, tmp_path):
+    """The MOVExtractor shim with its own LK provider (movfe_lk, the GPU tracker) at the reference's call sites: an intra picture in
+    mid-stream carries every track by Lucas-Kanade (src/MOVExtractor.cc:81-120). Against the oracle chain fed with the numpy LK
+    oracle's results: the same tracks survive, in the same order, with the same ids, ages, blocks and descriptors; carried
+    positions within 5e-3 px (the tolerance of the GPU tracker against OpenCV)."""
+    from oracle import lk as olk
+    _build()
+    W, H, NF, K, thr, iframe_at = 320, 240, 6, 2, 25, 4
+    sp = synth.Spec(W, H, n_frames=NF, refs=K + 1, seed=0x5EED0021, fx=160.0, fy=160.0)
+    recs, off, flags = synth.make_records(sp)
+    flags = flags.copy()
+    flags[iframe_at] &= ~np.uint8(T.FRAME_P)
+    grey = synth.make_grey(sp)
+    clip = orc.Clip(W, H, recs, off, flags, 10)
+    prev, cid, tracks = np.zeros(0, T.TRACK), 0, []
+    for f in range(iframe_at + 1):
+        lk = None
+        if f == iframe_at:
+            out, st, _ = olk.track(grey[f - 1], grey[f], np.stack([prev["pt_x"], prev["pt_y"]], 1))
+            lk = (st, out)
+        t, _, cid, _ = orc.extract_frame(W, H, flags[f], grey[f], clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f), prev, cid,
+                                         threshold=thr, coverage_threshold=0.20, max_tracks=8192,
+                                         lk_status=None if lk is None else lk[0], lk_pts=None if lk is None else lk[1])
+        tracks.append(t)
+        prev = t
+    mp = synth.map_from_tracks(sp, tracks[0], synth.pose_at(sp, 0))
+    pose0, cam = synth.pose_struct(synth.pose_at(sp, 0)), sp.camera()
+    d = str(tmp_path)
+    np.array([W, H, NF, 10, thr, len(mp), len(mp) // 2, 200], np.int32).tofile(d + "/meta.bin")
+    np.ascontiguousarray(recs, T.MV_RECORD).tofile(d + "/recs.bin")
+    off.tofile(d + "/off.bin"); flags.tofile(d + "/flags.bin"); grey.tofile(d + "/grey.bin"); mp.tofile(d + "/map.bin")
+    np.concatenate([pose0["R"], pose0["t"]]).astype(np.float64).tofile(d + "/pose0.bin")
+    np.array([cam["fx"], cam["fy"], cam["cx"], cam["cy"]], np.float32).tofile(d + "/cam.bin")
+    r = subprocess.run([os.path.join(SHIM, "test_shim"), d], capture_output=True, text=True, env=dict(os.environ, SHIM_LK="gpu"))
+    assert r.returncode == 0, r.stdout + r.stderr
+    for f in range(iframe_at):       # before the intra picture nothing is carried: bit-exact
+        assert np.fromfile(d + "/out_tracks_%d.bin" % f, T.TRACK).tobytes() == tracks[f].tobytes(), f
+    got, want = np.fromfile(d + "/out_tracks_%d.bin" % iframe_at, T.TRACK), tracks[iframe_at]
+    assert len(got) == len(want) and len(want) > 50
+    for name in ("track_id", "age", "q_indx", "flags", "mb", "desc"):
+        assert got[name].tobytes() == want[name].tobytes(), name
+    assert np.max(np.abs(got["pt_x"] - want["pt_x"])) <= 5e-3 and np.max(np.abs(got["pt_y"] - want["pt_y"])) <= 5e-3
+
+
+@pytest.mark.gpu
 def test_batched_cpp_driver(orc, tmp_path):
     """The batched front-end driven from C++ through the C ABI alone (shim/batched_frontend.cc, the loop of INTEGRATION.md
     section 3, nothing but movfe_download_poses waits for the GPU): last window's track tables bit-exact, poses within 1e-5."""
