@@ -242,6 +242,11 @@ int movfe_features_in_area(movfe_ctx *ctx, int n_problems, const float *pts_xy, 
  *    OpenCV to ~1e-3 px. The results are what movfe_set_lk_results / movfe_extract_frame take. */
 int movfe_lk(movfe_ctx *ctx, int n_problems, const uint8_t *prev, const uint8_t *next, int stride, const float *pts_xy, const int32_t *off,
              int win_size, int max_level, int max_count, double epsilon, double min_eig_threshold, float *out_xy, uint8_t *status, float *err);
+/* The same tracker for the batched path, device-resident: Lucas-Kanade results for frame `frame` of EVERY stream, from the grey planes
+ * of frame - 1 and frame in the ring and the track table of frame - 1 (an intra picture: every track in table order,
+ * src/MOVExtractor.cc:81-120; a P picture: the coverage tracks in sorted order, :337-377), installed as movfe_set_lk_results
+ * would install them. Call it between movfe_extract(.., frame - 1) and movfe_extract(frame, ..). Nothing crosses PCIe. */
+int movfe_lk_carry(movfe_ctx *ctx, int64_t frame);
 int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_camera *cam, const movfe_pose_params *pp,
                         const float *pts, const float *obs, const int32_t *off, movfe_pose *poses /* in/out */,
                         uint8_t *outlier, int32_t *n_inliers, int32_t *stats /* 4 per problem, may be NULL */);

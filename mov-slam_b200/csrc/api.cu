@@ -37,6 +37,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
                     ctx->d_poses, ctx->d_ninl, ctx->d_match, ctx->d_outlier, ctx->d_pose_scratch, ctx->d_op, ctx->d_pairs, ctx->d_npairs};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    if (ctx->d_lk_scratch) cudaFree(ctx->d_lk_scratch);
     if (ctx->d_store) cudaFree(ctx->d_store);
     if (ctx->d_store_stamp) cudaFree(ctx->d_store_stamp);
     if (ctx->d_lp_idx) cudaFree(ctx->d_lp_idx);

@@ -196,6 +196,8 @@ struct movfe_ctx {
     int64_t *d_lp_off = nullptr;           // [S + 1] offsets, then [S] keyframe entry counts as int32
     size_t   lp_idx_cap = 0;
     void    *h_lp_meta = nullptr;          // pinned copy of offsets + counts
+    void    *d_lk_scratch = nullptr;   // pyramids + derivatives of two frames of every stream (movfe_lk_carry), allocated on first use
+    size_t   lk_scratch_bytes = 0;
     void    *d_pose_scratch = nullptr;
     size_t   pose_scratch_bytes = 0;
     // split pose chain (join kernels + small solver kernels, pose.cu): correspondences of one frame per stream
@@ -327,6 +329,13 @@ int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n
 int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const void *d_recs, bool packed, const int64_t *d_rec_off,
                         int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey);
 // extract.cu
+struct movfe_lk_handover {
+    int32_t *n;         // [S] results installed for the next propagated frame (-1: none)
+    uint8_t *status;    // [S][max_tracks]
+    float   *pts;       // [S][max_tracks][2]
+    uint16_t *order;    // [S][max_tracks] sorted rank -> index in the newest table
+};
+void movfe_lk_buffers(const movfe_ctx *ctx, movfe_lk_handover *out);
 int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames);
 size_t movfe_extract_scratch_bytes(const movfe_ctx *ctx);
 int movfe_extract_init(movfe_ctx *ctx);

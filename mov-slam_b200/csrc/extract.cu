@@ -2055,6 +2055,16 @@ size_t movfe_extract_scratch_bytes(const movfe_ctx *ctx) {
     return total;
 }
 
+// The LK hand-over buffers and the sorted order of the newest table, for movfe_lk_carry (lk.cu): the device-side producer of what
+// movfe_set_lk_results installs from the host.
+void movfe_lk_buffers(const movfe_ctx *ctx, movfe_lk_handover *out) {
+    ExtScratch e = carve(ctx, nullptr);
+    out->n = e.lk.n;
+    out->status = e.lk.status;
+    out->pts = reinterpret_cast<float *>(e.lk.pts);
+    out->order = e.order;
+}
+
 static int tslot_of(const movfe_ctx *ctx, int64_t frame) {
     const int T = ctx->TSLOTS;
     return (int)(((frame % T) + T) % T);

@@ -86,25 +86,30 @@ __device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01,
 constexpr int LK_WARPS = 4;
 
 // cv::detail::LKTrackerInvoker::operator() for one point per warp. prev_pyr / next_pyr: [problem][pyramid]; dxy: [problem][pyramid][2].
+// Points: packed with offsets (off != nullptr: movfe_lk), or `slots` per problem of which the first counts[problem] are used
+// (blockIdx.y = problem: movfe_lk_carry, where a problem is a stream and the arrays are the LK hand-over buffers).
 template <int WIN>
 __global__ void __launch_bounds__(LK_WARPS * 32)
 lk_track_kernel(LkLevels lv, const uint8_t *__restrict__ prev_pyr, const uint8_t *__restrict__ next_pyr, const int16_t *__restrict__ dxy,
-                const float2 *__restrict__ pts, const int32_t *__restrict__ off, int n_problems, int max_count, double eps2, float min_eig_thr,
-                float2 *__restrict__ out, uint8_t *__restrict__ status, float *__restrict__ err) {
+                const float2 *__restrict__ pts, const int32_t *__restrict__ off, int n_problems, const int32_t *__restrict__ counts, int slots,
+                int max_count, double eps2, float min_eig_thr, float2 *__restrict__ out, uint8_t *__restrict__ status, float *__restrict__ err) {
     constexpr int NPX = WIN * WIN;
     __shared__ int16_t sI[LK_WARPS][NPX], sIx[LK_WARPS][NPX], sIy[LK_WARPS][NPX];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pi = blockIdx.x * LK_WARPS + warp;
-    const int n_total = off[n_problems];
-    if (pi >= n_total) return;
-    int prob = 0;  // problem of this point: last problem with off[prob] <= pi
-    {
+    int pi = blockIdx.x * LK_WARPS + warp;
+    int prob = 0;
+    if (off) {  // problem of this point: last problem with off[prob] <= pi
+        if (pi >= off[n_problems]) return;
         int lo = 0, hi = n_problems;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
             if (off[mid] <= pi) lo = mid; else hi = mid;
         }
         prob = lo;
+    } else {
+        prob = blockIdx.y;
+        if (pi >= counts[prob]) return;
+        pi += prob * slots;
     }
     const uint8_t *P = prev_pyr + (size_t)prob * lv.px, *N = next_pyr + (size_t)prob * lv.px;
     const int16_t *D = dxy + (size_t)prob * lv.px * 2;
@@ -220,8 +225,70 @@ lk_track_kernel(LkLevels lv, const uint8_t *__restrict__ prev_pyr, const uint8_t
     if (lane == 0) {
         out[pi] = make_float2(ox, oy);
         status[pi] = ok ? 1 : 0;
-        err[pi] = e0;
+        if (err) err[pi] = e0;
     }
+}
+
+// ---- device-resident carry-over (movfe_lk_carry) -----------------------------------------------------------------------------
+// The points the reference hands to calcOpticalFlowPyrLK before frame f: at an intra picture every track of the previous table in
+// TABLE order (src/MOVExtractor.cc:85-90), at a P picture the coverage tracks in SORTED order (:337-346; the i-th one owns result i).
+constexpr int LKP_THREADS = 1024;
+__global__ void __launch_bounds__(LKP_THREADS)
+lk_points_kernel(const movfe_track *__restrict__ tracks, const int32_t *__restrict__ ntracks, const uint16_t *__restrict__ order,
+                 const uint8_t *__restrict__ fflags, int TSLOTS, int tslot_prev, int RING, int gslot, int maxT, float2 *__restrict__ pts,
+                 int32_t *__restrict__ n_out) {
+    __shared__ int wsum[LKP_THREADS / 32];
+    __shared__ int s_total;
+    const int s = blockIdx.x;
+    const movfe_track *prev = tracks + ((size_t)s * TSLOTS + tslot_prev) * maxT;
+    const int n_prev = ntracks[s * TSLOTS + tslot_prev];
+    const uint16_t *ord = order + (size_t)s * maxT;
+    float2 *out = pts + (size_t)s * maxT;
+    const bool is_p = fflags[s * RING + gslot] & MOVFE_FRAME_P;
+    if (!is_p) {
+        for (int i = threadIdx.x; i < n_prev; i += LKP_THREADS) out[i] = *reinterpret_cast<const float2 *>(&prev[i].pt_x);
+        if (threadIdx.x == 0) n_out[s] = n_prev;
+        return;
+    }
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int base = 0; base < n_prev; base += LKP_THREADS) {
+        const int r = base + threadIdx.x;
+        int t = 0;
+        bool cov = false;
+        if (r < n_prev) {
+            t = ord[r];
+            cov = (prev[t].flags & MOVFE_TRACK_COVERAGE) != 0;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, cov);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int before = s_total, tot = 0;
+        for (int w = 0; w < LKP_THREADS / 32; w++) {
+            const int c = wsum[w];
+            before += w < warp ? c : 0;
+            tot += c;
+        }
+        if (cov) out[before + __popc(b & ((1u << lane) - 1u))] = *reinterpret_cast<const float2 *>(&prev[t].pt_x);
+        __syncthreads();
+        if (threadIdx.x == 0) s_total += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) n_out[s] = s_total;
+}
+
+// level 0 of the pyramids of two ring frames of every stream: rows of the pitched grey ring -> dense rows
+__global__ void lk_level0_kernel(const uint8_t *__restrict__ ring, int RING, int slot_prev, int slot_next, int W, int H, int pitch, int S,
+                                 uint8_t *__restrict__ pyr, size_t img_px) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, z = blockIdx.z;  // z: [prev of all streams][next of all streams]
+    if (x >= W) return;
+    const int s = z % S, slot = z < S ? slot_prev : slot_next;
+    const uint8_t *src = ring + (((size_t)s * RING + slot) * H + y) * pitch + x;
+    uint8_t *dst = pyr + (size_t)z * img_px + (size_t)y * W + x;
+    if (x + 4 <= W && (W & 3) == 0) *reinterpret_cast<uint32_t *>(dst) = *reinterpret_cast<const uint32_t *>(src);
+    else
+        for (int k = 0; k < 4 && x + k < W; k++) dst[k] = src[k];
 }
 
 struct LkCarve {
@@ -296,10 +363,10 @@ extern "C" int movfe_lk(movfe_ctx *ctx, int n_problems, const uint8_t *prev, con
         const dim3 grid((n + LK_WARPS - 1) / LK_WARPS);
         const double eps2 = epsilon * epsilon;
         if (win_size == 31)
-            lk_track_kernel<31><<<grid, LK_WARPS * 32, 0, st>>>(lv, d_pyr, d_pyr + (size_t)n_problems * px, d_dxy, d_pts, d_off, n_problems, max_count, eps2,
+            lk_track_kernel<31><<<grid, LK_WARPS * 32, 0, st>>>(lv, d_pyr, d_pyr + (size_t)n_problems * px, d_dxy, d_pts, d_off, n_problems, nullptr, 0, max_count, eps2,
                                                                  (float)min_eig_threshold, d_out, d_status, d_err);
         else
-            lk_track_kernel<21><<<grid, LK_WARPS * 32, 0, st>>>(lv, d_pyr, d_pyr + (size_t)n_problems * px, d_dxy, d_pts, d_off, n_problems, max_count, eps2,
+            lk_track_kernel<21><<<grid, LK_WARPS * 32, 0, st>>>(lv, d_pyr, d_pyr + (size_t)n_problems * px, d_dxy, d_pts, d_off, n_problems, nullptr, 0, max_count, eps2,
                                                                  (float)min_eig_threshold, d_out, d_status, d_err);
     }
     MOVFE_CUDA(ctx, cudaGetLastError());
@@ -309,5 +376,70 @@ extern "C" int movfe_lk(movfe_ctx *ctx, int n_problems, const uint8_t *prev, con
         MOVFE_CUDA(ctx, cudaMemcpyAsync(err, d_err, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+    return MOVFE_OK;
+}
+
+// Device-resident carry-over for the batched path: Lucas-Kanade results for frame `frame` of every stream, from the grey planes of
+// frame - 1 and frame in the ring and the track table of frame - 1, installed as movfe_set_lk_results would install them. Call it
+// between movfe_extract(.., frame - 1) and movfe_extract(frame, ..) - at an intra picture in mid-stream (every track is carried,
+// src/MOVExtractor.cc:81-120) or when coverage tracks are to be followed (:337-377). Nothing crosses PCIe.
+extern "C" int movfe_lk_carry(movfe_ctx *ctx, int64_t frame) {
+    if (!ctx) return MOVFE_E_INVALID;
+    const movfe_config &c = ctx->cfg;
+    if (!c.has_grey) MOVFE_FAIL(ctx, MOVFE_E_STATE, "lk_carry: the context has no grey planes");
+    const int64_t next = ctx->ext_first < 0 ? 0 : ctx->ext_first + ctx->ext_n;
+    if (frame != next || frame < 1) MOVFE_FAIL(ctx, MOVFE_E_STATE, "lk_carry: frame %lld is not the next frame to be propagated (%lld)", (long long)frame, (long long)next);
+    if (frame >= ctx->pushed || ctx->pushed - (frame - 1) > ctx->RING)
+        MOVFE_FAIL(ctx, MOVFE_E_STATE, "lk_carry: frames %lld and %lld are not both in the ring (pushed=%lld, ring=%d)", (long long)(frame - 1), (long long)frame,
+                   (long long)ctx->pushed, ctx->RING);
+    MOVFE_CUDA(ctx, cudaSetDevice(c.device));
+    const int W = c.width, H = c.height, S = c.n_streams, win = 31, max_level = 3;
+    LkLevels lv = {};
+    lv.w[0] = W;
+    lv.h[0] = H;
+    lv.n_levels = 1;
+    size_t px = (size_t)W * H;
+    for (int l = 1; l <= max_level; l++) {
+        const int w = (lv.w[l - 1] + 1) / 2, h = (lv.h[l - 1] + 1) / 2;
+        if (w <= win || h <= win) break;
+        lv.w[l] = w;
+        lv.h[l] = h;
+        lv.off[l] = px;
+        px += (size_t)w * h;
+        lv.n_levels = l + 1;
+    }
+    lv.px = px;
+    const size_t need = 2 * (size_t)S * px + (size_t)S * px * 4 + (size_t)S * c.max_tracks * sizeof(float2) + 4 * 256;
+    cudaStream_t st = ctx->stream;
+    if (ctx->lk_scratch_bytes < need) {
+        MOVFE_CUDA(ctx, cudaStreamSynchronize(st));
+        if (ctx->d_lk_scratch) cudaFree(ctx->d_lk_scratch);
+        ctx->d_lk_scratch = nullptr;
+        ctx->lk_scratch_bytes = 0;
+        MOVFE_CUDA(ctx, cudaMalloc(&ctx->d_lk_scratch, need));
+        ctx->lk_scratch_bytes = need;
+    }
+    LkCarve cv{(uint8_t *)ctx->d_lk_scratch};
+    uint8_t *d_pyr = cv.take<uint8_t>(2 * (size_t)S * px);
+    int16_t *d_dxy = cv.take<int16_t>((size_t)S * px * 2);
+    float2 *d_in = cv.take<float2>((size_t)S * c.max_tracks);
+    movfe_lk_handover hb;
+    movfe_lk_buffers(ctx, &hb);
+    // the raster stream wrote the ring (ingest): the newest push must have landed before the planes are read
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->raster_stream));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_tables, 0));
+    const int T = ctx->TSLOTS, ts_prev = (int)((((frame - 1) % T) + T) % T);
+    const int slot_prev = (int)((frame - 1) % ctx->RING), slot_next = (int)(frame % ctx->RING);
+    lk_points_kernel<<<S, LKP_THREADS, 0, st>>>(ctx->d_tracks, ctx->d_ntracks, hb.order, ctx->d_fflags, T, ts_prev, ctx->RING, slot_next, c.max_tracks, d_in, hb.n);
+    lk_level0_kernel<<<dim3((W / 4 + 127) / 128 + 1, H, 2 * S), 128, 0, st>>>(ctx->d_grey, ctx->RING, slot_prev, slot_next, W, H, ctx->grey_pitch, S, d_pyr, px);
+    for (int l = 1; l < lv.n_levels; l++)
+        pyr_down_kernel<<<dim3((lv.w[l] + 127) / 128, lv.h[l], 2 * S), 128, 0, st>>>(d_pyr, px, lv.off[l - 1], lv.off[l], lv.w[l - 1], lv.h[l - 1], lv.w[l], lv.h[l]);
+    for (int l = 0; l < lv.n_levels; l++)
+        scharr_kernel<<<dim3((lv.w[l] + 127) / 128, lv.h[l], S), 128, 0, st>>>(d_pyr, px, lv.off[l], lv.w[l], lv.h[l], d_dxy, px);
+    lk_track_kernel<31><<<dim3((c.max_tracks + LK_WARPS - 1) / LK_WARPS, S), LK_WARPS * 32, 0, st>>>(
+        lv, d_pyr, d_pyr + (size_t)S * px, d_dxy, d_in, nullptr, S, hb.n, c.max_tracks, 20, 0.01 * 0.01, 1e-4f, reinterpret_cast<float2 *>(hb.pts), hb.status,
+        nullptr);
+    MOVFE_CUDA(ctx, cudaGetLastError());
+    ctx->lk_pending = true;
     return MOVFE_OK;
 }

@@ -69,6 +69,7 @@ def load():
     L.movfe_set_camera.argtypes = [vp, vp, vp, C.c_float]
     L.movfe_set_map_points.argtypes = [vp, i32, vp, i32, i32]
     L.movfe_set_pose.argtypes = [vp, i32, vp]
+    L.movfe_lk_carry.argtypes = [vp, i64]
     L.movfe_lk.argtypes = [vp, i32, vp, vp, i32, vp, vp, i32, i32, i32, C.c_double, C.c_double, vp, vp, vp]
     L.movfe_reserve_map_store.argtypes = [vp, i32]
     L.movfe_set_map_store.argtypes = [vp, i32, i32, vp, i32]
@@ -98,7 +99,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_reserve_map_store", "movfe_set_map_store", "movfe_update_local_points", "movfe_download_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
            "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
-           "movfe_pose_optimize", "movfe_lk", "movfe_profile_enable", "movfe_profile_read", "movfe_workload_stats"]
+           "movfe_pose_optimize", "movfe_lk", "movfe_lk_carry", "movfe_profile_enable", "movfe_profile_read", "movfe_workload_stats"]
 
 
 def pack_records(recs, out=None):
@@ -342,6 +343,10 @@ class Context:
         n = self.L.movfe_download_map_points(self.h, stream, _p(out), capacity, C.byref(nk))
         self._ck(n if n < 0 else 0)
         return out[:n], nk.value
+
+    def lk_carry(self, frame):
+        """device-resident LK results for `frame` of every stream (call between extract(.., frame - 1) and extract(frame, ..))"""
+        self._ck(self.L.movfe_lk_carry(self.h, frame))
 
     def lk(self, prev, nxt, pts, off, win=31, max_level=3, max_count=20, eps=0.01, min_eig=1e-4):
         """cv::calcOpticalFlowPyrLK for len(off) - 1 image pairs of the context's size. -> (next points, status, err)."""

@@ -58,3 +58,66 @@ def test_batched_pairs_against_oracle():
             assert np.max(np.linalg.norm(out[sl][ok] - want[ok], axis=1)) <= POS_TOL, p
         assert np.max(np.abs(err[sl] - werr)) <= 1e-6, p
     assert st.sum() > 40
+
+
+def test_device_resident_carry_over(orc):
+    """movfe_lk_carry: the batched path follows coverage tracks (src/MOVExtractor.cc:337-377) and carries every track over an intra
+    picture in mid-stream (:81-120) without the host - LK on the ring's grey planes, results installed where movfe_set_lk_results
+    would put them. Against the oracle chain fed with the numpy LK oracle's results: same tracks, ids, ages, order, blocks and
+    descriptors in every frame up to and including the intra picture; positions of LK-carried tracks within 5e-3 px."""
+    from movfe import synth, types as T
+    from gpu_util import pack_streams
+    W, H, NF, K, thr, cov_thr, iframe_at = 320, 240, 5, 2, 25, 0.95, 4
+    specs = [synth.Spec(W, H, n_frames=NF + K + 1, refs=K + 1, seed=0x5EED0B30 + s, fx=160.0, fy=160.0, phase=0.2 * s) for s in range(2)]
+    streams, greys, want = [], [], []
+    for sp in specs:
+        recs, off, flags = synth.make_records(sp)
+        flags = flags.copy()
+        flags[iframe_at] &= ~np.uint8(T.FRAME_P)
+        grey = synth.make_grey(sp)
+        clip = orc.Clip(W, H, recs, off, flags, K)
+        prev, cid, tabs = np.zeros(0, T.TRACK), 0, []
+        for f in range(NF):
+            lkr = None
+            if f > 0 and len(prev):
+                if not (flags[f] & T.FRAME_P):
+                    pts = np.stack([prev["pt_x"], prev["pt_y"]], 1)
+                else:       # coverage tracks in the sorted order of the previous table (age desc, descriptor popcount desc, stable)
+                    pc = np.array([sum(bin(int(w)).count("1") for w in t["desc"]) for t in prev], np.int64)
+                    order = sorted(range(len(prev)), key=lambda i: (-int(prev["age"][i]), -int(pc[i])))
+                    cov = [i for i in order if prev["flags"][i] & T.TRACK_COVERAGE]
+                    pts = np.stack([prev["pt_x"][cov], prev["pt_y"][cov]], 1) if cov else np.zeros((0, 2), np.float32)
+                if len(pts):
+                    out, st, _ = olk.track(grey[f - 1], grey[f], pts)
+                    lkr = (st, out)
+                else:
+                    lkr = (np.zeros(0, np.uint8), np.zeros((0, 2), np.float32))
+            t, _, cid, _ = orc.extract_frame(W, H, flags[f], grey[f], clip.grid(f), clip.hops(f), clip.kps(f), clip.coverage(f), prev, cid, threshold=thr,
+                                             coverage_threshold=cov_thr, max_tracks=4096, lk_status=None if lkr is None else lkr[0],
+                                             lk_pts=None if lkr is None else lkr[1])
+            tabs.append(t)
+            prev = t
+        streams.append((recs, off, flags))
+        greys.append(grey)
+        want.append(tabs)
+    n_cov = sum(int(((t["flags"] & T.TRACK_COVERAGE) != 0).sum()) for t in want[0][:iframe_at])
+    assert n_cov > 0 and len(want[0][iframe_at]) > 50      # coverage tracks were followed, and the intra picture carried tracks
+    ctx = lib.Context(2, W, H, max_records_per_frame=4800, max_ref=K, window_frames=NF, max_tracks=4096, has_grey=True, express_threshold=thr,
+                      coverage_threshold=cov_thr)
+    n_all = NF + K + 1
+    r, o, fl = pack_streams(streams, n_all, 0, n_all)
+    ctx.push_frames(n_all, r, o, fl, np.stack([g[:n_all] for g in greys]))
+    ctx.raster(0, NF)
+    for f in range(NF):
+        if f > 0:
+            ctx.lk_carry(f)
+        ctx.extract(f, 1)
+    for s in range(2):
+        for f in range(NF):
+            got, w = ctx.tracks(s, f), want[s][f]
+            assert len(got) == len(w), (s, f, len(got), len(w))
+            for name in ("track_id", "age", "q_indx", "flags", "mb", "desc"):
+                assert got[name].tobytes() == w[name].tobytes(), (s, f, name)
+            assert np.max(np.abs(got["pt_x"] - w["pt_x"]), initial=0) <= POS_TOL and np.max(np.abs(got["pt_y"] - w["pt_y"]), initial=0) <= POS_TOL, (s, f)
+    assert ctx.dropped_lk_tracks() == 0
+    ctx.close()
