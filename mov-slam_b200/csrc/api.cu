@@ -173,6 +173,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     if (const char *e = getenv("MOVFE_CAND_LANE")) ctx->cand_lane = atoi(e) != 0;
     if (const char *e = getenv("MOVFE_GREY_DIRECT")) ctx->grey_direct = atoi(e) != 0;
     if (const char *e = getenv("MOVFE_BIRTH_CHUNKS")) ctx->birth_chunks = std::max(1, atoi(e));
+    if (const char *e = getenv("MOVFE_CAND_PAD_KB")) ctx->cand_pad_bytes = std::max(0, atoi(e)) * 1024;
+    if (const char *e = getenv("MOVFE_CAND_BPS")) ctx->cand_bps = std::max(0, atoi(e));
     ctx->ev_frame.resize((size_t)ctx->n_groups * c.window_frames, nullptr);
     for (auto &e : ctx->ev_frame) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &pl : ctx->pose_launches) {
@@ -637,9 +639,15 @@ extern "C" int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches,
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
+    const bool timeline = getenv("MOVFE_PROF_TIMELINE") != nullptr && !ctx->prof_spans.empty();  // development: every span against the first one's start
     for (auto &sp : ctx->prof_spans) {
         float t = 0.f;
         if (cudaEventElapsedTime(&t, sp.a, sp.b) == cudaSuccess) ctx->prof_ms[sp.stage] += t;
+        if (timeline) {
+            float t0 = 0.f;
+            cudaEventElapsedTime(&t0, ctx->prof_spans.front().a, sp.a);
+            fprintf(stderr, "span stage %d start %.3f end %.3f ms\n", sp.stage, t0, t0 + t);
+        }
         ctx->prof_free.push_back(sp.a);
         ctx->prof_free.push_back(sp.b);
     }

@@ -111,6 +111,8 @@ struct movfe_ctx {
     std::vector<int> ev_of_frame;      // [window_frames]
     int ev_batch = 4;                  // frames per event (MOVFE_EVENT_BATCH)
     bool cand_pipe = true;             // MOVFE_CAND_PIPE=0: candidate patches through registers instead of the cp.async window pipeline
+    int  cand_bps = 0;                 // MOVFE_CAND_BPS (development): CTAs per stream of the candidate / birth kernels (0: enough to fill the chip)
+    int  cand_pad_bytes = 0;           // MOVFE_CAND_PAD_KB (development): extra dynamic shared memory per cand_lane_kernel CTA, i.e. fewer of them per SM
     int  birth_chunks = 2;             // MOVFE_BIRTH_CHUNKS: 32-entry kps chunks a warp of birth_lane_kernel scans (more: fuller steps; fewer: more warps in flight)
     bool cand_lane = true;             // MOVFE_CAND_LANE=0: warp-level descriptor evaluation (cand_kernel / birth_kernel) instead of the thread-level kernels
     int pdl_mode = 0;                  // MOVFE_PDL: 0 off (default, see profiles/README.md), 1 every edge of the chain, 2 all but finalize -> next frame's cand

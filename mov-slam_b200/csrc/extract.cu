@@ -2154,12 +2154,12 @@ int movfe_extract_launch(movfe_ctx *ctx, int64_t first_frame, int n_frames) {
         cudaStream_t gs = ctx->ext_stream[g];
         p.s0 = s_lo;
         // grid-stride over tracks / kps: enough CTAs to fill the chip, never one CTA per (mostly empty) capacity slot
-        const int bps = std::max(4, (64 * ctx->sm_count + c.n_streams * CAND_WARPS - 1) / (c.n_streams * CAND_WARPS));
+        const int bps = ctx->cand_bps > 0 ? ctx->cand_bps : std::max(4, (64 * ctx->sm_count + c.n_streams * CAND_WARPS - 1) / (c.n_streams * CAND_WARPS));
         dim3 gc(std::min((c.max_tracks + CAND_THREADS - 1) / CAND_THREADS, bps), ns);  // a warp takes 32 tracks
         // thread-level descriptors (cand_lane_kernel / birth_lane_kernel) need an image and a threshold below 128
         const bool lane_mode = ctx->cand_lane && c.has_grey && c.express_threshold >= 0 && c.express_threshold <= xl::MAX_THR;
 #define MOVFE_CAND(PITCH)                                                                                              \
-    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, lane_mode ? cand_lane_kernel<PITCH> : ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), lane_mode ? LN_SMEM : 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
+    MOVFE_CUDA(ctx, launch_pdl(pdl_cand, lane_mode ? cand_lane_kernel<PITCH> : ctx->cand_pipe ? cand_kernel<PITCH, true> : cand_kernel<PITCH, false>, gc, dim3(CAND_THREADS), lane_mode ? LN_SMEM + (size_t)ctx->cand_pad_bytes : 0, gs, p, ctx->d_tracks, ctx->d_ntracks, e.order, \
                                src, w.d_hops, ctx->d_grey, ctx->d_fflags, e.stage, e.cinfo, e.claim, ctx->d_stats))
         switch (ctx->grey_pitch) {  // the usual pitches get compile-time row offsets
             case 1024: MOVFE_CAND(1024); break;
