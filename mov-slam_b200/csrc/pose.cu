@@ -765,6 +765,9 @@ track_poses_kernel(TrackPoseParams p, const movfe_track *__restrict__ tracks, co
 //    (One solver warp between two barriers instead - a third fewer instructions for the chain - measured 1.5 % slower for the
 //    step: the chain's latency, not its instruction count, is what the step sees.)
 // Sums are formed in the same order as in the first form, so both give the same bits.
+#ifndef MOVFE_SOLVE_LANE0
+#define MOVFE_SOLVE_LANE0 1
+#endif
 struct Solver2Shared {
     double part[2][TP_WARPS][32];  // per-warp partial sums (21 JtJ + 6 Jtr + outlier count), double-buffered by pass parity
     double tot[TP_WARPS][28];      // each warp's own copy of the totals
@@ -843,33 +846,43 @@ __device__ int pose_solve2(const Src &src, int n, const movfe_camera &cam_, cons
             pass++;
             __syncwarp();
             stats[0]++;
-            double dx[6];
-            int flag;
-            if (!solve6_d(sh.tot[warp], &sh.tot[warp][21], dx)) {
-                flag = 2;
-                stats[3]++;
-            } else {
-                double dR[9], dt[3], Rn[9], tn[3];
-                se3_exp_d(dx, dR, dt);
+            int flag = 0;
+#if MOVFE_SOLVE_LANE0
+            if (lane == 0)  // one lane per warp solves (the warp's own copy of the pose): the FP64 pipe sees one lane, not 32
+#endif
+            {
+                double dx[6];
+                if (!solve6_d(sh.tot[warp], &sh.tot[warp][21], dx)) {
+                    flag = 2;
+                } else {
+                    double dR[9], dt[3], Rn[9], tn[3];
+                    se3_exp_d(dx, dR, dt);
 #pragma unroll
-                for (int i = 0; i < 3; i++)
+                    for (int i = 0; i < 3; i++)
 #pragma unroll
-                    for (int j = 0; j < 3; j++) Rn[i * 3 + j] = dR[i * 3] * Rt[j] + dR[i * 3 + 1] * Rt[3 + j] + dR[i * 3 + 2] * Rt[6 + j];
+                        for (int j = 0; j < 3; j++) Rn[i * 3 + j] = dR[i * 3] * Rt[j] + dR[i * 3 + 1] * Rt[3 + j] + dR[i * 3 + 2] * Rt[6 + j];
 #pragma unroll
-                for (int r = 0; r < 3; r++) tn[r] = dR[r * 3] * Rt[9] + dR[r * 3 + 1] * Rt[10] + dR[r * 3 + 2] * Rt[11] + dt[r];
-                __syncwarp();  // every lane has read the old pose
-                if (lane == 0) {
+                    for (int r = 0; r < 3; r++) tn[r] = dR[r * 3] * Rt[9] + dR[r * 3 + 1] * Rt[10] + dR[r * 3 + 2] * Rt[11] + dt[r];
+#if !MOVFE_SOLVE_LANE0
+                    __syncwarp();  // every lane has read the old pose
+#endif
+                    if (lane == 0) {
 #pragma unroll
-                    for (int i = 0; i < 9; i++) Rt[i] = Rn[i];
+                        for (int i = 0; i < 9; i++) Rt[i] = Rn[i];
 #pragma unroll
-                    for (int i = 0; i < 3; i++) Rt[9 + i] = tn[i];
+                        for (int i = 0; i < 3; i++) Rt[9 + i] = tn[i];
+                    }
+                    double m = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; a++) m = fmax(m, fabs(dx[a]));
+                    flag = m < 1e-10 ? 1 : 0;
                 }
-                double m = 0;
-#pragma unroll
-                for (int a = 0; a < 6; a++) m = fmax(m, fabs(dx[a]));
-                flag = m < 1e-10 ? 1 : 0;
             }
             __syncwarp();
+#if MOVFE_SOLVE_LANE0
+            flag = __shfl_sync(0xffffffffu, flag, 0);
+#endif
+            if (flag == 2) stats[3]++;
             if (flag) break;
         }
         if (!stop) pending = true;
