@@ -231,7 +231,24 @@ int movfe_track_feature_grid(movfe_ctx *ctx, int stream, int64_t frame, int32_t 
 int movfe_features_in_area(movfe_ctx *ctx, int n_problems, const float *pts_xy, const int32_t *off,
                            const int32_t *cell_start, const int32_t *cell_items, int n_queries,
                            const movfe_area_query *queries, int capacity, int32_t *out, int32_t *counts);
-/* Optimizer::PoseOptimization for n_problems correspondence sets (pts xyz float, obs uv float, packed). */
+/* Grid-bucketed search by projection (north_star subsystem 3). The reference builds the
+ * bucket grid for every frame (src/Frame.cc:356-388) and keeps Frame::GetFeaturesInArea (:602-668), but its matcher joins by track
+ * id and never queries the grid; this operator is the query those two exist for, restated from the ORB-SLAM3 lineage for MoV-SLAM's
+ * types: for every map point that movfe_frustum left in view (and that is not bad / already matched / beyond th_far), the
+ * keypoints of GetFeaturesInArea(u, v, r) are visited in the reference's (ix, iy, insertion) order, features with taken[i] != 0
+ * (already holding an observed map point) are passed over, and the candidate with the smallest EXPRESS distance
+ * (descriptor1 ^ descriptor2).count() is kept with the second smallest beside it; th_high and the nn_ratio test decide whether
+ * it is a match. Map points are searched independently (that is what makes the search a batch); when two of them choose the same
+ * keypoint the smaller (distance, point index) holds it and the other stays unmatched - where the sequential original lets
+ * the later point take another keypoint. n_problems frames: feat = the frame's keypoints with their descriptors as track records
+ * (pt_x, pt_y, desc are read), feat_off / pt_off = n_problems + 1 offsets, pts / proj = the arrays given to and filled by
+ * movfe_frustum, pt_desc = 8 words per map point. Outputs: feat_match[i] = index (local to the frame's point list) of the
+ * map point matched to keypoint i or -1, pt_match[k] = keypoint index of map point k or -1, pt_dist[k] = its best distance when it
+ * passed th_high / nn_ratio (whether or not it then held the keypoint) or -1, n_matches[p]. At most 16384 keypoints per frame. */
+int movfe_search_by_projection(movfe_ctx *ctx, int n_problems, const movfe_track *feat, const uint8_t *feat_taken /* may be NULL */,
+                               const int32_t *feat_off, const movfe_map_point *pts, const movfe_projection *proj,
+                               const uint32_t *pt_desc, const int32_t *pt_off, const movfe_projection_search_params *prm,
+                               int32_t *feat_match, int32_t *pt_match, int32_t *pt_dist, int32_t *n_matches);
 /* -- pyramidal Lucas-Kanade: replaces cv::calcOpticalFlowPyrLK as the reference calls it for its carry-over branches
  *    (src/MOVExtractor.cc:91-92 I-frame carry-over, :196-197 lost relocalisation, :347-348 coverage tracks: win_size 31, max_level 3,
  *    max_count 20, epsilon 0.01, OPTFLOW_LK_GET_MIN_EIGENVALS, min_eig_threshold 1e-4; src/Frame.cc:305: win_size 21).
@@ -247,6 +264,7 @@ int movfe_lk(movfe_ctx *ctx, int n_problems, const uint8_t *prev, const uint8_t 
  * src/MOVExtractor.cc:81-120; a P picture: the coverage tracks in sorted order, :337-377), installed as movfe_set_lk_results
  * would install them. Call it between movfe_extract(.., frame - 1) and movfe_extract(frame, ..). Nothing crosses PCIe. */
 int movfe_lk_carry(movfe_ctx *ctx, int64_t frame);
+/* Optimizer::PoseOptimization for n_problems correspondence sets (pts xyz float, obs uv float, packed). */
 int movfe_pose_optimize(movfe_ctx *ctx, int n_problems, const movfe_camera *cam, const movfe_pose_params *pp,
                         const float *pts, const float *obs, const int32_t *off, movfe_pose *poses /* in/out */,
                         uint8_t *outlier, int32_t *n_inliers, int32_t *stats /* 4 per problem, may be NULL */);

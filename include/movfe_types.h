@@ -109,6 +109,17 @@ typedef struct movfe_area_query {
     float   x, y, r;
 } movfe_area_query;
 
+/* Parameters of the grid-bucketed search by projection (movfe_search_by_projection). The names are those of the ORB-SLAM3-lineage
+ * matcher MoV-SLAM descends from (ORBmatcher::SearchByProjection(Frame&, vector<MapPoint*>&, th, bFarPoints, thFarPoints),
+ * TH_HIGH, mfNNratio); distances are EXPRESS Hamming distances, 0..256 (include/EXPRESS.h:112-115). 20 bytes. */
+typedef struct movfe_projection_search_params {
+    float   th;          /* search radius = th * (view_cos > 0.998 ? 2.5 : 4.0) pixels (RadiusByViewingCos; one pyramid level) */
+    int32_t far_points;  /* bFarPoints: skip points whose depth exceeds th_far */
+    float   th_far;      /* thFarPoints */
+    int32_t th_high;     /* a best distance above this is no match */
+    float   nn_ratio;    /* with a second candidate: no match when best > nn_ratio * second best */
+} movfe_projection_search_params;
+
 /* Camera: GeometricCamera::mvParameters = [fx,fy,cx,cy,(k1..k4)] (GeometricCamera.h:61-101). */
 #define MOVFE_CAM_PINHOLE 0
 #define MOVFE_CAM_FISHEYE 1   /* KannalaBrandt8: not in the reference tree; ORB-SLAM3 lineage formulae */

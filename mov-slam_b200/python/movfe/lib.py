@@ -84,6 +84,7 @@ def load():
     L.movfe_assign_features_to_grid.argtypes = [vp, i32, vp, vp, vp, vp]
     L.movfe_track_feature_grid.argtypes = [vp, i32, i64, vp, vp, i32]
     L.movfe_features_in_area.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i32, vp, vp]
+    L.movfe_search_by_projection.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.movfe_pose_optimize.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.movfe_workload_stats.argtypes = [vp, vp, i32]
     L.movfe_profile_enable.argtypes = [vp, i32]
@@ -98,7 +99,7 @@ EXPORTS = ["movfe_create", "movfe_destroy", "movfe_last_error", "movfe_synchroni
            "movfe_rejected_records", "movfe_set_tracks", "movfe_set_lk_results", "movfe_dropped_lk_tracks", "movfe_extract", "movfe_extract_frame", "movfe_track_count",
            "movfe_download_tracks", "movfe_set_camera", "movfe_set_map_points", "movfe_set_map_points_batch", "movfe_reserve_map_store", "movfe_set_map_store", "movfe_update_local_points", "movfe_download_map_points", "movfe_set_pose",
            "movfe_track_poses", "movfe_download_poses", "movfe_download_matches", "movfe_frustum", "movfe_join",
-           "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid",
+           "movfe_assign_features_to_grid", "movfe_features_in_area", "movfe_track_feature_grid", "movfe_search_by_projection",
            "movfe_pose_optimize", "movfe_lk", "movfe_lk_carry", "movfe_profile_enable", "movfe_profile_read", "movfe_workload_stats"]
 
 
@@ -429,6 +430,27 @@ class Context:
                                                _p(np.ascontiguousarray(items, np.int32)), len(queries), _p(queries), capacity,
                                                _p(out), _p(counts)))
         return out[:, :capacity], counts[:len(queries)]
+
+    def search_by_projection(self, feat, feat_off, pts, proj, pt_desc, pt_off, prm, taken=None):
+        """Grid-bucketed search by projection for a batch of frames -> (feat_match, pt_match, pt_dist, n_matches)."""
+        feat = np.ascontiguousarray(feat, T.TRACK)
+        feat_off = np.ascontiguousarray(feat_off, np.int32)
+        pts = np.ascontiguousarray(pts, T.MAP_POINT)
+        proj = np.ascontiguousarray(proj, T.PROJECTION)
+        pt_desc = np.ascontiguousarray(pt_desc, np.uint32).reshape(-1, 8)
+        pt_off = np.ascontiguousarray(pt_off, np.int32)
+        prm = np.ascontiguousarray(prm, T.PROJECTION_SEARCH)
+        assert len(proj) == len(pts) == len(pt_desc)
+        if taken is not None:
+            taken = np.ascontiguousarray(taken, np.uint8)
+            assert len(taken) == len(feat)
+        fm = np.zeros(max(len(feat), 1), np.int32)
+        pm = np.zeros(max(len(pts), 1), np.int32)
+        pd = np.zeros(max(len(pts), 1), np.int32)
+        nm = np.zeros(len(feat_off) - 1, np.int32)
+        self._ck(self.L.movfe_search_by_projection(self.h, len(feat_off) - 1, _p(feat), None if taken is None else _p(taken), _p(feat_off),
+                                                   _p(pts), _p(proj), _p(pt_desc), _p(pt_off), _p(prm), _p(fm), _p(pm), _p(pd), _p(nm)))
+        return fm[:len(feat)], pm[:len(pts)], pd[:len(pts)], nm
 
     def pose_optimize(self, cam, pp, pts, obs, off, poses):
         cam = np.ascontiguousarray(cam, T.CAMERA)

@@ -33,6 +33,8 @@ assert POSE.itemsize == 96 and POSE_PARAMS.itemsize == 40
 FRAME_P = 0x1
 FRAME_MV = 0x2
 AREA_QUERY = np.dtype([("problem", "<i4"), ("x", "<f4"), ("y", "<f4"), ("r", "<f4")])
+PROJECTION_SEARCH = np.dtype([("th", "<f4"), ("far_points", "<i4"), ("th_far", "<f4"), ("th_high", "<i4"), ("nn_ratio", "<f4")])
+assert PROJECTION_SEARCH.itemsize == 20
 TRACK_COVERAGE = 0x1
 MP_BAD, MP_SKIP, MP_NULL = 0x1, 0x2, 0x4
 CAM_PINHOLE, CAM_FISHEYE = 0, 1

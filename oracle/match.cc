@@ -10,6 +10,7 @@
 // reference (Frame.cc:429-431); here it is -R^T t evaluated in double and rounded to float.
 #include "oracle.h"
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <vector>
@@ -223,6 +224,76 @@ extern "C" int orc_get_features_in_area(const movfe_track *tracks, int n, int wi
         }
     }
     return cnt;
+}
+
+// Grid-bucketed search by projection. NOT in the reference: its matcher joins by track id (include/MOVMatcher.h:35-68) and
+// Frame::GetFeaturesInArea (src/Frame.cc:602-668) has no caller. Restated from the ORB-SLAM3 lineage
+// (ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th, bFarPoints, thFarPoints); published algorithm, recalled) on
+// MoV-SLAM's types: EXPRESS distance (include/EXPRESS.h:112-115), every keypoint on octave 0. "Parity unpinned": CUDA == this.
+// One deliberate difference, stated in include/movfe.h: map points are searched independently and a keypoint chosen by several
+// goes to the smallest (distance, point index); the original walks the points in order and lets a later one skip a keypoint an
+// earlier one took.
+extern "C" int orc_search_by_projection(const movfe_track *feat, const uint8_t *taken, int n_feat, int width, int height,
+                                        const movfe_map_point *pts, const movfe_projection *proj, const uint32_t *pt_desc,
+                                        int n_pts, const movfe_projection_search_params *prm, int32_t *feat_match,
+                                        int32_t *pt_match, int32_t *pt_dist) {
+    std::vector<int32_t> cell_start(FRAME_GRID_COLS * FRAME_GRID_ROWS + 1), cell_items((size_t)std::max(n_feat, 1)), cand((size_t)std::max(n_feat, 1));
+    orc_assign_features_to_grid(feat, n_feat, width, height, cell_start.data(), cell_items.data());
+    std::vector<int> prop((size_t)std::max(n_pts, 1), -1);
+    for (int i = 0; i < n_feat; i++) feat_match[i] = -1;
+    for (int k = 0; k < n_pts; k++) {
+        pt_match[k] = -1;
+        pt_dist[k] = -1;
+        const movfe_map_point &mp = pts[k];
+        if (!proj[k].in_view) continue;                                          // if(!pMP->mbTrackInView) continue;
+        if (prm->far_points && proj[k].depth > prm->th_far) continue;            // if(bFarPoints && pMP->mTrackDepth>thFarPoints) continue;
+        if (mp.flags & (MOVFE_MP_BAD | MOVFE_MP_SKIP | MOVFE_MP_NULL)) continue;  // if(pMP->isBad()) continue;
+        float r = proj[k].view_cos > 0.998f ? 2.5f : 4.0f;                       // RadiusByViewingCos(pMP->mTrackViewCos)
+        r = r * prm->th;                                                         // if(bFactor) r*=th;  (scale factor of level 0 = 1)
+        const int nc = orc_get_features_in_area(feat, n_feat, width, height, cell_start.data(), cell_items.data(), proj[k].u,
+                                                proj[k].v, r, cand.data());
+        if (nc == 0) continue;
+        const uint32_t *MPdescriptor = pt_desc + (size_t)k * 8;
+        int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+        for (int c = 0; c < nc; c++) {
+            const int idx = cand[c];
+            if (taken && taken[idx]) continue;  // if(F.mvpMapPoints[idx]) if(F.mvpMapPoints[idx]->Observations()>0) continue;
+            int dist = 0;                        // (descriptor1 ^ descriptor2).count()
+            for (int w = 0; w < 8; w++) dist += __builtin_popcount(MPdescriptor[w] ^ feat[idx].desc[w]);
+            const int octave = 0;
+            if (dist < bestDist) {
+                bestDist2 = bestDist;
+                bestDist = dist;
+                bestLevel2 = bestLevel;
+                bestLevel = octave;
+                bestIdx = idx;
+            } else if (dist < bestDist2) {
+                bestLevel2 = octave;
+                bestDist2 = dist;
+            }
+        }
+        if (bestDist <= prm->th_high) {
+            if (bestLevel == bestLevel2 && (float)bestDist > prm->nn_ratio * (float)bestDist2) continue;
+            prop[(size_t)k] = bestIdx;
+            pt_dist[k] = bestDist;
+        }
+    }
+    // a keypoint chosen by several map points: the smallest (distance, point index) holds it
+    int nmatches = 0;
+    for (int k = 0; k < n_pts; k++) {
+        const int f = prop[(size_t)k];
+        if (f < 0) continue;
+        const int cur = feat_match[f];
+        if (cur < 0 || pt_dist[k] < pt_dist[cur]) feat_match[f] = k;  // ascending k: ties keep the earlier point
+    }
+    for (int k = 0; k < n_pts; k++) {
+        const int f = prop[(size_t)k];
+        if (f >= 0 && feat_match[f] == k) {
+            pt_match[k] = f;
+            nmatches++;
+        }
+    }
+    return nmatches;
 }
 
 // Tracking::UpdateLocalPoints (src/Tracking.cc:1171-1198) on index lists: `idx` is the concatenation of the local keyframes'

@@ -112,6 +112,13 @@ int orc_get_features_in_area(const movfe_track *tracks, int n, int width, int he
                              const int32_t *cell_start, const int32_t *cell_items, float x, float y, float r,
                              int32_t *out);
 
+/* Grid-bucketed search by projection for one frame (include/movfe.h: movfe_search_by_projection; ORB-SLAM3 lineage, not in the
+ * reference). taken may be NULL. Returns the number of matches. */
+int orc_search_by_projection(const movfe_track *feat, const uint8_t *taken, int n_feat, int width, int height,
+                             const movfe_map_point *pts, const movfe_projection *proj, const uint32_t *pt_desc, int n_pts,
+                             const movfe_projection_search_params *prm, int32_t *feat_match, int32_t *pt_match,
+                             int32_t *pt_dist);
+
 /* ---- pose-only Gauss-Newton / Huber (OptimizableTypes.cpp:54-69, Pinhole.cpp:77-88) --- */
 /* Camera model maths in double. */
 void orc_project(const movfe_camera *cam, const double Xc[3], double uv[2]);

@@ -63,6 +63,8 @@ def lib():
         L.orc_assign_features_to_grid.argtypes = [vp, i32, i32, i32, vp, vp]
         L.orc_get_features_in_area.restype = i32
         L.orc_get_features_in_area.argtypes = [vp, i32, i32, i32, vp, vp, f32, f32, f32, vp]
+        L.orc_search_by_projection.restype = i32
+        L.orc_search_by_projection.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp]
         L.orc_project.argtypes = [vp, vp, vp]
         L.orc_project_jac.argtypes = [vp, vp, vp]
         L.orc_pose_jacobian.argtypes = [vp, vp, vp]
@@ -238,6 +240,23 @@ def get_features_in_area(tracks, width, height, start, items, x, y, r):
     out = np.zeros(max(len(tracks), 1), np.int32)
     n = lib().orc_get_features_in_area(_p(tracks), len(tracks), width, height, _p(start), _p(items), x, y, r, _p(out))
     return out[:n].copy()
+
+
+def search_by_projection(feat, width, height, pts, proj, pt_desc, prm, taken=None):
+    """Grid-bucketed search by projection for one frame -> (feat_match, pt_match, pt_dist, n_matches)."""
+    feat = np.ascontiguousarray(feat, T.TRACK)
+    pts = np.ascontiguousarray(pts, T.MAP_POINT)
+    proj = np.ascontiguousarray(proj, T.PROJECTION)
+    pt_desc = np.ascontiguousarray(pt_desc, np.uint32).reshape(-1, 8)
+    prm = np.ascontiguousarray(prm, T.PROJECTION_SEARCH)
+    if taken is not None:
+        taken = np.ascontiguousarray(taken, np.uint8)
+    fm = np.zeros(max(len(feat), 1), np.int32)
+    pm = np.zeros(max(len(pts), 1), np.int32)
+    pd = np.zeros(max(len(pts), 1), np.int32)
+    n = lib().orc_search_by_projection(_p(feat), None if taken is None else _p(taken), len(feat), width, height, _p(pts), _p(proj),
+                                       _p(pt_desc), len(pts), _p(prm), _p(fm), _p(pm), _p(pd))
+    return fm[:len(feat)], pm[:len(pts)], pd[:len(pts)], n
 
 
 def project(cam, Xc):
