@@ -19,6 +19,7 @@ namespace movfe_shim {
 // (SURVEY.md §8b), so there is no locking; a context is created on first use and lives until process exit.
 movfe_ctx *extractor_context(int width, int height, int threshold, double coverage_threshold, bool has_grey);
 movfe_ctx *operator_context();  // joins / frustum / pose: geometry-only, no frame buffers
+movfe_ctx *frame_operator_context(int width, int height);  // the same for operators that read the frame size (bucket grid)
 void fail(movfe_ctx *ctx, const char *what);  // prints movfe_last_error to stderr like the reference's cerr paths
 
 // Test hook: when set, replaces cv::calcOpticalFlowPyrLK at the three call sites of MOVExtractor::operator() (outside the

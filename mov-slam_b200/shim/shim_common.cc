@@ -3,6 +3,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <map>
 #include <tuple>
 
 #include "movfe_shim.h"
@@ -54,6 +55,25 @@ movfe_ctx *operator_context() {
     cfg.max_map_points = 1;
     cfg.express_threshold = 20;
     return ctx = create(cfg, "operator context");
+}
+
+// operators that need the frame size (the bucket grid's cell size): geometry-only contexts, one per size
+movfe_ctx *frame_operator_context(int width, int height) {
+    static std::map<std::pair<int, int>, movfe_ctx *> cache;
+    const auto key = std::make_pair(width, height);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    movfe_config cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.n_streams = 1;
+    cfg.width = width;
+    cfg.height = height;
+    cfg.max_records_per_frame = 1;
+    cfg.window_frames = 1;
+    cfg.max_tracks = 1;
+    cfg.max_map_points = 1;
+    cfg.express_threshold = 20;
+    return cache[key] = create(cfg, "frame operator context");
 }
 
 movfe_track pack(const MOV_SLAM::VideoFeature &vf) {

@@ -142,6 +142,11 @@ public:
     bool mbTrackInView = false;
     float mTrackProjX = 0.f, mTrackProjY = 0.f;
     float mTrackDepth = 0.f;
+    float mTrackViewCos = 0.f;
+    std::bitset<256> GetDescriptor() { return mDescriptor; }   // include/MapPoint.h:112
+    int Observations() { return nObs; }                        // include/MapPoint.h:90
+    std::bitset<256> mDescriptor;
+    int nObs = 0;
     Eigen::Vector3f mWorldPos;
     bool mbBad = false;
 };

@@ -167,6 +167,30 @@ int main(int argc, char **argv) {
         produced++;
     };
     while (auto img = decoder.NextImage(true)) consume(img);
+    if (!frames.empty() && frames.back()->N > 0) {
+        // MOVMatcher::SearchByProjection (the shim's addition): every keypoint of the last frame as a map point that projects onto
+        // it and carries its descriptor. Keypoints with a twin (same descriptor within reach) may trade places; the others must
+        // come back as the identity.
+        Frame &F = *frames.back();
+        F.imageCols = W;
+        F.imageRows = H;
+        std::vector<MapPoint> mps((size_t)F.N);
+        std::vector<MapPoint *> list;
+        for (int i = 0; i < F.N; i++) {
+            mps[i].mbTrackInView = true;
+            mps[i].mTrackProjX = F.mvKeysUn[i].pt.x;
+            mps[i].mTrackProjY = F.mvKeysUn[i].pt.y;
+            mps[i].mTrackViewCos = 0.9f;
+            mps[i].mTrackDepth = 1.f;
+            mps[i].mDescriptor = F.mvVF[i].desc;
+            list.push_back(&mps[i]);
+        }
+        F.mvpMapPoints.assign(F.N, nullptr);
+        const int nsp = MOVMatcher::SearchByProjection(F, list, 1.0f, false, 0.f, 100, 1.0f);
+        int ident = 0;
+        for (int i = 0; i < F.N; i++) ident += F.mvpMapPoints[i] == &mps[i];
+        printf("test_shim: search_by_projection %d matches, %d identities of %d keypoints\n", nsp, ident, F.N);
+    }
     printf("test_shim: %d frames, %lld carried tracks dropped for want of LK results\n", produced,
            (long long)movfe_dropped_lk_tracks(movfe_shim::extractor_context(W, H, thr, cov_thr, true)));
     return produced == NF ? 0 : 4;

@@ -127,6 +127,19 @@ def test_shims_against_oracle(orc, tmp_path, cov_thr, iframe_at):
     r = subprocess.run([os.path.join(SHIM, "test_shim"), d], capture_output=True, text=True, )
     assert r.returncode == 0, r.stdout + r.stderr
     assert "0 carried tracks dropped" in r.stdout, r.stdout        # every carried track got its LK result
+    # MOVMatcher::SearchByProjection (the shim's addition) on the last frame: its keypoints as map points projecting onto themselves
+    import re
+    msp = re.search(r"search_by_projection (\d+) matches, (\d+) identities of (\d+) keypoints", r.stdout)
+    assert msp, r.stdout
+    lt = tracks[NF - 1]
+    sp_pts = np.zeros(len(lt), T.MAP_POINT)
+    sp_proj = np.zeros(len(lt), T.PROJECTION)
+    sp_proj["u"], sp_proj["v"], sp_proj["view_cos"], sp_proj["depth"], sp_proj["in_view"] = lt["pt_x"], lt["pt_y"], 0.9, 1.0, 1
+    sp_prm = np.zeros(1, T.PROJECTION_SEARCH)
+    sp_prm["th"], sp_prm["th_high"], sp_prm["nn_ratio"] = 1.0, 100, 1.0
+    _, sp_pm, _, sp_n = orc.search_by_projection(lt, W, H, sp_pts, sp_proj, lt["desc"], sp_prm)
+    assert [int(v) for v in msp.groups()] == [sp_n, int((sp_pm == np.arange(len(lt))).sum()), len(lt)], (msp.groups(), sp_n)
+    assert sp_n > 0.9 * len(lt) > 0
 
     def f32(p):  # the Frame stores Sophus::SE3f: the pose is rounded to float between calls
         q = p.copy()
