@@ -27,6 +27,7 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->pose_stream) cudaStreamSynchronize(ctx->pose_stream);
+    if (ctx->ingest_split && ctx->ingest_stream) cudaStreamSynchronize(ctx->ingest_stream);
     if (ctx->raster_stream) cudaStreamSynchronize(ctx->raster_stream);
     for (int g = 1; g < movfe_ctx::MAX_GROUPS; g++)
         if (ctx->ext_stream[g]) cudaStreamSynchronize(ctx->ext_stream[g]);
@@ -78,6 +79,8 @@ extern "C" void movfe_destroy(movfe_ctx *ctx) {
         if (pl.done) cudaEventDestroy(pl.done);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->pose_stream) cudaStreamDestroy(ctx->pose_stream);
+    if (ctx->ingest_split && ctx->ingest_stream) cudaStreamDestroy(ctx->ingest_stream);
+    if (ctx->ev_ingested) cudaEventDestroy(ctx->ev_ingested);
     if (ctx->raster_stream) cudaStreamDestroy(ctx->raster_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -140,6 +143,10 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     // MOVFE_RASTER_PRIO=1 (development): the raster stream at the propagation priority
     CK(cudaStreamCreateWithPriority(&ctx->raster_stream, cudaStreamNonBlocking, (getenv("MOVFE_RASTER_PRIO") && atoi(getenv("MOVFE_RASTER_PRIO"))) ? prio_hi : prio_lo));
     CK(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_lo));
+    ctx->ingest_split = getenv("MOVFE_INGEST_STREAM") && atoi(getenv("MOVFE_INGEST_STREAM"));
+    if (ctx->ingest_split) CK(cudaStreamCreateWithPriority(&ctx->ingest_stream, cudaStreamNonBlocking, prio_lo));
+    else ctx->ingest_stream = ctx->raster_stream;
+    CK(cudaEventCreateWithFlags(&ctx->ev_ingested, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ctx->ev_serial, cudaEventDisableTiming));
     for (RasterBuf &w : ctx->rb) {
@@ -195,6 +202,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     // two windows deep: the push + raster of window k+1 overwrite the slots of window k-1 while propagation still reads
     // the grey planes of window k
     ctx->RING = 2 * c.window_frames + ctx->LA;
+    if (getenv("MOVFE_RING_EXTRA")) ctx->RING += std::max(0, atoi(getenv("MOVFE_RING_EXTRA"))) * c.window_frames;  // development: deeper ring
     ctx->NB = (c.height + 7) / 8;
     ctx->NT = (c.width + 31) / 32;
     ctx->NTR = (c.height + 31) / 32;
@@ -301,6 +309,7 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
 
 extern "C" int movfe_synchronize(movfe_ctx *ctx) {
     if (!ctx) return MOVFE_E_INVALID;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->ingest_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));
@@ -315,6 +324,10 @@ extern "C" int movfe_fence(movfe_ctx *ctx) {
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tables, 0));
     MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tables, 0));
+    if (ctx->ingest_split) {
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->ingest_stream));
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_tables, 0));
+    }
     return MOVFE_OK;
 }
 
@@ -324,6 +337,7 @@ extern "C" int64_t movfe_frames_pushed(const movfe_ctx *ctx) { return ctx ? ctx-
 static int ensure_stage(movfe_ctx *ctx, int b, size_t bytes) {
     if (bytes <= ctx->stage_bytes[b]) return MOVFE_OK;
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->ingest_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->d_stage[b]) cudaFree(ctx->d_stage[b]);
@@ -353,9 +367,18 @@ int movfe_ensure_op_scratch(movfe_ctx *ctx, size_t bytes) { return ensure_op(ctx
 // one stream, so waiting for the newest launch that starts at or before the last overwritten frame covers all of them;
 // when that launch has already left the bookkeeping ring, its oldest entry (a later launch) stands in for it.
 static int wait_ring_readers(movfe_ctx *ctx, int n_frames, cudaStream_t waiter = nullptr) {
-    if (!waiter) waiter = ctx->raster_stream;
+    if (!waiter) waiter = ctx->ingest_stream;
     const int64_t last_overwritten = ctx->pushed + n_frames - 1 - ctx->RING;
-    if (last_overwritten < 0 || ctx->ext_launch_count == 0) return MOVFE_OK;
+    if (last_overwritten < 0) return MOVFE_OK;
+    if (waiter != ctx->raster_stream) {
+        // the raster launches read the record slots as well: on their own stream nothing orders them implicitly any more. A raster
+        // whose input frames meet the overwritten ones must have finished (an older raster precedes these on the raster stream).
+        const int64_t first_overwritten = ctx->pushed - ctx->RING;
+        for (const RasterBuf &w : ctx->rb)
+            if (w.first >= 0 && w.first <= last_overwritten && w.first + w.nin > first_overwritten)
+                MOVFE_CUDA(ctx, cudaStreamWaitEvent(waiter, w.done, 0));
+    }
+    if (ctx->ext_launch_count == 0) return MOVFE_OK;
     const int N = movfe_ctx::N_EXT_LAUNCHES;
     const int live = (int)std::min<int64_t>(ctx->ext_launch_count, N);
     const movfe_ctx::ExtLaunch *pick = nullptr;
@@ -368,6 +391,15 @@ static int wait_ring_readers(movfe_ctx *ctx, int n_frames, cudaStream_t waiter =
     }
     if (!pick && ctx->ext_launch_count > N) pick = &ctx->ext_launches[ctx->ext_launch_head];  // oldest entry
     if (pick) MOVFE_CUDA(ctx, cudaStreamWaitEvent(waiter, pick->done, 0));
+    return MOVFE_OK;
+}
+
+// whatever reads the ring is ordered behind the raster stream (the raster itself, then propagation through RasterBuf::done; the
+// LK carry-over through its own wait): with the ingest kernels on a stream of their own the raster stream waits for them here
+static int after_ingest(movfe_ctx *ctx) {
+    if (!ctx->ingest_split) return MOVFE_OK;
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_ingested, ctx->ingest_stream));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_ingested, 0));
     return MOVFE_OK;
 }
 
@@ -389,6 +421,8 @@ extern "C" int movfe_push_frames_device(movfe_ctx *ctx, int n_frames, const movf
     rc = wait_ring_readers(ctx, n_frames);
     if (rc) return rc;
     rc = movfe_ingest_launch(ctx, n_frames, d_recs, false, d_rec_off, n_records, d_frame_flags, d_grey);
+    if (rc) return rc;
+    rc = after_ingest(ctx);
     if (rc) return rc;
     ctx->pushed += n_frames;
     return MOVFE_OK;
@@ -468,13 +502,15 @@ static int push_host(movfe_ctx *ctx, int n_frames, const void *recs, size_t rec_
         }
     }
     MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_copied[b], cs));
-    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_copied[b], 0));
+    MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->ingest_stream, ctx->ev_copied[b], 0));
     rc = wait_ring_readers(ctx, n_frames);
     if (rc) return rc;
     rc = movfe_ingest_launch(ctx, n_frames, base, rec_size == sizeof(movfe_packed_record), (const int64_t *)(base + rec_bytes), n_records,
                              base + rec_bytes + off_bytes, d_grey);
     if (rc) return rc;
-    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->raster_stream));
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_consumed[b], ctx->ingest_stream));
+    rc = after_ingest(ctx);
+    if (rc) return rc;
     ctx->stage_used[b] = true;
     ctx->push_parity ^= 1;
     ctx->pushed += n_frames;
@@ -614,6 +650,7 @@ extern "C" int movfe_download_kps(movfe_ctx *ctx, int stream, int64_t frame, mov
 extern "C" int64_t movfe_rejected_records(movfe_ctx *ctx) {
     if (!ctx) return -1;
     unsigned long long v = 0;
+    if (cudaStreamSynchronize(ctx->ingest_stream) != cudaSuccess) return -1;  // the ingest kernels count rejects as well
     if (cudaMemcpyAsync(&v, ctx->d_rejected, sizeof v, cudaMemcpyDeviceToHost, ctx->raster_stream) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(ctx->raster_stream) != cudaSuccess) return -1;
     return (int64_t)v;
@@ -636,6 +673,7 @@ extern "C" int movfe_profile_enable(movfe_ctx *ctx, int on) {
 
 extern "C" int movfe_profile_read(movfe_ctx *ctx, double *ms, int64_t *launches, int reset) {
     if (!ctx) return MOVFE_E_INVALID;
+    MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->ingest_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->raster_stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     MOVFE_CUDA(ctx, cudaStreamSynchronize(ctx->pose_stream));

@@ -155,6 +155,12 @@ struct movfe_ctx {
     RasterBuf rb[2];
     int rb_cur = 0;
     cudaStream_t raster_stream = nullptr;  // ingest kernels + raster kernels (low priority: they fill what propagation leaves)
+    // MOVFE_INGEST_STREAM=1: the ingest kernels of a push on a stream of their own (low priority), so that the ingest of window
+    // k+2 runs beside the hop lists / slot resolution of window k+1 instead of queueing behind them; otherwise an alias of
+    // raster_stream. ev_ingested orders the raster after the pushes it reads.
+    cudaStream_t ingest_stream = nullptr;
+    bool ingest_split = false;
+    cudaEvent_t ev_ingested = nullptr;
     bool serial_raster = false;            // MOVFE_CFG_SERIAL_RASTER: raster waits for all earlier propagation (timing a kernel alone)
     cudaEvent_t ev_serial = nullptr;
     struct ExtLaunch { int64_t first; int n; cudaEvent_t done; };

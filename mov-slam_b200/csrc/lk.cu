@@ -426,7 +426,7 @@ extern "C" int movfe_lk_carry(movfe_ctx *ctx, int64_t frame) {
     movfe_lk_handover hb;
     movfe_lk_buffers(ctx, &hb);
     // the raster stream wrote the ring (ingest): the newest push must have landed before the planes are read
-    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->raster_stream));
+    MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_tables, ctx->ingest_stream));
     MOVFE_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_tables, 0));
     const int T = ctx->TSLOTS, ts_prev = (int)((((frame - 1) % T) + T) % T);
     const int slot_prev = (int)((frame - 1) % ctx->RING), slot_next = (int)(frame % ctx->RING);

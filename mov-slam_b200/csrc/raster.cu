@@ -468,27 +468,27 @@ int movfe_ingest_launch(movfe_ctx *ctx, int n_frames, const void *d_recs, bool p
                         int64_t n_records, const uint8_t *d_flags, const uint8_t *d_grey) {
     const movfe_config &c = ctx->cfg;
     const int n_seg = c.n_streams * n_frames;
-    ProfScope prof(ctx, MOVFE_STAGE_INGEST, ctx->raster_stream);
+    ProfScope prof(ctx, MOVFE_STAGE_INGEST, ctx->ingest_stream);
     prof.launches(n_records > 0 ? 2 : 1);
     if (n_records > 0 && packed) {
-        ingest_packed_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->raster_stream>>>(
+        ingest_packed_kernel<<<(unsigned)((n_records + 255) / 256), 256, 0, ctx->ingest_stream>>>(
             reinterpret_cast<const uint4 *>(d_recs), n_records, d_rec_off, n_seg, n_frames, ctx->pushed, ctx->RING, c.max_records_per_frame,
             ctx->d_rec, ctx->d_rejected);
     } else if (n_records > 0) {
         const int64_t warps = (n_records + INGEST_REC_PER_WARP - 1) / INGEST_REC_PER_WARP;
         const int blocks = (int)((warps + INGEST_WARPS - 1) / INGEST_WARPS);
-        ingest_kernel<<<blocks, INGEST_WARPS * 32, 0, ctx->raster_stream>>>(
+        ingest_kernel<<<blocks, INGEST_WARPS * 32, 0, ctx->ingest_stream>>>(
             reinterpret_cast<const uint4 *>(d_recs), n_records, d_rec_off, n_seg, n_frames, ctx->pushed, ctx->RING,
             c.max_records_per_frame, ctx->d_rec, ctx->d_rejected);
     }
-    ingest_meta_kernel<<<(n_seg + 255) / 256, 256, 0, ctx->raster_stream>>>(d_rec_off, d_flags, n_seg, n_frames, ctx->pushed,
+    ingest_meta_kernel<<<(n_seg + 255) / 256, 256, 0, ctx->ingest_stream>>>(d_rec_off, d_flags, n_seg, n_frames, ctx->pushed,
                                                                      ctx->RING, c.max_records_per_frame,
                                                                      ctx->d_rec_cnt, ctx->d_fflags);
     if (c.has_grey && d_grey) {
         const int vec = (c.width % 16 == 0 && ((uintptr_t)d_grey & 15) == 0) ? 16 : 1;
         const int64_t total = (int64_t)n_seg * c.height * (c.width / vec);
         const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->sm_count * 16);
-        grey_ingest_kernel<<<blocks, 256, 0, ctx->raster_stream>>>(d_grey, n_seg, n_frames, c.width, c.height, ctx->grey_pitch, vec, ctx->pushed,
+        grey_ingest_kernel<<<blocks, 256, 0, ctx->ingest_stream>>>(d_grey, n_seg, n_frames, c.width, c.height, ctx->grey_pitch, vec, ctx->pushed,
                                                           ctx->RING, ctx->d_grey);
         prof.launches(1);
     }
