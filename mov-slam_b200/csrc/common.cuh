@@ -161,6 +161,11 @@ struct movfe_ctx {
     cudaStream_t ingest_stream = nullptr;
     bool ingest_split = false;
     cudaEvent_t ev_ingested = nullptr;
+    // (default; MOVFE_HOPS_PRIO=0 turns it off) the five short hop-list kernels of a raster (count .. bbox, ~0.12 ms alone) on a HIGH-priority stream between
+    // two events, the long slot-resolution kernel stays on the low-priority raster stream (a chain of short launches at low priority
+    // waits for a free SM five times over)
+    cudaStream_t hops_stream = nullptr;
+    cudaEvent_t ev_hops = nullptr;
     bool serial_raster = false;            // MOVFE_CFG_SERIAL_RASTER: raster waits for all earlier propagation (timing a kernel alone)
     cudaEvent_t ev_serial = nullptr;
     struct ExtLaunch { int64_t first; int n; cudaEvent_t done; };

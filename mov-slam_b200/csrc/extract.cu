@@ -35,7 +35,10 @@ namespace {
 #define MOVFE_CAND_WARPS 4   // 128-thread CTAs pack better around the pose / finalize / raster CTAs they share SMs with
 #endif
 constexpr int CAND_WARPS = MOVFE_CAND_WARPS;
-constexpr int FIN_THREADS = 1024;
+#ifndef MOVFE_FIN_THREADS
+#define MOVFE_FIN_THREADS 512   // a 1024-thread CTA holds every register of its SM: with 512 two candidate CTAs fit beside it (3.22 against 3.27 ms per C2 step)
+#endif
+constexpr int FIN_THREADS = MOVFE_FIN_THREADS;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int MAX_TRACKS_CAP = 8192;
 
@@ -1426,13 +1429,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int *wsum, int &total) {
     if (lane == 31) wsum[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        int w = wsum[lane];
+        int w = lane < FIN_WARPS ? wsum[lane] : 0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, w, o);
             if (lane >= o) w += y;
         }
-        wsum[lane] = w;  // inclusive
+        if (lane < FIN_WARPS) wsum[lane] = w;  // inclusive
     }
     __syncthreads();
     total = wsum[FIN_WARPS - 1];
@@ -1531,7 +1534,8 @@ __device__ void sort_keys(unsigned long long *keys, int n, uint16_t *__restrict_
     for (int i = n + threadIdx.x; i < N; i += blockDim.x) keys[i] = ~0ull;
     __syncthreads();
     if (N <= 4 * FIN_THREADS) bitonic_sort<4>(keys, N);
-    else bitonic_sort<8>(keys, N);
+    else if (N <= 8 * FIN_THREADS) bitonic_sort<8>(keys, N);
+    else bitonic_sort<16>(keys, N);
     for (int i = threadIdx.x; i < n; i += blockDim.x) order_out[i] = (uint16_t)(keys[i] & 0xffffu);
     __syncthreads();
 }
@@ -1680,9 +1684,12 @@ __device__ void lattice_pass(const ExtParams &p, const uint8_t *__restrict__ img
     }
 }
 
-constexpr int FIN_IPT = 8;  // consecutive entries a thread owns per round of the ordered compactions
+#ifndef MOVFE_FIN_IPT
+#define MOVFE_FIN_IPT 8
+#endif
+constexpr int FIN_IPT = MOVFE_FIN_IPT;  // consecutive entries a thread owns per round of the ordered compactions
 
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(FIN_THREADS, 1024 / FIN_THREADS)
 finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restrict__ ntracks,
                 int32_t *__restrict__ cur_id, uint16_t *__restrict__ order, const movfe_track *__restrict__ stage,
                 const int2 *__restrict__ cinfo, int32_t *__restrict__ claim, const movfe_rect *__restrict__ kps,
@@ -1978,7 +1985,7 @@ finalize_kernel(ExtParams p, movfe_track *__restrict__ tracks, int32_t *__restri
 }
 
 // Sorts a table that was installed from the host (movfe_set_tracks).
-__global__ void __launch_bounds__(FIN_THREADS)
+__global__ void __launch_bounds__(FIN_THREADS, 1024 / FIN_THREADS)
 sort_only_kernel(int maxT, int TSLOTS, int tslot, int stream, const movfe_track *__restrict__ tracks,
                  const int32_t *__restrict__ ntracks, uint16_t *__restrict__ order) {
     extern __shared__ unsigned long long keys[];
@@ -2043,7 +2050,7 @@ size_t sort_smem(int maxT) {
     int N = SORT_MIN_N;
     while (N < maxT) N <<= 1;
     const size_t general = (size_t)N * sizeof(unsigned long long);
-    const size_t runs = (size_t)maxT * 8 + (size_t)FIN_WARPS * HIST_STRIDE * sizeof(int) + (size_t)FIN_THREADS * 8 * sizeof(uint16_t);
+    const size_t runs = (size_t)maxT * 8 + (size_t)FIN_WARPS * HIST_STRIDE * sizeof(int) + (size_t)FIN_THREADS * FIN_IPT * sizeof(uint16_t);
     return std::max(general, runs);
 }
 

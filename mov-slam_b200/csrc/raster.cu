@@ -523,21 +523,31 @@ int movfe_raster_launch(movfe_ctx *ctx, RasterBuf &w, int64_t first_frame, int n
     p.max_kps = ctx->max_kps;
     p.max_chunks = ctx->max_chunks;
     const int SF = p.S * n_in;
+    // the hop-list kernels: on the raster stream, or (MOVFE_HOPS_PRIO) on a high-priority stream between two events
+    cudaStream_t hs = ctx->hops_stream ? ctx->hops_stream : ctx->raster_stream;
+    if (ctx->hops_stream) {
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_hops, ctx->raster_stream));
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(hs, ctx->ev_hops, 0));
+    }
     {
-    ProfScope prof(ctx, MOVFE_STAGE_HOPS, ctx->raster_stream);
+    ProfScope prof(ctx, MOVFE_STAGE_HOPS, hs);
     prof.launches(5);
     const dim3 gseg(SF, ctx->n_rseg);
-    count_kernel<<<gseg, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->rseg, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_seg_cnt);
-    seg_sum_kernel<<<SF, 32, 0, ctx->raster_stream>>>(p, ctx->n_rseg, w.d_seg_cnt, w.d_cls_cnt, w.d_area, ctx->d_rejected);
-    bases_kernel<<<(SF + 127) / 128, 128, 0, ctx->raster_stream>>>(p, w.d_cls_cnt, w.d_area, w.d_hop_base,
+    count_kernel<<<gseg, CNT_THREADS, 0, hs>>>(p, ctx->rseg, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags, w.d_seg_cnt);
+    seg_sum_kernel<<<SF, 32, 0, hs>>>(p, ctx->n_rseg, w.d_seg_cnt, w.d_cls_cnt, w.d_area, ctx->d_rejected);
+    bases_kernel<<<(SF + 127) / 128, 128, 0, hs>>>(p, w.d_cls_cnt, w.d_area, w.d_hop_base,
                                                             w.d_kps_base, w.d_nhops, w.d_nkps, w.d_cov, ctx->d_stats);
-    emit_kernel<<<gseg, CNT_THREADS, 0, ctx->raster_stream>>>(p, ctx->rseg, w.d_seg_cnt, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags,
+    emit_kernel<<<gseg, CNT_THREADS, 0, hs>>>(p, ctx->rseg, w.d_seg_cnt, ctx->d_rec, ctx->d_rec_cnt, ctx->d_fflags,
                                                        w.d_hop_base, w.d_kps_base, w.d_hops, w.d_hop_rect, w.d_kps);
     {
         // capacity would be max_chunks warps per (stream, frame); frames hold a fraction of it, so a few CTAs stride instead
         dim3 g(std::min((ctx->max_chunks * 32 + 255) / 256, 16), p.S * n_out);
-        bbox_kernel<<<g, 256, 0, ctx->raster_stream>>>(p, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox);
+        bbox_kernel<<<g, 256, 0, hs>>>(p, w.d_hop_rect, w.d_nhops, w.d_chunk_bbox);
     }
+    }
+    if (ctx->hops_stream) {
+        MOVFE_CUDA(ctx, cudaEventRecord(ctx->ev_hops, hs));
+        MOVFE_CUDA(ctx, cudaStreamWaitEvent(ctx->raster_stream, ctx->ev_hops, 0));
     }
     if (int rc = movfe_grid_launch(ctx, p, w)) return rc;
     MOVFE_CUDA(ctx, cudaGetLastError());
