@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("serial_raster,env,output_grid", [(False, {}, True), (True, {}, True), (False, {"MOVFE_POSE_SPLIT": "1"}, True),
                                                            (False, {"MOVFE_PDL": "1"}, True), (False, {"MOVFE_EXTRACT_GROUPS": "3"}, True), (False, {"MOVFE_EXTRACT_GROUPS": "1"}, False),
                                                            (False, {}, False), (True, {}, False), (False, {"MOVFE_PDL": "1"}, False),
-                                                           (False, {"MOVFE_CAND_LANE": "0"}, False), (False, {"MOVFE_POSE_V1": "1"}, False), (False, {"MOVFE_CAND_LANE": "0", "MOVFE_CAND_PIPE": "0"}, True)])
+                                                           (False, {"MOVFE_CAND_LANE": "0"}, False), (False, {"MOVFE_POSE_V1": "1"}, False), (False, {"MOVFE_CAND_LANE": "0", "MOVFE_CAND_PIPE": "0"}, True),
+                                                           (False, {"MOVFE_HOPS_PRIO": "0"}, False), (False, {"MOVFE_INGEST_STREAM": "1"}, False),
+                                                           (False, {"MOVFE_INGEST_STREAM": "2", "MOVFE_RING_EXTRA": "1"}, True)])
 def test_pipelined_windows_match_oracle(orc, serial_raster, env, output_grid, monkeypatch):
     """output_grid False = MOVFE_CFG_NO_GRID, the fused mode bench.py's headline uses: slots resolved from the per-tile hop
     queues, same tables bit for bit."""
