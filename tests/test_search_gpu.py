@@ -107,6 +107,39 @@ def test_projected_map_points(orc, ctx, model):
         assert found > 0.9, (model, i, found)
 
 
+def test_properties_at_batch_scale(orc, ctx):
+    """64 frames x 4000 keypoints x 1024 map points (the shape of one C2 window's last frames): properties that do not need the
+    oracle on every frame - matches are mutual and unique, within the radius and the distance bound, independent of where a frame
+    sits in the batch - and three frames against the oracle."""
+    rng = np.random.Generator(np.random.PCG64(0x5EED0043))
+    S = 64
+    base = [make_frame(rng, 640, 480, 4000, 1024) for _ in range(4)]
+    frames = [base[i % 4] for i in range(S)]
+    foff = np.arange(S + 1, dtype=np.int32) * 4000
+    poff = np.arange(S + 1, dtype=np.int32) * 1024
+    cat = lambda i: np.concatenate([f[i] for f in frames])
+    prm = params(th=1.0, th_high=60, ratio=0.8)
+    feat, pts, proj, desc = cat(0), cat(1), cat(2), cat(3)
+    fm, pm, pd, nm = ctx.search_by_projection(feat, foff, pts, proj, desc, poff, prm)
+    assert nm.sum() > 64 * 150
+    for i in range(S):
+        f, p_, d = fm[foff[i]:foff[i + 1]], pm[poff[i]:poff[i + 1]], pd[poff[i]:poff[i + 1]]
+        k = np.nonzero(p_ >= 0)[0]
+        assert nm[i] == len(k) == (f >= 0).sum()
+        assert np.array_equal(f[p_[k]], k)                          # mutual
+        assert len(np.unique(p_[k])) == len(k)                      # a keypoint holds at most one map point
+        assert (d[k] >= 0).all() and (d[k] <= 60).all() and (d[p_ < 0] <= 60).all()
+        ft, pr = frames[i][0], frames[i][2]
+        r = np.where(pr["view_cos"][k] > np.float32(0.998), 2.5, 4.0)
+        assert (np.abs(ft["pt_x"][p_[k]] - pr["u"][k]) < r).all() and (np.abs(ft["pt_y"][p_[k]] - pr["v"][k]) < r).all()
+        j = i % 4                                                   # the same frame elsewhere in the batch: same answer
+        assert np.array_equal(p_, pm[poff[j]:poff[j + 1]]) and np.array_equal(f, fm[foff[j]:foff[j + 1]])
+    for i in (0, 1, 2):
+        w = orc.search_by_projection(frames[i][0], 640, 480, frames[i][1], frames[i][2], frames[i][3], prm)
+        assert np.array_equal(fm[foff[i]:foff[i + 1]], w[0]) and np.array_equal(pm[poff[i]:poff[i + 1]], w[1])
+        assert np.array_equal(pd[poff[i]:poff[i + 1]], w[2]) and nm[i] == w[3]
+
+
 def test_argument_errors(ctx):
     feat = np.zeros(2, T.TRACK)
     pts, proj, desc = np.zeros(1, T.MAP_POINT), np.zeros(1, T.PROJECTION), np.zeros((1, 8), np.uint32)
