@@ -1310,8 +1310,11 @@ birth_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__r
 constexpr int BL_BATCH = 32;
 constexpr size_t BL_SMEM = (size_t)CAND_WARPS * BL_BATCH * xl::WIN_STRIDE * sizeof(uint32_t);
 
+#ifndef BIRTH_LANE_MINB
+#define BIRTH_LANE_MINB 4
+#endif
 template <int PITCH>
-__global__ void __launch_bounds__(CAND_THREADS, 4)
+__global__ void __launch_bounds__(CAND_THREADS, BIRTH_LANE_MINB)
 birth_lane_kernel(ExtParams p, const movfe_rect *__restrict__ kps, const int32_t *__restrict__ nkps,
                   const uint8_t *__restrict__ grey, const uint8_t *__restrict__ fflags, const int32_t *__restrict__ claim,
                   uint8_t *__restrict__ birth_flag, uint32_t *__restrict__ birth_desc) {
