@@ -669,13 +669,25 @@ def run_product(args, cfg):
     push_host(0)
     map_host(0)
 
+    copy_only = bool(os.environ.get("BENCH_E2E_COPY_ONLY"))    # development: the pushes alone (what the push path does without kernels beside it)
+
     def step_host(k):
         first = F * (k + 1)
+        if copy_only:
+            if k + 1 < n_steps:
+                map_host(k + 1)
+            push_host(k + 1)
+            if k % 2:
+                ctx.synchronize()
+            return
         ctx.raster(first, F)
         ctx.extract(first, F)
         ctx.track_poses(first, F)
         # the next window's inputs: its local maps first (a small copy that must not queue behind the big one: the pose chain
-        # of window k+1 waits for it), then records + grey planes; both are one step's inputs, counted in h2d_bytes_per_step
+        # of window k+1 waits for it), then records + grey planes; both are one step's inputs, counted in h2d_bytes_per_step.
+        # (Pushing TWO windows ahead, so that the link never waits for the host to come back from the pose read: 7.12 ms per step
+        # against 7.09 - the host is not what the copy waits for. The pushes alone, BENCH_E2E_COPY_ONLY=1, run at 6.48 ms per step
+        # = 54.4 GB/s of the link's 55.5; beside the kernels the same copies reach 49.5-49.8 GB/s.)
         if k + 1 < n_steps:
             map_host(k + 1)
         push_host(k + 1)
@@ -683,6 +695,9 @@ def run_product(args, cfg):
 
     _, e2e_wall_ms, e2e_stage_ms, _, _ = timed(ctx, ext, step_host, "end-to-end")
     e2e_value = frames_total / (e2e_wall_ms / 1e3)
+    if copy_only:
+        log("[rank %d] BENCH_E2E_COPY_ONLY: %.3f ms per step = %.2f GB/s" % (rank, e2e_wall_ms / args.steps, h2d / 1e9 / (e2e_wall_ms / args.steps / 1e3)))
+        last["ninl"] = ninl_last
     e2e_same = bool(np.array_equal(last["ninl"], ninl_last))
     ctx.close()
 

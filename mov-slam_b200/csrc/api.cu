@@ -144,7 +144,8 @@ extern "C" int movfe_create(const movfe_config *cfg, movfe_ctx **out) {
     CK(cudaStreamCreateWithPriority(&ctx->pose_stream, cudaStreamNonBlocking, prio_hi));
     // MOVFE_RASTER_PRIO=1 (development): the raster stream at the propagation priority
     CK(cudaStreamCreateWithPriority(&ctx->raster_stream, cudaStreamNonBlocking, (getenv("MOVFE_RASTER_PRIO") && atoi(getenv("MOVFE_RASTER_PRIO"))) ? prio_hi : prio_lo));
-    CK(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_lo));
+    // MOVFE_COPY_PRIO=1 (development): the host->device copies on a high-priority stream
+    CK(cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, (getenv("MOVFE_COPY_PRIO") && atoi(getenv("MOVFE_COPY_PRIO"))) ? prio_hi : prio_lo));
     ctx->ingest_split = getenv("MOVFE_INGEST_STREAM") && atoi(getenv("MOVFE_INGEST_STREAM"));
     if (ctx->ingest_split) CK(cudaStreamCreateWithPriority(&ctx->ingest_stream, cudaStreamNonBlocking, atoi(getenv("MOVFE_INGEST_STREAM")) >= 2 ? prio_hi : prio_lo));
     else ctx->ingest_stream = ctx->raster_stream;
